@@ -1,0 +1,55 @@
+// Convolution problem descriptor shared by the SIMT (fp32 CUDA-core) and the
+// tcgen05 (split-bf16 tensor-core) implicit-GEMM kernels.
+//
+// All activations are NHWC.  The GEMM view is
+//   M = N*Hout*Wout output pixels, Ncol = cout (packed), K = kh*kw*(c1+c2)
+// with k = (r*kw + s)*(c1+c2) + c and torch.cat((x1, x2), 1) expressed as two
+// channel ranges so it is never materialised.
+#pragma once
+#include "evk_common.cuh"
+
+namespace evk {
+
+enum Epilogue : int {
+    EPI_LINEAR = 0,   // y = act(acc + bias [+ res])                       ConvLayer / ResidualBlock / decoder
+    EPI_LSTM = 1,     // packed cout = 4*C (ch*4 + {in,remember,out,cell}) ConvLSTM (model/submodules.py:231-243)
+    EPI_GRU_UR = 2,   // packed cout = 2*C (ch*2 + {update,reset})         ConvGRU  (model/submodules.py:281-282)
+    EPI_GRU_OUT = 3,  // cout = C: o = tanh(.), h' = h(1-u) + o*u          ConvGRU  (model/submodules.py:283-285)
+};
+
+struct ConvParams {
+    // inputs
+    const float* x1 = nullptr; int c1 = 0;
+    const float* x2 = nullptr; int c2 = 0;
+    int N = 0, Hin = 0, Win = 0, Hout = 0, Wout = 0;
+    int kh = 0, kw = 0, stride = 1, pad = 0;
+    // weights: SIMT layout [K][cout] fp32 (cout contiguous); bias [cout] (BatchNorm folded)
+    const float* w = nullptr;
+    const float* bias = nullptr;
+    int cout = 0;
+    int epi = EPI_LINEAR;
+    int act = ACT_NONE;
+    const float* res = nullptr;     // EPI_LINEAR: residual added before the activation, NHWC [.,cout]
+    float* y = nullptr;             // EPI_LINEAR output NHWC [.,cout]
+    // recurrent epilogues (C = hidden channels)
+    const float* c_prev = nullptr; float* c_new = nullptr;   // LSTM cell (may alias: pointwise)
+    float* h_new = nullptr;                                   // LSTM / GRU_OUT new hidden state
+    const float* h_prev = nullptr;                            // GRU_UR / GRU_OUT previous hidden state
+    float* u_out = nullptr; float* hr_out = nullptr;          // GRU_UR outputs: update gate, h*reset
+    const float* u_in = nullptr;                              // GRU_OUT input: update gate
+};
+
+int launch_conv_simt(const ConvParams& p, cudaStream_t st);
+// dispatcher: tensor-core split-bf16 kernel when the shape qualifies and precision == 0, else fp32 SIMT
+int launch_conv(const ConvParams& p, int precision, cudaStream_t st);
+
+// head ConvLayer on the NCHW event tensor (Cin = num_bins): NCHW in -> NHWC out, ReLU
+int launch_head_conv(const float* x_nchw, const float* w /*[k*k*cin][cout]*/, const float* bias, float* y_nhwc,
+                     int N, int cin, int H, int W, int k, int cout, cudaStream_t st);
+// prediction ConvLayer: 1x1 conv on (x [+ skip]) NHWC -> channel 0 only, NCHW [N,1,H,W]; optional sigmoid
+int launch_pred(const float* x, const float* skip, const float* w /*[cin]*/, float bias, float* y, int64_t pixels,
+                int cin, int sigmoid, cudaStream_t st);
+// y[N,2H,2W,C] = bilinear_x2(x + skip), align_corners=False (model/unet.py:130-134 + submodules.py:88)
+int launch_upsample2x_add(const float* x, const float* skip, float* y, int N, int H, int W, int C, cudaStream_t st);
+
+}  // namespace evk

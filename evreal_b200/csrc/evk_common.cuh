@@ -1,0 +1,51 @@
+// Shared helpers for the evreal_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/evreal_b200.h"
+
+namespace evk {
+
+void set_error(const char* fmt, ...);
+
+#define EVK_CHECK_CUDA(expr)                                                         \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            evk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                      \
+            return EVK_ERR_CUDA;                                                     \
+        }                                                                            \
+    } while (0)
+
+#define EVK_REQUIRE(cond, code, ...)      \
+    do {                                  \
+        if (!(cond)) {                    \
+            evk::set_error(__VA_ARGS__);  \
+            return (code);                \
+        }                                 \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr int kNumSMs = 148;   // B200
+
+// ---- activations used by conv epilogues
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_TANH = 3 };
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(v, 0.0f);
+        case ACT_SIGMOID: return sigmoidf_(v);
+        case ACT_TANH: return tanhf(v);
+        default: return v;
+    }
+}
+
+}  // namespace evk

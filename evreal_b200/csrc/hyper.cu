@@ -1,0 +1,124 @@
+// HyperE2VID dynamic decoder: context fusion input, per-pixel atom generation
+// and per-pixel dynamic convolution.  The reference materialises a
+// [N, 256*25, h, w] im2col (nn.functional.unfold) and permutes it for a bmm
+// (model/hyper/hyper_dynamic.py:87-91, 60 % of its CPU time); here the 5x5
+// neighbourhood is read from a shared-memory halo tile instead and only the
+// [N,h,w,C*A] intermediate that feeds the 1x1 compositional conv is written.
+#include "hyper.cuh"
+
+namespace evk {
+
+// (0) context = interpolate(cat(ev, prev), scale 0.25, bilinear, align_corners=False)
+// src = 4*(dst+0.5)-0.5 = 4*dst+1.5 -> taps 4*dst+1 and 4*dst+2 with weight 0.5 each.
+__global__ void __launch_bounds__(256) hyper_context_kernel(const HyperParams p) {
+    const int h = p.H / 4, w = p.W / 4;
+    const int64_t total = (int64_t)p.N * h * w * 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % 8);
+        const int x = (int)((i / 8) % w);
+        const int y = (int)((i / (8 * (int64_t)w)) % h);
+        const int n = (int)(i / (8 * (int64_t)w * h));
+        float v = 0.f;
+        if (ch <= p.bins) {
+            const float* src = (ch < p.bins) ? p.ev_nchw + ((size_t)n * p.bins + ch) * p.H * p.W : p.prev + (size_t)n * p.H * p.W;
+            const int y0 = 4 * y + 1, x0 = 4 * x + 1;
+            const float v00 = src[(size_t)y0 * p.W + x0], v01 = src[(size_t)y0 * p.W + x0 + 1];
+            const float v10 = src[(size_t)(y0 + 1) * p.W + x0], v11 = src[(size_t)(y0 + 1) * p.W + x0 + 1];
+            v = 0.5f * (0.5f * v00 + 0.5f * v01) + 0.5f * (0.5f * v10 + 0.5f * v11);
+        }
+        p.ctx[i] = v;
+    }
+}
+
+// (1) atoms[pix][a][l] = sum_k coef[pix][a*K+k] * bases[k][l]
+__global__ void __launch_bounds__(256) hyper_atoms_kernel(const HyperParams p) {
+    extern __shared__ float sb[];   // bases [K][L]
+    for (int i = threadIdx.x; i < p.K * p.L; i += blockDim.x) sb[i] = p.bases[i];
+    __syncthreads();
+    const int64_t total = (int64_t)p.N * p.h * p.w * p.A * p.L;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)(i % p.L);
+        const int a = (int)((i / p.L) % p.A);
+        const int64_t pix = i / ((int64_t)p.L * p.A);
+        const float* c = p.coef + pix * (p.A * p.K) + a * p.K;
+        float acc = 0.f;
+        for (int k = 0; k < p.K; ++k) acc = fmaf(c[k], sb[k * p.L + l], acc);
+        p.atoms[i] = acc;
+    }
+}
+
+// (2) dynamic per-pixel convolution.  CTA = 8x4 pixels x 32 channels.
+constexpr int kATW = 8, kATH = 4, kACH = 32;
+
+template <int A, int KS>
+__global__ void __launch_bounds__(256) hyper_apply_kernel(const HyperParams p) {
+    constexpr int L = KS * KS, R = KS / 2;
+    constexpr int HW_ = kATW + 2 * R, HH_ = kATH + 2 * R;
+    __shared__ __align__(16) float s_x[HH_ * HW_][kACH];
+    __shared__ float s_a[kATH * kATW][A * L];
+    const int tid = threadIdx.x;
+    const int chunks = p.C / kACH;
+    const int n = blockIdx.z / chunks, c0 = (blockIdx.z % chunks) * kACH;
+    const int y0 = blockIdx.y * kATH, x0 = blockIdx.x * kATW;
+    for (int i = tid; i < HH_ * HW_ * (kACH / 4); i += 256) {
+        const int c4 = i % (kACH / 4), pix = i / (kACH / 4);
+        const int gy = y0 + pix / HW_ - R, gx = x0 + pix % HW_ - R;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w)
+            v = __ldg(reinterpret_cast<const float4*>(p.xu + (((size_t)n * p.h + gy) * p.w + gx) * p.C + c0) + c4);
+        *reinterpret_cast<float4*>(&s_x[pix][c4 * 4]) = v;
+    }
+    for (int i = tid; i < kATH * kATW * A * L; i += 256) {
+        const int q = i % (A * L), pix = i / (A * L);
+        const int gy = y0 + pix / kATW, gx = x0 + pix % kATW;
+        s_a[pix][q] = (gy < p.h && gx < p.w) ? p.atoms[(((size_t)n * p.h + gy) * p.w + gx) * (A * L) + q] : 0.f;
+    }
+    __syncthreads();
+    const int pix = tid / 8, lane = tid % 8;           // 32 pixels x 8 channel lanes (4 channels each)
+    const int py = pix / kATW, px = pix % kATW;
+    const int gy = y0 + py, gx = x0 + px;
+    float acc[4][A];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int a = 0; a < A; ++a) acc[c][a] = 0.f;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        const int dy = l / KS, dx = l % KS;
+        const float4 xv = *reinterpret_cast<const float4*>(&s_x[(py + dy) * HW_ + px + dx][lane * 4]);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const float at = s_a[pix][a * L + l];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c][a] = fmaf(at, xs[c], acc[c][a]);
+        }
+    }
+    if (gy < p.h && gx < p.w) {
+        float* o = p.inter + (((size_t)n * p.h + gy) * p.w + gx) * ((size_t)p.C * A) + (size_t)(c0 + lane * 4) * A;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int a = 0; a < A; ++a) o[c * A + a] = acc[c][a];
+    }
+}
+
+int launch_hyper(int which, const HyperParams& p, cudaStream_t st) {
+    if (which == 0) {
+        EVK_REQUIRE(p.H % 4 == 0 && p.W % 4 == 0 && p.bins + 1 <= 8, EVK_ERR_ARG, "hyper context: H, W must be multiples of 4 and bins <= 7");
+        const int64_t total = (int64_t)p.N * (p.H / 4) * (p.W / 4) * 8;
+        hyper_context_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 1184), 256, 0, st>>>(p);
+    } else if (which == 1) {
+        const int64_t total = (int64_t)p.N * p.h * p.w * p.A * p.L;
+        hyper_atoms_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, sizeof(float) * p.K * p.L, st>>>(p);
+    } else {
+        EVK_REQUIRE(p.A == 6 && p.ks == 5 && p.C % kACH == 0, EVK_ERR_ARG,
+                    "hyper apply: only num_atoms=6, kernel_size=5, C%%32==0 is built (got A=%d ks=%d C=%d)", p.A, p.ks, p.C);
+        dim3 grid(ceil_div(p.w, kATW), ceil_div(p.h, kATH), p.N * (p.C / kACH));
+        hyper_apply_kernel<6, 5><<<grid, 256, 0, st>>>(p);
+    }
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+}  // namespace evk

@@ -1,0 +1,304 @@
+// Stage 3 + post-processing: fused clip + MSE + Gaussian SSIM, and the
+// percentile ("robust") normalisation that sits between the network and the
+// metrics for E2VID.
+//
+// Reference semantics: utils/eval_metrics.py:77-97,253-255 (scikit-image
+// mean_squared_error / structural_similarity, sigma 1.5, 11 taps, float32 maps,
+// float64 mean over the interior crop), utils/eval_utils.py:15-35 and
+// eval.py:380-395 (np.percentile linear interpolation).
+//
+// HBM traffic is 2*H*W*4 bytes per frame (345 kB at 240x180): these kernels
+// are launch-latency bound; everything per frame is one pass.
+#include "evk_common.cuh"
+
+namespace evk {
+
+// ----------------------------------------------------------------- SSIM/MSE
+constexpr int kTapR = 5;                 // int(3.5*1.5 + 0.5)
+constexpr int kTaps = 2 * kTapR + 1;
+constexpr int kTH = 16, kTW = 32;        // owned pixels per CTA
+constexpr int kIH = kTH + 2 * kTapR, kIW = kTW + 2 * kTapR;
+
+__constant__ double c_taps[kTaps];
+static bool g_taps_ready = false;
+
+static int upload_taps() {
+    if (g_taps_ready) return EVK_OK;
+    double w[kTaps], s = 0.0;
+    const double sigma = 1.5;
+    for (int i = -kTapR; i <= kTapR; ++i) { w[i + kTapR] = exp(-0.5 / (sigma * sigma) * (double)(i * i)); s += w[i + kTapR]; }
+    for (int i = 0; i < kTaps; ++i) w[i] /= s;
+    EVK_CHECK_CUDA(cudaMemcpyToSymbol(c_taps, w, sizeof(w)));
+    g_taps_ready = true;
+    return EVK_OK;
+}
+
+// scipy correlate1d, symmetric branch: centre tap first, then pairs from the
+// outside in, float64 accumulate, float32 store.
+__device__ __forceinline__ float sym_filter(const float* v, int stride) {
+    double acc = (double)v[0] * c_taps[kTapR];
+#pragma unroll
+    for (int j = kTapR; j >= 1; --j) acc += ((double)v[-j * stride] + (double)v[j * stride]) * c_taps[kTapR - j];
+    return (float)acc;
+}
+
+__global__ void __launch_bounds__(256)
+mse_ssim_kernel(const float* __restrict__ img, const float* __restrict__ ref, int H, int W, int clip,
+                double* __restrict__ sums /* [n][2] */) {
+    __shared__ float sx[kIH][kIW], sy[kIH][kIW];          // x = ref, y = img (skimage argument order)
+    __shared__ float vert[5][kTH][kIW];
+    __shared__ double red[2][8];
+    const int n = blockIdx.z;
+    const float* X = ref + (size_t)n * H * W;
+    const float* Y = img + (size_t)n * H * W;
+    const int y0 = blockIdx.y * kTH, x0 = blockIdx.x * kTW;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < kIH * kIW; i += 256) {
+        const int r = i / kIW, c = i % kIW;
+        const int gy = y0 + r - kTapR, gx = x0 + c - kTapR;
+        float a = 0.0f, b = 0.0f;
+        if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
+            a = X[(size_t)gy * W + gx];
+            b = Y[(size_t)gy * W + gx];
+            if (clip) { a = fminf(fmaxf(a, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f); }
+        }
+        sx[r][c] = a;
+        sy[r][c] = b;
+    }
+    __syncthreads();
+
+    // MSE over owned pixels: float32 difference squared, float64 accumulation
+    double mse = 0.0;
+    for (int i = tid; i < kTH * kTW; i += 256) {
+        const int r = i / kTW, c = i % kTW;
+        if (y0 + r < H && x0 + c < W) {
+            const float d = __fsub_rn(sx[r + kTapR][c + kTapR], sy[r + kTapR][c + kTapR]);
+            mse += (double)__fmul_rn(d, d);
+        }
+    }
+
+    // vertical pass (axis 0 first, like scipy.ndimage.gaussian_filter)
+    for (int i = tid; i < kTH * kIW; i += 256) {
+        const int r = i / kIW, c = i % kIW;
+        float col[5][kTaps];
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+            const float a = sx[r + k][c], b = sy[r + k][c];
+            col[0][k] = a;
+            col[1][k] = b;
+            col[2][k] = __fmul_rn(a, a);
+            col[3][k] = __fmul_rn(b, b);
+            col[4][k] = __fmul_rn(a, b);
+        }
+#pragma unroll
+        for (int m = 0; m < 5; ++m) vert[m][r][c] = sym_filter(&col[m][kTapR], 1);
+    }
+    __syncthreads();
+
+    // horizontal pass + SSIM map on interior owned pixels
+    const float C1 = (float)(0.01 * 0.01), C2 = (float)(0.03 * 0.03);
+    double ssim = 0.0;
+    for (int i = tid; i < kTH * kTW; i += 256) {
+        const int r = i / kTW, c = i % kTW;
+        const int gy = y0 + r, gx = x0 + c;
+        if (gy >= kTapR && gy < H - kTapR && gx >= kTapR && gx < W - kTapR) {
+            const float ux = sym_filter(&vert[0][r][c + kTapR], 1);
+            const float uy = sym_filter(&vert[1][r][c + kTapR], 1);
+            const float uxx = sym_filter(&vert[2][r][c + kTapR], 1);
+            const float uyy = sym_filter(&vert[3][r][c + kTapR], 1);
+            const float uxy = sym_filter(&vert[4][r][c + kTapR], 1);
+            const float vx = __fsub_rn(uxx, __fmul_rn(ux, ux));
+            const float vy = __fsub_rn(uyy, __fmul_rn(uy, uy));
+            const float vxy = __fsub_rn(uxy, __fmul_rn(ux, uy));
+            const float A1 = __fadd_rn(__fmul_rn(__fmul_rn(2.0f, ux), uy), C1);
+            const float A2 = __fadd_rn(__fmul_rn(2.0f, vxy), C2);
+            const float B1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), C1);
+            const float B2 = __fadd_rn(__fadd_rn(vx, vy), C2);
+            ssim += (double)__fdiv_rn(__fmul_rn(A1, A2), __fmul_rn(B1, B2));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mse += __shfl_xor_sync(0xffffffffu, mse, o);
+        ssim += __shfl_xor_sync(0xffffffffu, ssim, o);
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = mse; red[1][tid >> 5] = ssim; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) { mse += red[0][w]; ssim += red[1][w]; }
+        atomicAdd(&sums[2 * n + 0], mse);
+        atomicAdd(&sums[2 * n + 1], ssim);
+    }
+}
+
+__global__ void mse_ssim_finalize_kernel(double* sums, int n, double inv_all, double inv_interior) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        sums[2 * i + 0] *= inv_all;
+        sums[2 * i + 1] *= inv_interior;
+    }
+}
+
+int mse_ssim(const float* img, const float* ref, int n, int H, int W, int clip, double* scores, cudaStream_t st) {
+    EVK_REQUIRE(n > 0 && H >= kTaps && W >= kTaps, EVK_ERR_ARG,
+                "evk_mse_ssim: images must be at least %dx%d (got n=%d %dx%d)", kTaps, kTaps, n, H, W);
+    int rc = upload_taps();
+    if (rc != EVK_OK) return rc;
+    EVK_CHECK_CUDA(cudaMemsetAsync(scores, 0, sizeof(double) * 2 * n, st));
+    dim3 grid(ceil_div(W, kTW), ceil_div(H, kTH), n);
+    mse_ssim_kernel<<<grid, 256, 0, st>>>(img, ref, H, W, clip, scores);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    const double inv_all = 1.0 / ((double)H * W);
+    const double inv_int = 1.0 / ((double)(H - 2 * kTapR) * (W - 2 * kTapR));
+    mse_ssim_finalize_kernel<<<ceil_div(n, 128), 128, 0, st>>>(scores, n, inv_all, inv_int);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+// ---------------------------------------------------- percentile normalise
+// One CTA per image: exact order statistics by 4-pass 8-bit radix select on
+// order-preserving integer keys (warp-private histograms), for the two ranks
+// floor(q*(n-1)) of q_min and q_max at once; a fifth scan finds the successors
+// (rank+1).  Then out = (v - P_lo) / (P_hi - P_lo) in float32.
+constexpr int kSelThreads = 1024;
+constexpr int kSelWarps = kSelThreads / 32;
+
+__device__ __forceinline__ unsigned int float_key(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned int k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ __forceinline__ float load_val(const float* v, int i, int apply_exp) {
+    const float a = v[i];
+    return apply_exp ? expf(a) : a;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+percentile_normalize_kernel(const float* __restrict__ img, float* __restrict__ out, int numel, double q_lo, double q_hi,
+                            int apply_exp) {
+    extern __shared__ unsigned int hist[];          // [2][kSelWarps][256]
+    __shared__ unsigned int s_prefix[2], s_rank[2];
+    __shared__ unsigned int s_le[2], s_next[2];
+    __shared__ float s_p[2];
+    const float* v = img + (size_t)blockIdx.x * numel;
+    float* o = out + (size_t)blockIdx.x * numel;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // numpy method 'linear' (alpha = beta = 1): virtual index = n*q + (alpha + q*(1-alpha-beta)) - 1,
+    // evaluated in float64 in numpy's own operation order; gamma = its fractional part
+    const double qf[2] = {q_lo / 100.0, q_hi / 100.0};
+    const double vi[2] = {(double)numel * qf[0] + (1.0 + qf[0] * (1.0 - 1.0 - 1.0)) - 1.0,
+                          (double)numel * qf[1] + (1.0 + qf[1] * (1.0 - 1.0 - 1.0)) - 1.0};
+    if (tid < 2) {
+        double f = floor(vi[tid]);
+        if (f < 0) f = 0;
+        if (f > numel - 1) f = numel - 1;
+        s_rank[tid] = (unsigned int)f;   // rank still to find inside the current prefix bucket
+        s_prefix[tid] = 0;
+    }
+    __syncthreads();
+
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 2 * kSelWarps * 256; i += kSelThreads) hist[i] = 0;
+        __syncthreads();
+        const unsigned int pre0 = s_prefix[0], pre1 = s_prefix[1];
+        const unsigned int mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        unsigned int* h0 = hist + (0 * kSelWarps + warp) * 256;
+        unsigned int* h1 = hist + (1 * kSelWarps + warp) * 256;
+        for (int i = tid; i < numel; i += kSelThreads) {
+            const unsigned int k = float_key(load_val(v, i, apply_exp));
+            const unsigned int d = (k >> shift) & 0xffu;
+            if ((k & mask) == pre0) atomicAdd(&h0[d], 1u);
+            if ((k & mask) == pre1) atomicAdd(&h1[d], 1u);
+        }
+        __syncthreads();
+        // fold warp-private histograms: thread t (< 512) owns bin t%256 of target t/256
+        if (tid < 512) {
+            const int tgt = tid >> 8, bin = tid & 255;
+            unsigned int c = 0;
+            for (int w = 0; w < kSelWarps; ++w) c += hist[(tgt * kSelWarps + w) * 256 + bin];
+            hist[(tgt * kSelWarps) * 256 + bin] = c;
+        }
+        __syncthreads();
+        if (tid < 2) {
+            const unsigned int* h = hist + (tid * kSelWarps) * 256;
+            unsigned int r = s_rank[tid], acc = 0;
+            int b = 0;
+            for (; b < 256; ++b) {
+                if (acc + h[b] > r) break;
+                acc += h[b];
+            }
+            if (b > 255) b = 255;
+            s_rank[tid] = r - acc;
+            s_prefix[tid] |= ((unsigned int)b << shift);
+        }
+        __syncthreads();
+    }
+    // s_prefix[t] is now the key of the rank-th smallest value.  Successor scan.
+    if (tid < 2) { s_le[tid] = 0; s_next[tid] = 0xffffffffu; }
+    __syncthreads();
+    {
+        const unsigned int k0 = s_prefix[0], k1 = s_prefix[1];
+        unsigned int le0 = 0, le1 = 0, nx0 = 0xffffffffu, nx1 = 0xffffffffu;
+        for (int i = tid; i < numel; i += kSelThreads) {
+            const unsigned int k = float_key(load_val(v, i, apply_exp));
+            if (k <= k0) le0++; else nx0 = min(nx0, k);
+            if (k <= k1) le1++; else nx1 = min(nx1, k);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            le0 += __shfl_xor_sync(0xffffffffu, le0, off);
+            le1 += __shfl_xor_sync(0xffffffffu, le1, off);
+            nx0 = min(nx0, __shfl_xor_sync(0xffffffffu, nx0, off));
+            nx1 = min(nx1, __shfl_xor_sync(0xffffffffu, nx1, off));
+        }
+        if ((tid & 31) == 0) {
+            atomicAdd(&s_le[0], le0);
+            atomicAdd(&s_le[1], le1);
+            atomicMin(&s_next[0], nx0);
+            atomicMin(&s_next[1], nx1);
+        }
+    }
+    __syncthreads();
+    if (tid < 2) {
+        double f = floor(vi[tid]);
+        if (f < 0) f = 0;
+        const unsigned int rank = (unsigned int)f;
+        const double gamma = vi[tid] - f;
+        const float a = key_float(s_prefix[tid]);
+        // rank+1 is the same value when duplicates extend past it, else the next distinct key
+        float b = a;
+        if (rank + 1 < (unsigned int)numel) b = (s_le[tid] > rank + 1) ? a : key_float(s_next[tid]);
+        // numpy _lerp: a + (b-a)*t, and b - (b-a)*(1-t) when t >= 0.5
+        const double d = (double)__fsub_rn(b, a);
+        double r = (double)a + d * gamma;
+        if (gamma >= 0.5) r = (double)b - d * (1.0 - gamma);
+        s_p[tid] = (float)r;
+    }
+    __syncthreads();
+    const float lo = s_p[0];
+    const float range = __fsub_rn(s_p[1], lo);
+    for (int i = tid; i < numel; i += kSelThreads) o[i] = __fdiv_rn(__fsub_rn(load_val(v, i, apply_exp), lo), range);
+}
+
+int percentile_normalize(const float* img, float* out, int n, int numel, double q_lo, double q_hi, int apply_exp,
+                         cudaStream_t st) {
+    EVK_REQUIRE(n > 0 && numel > 0, EVK_ERR_ARG, "evk_percentile_normalize: empty input");
+    EVK_REQUIRE(q_lo >= 0 && q_hi <= 100 && q_lo <= q_hi, EVK_ERR_ARG, "evk_percentile_normalize: bad percentiles");
+    const size_t smem = sizeof(unsigned int) * 2 * kSelWarps * 256;   // 64 KB
+    static bool attr_set = false;
+    if (!attr_set) {
+        EVK_CHECK_CUDA(cudaFuncSetAttribute(percentile_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    percentile_normalize_kernel<<<n, kSelThreads, smem, st>>>(img, out, numel, q_lo, q_hi, apply_exp);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+}  // namespace evk

@@ -1,0 +1,674 @@
+// Stage 2 runner: builds a per-(architecture, shape) launch program from a
+// reference state_dict and replays it as a CUDA graph, one frame per call.
+//
+// Reference semantics: eval.py:124-158 (factory), model/model.py:108-190,
+// model/unet.py:85-143, model/legacy.py:32-187, model/submodules.py.
+//
+// HBM layout: activations NHWC fp32 (channel-contiguous so that the implicit
+// GEMM K dimension is contiguous); recurrent state lives in the handle: ConvLSTM
+// hidden state is ping-ponged between two buffers (neighbouring CTAs still read
+// h(t-1) through the 3x3 window while h(t) is written), the cell state and the
+// ConvGRU state are updated in place (pointwise).  Weights are repacked once at
+// finalize(): eval-mode BatchNorm folded, K-major [kh*kw*Cin][Cout], LSTM/GRU
+// gate channels interleaved so one thread owns all gates of a hidden channel.
+#include <map>
+#include <memory>
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
+
+#include "conv.cuh"
+#include "hyper.cuh"
+
+namespace evk {
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY };
+
+struct Op {
+    OpKind kind;
+    ConvParams cp;              // OP_CONV
+    // OP_HEAD
+    const float* in = nullptr; const float* w = nullptr; const float* b = nullptr; float* out = nullptr;
+    int N = 0, cin = 0, H = 0, W = 0, k = 0, cout = 0;
+    // OP_UPSAMPLE_ADD / OP_PRED
+    const float* skip = nullptr;
+    float bias0 = 0.f;
+    int sigmoid = 0;
+    HyperParams hp;             // OP_HYPER_*
+    double flops = 0.0;
+};
+
+struct StateBuf {
+    float* buf[2] = {nullptr, nullptr};   // buf[1] only for ping-ponged LSTM hidden state
+    int C = 0, H = 0, W = 0;
+    bool pingpong = false;
+};
+
+}  // namespace evk
+
+using namespace evk;
+
+struct evk_model {
+    evk_model_config cfg;
+    std::map<std::string, HostTensor> sd;
+    bool finalized = false;
+    std::vector<void*> allocs;
+    std::vector<Op> ops[2];          // per hidden-state parity
+    std::vector<StateBuf> states;
+    float* in_buf = nullptr;         // [N,bins,H,W]
+    float* out_buf = nullptr;        // [N,1,H,W]
+    float* prev_rec = nullptr;       // HyperE2VID: previous padded reconstruction
+    int parity = 0;
+    int last_launches = 0;
+    double flops = 0.0;
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    bool use_graph = true;
+
+    float* dalloc(size_t nfloat) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, nfloat * sizeof(float)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, nfloat * sizeof(float));
+        allocs.push_back(p);
+        return (float*)p;
+    }
+    float* upload(const std::vector<float>& v) {
+        float* p = dalloc(v.size());
+        if (p) cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+        return p;
+    }
+    const HostTensor* find(const std::string& name) const {
+        auto it = sd.find(name);
+        return it == sd.end() ? nullptr : &it->second;
+    }
+};
+
+namespace evk {
+
+// ---------------------------------------------------------------- packing
+struct Packed {
+    std::vector<float> w;   // [kh*kw*cin][cout_packed]
+    std::vector<float> b;   // [cout_packed]
+    int cout = 0, cin = 0, kh = 0, kw = 0;
+};
+
+// Folds an optional eval-mode BatchNorm (prefix bn) and an optional bias into
+// one conv (float64 arithmetic), and permutes output channels: packed channel
+// n takes reference channel perm[n].
+static int pack_conv(const evk_model* m, const std::string& wname, const std::string& bname, const std::string& bn,
+                     const std::vector<int>* perm, Packed& out) {
+    const HostTensor* w = m->find(wname);
+    EVK_REQUIRE(w && w->shape.size() == 4, EVK_ERR_KEY, "missing weight tensor '%s'", wname.c_str());
+    const int co = (int)w->shape[0], ci = (int)w->shape[1], kh = (int)w->shape[2], kw = (int)w->shape[3];
+    const HostTensor* bias = bname.empty() ? nullptr : m->find(bname);
+    const HostTensor *g = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr;
+    if (!bn.empty() && m->find(bn + ".running_mean")) {
+        g = m->find(bn + ".weight"); beta = m->find(bn + ".bias");
+        mean = m->find(bn + ".running_mean"); var = m->find(bn + ".running_var");
+        EVK_REQUIRE(g && beta && mean && var, EVK_ERR_KEY, "incomplete BatchNorm '%s'", bn.c_str());
+    }
+    const int cop = perm ? (int)perm->size() : co;
+    out.cout = cop; out.cin = ci; out.kh = kh; out.kw = kw;
+    out.w.assign((size_t)kh * kw * ci * cop, 0.f);
+    out.b.assign(cop, 0.f);
+    for (int n = 0; n < cop; ++n) {
+        const int r = perm ? (*perm)[n] : n;
+        if (r < 0) continue;   // padding channel
+        double scale = 1.0, shift = bias ? (double)bias->data[r] : 0.0;
+        if (g) {
+            scale = (double)g->data[r] / std::sqrt((double)var->data[r] + 1e-5);
+            shift = (shift - (double)mean->data[r]) * scale + (double)beta->data[r];
+        }
+        out.b[n] = (float)shift;
+        for (int c = 0; c < ci; ++c)
+            for (int y = 0; y < kh; ++y)
+                for (int x = 0; x < kw; ++x) {
+                    const double v = (double)w->data[(((size_t)r * ci + c) * kh + y) * kw + x] * scale;
+                    out.w[((size_t)(y * kw + x) * ci + c) * cop + n] = (float)v;
+                }
+    }
+    return EVK_OK;
+}
+
+static double conv_flops(const ConvParams& p, int real_cout) {
+    return 2.0 * real_cout * (p.c1 + p.c2) * p.kh * p.kw * (double)p.N * p.Hout * p.Wout;
+}
+
+struct Builder {
+    evk_model* m;
+    int N;
+    int rc = EVK_OK;
+
+    float* act(int H, int W, int C) { return m->dalloc((size_t)N * H * W * C); }
+
+    // generic ConvLayer-like op appended to both parities
+    int conv(const std::string& wname, const std::string& bname, const std::string& bn, const float* x, int cin, int Hin,
+             int Win, int stride, int pad, int act, const float* res, float* y, int* cout_out) {
+        Packed pk;
+        int r = pack_conv(m, wname, bname, bn, nullptr, pk);
+        if (r != EVK_OK) return r;
+        EVK_REQUIRE(pk.cin == cin, EVK_ERR_KEY, "'%s': expected %d input channels, checkpoint has %d", wname.c_str(), cin, pk.cin);
+        return conv_packed(pk, x, cin, Hin, Win, stride, pad, act, res, y, cout_out);
+    }
+
+    int conv_packed(const Packed& pk, const float* x, int cin, int Hin, int Win, int stride, int pad, int act,
+                    const float* res, float* y, int* cout_out) {
+        Op op; op.kind = OP_CONV;
+        ConvParams& p = op.cp;
+        p.x1 = x; p.c1 = cin; p.N = N; p.Hin = Hin; p.Win = Win;
+        p.kh = pk.kh; p.kw = pk.kw; p.stride = stride; p.pad = pad;
+        p.Hout = (Hin + 2 * pad - pk.kh) / stride + 1;
+        p.Wout = (Win + 2 * pad - pk.kw) / stride + 1;
+        p.w = m->upload(pk.w); p.bias = m->upload(pk.b); p.cout = pk.cout;
+        p.epi = EPI_LINEAR; p.act = act; p.res = res; p.y = y;
+        op.flops = conv_flops(p, pk.cout);
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+        if (cout_out) *cout_out = pk.cout;
+        return EVK_OK;
+    }
+};
+
+static int make_state(evk_model* m, int C, int H, int W, bool pingpong) {
+    StateBuf s; s.C = C; s.H = H; s.W = W; s.pingpong = pingpong;
+    const size_t n = (size_t)m->cfg.batch * H * W * C;
+    s.buf[0] = m->dalloc(n);
+    s.buf[1] = pingpong ? m->dalloc(n) : s.buf[0];
+    EVK_REQUIRE(s.buf[0] && s.buf[1], EVK_ERR_CUDA, "out of device memory for recurrent state");
+    m->states.push_back(s);
+    return (int)m->states.size() - 1;
+}
+
+// ---- ConvLSTM: gates = conv3x3(cat(x,h)); packed channel ch*4+g <- reference g*C+ch
+static int add_lstm(Builder& B, const std::string& pfx, const float* x, int C, int H, int W, int hs, int cs) {
+    evk_model* m = B.m;
+    std::vector<int> perm(4 * C);
+    for (int ch = 0; ch < C; ++ch)
+        for (int g = 0; g < 4; ++g) perm[ch * 4 + g] = g * C + ch;
+    Packed pk;
+    int r = pack_conv(m, pfx + ".Gates.weight", pfx + ".Gates.bias", "", &perm, pk);
+    if (r != EVK_OK) return r;
+    EVK_REQUIRE(pk.cin == 2 * C && pk.kh == 3, EVK_ERR_KEY, "'%s.Gates': unexpected shape", pfx.c_str());
+    const float* w = m->upload(pk.w);
+    const float* b = m->upload(pk.b);
+    for (int par = 0; par < 2; ++par) {
+        Op op; op.kind = OP_CONV;
+        ConvParams& p = op.cp;
+        p.x1 = x; p.c1 = C; p.x2 = m->states[hs].buf[par]; p.c2 = C;
+        p.N = B.N; p.Hin = p.Hout = H; p.Win = p.Wout = W; p.kh = p.kw = 3; p.stride = 1; p.pad = 1;
+        p.w = w; p.bias = b; p.cout = 4 * C; p.epi = EPI_LSTM;
+        p.c_prev = m->states[cs].buf[0]; p.c_new = m->states[cs].buf[0];
+        p.h_new = m->states[hs].buf[par ^ 1];
+        op.flops = conv_flops(p, 4 * C);
+        m->ops[par].push_back(op);
+    }
+    return EVK_OK;
+}
+
+// ---- ConvGRU: (update, reset) fused into one conv, then the candidate conv on cat(x, h*r)
+static int add_gru(Builder& B, const std::string& pfx, const float* x, int C, int H, int W, int hs, float* u_buf, float* hr_buf) {
+    evk_model* m = B.m;
+    const HostTensor* wu = m->find(pfx + ".update_gate.weight");
+    const HostTensor* wr = m->find(pfx + ".reset_gate.weight");
+    const HostTensor* bu = m->find(pfx + ".update_gate.bias");
+    const HostTensor* br = m->find(pfx + ".reset_gate.bias");
+    EVK_REQUIRE(wu && wr && bu && br, EVK_ERR_KEY, "missing ConvGRU gates under '%s'", pfx.c_str());
+    const int cin = (int)wu->shape[1], k = (int)wu->shape[2];
+    EVK_REQUIRE(cin == 2 * C && (int)wu->shape[0] == C, EVK_ERR_KEY, "'%s': unexpected ConvGRU shape", pfx.c_str());
+    std::vector<float> w((size_t)k * k * cin * 2 * C), b(2 * C);
+    for (int ch = 0; ch < C; ++ch) {
+        b[ch * 2 + 0] = bu->data[ch];
+        b[ch * 2 + 1] = br->data[ch];
+        for (int c = 0; c < cin; ++c)
+            for (int y = 0; y < k; ++y)
+                for (int xx = 0; xx < k; ++xx) {
+                    const size_t src = (((size_t)ch * cin + c) * k + y) * k + xx;
+                    const size_t dst = ((size_t)(y * k + xx) * cin + c) * (2 * C) + ch * 2;
+                    w[dst + 0] = wu->data[src];
+                    w[dst + 1] = wr->data[src];
+                }
+    }
+    float* h = m->states[hs].buf[0];
+    {
+        Op op; op.kind = OP_CONV;
+        ConvParams& p = op.cp;
+        p.x1 = x; p.c1 = C; p.x2 = h; p.c2 = C; p.N = B.N; p.Hin = p.Hout = H; p.Win = p.Wout = W;
+        p.kh = p.kw = k; p.stride = 1; p.pad = k / 2;
+        p.w = m->upload(w); p.bias = m->upload(b); p.cout = 2 * C; p.epi = EPI_GRU_UR;
+        p.h_prev = h; p.u_out = u_buf; p.hr_out = hr_buf;
+        op.flops = conv_flops(p, 2 * C);
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+    }
+    {
+        Packed pk;
+        int r = pack_conv(m, pfx + ".out_gate.weight", pfx + ".out_gate.bias", "", nullptr, pk);
+        if (r != EVK_OK) return r;
+        Op op; op.kind = OP_CONV;
+        ConvParams& p = op.cp;
+        p.x1 = x; p.c1 = C; p.x2 = hr_buf; p.c2 = C; p.N = B.N; p.Hin = p.Hout = H; p.Win = p.Wout = W;
+        p.kh = p.kw = k; p.stride = 1; p.pad = k / 2;
+        p.w = m->upload(pk.w); p.bias = m->upload(pk.b); p.cout = C; p.epi = EPI_GRU_OUT;
+        p.h_prev = h; p.u_in = u_buf; p.h_new = h;
+        op.flops = conv_flops(p, C);
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+    }
+    return EVK_OK;
+}
+
+static int add_resblock(Builder& B, const std::string& pfx, const float* x, float* tmp, float* y, int C, int H, int W) {
+    int r = B.conv(pfx + ".conv1.weight", pfx + ".conv1.bias", pfx + ".bn1", x, C, H, W, 1, 1, ACT_RELU, nullptr, tmp, nullptr);
+    if (r != EVK_OK) return r;
+    return B.conv(pfx + ".conv2.weight", pfx + ".conv2.bias", pfx + ".bn2", tmp, C, H, W, 1, 1, ACT_RELU, x, y, nullptr);
+}
+
+static int add_head(Builder& B, const std::string& conv_pfx, const std::string& bn, float* y, int cout_expected) {
+    evk_model* m = B.m;
+    Packed pk;
+    int r = pack_conv(m, conv_pfx + ".weight", conv_pfx + ".bias", bn, nullptr, pk);
+    if (r != EVK_OK) return r;
+    EVK_REQUIRE(pk.cin == m->cfg.num_bins && pk.cout == cout_expected, EVK_ERR_KEY,
+                "'%s': expected [%d,%d,k,k], checkpoint has [%d,%d,%d,%d]", conv_pfx.c_str(), cout_expected,
+                m->cfg.num_bins, pk.cout, pk.cin, pk.kh, pk.kw);
+    Op op; op.kind = OP_HEAD;
+    op.in = m->in_buf; op.w = m->upload(pk.w); op.b = m->upload(pk.b); op.out = y;
+    op.N = B.N; op.cin = pk.cin; op.H = m->cfg.height; op.W = m->cfg.width; op.k = pk.kh; op.cout = pk.cout;
+    op.flops = 2.0 * pk.cout * pk.cin * pk.kh * pk.kw * (double)B.N * op.H * op.W;
+    m->ops[0].push_back(op); m->ops[1].push_back(op);
+    return EVK_OK;
+}
+
+static int add_pred(Builder& B, const std::string& pfx, const float* x, const float* skip, int cin, int H, int W) {
+    evk_model* m = B.m;
+    Packed pk;
+    int r = pack_conv(m, pfx + ".conv2d.weight", pfx + ".conv2d.bias", pfx + ".norm_layer", nullptr, pk);
+    if (r != EVK_OK) return r;
+    EVK_REQUIRE(pk.cin == cin && pk.kh == 1, EVK_ERR_KEY, "'%s': unexpected prediction layer shape", pfx.c_str());
+    std::vector<float> w0(cin);
+    for (int c = 0; c < cin; ++c) w0[c] = pk.w[(size_t)c * pk.cout + 0];   // image = output channel 0
+    Op op; op.kind = OP_PRED;
+    op.in = x; op.skip = skip; op.w = m->upload(w0); op.bias0 = pk.b[0]; op.out = m->out_buf;
+    op.N = B.N; op.cin = cin; op.H = H; op.W = W; op.sigmoid = m->cfg.final_sigmoid;
+    op.flops = 2.0 * pk.cout * cin * (double)B.N * H * W;
+    m->ops[0].push_back(op); m->ops[1].push_back(op);
+    return EVK_OK;
+}
+
+// DynamicUpsampleLayer after the shared x2 upsample (model/submodules.py:120-127):
+// context fusion -> atom generation -> per-pixel dynamic conv -> 1x1 compositional conv -> ReLU.
+static int add_hyper_decoder(Builder& B, const std::string& pfx, const float* xu, int C, int h, int w, float* y) {
+    evk_model* m = B.m;
+    const evk_model_config& c = m->cfg;
+    EVK_REQUIRE(h * 4 == c.height && w * 4 == c.width, EVK_ERR_ARG,
+                "dynamic decoder: context (%dx%d)/4 does not match decoder resolution %dx%d", c.height, c.width, h, w);
+    const std::string gen = pfx + ".dynamic_atom_generation";
+    const HostTensor* bases = m->find(gen + ".bases");
+    EVK_REQUIRE(bases && bases->shape.size() == 2, EVK_ERR_KEY, "missing '%s.bases'", gen.c_str());
+    const int K = (int)bases->shape[0], L = (int)bases->shape[1], ks = c.kernel_size;
+    EVK_REQUIRE(L == ks * ks, EVK_ERR_KEY, "'%s.bases' has %d taps, kernel_size is %d", gen.c_str(), L, ks);
+
+    float* ctx = B.act(h, w, 8);
+    {
+        Op op; op.kind = OP_HYPER_CONTEXT;
+        op.hp.N = B.N; op.hp.ev_nchw = m->in_buf; op.hp.prev = m->prev_rec; op.hp.ctx = ctx;
+        op.hp.bins = c.num_bins; op.hp.H = c.height; op.hp.W = c.width;
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+    }
+    // context fusion conv: 6 input channels padded to 8 (zero weight rows)
+    Packed pk;
+    int r = pack_conv(m, pfx + ".context_fusion.conv.weight", pfx + ".context_fusion.conv.bias", "", nullptr, pk);
+    if (r != EVK_OK) return r;
+    EVK_REQUIRE(pk.cin == c.num_bins + 1, EVK_ERR_KEY, "context fusion expects %d input channels", c.num_bins + 1);
+    Packed pk8 = pk;
+    pk8.cin = 8;
+    pk8.w.assign((size_t)pk.kh * pk.kw * 8 * pk.cout, 0.f);
+    for (int t = 0; t < pk.kh * pk.kw; ++t)
+        for (int ci = 0; ci < pk.cin; ++ci)
+            for (int n = 0; n < pk.cout; ++n)
+                pk8.w[((size_t)t * 8 + ci) * pk.cout + n] = pk.w[((size_t)t * pk.cin + ci) * pk.cout + n];
+    int c1 = 0, c2 = 0, c3 = 0;
+    float* f1 = B.act(h, w, pk.cout);
+    r = B.conv_packed(pk8, ctx, 8, h, w, 1, pk.kh / 2, ACT_NONE, nullptr, f1, &c1);
+    if (r != EVK_OK) return r;
+    const HostTensor* w0 = m->find(gen + ".bases_net.0.weight");
+    const HostTensor* w3 = m->find(gen + ".bases_net.3.weight");
+    EVK_REQUIRE(w0 && w3, EVK_ERR_KEY, "missing '%s.bases_net' weights", gen.c_str());
+    float* f2 = B.act(h, w, (int)w0->shape[0]);
+    r = B.conv(gen + ".bases_net.0.weight", gen + ".bases_net.0.bias", gen + ".bases_net.1", f1, c1, h, w, 1, 1, ACT_TANH, nullptr, f2, &c2);
+    if (r != EVK_OK) return r;
+    float* f3 = B.act(h, w, (int)w3->shape[0]);
+    r = B.conv(gen + ".bases_net.3.weight", gen + ".bases_net.3.bias", gen + ".bases_net.4", f2, c2, h, w, 1, 1, ACT_TANH, nullptr, f3, &c3);
+    if (r != EVK_OK) return r;
+    EVK_REQUIRE(c3 % K == 0, EVK_ERR_KEY, "basis coefficient channels (%d) not a multiple of the %d bases", c3, K);
+    const int A = c3 / K;
+    float* atoms = B.act(h, w, A * L);
+    float* inter = B.act(h, w, C * A);
+    {
+        Op op; op.kind = OP_HYPER_ATOMS;
+        op.hp.N = B.N; op.hp.coef = f3; op.hp.bases = m->upload(bases->data); op.hp.atoms = atoms;
+        op.hp.h = h; op.hp.w = w; op.hp.A = A; op.hp.K = K; op.hp.L = L; op.hp.ks = ks;
+        op.flops = 2.0 * A * K * L * (double)B.N * h * w;
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+        Op ap = op; ap.kind = OP_HYPER_APPLY;
+        ap.hp.xu = xu; ap.hp.inter = inter; ap.hp.C = C;
+        ap.flops = 2.0 * A * L * C * (double)B.N * h * w;
+        m->ops[0].push_back(ap); m->ops[1].push_back(ap);
+    }
+    return B.conv(pfx + ".dynamic_conv.compositional_coefficients", pfx + ".dynamic_conv.bias", "", inter, C * A, h, w, 1, 0,
+                  ACT_RELU, nullptr, y, nullptr);
+}
+
+// E2VID / E2VID+ / SSL-E2VID / HyperE2VID (model/unet.py:107-143)
+static int build_unet(evk_model* m) {
+    const evk_model_config& c = m->cfg;
+    Builder B{m, c.batch};
+    const int E = c.num_encoders, k = c.kernel_size;
+    EVK_REQUIRE(E >= 1 && E <= 5, EVK_ERR_ARG, "num_encoders=%d unsupported", E);
+    EVK_REQUIRE(c.height % (1 << E) == 0 && c.width % (1 << E) == 0, EVK_ERR_ARG,
+                "input %dx%d must be a multiple of 2^num_encoders (CropParameters.pad)", c.height, c.width);
+    int H = c.height, W = c.width, C = c.base_channels;
+    float* head = B.act(H, W, C);
+    int r = add_head(B, "head.conv2d", "head.norm_layer", head, C);
+    if (r != EVK_OK) return r;
+    const float* x = head;
+    std::vector<int> hstate(E);
+    for (int i = 0; i < E; ++i) {
+        const std::string pfx = "encoders." + std::to_string(i);
+        const int Co = 2 * C, Ho = (H + 2 * (k / 2) - k) / 2 + 1, Wo = (W + 2 * (k / 2) - k) / 2 + 1;
+        float* xe = B.act(Ho, Wo, Co);
+        r = B.conv(pfx + ".conv.conv2d.weight", pfx + ".conv.conv2d.bias", pfx + ".conv.norm_layer", x, C, H, W, 2, k / 2,
+                   ACT_RELU, nullptr, xe, nullptr);
+        if (r != EVK_OK) return r;
+        const int hs = make_state(m, Co, Ho, Wo, true);
+        if (hs < 0) return hs;
+        const int cs = make_state(m, Co, Ho, Wo, false);
+        if (cs < 0) return cs;
+        r = add_lstm(B, pfx + ".recurrent_block", xe, Co, Ho, Wo, hs, cs);
+        if (r != EVK_OK) return r;
+        hstate[i] = hs;
+        C = Co; H = Ho; W = Wo;
+        // Consumers of the new hidden state are built against the parity-0 target (buf[1]);
+        // the parity-1 program is patched after the build (see the fix-up loop below).
+        x = m->states[hs].buf[1];
+    }
+    // residual blocks
+    float* tmp = B.act(H, W, C);
+    for (int j = 0; j < c.num_residual_blocks; ++j) {
+        float* y = B.act(H, W, C);
+        r = add_resblock(B, "resblocks." + std::to_string(j), x, tmp, y, C, H, W);
+        if (r != EVK_OK) return r;
+        x = y;
+    }
+    // decoders
+    for (int i = 0; i < E; ++i) {
+        const int e = E - 1 - i;
+        const std::string pfx = "decoders." + std::to_string(i);
+        const float* skip = m->states[hstate[e]].buf[1];   // placeholder, fixed per parity below
+        float* up = B.act(2 * H, 2 * W, C);
+        {
+            Op op; op.kind = OP_UPSAMPLE_ADD;
+            op.in = x; op.skip = skip; op.out = up; op.N = B.N; op.H = H; op.W = W; op.cin = C;
+            m->ops[0].push_back(op); m->ops[1].push_back(op);
+        }
+        if (i == 0 && c.dynamic_decoder) {
+            float* y = B.act(2 * H, 2 * W, C / 2);
+            r = add_hyper_decoder(B, pfx, up, C, 2 * H, 2 * W, y);
+            if (r != EVK_OK) return r;
+            x = y;
+        } else {
+            float* y = B.act(2 * H, 2 * W, C / 2);
+            EVK_REQUIRE(m->find(pfx + ".conv2d.weight") != nullptr, EVK_ERR_KEY,
+                        "'%s.conv2d.weight' missing (transposed-conv decoders are not supported: every shipped "
+                        "checkpoint uses use_upsample_conv=True)", pfx.c_str());
+            r = B.conv(pfx + ".conv2d.weight", pfx + ".conv2d.bias", pfx + ".norm_layer", up, C, 2 * H, 2 * W, 1, k / 2,
+                       ACT_RELU, nullptr, y, nullptr);
+            if (r != EVK_OK) return r;
+            x = y;
+        }
+        C /= 2; H *= 2; W *= 2;
+    }
+    r = add_pred(B, "pred", x, head, C, H, W);
+    if (r != EVK_OK) return r;
+    // Parity fix-up: every pointer equal to "new hidden state of parity 0" (buf[1]) in the
+    // parity-1 program must read buf[0] instead (that is where parity 1 writes h_new).
+    for (Op& op : m->ops[1]) {
+        for (int i = 0; i < E; ++i) {
+            const StateBuf& s = m->states[hstate[i]];
+            auto fix = [&](const float*& p) { if (p == s.buf[1]) p = s.buf[0]; };
+            if (op.kind == OP_CONV && op.cp.epi == EPI_LSTM) { fix(op.cp.x1); continue; }   // x2/h_new already per parity
+            if (op.kind == OP_CONV) { fix(op.cp.x1); fix(op.cp.res); }
+            if (op.kind == OP_UPSAMPLE_ADD || op.kind == OP_PRED) { fix(op.in); fix(op.skip); }
+        }
+    }
+    return EVK_OK;
+}
+
+// FireNet_legacy (model/legacy.py:79-111) and FireNet (model/model.py:178-190)
+static int build_firenet(evk_model* m, bool legacy) {
+    const evk_model_config& c = m->cfg;
+    Builder B{m, c.batch};
+    const int H = c.height, W = c.width, C = c.base_channels;
+    const char* n_head = legacy ? "head.conv.conv2d" : "head.conv2d";
+    const char* n_g1 = legacy ? "head.recurrent_block" : "G1";
+    const char* n_r1 = legacy ? "resblocks.0.conv" : "R1";
+    const char* n_g2 = legacy ? "resblocks.0.recurrent_block" : "G2";
+    const char* n_r2 = legacy ? "resblocks.1" : "R2";
+    float* xh = B.act(H, W, C);
+    int r = add_head(B, n_head, "", xh, C);
+    if (r != EVK_OK) return r;
+    float* u = B.act(H, W, C);
+    float* hr = B.act(H, W, C);
+    float* tmp = B.act(H, W, C);
+    const int s1 = make_state(m, C, H, W, false);
+    if (s1 < 0) return s1;
+    r = add_gru(B, n_g1, xh, C, H, W, s1, u, hr);
+    if (r != EVK_OK) return r;
+    float* r1 = B.act(H, W, C);
+    r = add_resblock(B, n_r1, m->states[s1].buf[0], tmp, r1, C, H, W);
+    if (r != EVK_OK) return r;
+    const int s2 = make_state(m, C, H, W, false);
+    if (s2 < 0) return s2;
+    r = add_gru(B, n_g2, r1, C, H, W, s2, u, hr);
+    if (r != EVK_OK) return r;
+    float* r2 = B.act(H, W, C);
+    r = add_resblock(B, n_r2, m->states[s2].buf[0], tmp, r2, C, H, W);
+    if (r != EVK_OK) return r;
+    return add_pred(B, "pred", r2, nullptr, C, H, W);
+}
+
+static int run_ops(evk_model* m, int par, cudaStream_t st) {
+    for (const Op& op : m->ops[par]) {
+        int r = EVK_OK;
+        switch (op.kind) {
+            case OP_HEAD: r = launch_head_conv(op.in, op.w, op.b, op.out, op.N, op.cin, op.H, op.W, op.k, op.cout, st); break;
+            case OP_CONV: r = launch_conv(op.cp, m->cfg.precision, st); break;
+            case OP_UPSAMPLE_ADD: r = launch_upsample2x_add(op.in, op.skip, op.out, op.N, op.H, op.W, op.cin, st); break;
+            case OP_PRED: r = launch_pred(op.in, op.skip, op.w, op.bias0, op.out, (int64_t)op.N * op.H * op.W, op.cin, op.sigmoid, st); break;
+            default: r = launch_hyper(op.kind - OP_HYPER_CONTEXT, op.hp, st); break;
+        }
+        if (r != EVK_OK) return r;
+    }
+    return EVK_OK;
+}
+
+}  // namespace evk
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int evk_model_create(const evk_model_config* cfg, evk_model** out) {
+    EVK_REQUIRE(cfg && out, EVK_ERR_ARG, "evk_model_create: null argument");
+    EVK_REQUIRE(cfg->arch >= 0 && cfg->arch <= 2, EVK_ERR_ARG, "evk_model_create: unknown arch %d", cfg->arch);
+    EVK_REQUIRE(cfg->batch >= 1 && cfg->height > 0 && cfg->width > 0 && cfg->num_bins > 0 && cfg->base_channels > 0 &&
+                    cfg->base_channels % 4 == 0,
+                EVK_ERR_ARG, "evk_model_create: bad config (batch=%d %dx%d bins=%d base=%d)", cfg->batch, cfg->height,
+                cfg->width, cfg->num_bins, cfg->base_channels);
+    int ndev = 0;
+    EVK_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+    EVK_REQUIRE(ndev > 0, EVK_ERR_CUDA, "evk_model_create: no CUDA device (there is no CPU implementation)");
+    evk_model* m = new evk_model();
+    m->cfg = *cfg;
+    const char* ng = getenv("EVK_NO_GRAPH");
+    m->use_graph = !(ng && ng[0] == '1');
+    *out = m;
+    return EVK_OK;
+}
+
+int evk_model_load_tensor(evk_model* m, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+    EVK_REQUIRE(m && name && host_data && ndim >= 0 && ndim <= 8, EVK_ERR_ARG, "evk_model_load_tensor: bad argument");
+    EVK_REQUIRE(!m->finalized, EVK_ERR_STATE, "evk_model_load_tensor: model already finalized");
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= shape[i]; }
+    t.data.assign(host_data, host_data + n);
+    m->sd[name] = std::move(t);
+    return EVK_OK;
+}
+
+int evk_model_finalize(evk_model* m, void* stream) {
+    EVK_REQUIRE(m, EVK_ERR_ARG, "evk_model_finalize: null model");
+    EVK_REQUIRE(!m->finalized, EVK_ERR_STATE, "evk_model_finalize: already finalized");
+    const evk_model_config& c = m->cfg;
+    m->in_buf = m->dalloc((size_t)c.batch * c.num_bins * c.height * c.width);
+    m->out_buf = m->dalloc((size_t)c.batch * c.height * c.width);
+    m->prev_rec = m->dalloc((size_t)c.batch * c.height * c.width);
+    EVK_REQUIRE(m->in_buf && m->out_buf && m->prev_rec, EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
+    int r = (c.arch == EVK_ARCH_UNET_RECURRENT) ? build_unet(m) : build_firenet(m, c.arch == EVK_ARCH_FIRENET_LEGACY);
+    if (r != EVK_OK) return r;
+    for (void* p : m->allocs) EVK_REQUIRE(p != nullptr, EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
+    m->flops = 0.0;
+    for (const Op& op : m->ops[0]) m->flops += op.flops;
+    EVK_CHECK_CUDA(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+    EVK_CHECK_CUDA(cudaDeviceSynchronize());
+    m->sd.clear();
+    m->finalized = true;
+    (void)stream;
+    return EVK_OK;
+}
+
+int evk_model_reset_states(evk_model* m, void* stream) {
+    EVK_REQUIRE(m && m->finalized, EVK_ERR_STATE, "evk_model_reset_states: model not finalized");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (const StateBuf& s : m->states) {
+        const size_t bytes = sizeof(float) * (size_t)m->cfg.batch * s.H * s.W * s.C;
+        EVK_CHECK_CUDA(cudaMemsetAsync(s.buf[0], 0, bytes, st));
+        if (s.pingpong) EVK_CHECK_CUDA(cudaMemsetAsync(s.buf[1], 0, bytes, st));
+    }
+    EVK_CHECK_CUDA(cudaMemsetAsync(m->prev_rec, 0, sizeof(float) * (size_t)m->cfg.batch * m->cfg.height * m->cfg.width, st));
+    m->parity = 0;
+    return EVK_OK;
+}
+
+int evk_model_forward(evk_model* m, const float* voxel, float* image, void* stream) {
+    EVK_REQUIRE(m && m->finalized, EVK_ERR_STATE, "evk_model_forward: model not finalized");
+    EVK_REQUIRE(voxel && image, EVK_ERR_ARG, "evk_model_forward: null tensor");
+    cudaStream_t st = (cudaStream_t)stream;
+    const evk_model_config& c = m->cfg;
+    const size_t in_bytes = sizeof(float) * (size_t)c.batch * c.num_bins * c.height * c.width;
+    const size_t out_bytes = sizeof(float) * (size_t)c.batch * c.height * c.width;
+    if (voxel != m->in_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(m->in_buf, voxel, in_bytes, cudaMemcpyDeviceToDevice, st));
+    const int par = m->parity;
+    if (m->use_graph) {
+        if (!m->graph[par]) {
+            cudaGraph_t g = nullptr;
+            EVK_CHECK_CUDA(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+            int r = run_ops(m, par, m->cap_stream);
+            cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
+            if (r != EVK_OK) { if (g) cudaGraphDestroy(g); return r; }
+            EVK_CHECK_CUDA(e);
+            EVK_CHECK_CUDA(cudaGraphInstantiate(&m->graph[par], g, 0));
+            cudaGraphDestroy(g);
+        }
+        EVK_CHECK_CUDA(cudaGraphLaunch(m->graph[par], st));
+    } else {
+        int r = run_ops(m, par, st);
+        if (r != EVK_OK) return r;
+    }
+    m->last_launches = (int)m->ops[par].size();
+    if (c.dynamic_decoder) EVK_CHECK_CUDA(cudaMemcpyAsync(m->prev_rec, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
+    if (image != m->out_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(image, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
+    m->parity ^= 1;
+    return EVK_OK;
+}
+
+int evk_model_io_buffers(evk_model* m, float** in, float** out) {
+    EVK_REQUIRE(m && m->finalized, EVK_ERR_STATE, "evk_model_io_buffers: model not finalized");
+    if (in) *in = m->in_buf;
+    if (out) *out = m->out_buf;
+    return EVK_OK;
+}
+
+int evk_model_num_states(evk_model* m) { return m ? (int)m->states.size() : EVK_ERR_ARG; }
+
+int evk_model_state_shape(evk_model* m, int index, int64_t shape[4]) {
+    EVK_REQUIRE(m && index >= 0 && index < (int)m->states.size(), EVK_ERR_ARG, "evk_model_state_shape: bad index %d", index);
+    const StateBuf& s = m->states[index];
+    shape[0] = m->cfg.batch; shape[1] = s.C; shape[2] = s.H; shape[3] = s.W;
+    return EVK_OK;
+}
+
+int evk_model_last_launch_count(evk_model* m) { return m ? m->last_launches : EVK_ERR_ARG; }
+double evk_model_flops(evk_model* m) { return m ? m->flops : 0.0; }
+
+int evk_model_destroy(evk_model* m) {
+    if (!m) return EVK_OK;
+    for (int i = 0; i < 2; ++i)
+        if (m->graph[i]) cudaGraphExecDestroy(m->graph[i]);
+    if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+    for (void* p : m->allocs)
+        if (p) cudaFree(p);
+    delete m;
+    return EVK_OK;
+}
+
+}  // extern "C"
+
+// state get/set need a layout transpose (NHWC <-> NCHW)
+namespace evk {
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int C, int HW) {
+    const int64_t total = (int64_t)N * C * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i % HW);
+        const int c = (int)((i / HW) % C);
+        const int n = (int)(i / ((int64_t)HW * C));
+        out[i] = in[((size_t)n * HW + p) * C + c];
+    }
+}
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int C, int HW) {
+    const int64_t total = (int64_t)N * C * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int p = (int)((i / C) % HW);
+        const int n = (int)(i / ((int64_t)HW * C));
+        out[i] = in[((size_t)n * C + c) * HW + p];
+    }
+}
+}  // namespace evk
+
+extern "C" {
+
+int evk_model_get_state(evk_model* m, int index, float* out_nchw, void* stream) {
+    EVK_REQUIRE(m && m->finalized && index >= 0 && index < (int)m->states.size() && out_nchw, EVK_ERR_ARG, "evk_model_get_state: bad argument");
+    const StateBuf& s = m->states[index];
+    const float* cur = s.pingpong ? s.buf[m->parity] : s.buf[0];   // buffer the next forward will read
+    const int64_t total = (int64_t)m->cfg.batch * s.C * s.H * s.W;
+    nhwc_to_nchw_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 1184), 256, 0, (cudaStream_t)stream>>>(cur, out_nchw, m->cfg.batch, s.C, s.H * s.W);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+int evk_model_set_state(evk_model* m, int index, const float* in_nchw, void* stream) {
+    EVK_REQUIRE(m && m->finalized && index >= 0 && index < (int)m->states.size() && in_nchw, EVK_ERR_ARG, "evk_model_set_state: bad argument");
+    const StateBuf& s = m->states[index];
+    float* cur = s.pingpong ? s.buf[m->parity] : s.buf[0];
+    const int64_t total = (int64_t)m->cfg.batch * s.C * s.H * s.W;
+    nchw_to_nhwc_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 1184), 256, 0, (cudaStream_t)stream>>>(in_nchw, cur, m->cfg.batch, s.C, s.H * s.W);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// Stage 1: event window -> voxel grid, plus the glue around it
+// (normalize_event_tensor, CropParameters.pad/crop, uint8 frame -> float).
+//
+// Reference semantics: utils/event_utils.py:4-59, dataset.py:52-58,222-228,
+// eval.py:398-410, utils/util.py:30-59 (paths in the EVREAL tree).
+//
+// HBM-bound integer/float scatter: every event is read exactly once with
+// 128-bit loads (4 events per thread per array) and contributes to at most two
+// temporal bins, each with one fire-and-forget RED.ADD.F32 into the L2-resident
+// grid (<= 6.1 MB at 5x480x640).  Algorithmic bytes per window:
+// 16*N (f32 SoA) or 13*N (raw int16/f64/u8) + 4*bins*H*W for the grid.
+#include "evk_common.cuh"
+
+namespace evk {
+
+constexpr int kVoxThreads = 256;
+
+struct VoxGeom {
+    int bins, H, W;
+};
+
+// One event's contribution.  tn is the normalised time in [0, bins-1]; only
+// floor(tn) and floor(tn)+1 can have weight max(0, 1-|tn-b|) > 0, so the
+// reference's five passes collapse to two adds with identical float values.
+__device__ __forceinline__ void scatter_event(float xf, float yf, float tn, float pol, const VoxGeom g,
+                                              float* __restrict__ grid, int& oob) {
+    int xi = (int)xf;   // truncation toward zero == tensor.long()
+    int yi = (int)yf;
+    if (xi < 0) xi += g.W;   // python-style wrap of negative indices (index_put_)
+    if (yi < 0) yi += g.H;
+    if ((unsigned)xi >= (unsigned)g.W || (unsigned)yi >= (unsigned)g.H) {
+        oob++;
+        return;
+    }
+    const float fb = floorf(tn);
+    const int b0 = (int)fb;
+    float* cell = grid + (size_t)yi * g.W + xi;
+    const size_t plane = (size_t)g.H * g.W;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int b = b0 + k;
+        if (b < 0 || b >= g.bins) continue;
+        const float w = 1.0f - fabsf(tn - (float)b);
+        if (w > 0.0f) atomicAdd(cell + (size_t)b * plane, pol * w);
+    }
+}
+
+// torch.linspace(0, bins-1, n)[i] in float32 (scalar ATen formula).
+__device__ __forceinline__ float linspace_at(int64_t i, int64_t n, float end) {
+    if (n == 1) return 0.0f;
+    const float step = end / (float)(n - 1);
+    return (i < n / 2) ? (0.0f + step * (float)i) : (end - step * (float)(n - 1 - i));
+}
+
+struct TimeNorm {
+    float t0, dt, scale;
+    bool degenerate;   // dt < 1e-9 -> linspace branch (utils/event_utils.py:48-49)
+    int64_t n;
+    __device__ __forceinline__ float operator()(float t, int64_t i) const {
+        if (degenerate) return linspace_at(i, n, scale);
+        return __fmul_rn(__fdiv_rn(__fsub_rn(t, t0), dt), scale);
+    }
+};
+
+template <bool kVec>
+__global__ void __launch_bounds__(kVoxThreads)
+voxelize_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ t,
+                    const float* __restrict__ p, int64_t n, int64_t head, VoxGeom g,
+                    float* __restrict__ grid, int* __restrict__ oob_count) {
+    TimeNorm tn;
+    tn.t0 = __ldg(t);
+    tn.dt = __fsub_rn(__ldg(t + n - 1), tn.t0);
+    tn.scale = (float)(g.bins - 1);
+    tn.degenerate = (double)tn.dt < 1e-9;
+    tn.n = n;
+    int oob = 0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (kVec) {
+        // unaligned head and tail handled scalar; the body is 128-bit aligned
+        const int64_t nvec = (n - head) / 4;
+        const float4* x4 = reinterpret_cast<const float4*>(x + head);
+        const float4* y4 = reinterpret_cast<const float4*>(y + head);
+        const float4* t4 = reinterpret_cast<const float4*>(t + head);
+        const float4* p4 = reinterpret_cast<const float4*>(p + head);
+        for (int64_t v = tid; v < nvec; v += nthreads) {
+            const float4 xv = __ldcs(x4 + v), yv = __ldcs(y4 + v), tv = __ldcs(t4 + v), pv = __ldcs(p4 + v);
+            const int64_t i = head + v * 4;
+            scatter_event(xv.x, yv.x, tn(tv.x, i + 0), pv.x, g, grid, oob);
+            scatter_event(xv.y, yv.y, tn(tv.y, i + 1), pv.y, g, grid, oob);
+            scatter_event(xv.z, yv.z, tn(tv.z, i + 2), pv.z, g, grid, oob);
+            scatter_event(xv.w, yv.w, tn(tv.w, i + 3), pv.w, g, grid, oob);
+        }
+        const int64_t tail0 = head + nvec * 4;
+        const int64_t nscalar = head + (n - tail0);
+        for (int64_t s = tid; s < nscalar; s += nthreads) {
+            const int64_t i = s < head ? s : tail0 + (s - head);
+            scatter_event(x[i], y[i], tn(t[i], i), p[i], g, grid, oob);
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += nthreads) scatter_event(x[i], y[i], tn(t[i], i), p[i], g, grid, oob);
+    }
+    if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
+}
+
+// Raw on-disk layout: xy int16 pairs, t float64 absolute, pol uint8 {0,1}.
+__global__ void __launch_bounds__(kVoxThreads)
+voxelize_raw_kernel(const int16_t* __restrict__ xy, const double* __restrict__ t, const uint8_t* __restrict__ pol,
+                    int64_t n, VoxGeom g, float* __restrict__ grid, int* __restrict__ oob_count) {
+    const double t0d = __ldg(t);
+    TimeNorm tn;
+    tn.t0 = 0.0f;   // (t - t[0]).astype(f32)[0] == 0
+    tn.dt = (float)(__ldg(t + n - 1) - t0d);
+    tn.scale = (float)(g.bins - 1);
+    tn.degenerate = (double)tn.dt < 1e-9;
+    tn.n = n;
+    int oob = 0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int* xy32 = reinterpret_cast<const int*>(xy);   // int16 pairs are 4-byte aligned by construction
+    for (int64_t i = tid; i < n; i += nthreads) {
+        const int c = __ldcs(xy32 + i);
+        const float xf = (float)(short)(c & 0xffff);
+        const float yf = (float)(short)(c >> 16);
+        const float tf = (float)(__ldcs(t + i) - t0d);
+        const float pf = (float)((double)pol[i] * 2.0 - 1.0);
+        scatter_event(xf, yf, tn(tf, i), pf, g, grid, oob);
+    }
+    if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
+}
+
+static int vox_grid_blocks(int64_t n, int per_thread) {
+    int64_t blocks = ceil_div64(n, (int64_t)kVoxThreads * per_thread);
+    const int64_t cap = (int64_t)kNumSMs * 8;   // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int voxelize_f32(const float* x, const float* y, const float* t, const float* p, int64_t n, int bins, int H, int W,
+                 float* grid, int* oob_count, cudaStream_t st) {
+    EVK_REQUIRE(n > 0, EVK_ERR_ARG, "evk_voxelize: empty window (n=%lld); the reference indexes ts[-1]", (long long)n);
+    EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize: bad geometry bins=%d H=%d W=%d", bins, H, W);
+    EVK_CHECK_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)bins * H * W, st));
+    if (oob_count) EVK_CHECK_CUDA(cudaMemsetAsync(oob_count, 0, sizeof(int), st));
+    VoxGeom g{bins, H, W};
+    // all four arrays must share the same 16-byte phase for the vector body
+    auto phase = [](const void* q) { return (int)(((uintptr_t)q >> 2) & 3); };
+    const bool same = phase(x) == phase(y) && phase(y) == phase(t) && phase(t) == phase(p) &&
+                      (((uintptr_t)x | (uintptr_t)y | (uintptr_t)t | (uintptr_t)p) & 3) == 0;
+    if (same && n >= 64) {
+        int64_t head = (4 - phase(x)) & 3;
+        voxelize_f32_kernel<true><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, grid, oob_count);
+    } else {
+        voxelize_f32_kernel<false><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, grid, oob_count);
+    }
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+int voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int64_t n, int bins, int H, int W,
+                 float* grid, int* oob_count, cudaStream_t st) {
+    EVK_REQUIRE(n > 0, EVK_ERR_ARG, "evk_voxelize_raw: empty window");
+    EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize_raw: bad geometry");
+    EVK_REQUIRE(((uintptr_t)xy & 3) == 0 && ((uintptr_t)t & 7) == 0, EVK_ERR_ARG, "evk_voxelize_raw: misaligned arrays");
+    EVK_CHECK_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)bins * H * W, st));
+    if (oob_count) EVK_CHECK_CUDA(cudaMemsetAsync(oob_count, 0, sizeof(int), st));
+    VoxGeom g{bins, H, W};
+    voxelize_raw_kernel<<<vox_grid_blocks(n, 2), kVoxThreads, 0, st>>>(xy, t, pol, n, g, grid, oob_count);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// normalize_event_tensor (eval.py:398-410) fused with CropParameters.pad.
+// Pass 1: per-sample (count of non-zeros, sum, sum of squares) in float64.
+// Pass 2: out = mask * (v - mean) / std written into the zero-padded frame.
+// ---------------------------------------------------------------------------
+struct EvStats {
+    double sum, sumsq;
+    unsigned long long nnz;
+};
+
+__global__ void __launch_bounds__(256) event_stats_kernel(const float* __restrict__ in, int64_t numel, EvStats* stats) {
+    const int s = blockIdx.y;
+    const float* v = in + (size_t)s * numel;
+    double sum = 0.0, sq = 0.0;
+    unsigned int nnz = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = v[i];
+        if (a != 0.0f) {
+            nnz++;
+            sum += (double)a;
+            sq += (double)a * (double)a;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        nnz += __shfl_xor_sync(0xffffffffu, nnz, o);
+    }
+    __shared__ double ssum[8], ssq[8];
+    __shared__ unsigned int snz[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { ssum[warp] = sum; ssq[warp] = sq; snz[warp] = nnz; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { sum += ssum[w]; sq += ssq[w]; nnz += snz[w]; }
+        atomicAdd(&stats[s].sum, sum);
+        atomicAdd(&stats[s].sumsq, sq);
+        atomicAdd(&stats[s].nnz, (unsigned long long)nnz);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+normalize_pad_kernel(const float* __restrict__ in, float* __restrict__ out, const EvStats* __restrict__ stats,
+                     int C, int H, int W, int Hp, int Wp, int top, int left, int do_norm) {
+    const int s = blockIdx.y;
+    const int64_t total = (int64_t)C * Hp * Wp;
+    float mean = 0.0f, stddev = 1.0f;
+    bool active = false;
+    if (do_norm) {
+        const EvStats st = stats[s];
+        if (st.nnz > 0) {
+            active = true;
+            const float nf = (float)st.nnz;
+            mean = (float)st.sum / nf;
+            stddev = sqrtf((float)st.sumsq / nf - mean * mean);
+            stddev = fmaxf(stddev, 1e-6f);
+        }
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xo = (int)(i % Wp);
+        const int yo = (int)((i / Wp) % Hp);
+        const int c = (int)(i / ((int64_t)Wp * Hp));
+        const int yi = yo - top, xi = xo - left;
+        float v = 0.0f;
+        if ((unsigned)yi < (unsigned)H && (unsigned)xi < (unsigned)W) {
+            v = in[((size_t)s * C + c) * H * W + (size_t)yi * W + xi];
+            if (active) v = (v != 0.0f) ? __fdiv_rn(__fsub_rn(v, mean), stddev) : 0.0f;
+        }
+        out[(size_t)s * total + i] = v;
+    }
+}
+
+int normalize_pad(const float* in, float* out, int n_samples, int C, int H, int W, int Hp, int Wp, int do_norm,
+                  cudaStream_t st) {
+    EVK_REQUIRE(n_samples > 0 && C > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, EVK_ERR_ARG,
+                "evk_normalize_pad: bad shape n=%d C=%d %dx%d -> %dx%d", n_samples, C, H, W, Hp, Wp);
+    EVK_REQUIRE(!(in == out && (Hp != H || Wp != W)), EVK_ERR_ARG, "evk_normalize_pad: in-place padding is not possible");
+    EvStats* stats = nullptr;
+    if (do_norm) {
+        EVK_CHECK_CUDA(cudaMallocAsync(&stats, sizeof(EvStats) * n_samples, st));
+        EVK_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(EvStats) * n_samples, st));
+        const int64_t numel = (int64_t)C * H * W;
+        dim3 grid((unsigned)std::min<int64_t>(ceil_div64(numel, 256 * 4), 256), n_samples);
+        event_stats_kernel<<<grid, 256, 0, st>>>(in, numel, stats);
+        EVK_CHECK_CUDA(cudaGetLastError());
+    }
+    // CropParameters: top/left get the ceil half (utils/util.py:43-46)
+    const int top = (Hp - H + 1) / 2, left = (Wp - W + 1) / 2;
+    const int64_t total = (int64_t)C * Hp * Wp;
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div64(total, 256 * 2), 1184), n_samples);
+    normalize_pad_kernel<<<grid, 256, 0, st>>>(in, out, stats, C, H, W, Hp, Wp, top, left, do_norm);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    if (stats) EVK_CHECK_CUDA(cudaFreeAsync(stats, st));
+    return EVK_OK;
+}
+
+// CropParameters.crop: iy0 = floor(Hp/2) - floor(H/2) (utils/util.py:50-59)
+__global__ void __launch_bounds__(256)
+crop_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t planes, int Hp, int Wp, int H, int W, int iy0, int ix0) {
+    const int64_t total = planes * H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const int y = (int)((i / W) % H);
+        const int64_t pl = i / ((int64_t)W * H);
+        out[i] = in[(pl * Hp + (y + iy0)) * Wp + (x + ix0)];
+    }
+}
+
+int crop(const float* in, float* out, int n, int C, int Hp, int Wp, int H, int W, cudaStream_t st) {
+    EVK_REQUIRE(n > 0 && C > 0 && Hp >= H && Wp >= W && H > 0 && W > 0, EVK_ERR_ARG, "evk_crop: bad shape");
+    const int iy0 = Hp / 2 - H / 2, ix0 = Wp / 2 - W / 2;
+    const int64_t total = (int64_t)n * C * H * W;
+    crop_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 1184), 256, 0, st>>>(in, out, (int64_t)n * C, Hp, Wp, H, W, iy0, ix0);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __fdiv_rn((float)in[i], 255.0f);
+}
+
+int u8_to_f32(const uint8_t* in, float* out, int64_t n, cudaStream_t st) {
+    EVK_REQUIRE(n > 0, EVK_ERR_ARG, "evk_u8_to_f32: empty input");
+    u8_to_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 1184), 256, 0, st>>>(in, out, n);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+}  // namespace evk

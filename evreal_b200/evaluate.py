@@ -1,0 +1,280 @@
+"""Host-side mirror of EVREAL's ``eval.py`` driving the CUDA hot path.
+
+Keeps the reference's plugin surface -- ``config/method/*.json``,
+``config/eval/*.json``, ``config/dataset/*.json`` (read relative to a config
+root), the checkpoint -> model factory (eval.py:124-158), the per-sequence loop
+(eval.py:189-246) and the count-weighted dataset means (eval.py:249-276,
+:367-368) -- and adds what the reference lacks: sequences sharded over ranks
+(one process per GPU) with a single all-reduce of the ``[sum(score*n), sum(n)]``
+vectors at the end.
+
+Everything per frame stays on the GPU: raw events are resident in HBM, the
+voxel grid, normalisation+padding, network, crop, percentile normalisation and
+MSE/SSIM are kernels of libevreal_b200.so; scores come back to the host once per
+sequence.
+"""
+import glob
+import os
+from collections import OrderedDict
+
+import torch
+
+from . import model as model_arch
+from . import parse_config
+from .dataset import MemMapDataset
+from .eval_metrics import EvalMetricsTracker
+from .eval_utils import post_process_normalization
+from .util import CropParameters, read_json, normalize_pad
+
+
+# ------------------------------------------------------------------ configs
+def get_eval_configs(eval_config_names, config_root="config"):
+    out = []
+    for name in eval_config_names:
+        cfg = read_json(os.path.join(config_root, "eval", name + ".json"))
+        cfg['name'] = name
+        out.append(cfg)
+    return out
+
+
+def get_dataset_configs(dataset_names, config_root="config"):
+    out = []
+    for name in dataset_names:
+        cfg = read_json(os.path.join(config_root, "dataset", name + ".json"))
+        cfg['name'] = name
+        out.append(cfg)
+    return out
+
+
+def get_method_config(method_name, config_root="config"):
+    return read_json(os.path.join(config_root, "method", method_name + ".json"))
+
+
+def get_sequences(dataset_config, dataset_kwargs):
+    """eval.py:38-79, with sequence names sorted (the reference iterates an unsorted glob)."""
+    dataset_root = dataset_config['root_path']
+    dataset_kwargs = dict(dataset_kwargs)
+    dataset_kwargs.update(dataset_config.get('dataset_kwargs', {}))
+    if dataset_config.get('get_all_sequences', False):
+        pattern = os.path.join(dataset_root, '*', '*') if dataset_config.get('has_subfolders', False) \
+            else os.path.join(dataset_root, '*')
+        sequences_config = OrderedDict()
+        for path in sorted(glob.glob(pattern)):
+            name = os.path.basename(path)
+            if dataset_config.get('has_subfolders', False):
+                name = os.path.basename(os.path.dirname(path)) + "_" + name
+            sequences_config[name] = {'sequence_path': path}
+    else:
+        sequences_config = dataset_config.get('sequences', {})
+    sequences = []
+    for name, seq in sequences_config.items():
+        seq = dict(seq)
+        seq['name'] = name
+        seq['sequence_path'] = seq.get('sequence_path', os.path.join(dataset_root, name))
+        seq['dataset_kwargs'] = dataset_kwargs
+        sequences.append(seq)
+    return sequences
+
+
+def open_sequence(sequence, device=None):
+    """Instantiate the dataset of one sequence and fill in the default evaluation window (eval.py:71-77)."""
+    ds = MemMapDataset(sequence['sequence_path'], device=device, **sequence['dataset_kwargs'])
+    min_t, max_t = ds.get_min_max_t()
+    sequence.setdefault('start_time_s', min_t)
+    sequence.setdefault('end_time_s', max_t)
+    sequence['dataset'] = ds
+    return ds
+
+
+# ------------------------------------------------------------------ model factory
+def build_model(model_name, checkpoint):
+    """Checkpoint dialects by method name (eval.py:124-158) -> (model, state_dict)."""
+    if model_name in ("SPADE-E2VID", "ET-Net"):
+        raise NotImplementedError(f"{model_name} is outside the accelerated hot path (SURVEY 2: out of scope)")
+    if model_name == "SSL-E2VID":
+        unet_kwargs = {"base_num_channels": 32, "kernel_size": 5, "num_bins": 5, "num_encoders": 3,
+                       "recurrent_block_type": "convlstm", "num_residual_blocks": 2, "skip_type": "sum", "norm": None,
+                       "use_upsample_conv": True}
+        return model_arch.E2VIDRecurrent(unet_kwargs), checkpoint
+    if model_name == "E2VID":
+        unet_kwargs = dict(checkpoint['model'])
+        unet_kwargs['final_activation'] = 'sigmoid'
+        model = model_arch.E2VIDRecurrent(unet_kwargs)
+    elif model_name == "FireNet":
+        unet_kwargs = dict(checkpoint['config']['model'])
+        unet_kwargs['final_activation'] = ''
+        model = model_arch.FireNet_legacy(unet_kwargs)
+    else:
+        model = checkpoint['config'].init_obj('arch', model_arch)
+        if model_name == "FireNet+":
+            model.num_encoders = 0
+    return model, checkpoint['state_dict']
+
+
+def get_model_from_checkpoint_path(model_name, checkpoint_path, device=None):
+    parse_config.install()
+    checkpoint = torch.load(checkpoint_path, map_location='cpu', weights_only=False)
+    model, state_dict = build_model(model_name, checkpoint)
+    model.load_state_dict(state_dict)
+    model.to(device if device is not None else torch.device('cuda', torch.cuda.current_device()))
+    model.eval()
+    return model
+
+
+# ------------------------------------------------------------------ per-sequence loop
+def eval_method_on_sequence(dataset_name, eval_config, method_name, model, method_config, sequence, metrics,
+                            output_root="outputs", write_files=True, collect_images=None):
+    """eval.py:189-246 on the GPU.  Returns (num_evaluated, mean_scores, num_frames_reconstructed, num_events)."""
+    dataset = sequence.get('dataset') or open_sequence(sequence)
+    has_reference_frames = dataset.has_images
+    output_dir = os.path.join(output_root, eval_config['name'], dataset_name, sequence['name'], method_name)
+    tracker = EvalMetricsTracker(save_images=eval_config.get('save_images', True) and write_files,
+                                 output_dir=output_dir, hist_eq=eval_config['histeq'],
+                                 quan_eval_metric_names=metrics,
+                                 quan_eval_start_time=sequence['start_time_s'],
+                                 quan_eval_end_time=sequence['end_time_s'],
+                                 quan_eval_ts_tol_ms=eval_config['ts_tol_ms'],
+                                 has_reference_frames=has_reference_frames,
+                                 color=eval_config.get('color', False), defer=True, write_files=write_files)
+    if eval_config.get('color', False):
+        raise NotImplementedError("ColorNet / CED colour evaluation is outside the accelerated hot path")
+    height, width = int(dataset.sensor_resolution[0]), int(dataset.sensor_resolution[1])
+    cropper = CropParameters(width, height, model.num_encoders)
+    model.reset_states()
+    eval_infer_all = eval_config.get('eval_infer_all', False)
+    post_process_norm = method_config.get('post_process_norm', "none")
+    event_tensor_normalization = method_config.get('event_tensor_normalization', False)
+    idx = 0
+    frames = 0
+    events = 0
+    for idx in range(len(dataset)):
+        item = dataset[idx]
+        ref_frame = item['frame'] if has_reference_frames else None
+        ref_frame_ts = item['frame_timestamp'].item() if has_reference_frames else None
+        pred_frame_ts = item['voxel_timestamp'].item()
+        # Only start reconstruction when close to eval start (10 seconds)   eval.py:210-216
+        if pred_frame_ts < sequence['start_time_s'] - 10 and not eval_infer_all:
+            continue
+        if pred_frame_ts > sequence['end_time_s'] and not eval_infer_all:
+            idx -= 1
+            break
+        if item['event_count'] <= 1 or item['dt'].item() == 0:
+            event_rate = 0
+        else:
+            event_rate = item['event_count'] / item['dt'].item()
+        voxel = item['events'].unsqueeze(0)
+        # normalize_event_tensor + cropper.pad in one kernel (eval.py:222-226)
+        voxel = normalize_pad(voxel, cropper.height_crop_size, cropper.width_crop_size, event_tensor_normalization)
+        output = model(voxel)
+        image = cropper.crop(output['image'])
+        image = post_process_normalization(image, post_process_norm)
+        image2d = image[0, 0]
+        if collect_images is not None:
+            collect_images.append(image2d.clone())
+        tracker.update(idx, image2d, ref_frame[0] if has_reference_frames else None, pred_frame_ts, ref_frame_ts)
+        tracker.save_custom_metric(idx, "event_rate", event_rate)
+        frames += 1
+        events += item['event_count']
+    tracker.finalize(idx)
+    dataset.check_bounds()
+    return tracker.get_num_quan_evaluations(), tracker.get_mean_scores(), frames, events
+
+
+class MetricTracker:
+    """Count-weighted running means per metric (eval.py:249-276)."""
+
+    def __init__(self):
+        self.data_dict = {}
+
+    def init_key(self, key):
+        self.data_dict[key] = {'total': 0.0, 'count': 0, 'average': 0.0}
+
+    def update(self, key, value, count=1):
+        if count == 0:
+            return
+        if key not in self.data_dict:
+            self.init_key(key)
+        d = self.data_dict[key]
+        d['total'] += value * count
+        d['count'] += count
+        d['average'] = d['total'] / d['count']
+
+    def get_average(self, key):
+        if key not in self.data_dict:
+            self.init_key(key)
+        return self.data_dict[key]['average']
+
+    def get_count(self, key):
+        if key not in self.data_dict:
+            self.init_key(key)
+        return self.data_dict[key]['count']
+
+
+# ------------------------------------------------------------------ sharding over ranks
+def shard_sequences(sequences, weights, world_size):
+    """Longest-processing-time assignment of sequences to ranks.  Deterministic: ties broken by name.
+    Returns a list (per rank) of indices into ``sequences``."""
+    order = sorted(range(len(sequences)), key=lambda i: (-weights[i], sequences[i]['name']))
+    loads = [0.0] * world_size
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        shards[r].append(i)
+        loads[r] += weights[i]
+    return [sorted(s) for s in shards]
+
+
+def reduce_metric_sums(local, metric_names, group=None):
+    """One all-reduce(SUM) of [sum(score*n), sum(n)] per metric -> MetricTracker semantics over all ranks."""
+    import torch.distributed as dist
+    vec = torch.zeros(2 * len(metric_names), dtype=torch.float64)
+    for j, name in enumerate(metric_names):
+        if name in local.data_dict:
+            vec[2 * j] = local.data_dict[name]['total']
+            vec[2 * j + 1] = local.data_dict[name]['count']
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if dist.get_backend(group) == 'nccl':
+            vec = vec.cuda()
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        vec = vec.cpu()
+    out = MetricTracker()
+    for j, name in enumerate(metric_names):
+        total, count = float(vec[2 * j]), int(round(float(vec[2 * j + 1])))
+        if count > 0:
+            out.data_dict[name] = {'total': total, 'count': count, 'average': total / count}
+    return out
+
+
+def evaluate(method_names, eval_config_names=None, dataset_names=None, metrics=None, config_root="config",
+             output_root="outputs", write_files=True, rank=0, world_size=1):
+    """eval.py:413-444.  Returns {eval_config: {method: {dataset: MetricTracker}}} (identical on every rank)."""
+    if eval_config_names is None:
+        eval_config_names = ['std']
+    if metrics is None:
+        metrics = ['mse', 'ssim']
+    results = OrderedDict()
+    for eval_config in get_eval_configs(eval_config_names, config_root):
+        per_method = OrderedDict()
+        dataset_configs = get_dataset_configs(dataset_names, config_root)
+        for method_name in method_names:
+            method_config = get_method_config(method_name, config_root)
+            model = get_model_from_checkpoint_path(method_config['model_name'], method_config['model_path'])
+            per_dataset = OrderedDict()
+            for dataset_config in dataset_configs:
+                sequences = get_sequences(dataset_config, eval_config.get('dataset_kwargs', {}))
+                weights = [os.path.getsize(os.path.join(s['sequence_path'], 'events_ts.npy')) for s in sequences]
+                mine = shard_sequences(sequences, weights, world_size)[rank]
+                local = MetricTracker()
+                for i in mine:
+                    seq = sequences[i]
+                    open_sequence(seq)
+                    n_eval, mean_scores, _, _ = eval_method_on_sequence(
+                        dataset_config['name'], eval_config, method_name, model, method_config, seq, metrics,
+                        output_root, write_files)
+                    for metric_name, score in mean_scores.items():
+                        local.update(metric_name, score, n_eval)
+                    seq.pop('dataset', None)
+                per_dataset[dataset_config['name']] = reduce_metric_sums(local, metrics)
+            per_method[method_name] = per_dataset
+        results[eval_config['name']] = per_method
+    return results

@@ -1,0 +1,298 @@
+"""Host-side mirror of EVREAL's model plugin classes (``model/model.py``, ``model/legacy.py``).
+
+Same class names, constructor arguments, attributes (``num_encoders``,
+``num_bins``, ``states``, ``prev_recs``) and methods (``reset_states``,
+``forward -> {'image': ...}``, ``load_state_dict``, ``to``, ``eval``,
+``parameters``) as the reference, so ``eval.py:124-158``'s factory and
+``eval.py:109-115``'s ``load_model`` work on them unchanged.  The arithmetic
+runs in the CUDA library through the C ABI (``evk_model_*``); these classes
+hold no torch parameters and there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ARCH_UNET, ARCH_FIRENET_LEGACY, ARCH_FIRENET = 0, 1, 2
+
+
+class _NativeModel:
+    _prefix = ''
+    _arch = ARCH_UNET
+
+    def __init__(self):
+        self._sd = None
+        self._handle = None
+        self._key = None
+        self._device = None
+        self.precision = 0        # 0: tensor-core split-bf16 where applicable, 1: fp32 SIMT everywhere
+
+    # ---- nn.Module-like surface used by eval.py:109-115
+    def load_state_dict(self, state_dict, strict=True):
+        sd = {}
+        for k, v in state_dict.items():
+            if k.endswith('num_batches_tracked'):
+                continue
+            if self._prefix:
+                if not k.startswith(self._prefix):
+                    if strict:
+                        raise RuntimeError("Unexpected key(s) in state_dict: \"%s\"" % k)
+                    continue
+                k = k[len(self._prefix):]
+            sd[k] = v.detach().to(device='cpu', dtype=torch.float32).contiguous()
+        self._sd = sd
+        self._release()
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise _lib.EvkError("evreal_b200 models run on CUDA only (got device %s)" % device)
+        self._device = device if device.index is not None else torch.device('cuda', torch.cuda.current_device())
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device('cuda', torch.cuda.current_device() if device is None else device))
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter(())
+
+    def state_dict(self):
+        return {self._prefix + k: v for k, v in (self._sd or {}).items()}
+
+    # ---- handle management
+    def _config(self, batch, height, width):
+        raise NotImplementedError
+
+    def _release(self):
+        if self._handle is not None:
+            _lib.load().evk_model_destroy(self._handle)
+            self._handle = None
+            self._key = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure(self, batch, height, width, device):
+        key = (batch, height, width, device, self.precision)
+        if self._handle is not None and self._key == key:
+            return
+        if self._sd is None:
+            raise _lib.EvkError("load_state_dict() must be called before the first forward")
+        self._release()
+        lib = _lib.load()
+        cfg = self._config(batch, height, width)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.evk_model_create(ctypes.byref(cfg), ctypes.byref(handle)))
+            try:
+                for name, t in self._sd.items():
+                    shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+                    _lib.check(lib.evk_model_load_tensor(handle, name.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()))
+                _lib.check(lib.evk_model_finalize(handle, _lib.stream_ptr(device)))
+                _lib.check(lib.evk_model_reset_states(handle, _lib.stream_ptr(device)))
+            except Exception:
+                lib.evk_model_destroy(handle)
+                raise
+        self._handle, self._key = handle, key
+
+    # ---- reference API
+    def reset_states(self):
+        if self._handle is not None:
+            dev = self._key[3]
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().evk_model_reset_states(self._handle, _lib.stream_ptr(dev)))
+
+    def forward(self, event_tensor):
+        _lib.require_cuda()
+        x = event_tensor
+        if not x.is_cuda:
+            x = x.to(self._device or torch.device('cuda', torch.cuda.current_device()), non_blocking=True)
+        x = x.float().contiguous()
+        assert x.dim() == 4, "expected N x num_bins x H x W"
+        N, C, H, W = x.shape
+        assert C == self.num_bins, "expected %d bins, got %d" % (self.num_bins, C)
+        self._ensure(N, H, W, x.device)
+        out = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().evk_model_forward(self._handle, _lib.ptr(x), _lib.ptr(out), _lib.stream_ptr(x.device)))
+        return {'image': out}
+
+    __call__ = forward
+
+    # ---- introspection used by bench / tests
+    def flops_per_forward(self):
+        return float(_lib.load().evk_model_flops(self._handle)) if self._handle else 0.0
+
+    def last_launch_count(self):
+        return int(_lib.load().evk_model_last_launch_count(self._handle)) if self._handle else 0
+
+    def _get_states(self):
+        if self._handle is None:
+            return None
+        lib = _lib.load()
+        dev = self._key[3]
+        out = []
+        with torch.cuda.device(dev):
+            for i in range(lib.evk_model_num_states(self._handle)):
+                shp = (ctypes.c_int64 * 4)()
+                _lib.check(lib.evk_model_state_shape(self._handle, i, shp))
+                t = torch.empty(tuple(shp), dtype=torch.float32, device=dev)
+                _lib.check(lib.evk_model_get_state(self._handle, i, _lib.ptr(t), _lib.stream_ptr(dev)))
+                out.append(t)
+        return out
+
+    def _set_states(self, tensors):
+        lib = _lib.load()
+        dev = self._key[3]
+        with torch.cuda.device(dev):
+            for i, t in enumerate(tensors):
+                t = t.to(device=dev, dtype=torch.float32).contiguous()
+                _lib.check(lib.evk_model_set_state(self._handle, i, _lib.ptr(t), _lib.stream_ptr(dev)))
+
+
+class _UNetFamily(_NativeModel):
+    _arch = ARCH_UNET
+
+    def __init__(self, unet_kwargs):
+        super().__init__()
+        kw = dict(unet_kwargs)
+        self.num_bins = kw['num_bins']            # legacy attribute names of the reference
+        self.num_encoders = kw['num_encoders']
+        self._base = kw.get('base_num_channels', 32)
+        self._num_res = kw.get('num_residual_blocks', 2)
+        self._k = kw.get('kernel_size', 5)
+        self._num_out = kw.get('num_output_channels', 1)
+        self._sigmoid = kw.get('final_activation', 'none') == 'sigmoid'
+        self._dynamic = bool(kw.get('use_dynamic_decoder', False))
+        if kw.get('skip_type', 'sum') != 'sum':
+            raise NameError("name 'skip_%s' is not defined" % kw.get('skip_type'))     # model/unet.py:31
+        if kw.get('recurrent_block_type', 'convlstm') != 'convlstm':
+            raise _lib.EvkError("UNetRecurrent with recurrent_block_type=%r is not built (all shipped checkpoints use "
+                                "convlstm)" % kw.get('recurrent_block_type'))
+        if not kw.get('use_upsample_conv', True):
+            raise _lib.EvkError("use_upsample_conv=False (TransposedConvLayer) is not built: every shipped checkpoint "
+                                "uses UpsampleConvLayer")
+        if kw.get('channel_multiplier', 2) != 2:
+            raise _lib.EvkError("channel_multiplier != 2 is not built")
+
+    def _config(self, batch, height, width):
+        return _lib.ModelConfig(arch=ARCH_UNET, num_bins=self.num_bins, base_channels=self._base,
+                                num_encoders=self.num_encoders, num_residual_blocks=self._num_res,
+                                kernel_size=self._k, num_output_channels=self._num_out,
+                                final_sigmoid=int(self._sigmoid), dynamic_decoder=int(self._dynamic), batch=batch,
+                                height=height, width=width, precision=self.precision)
+
+    @property
+    def states(self):
+        """[(hidden, cell), ...] per encoder, NCHW copies (model/model.py:116-118)."""
+        s = self._get_states()
+        if s is None:
+            return [None] * self.num_encoders
+        return [(s[2 * i], s[2 * i + 1]) for i in range(self.num_encoders)]
+
+    @states.setter
+    def states(self, states):
+        if self._handle is None:
+            if all(s is None for s in states):
+                return
+            raise _lib.EvkError("states can only be set after the first forward fixed the tensor shapes")
+        if all(s is None for s in states):
+            _NativeModel.reset_states(self)
+            return
+        flat = []
+        for h, c in states:
+            flat += [h, c]
+        self._set_states(flat)
+
+
+class E2VIDRecurrent(_UNetFamily):
+    """model/model.py:108-144 (E2VID, SSL-E2VID, HyperE2VID checkpoints)."""
+    _prefix = 'unetrecurrent.'
+
+    def __init__(self, unet_kwargs):
+        super().__init__(unet_kwargs)
+        self.prev_recs = None
+
+    def reset_states(self):
+        super().reset_states()
+        self.prev_recs = None
+
+    def forward(self, event_tensor):
+        out = super().forward(event_tensor)
+        self.prev_recs = out['image']
+        return out
+
+    __call__ = forward
+
+
+class FlowNet(_UNetFamily):
+    """model/model.py:14-43 (E2VID+ checkpoint).  Only the image channel is computed:
+    eval.py never reads 'flow'."""
+    _prefix = 'unetflow.'
+
+
+class _FireNetBase(_NativeModel):
+    def _fire_config(self, arch, batch, height, width):
+        return _lib.ModelConfig(arch=arch, num_bins=self.num_bins, base_channels=self._base, num_encoders=0,
+                                num_residual_blocks=2, kernel_size=self._k, num_output_channels=1, final_sigmoid=0,
+                                dynamic_decoder=0, batch=batch, height=height, width=width, precision=self.precision)
+
+    @property
+    def states(self):
+        s = self._get_states()
+        return [None, None] if s is None else s
+
+    @states.setter
+    def states(self, states):
+        if self._handle is None or all(s is None for s in states):
+            _NativeModel.reset_states(self)
+            return
+        self._set_states(list(states))
+
+
+class FireNet_legacy(_FireNetBase):
+    """model/legacy.py:155-187 (pretrained/FireNet)."""
+    _prefix = 'net.'
+    _arch = ARCH_FIRENET_LEGACY
+
+    def __init__(self, config={}, unet_kwargs={}):
+        super().__init__()
+        if unet_kwargs:
+            config = unet_kwargs
+        assert 'num_bins' in config
+        self.num_bins = int(config['num_bins'])
+        self.num_encoders = int(config.get('num_encoders', 4))            # legacy.py:127-130
+        self._base = int(config.get('base_num_channels', 32))
+        self._k = int(config.get('kernel_size', 5))
+        if str(config.get('recurrent_block_type', 'convgru')) != 'convgru':
+            raise _lib.EvkError("FireNet_legacy with convlstm is not built")
+        if int(config.get('num_residual_blocks', 2)) != 2 or config.get('recurrent_blocks', {'resblock': [0]}) != {'resblock': [0]}:
+            raise _lib.EvkError("only the shipped FireNet topology (2 residual blocks, recurrent resblock 0) is built")
+        self.num_recurrent_units = 2
+
+    def _config(self, batch, height, width):
+        return self._fire_config(ARCH_FIRENET_LEGACY, batch, height, width)
+
+
+class FireNet(_FireNetBase):
+    """model/model.py:147-190 (pretrained/FireNet+)."""
+    _prefix = ''
+    _arch = ARCH_FIRENET
+
+    def __init__(self, num_bins=5, base_num_channels=16, kernel_size=3):
+        super().__init__()
+        self.num_bins = num_bins
+        self._base = base_num_channels
+        self._k = kernel_size
+        self.num_recurrent_units = 2
+
+    def _config(self, batch, height, width):
+        return self._fire_config(ARCH_FIRENET, batch, height, width)

@@ -1,0 +1,142 @@
+/*
+ * evreal_b200 -- C ABI of the B200-native event->video hot path.
+ *
+ * Every entry point replaces one piece of EVREAL's per-frame loop
+ * (reference paths are relative to the EVREAL tree).
+ * Plain pointers and sizes only: no torch types, no C++ exceptions cross this
+ * boundary.  All pointers are DEVICE pointers unless the name says "host".
+ * `stream` is a cudaStream_t passed as void*.  Every function returns 0 on
+ * success or a negative EVK_ERR_* code; evk_last_error() gives the message of
+ * the last failure on the calling thread.
+ *
+ * There is no CPU implementation behind this ABI: if no sm_100 device is
+ * present the calls fail with EVK_ERR_CUDA.
+ */
+#ifndef EVREAL_B200_H
+#define EVREAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVK_OK 0
+#define EVK_ERR_ARG (-1)     /* bad argument (python adapter raises ValueError/AssertionError) */
+#define EVK_ERR_CUDA (-2)    /* CUDA runtime error */
+#define EVK_ERR_INDEX (-3)   /* event coordinate outside the sensor (reference: IndexError) */
+#define EVK_ERR_STATE (-4)   /* call order violated (e.g. forward before finalize) */
+#define EVK_ERR_KEY (-5)     /* missing / unexpected weight tensor (reference: load_state_dict error) */
+
+int evk_version(void);
+const char* evk_last_error(void);
+
+/* ---------------------------------------------------------------- stage 1 --
+ * events_to_voxel_torch(xs, ys, ts, ps, num_bins, device, sensor_size)
+ *   reference: utils/event_utils.py:27-59 (+ events_to_image_torch :4-24)
+ * x,y,t,p: [n] float32 (x,y integer valued, t seconds relative to the window's
+ * first event, p in {-1,+1} or any weight).  grid: [num_bins,H,W] float32,
+ * zeroed by the call.  Coordinates are truncated toward zero like .long();
+ * coordinates in [-W,0) / [-H,0) wrap like python indexing; anything else is
+ * skipped and counted in *oob_count (int32 device scalar, may be NULL; the
+ * python adapter turns a non-zero count into IndexError like the reference).
+ * n == 0 is rejected with EVK_ERR_ARG (the reference indexes ts[-1]).
+ */
+int evk_voxelize(const float* x, const float* y, const float* t, const float* p, int64_t n,
+                 int num_bins, int H, int W, float* grid, int* oob_count, void* stream);
+
+/* Raw on-disk window variant, fusing MemMapDataset.get_events / __getitem__
+ * casts (dataset.py:222-228, :52-58): xy int16 [n,2] (x,y), t float64 [n]
+ * absolute seconds, pol uint8 [n] in {0,1}.  ts = (t - t[0]) rounded to f32,
+ * ps = pol*2-1. */
+int evk_voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int64_t n,
+                     int num_bins, int H, int W, float* grid, int* oob_count, void* stream);
+
+/* normalize_event_tensor(event_tensor)   reference: eval.py:398-410
+ * in/out: [n_samples, numel] float32 (may alias).  Statistics are per sample
+ * over non-zero entries.  Optionally fuses CropParameters.pad
+ * (utils/util.py:30-48): when Hp/Wp differ from H/W the output is
+ * [n_samples, C, Hp, Wp] with the input centred per the reference's
+ * ceil/floor rule and zero borders.  Pass do_normalize=0 for pad only. */
+int evk_normalize_pad(const float* in, float* out, int n_samples, int C, int H, int W,
+                      int Hp, int Wp, int do_normalize, void* stream);
+
+/* ---------------------------------------------------------------- stage 2 --
+ * Recurrent reconstruction networks.   reference: model/model.py:108-190,
+ * model/unet.py:85-143, model/legacy.py:32-187, model/submodules.py,
+ * model/hyper/hyper_dynamic.py; factory eval.py:124-158.
+ */
+typedef struct evk_model evk_model;
+
+#define EVK_ARCH_UNET_RECURRENT 0   /* E2VIDRecurrent / FlowNet: E2VID, E2VID+, SSL-E2VID, HyperE2VID */
+#define EVK_ARCH_FIRENET_LEGACY 1   /* FireNet_legacy  (pretrained/FireNet)  */
+#define EVK_ARCH_FIRENET 2          /* FireNet         (pretrained/FireNet+) */
+
+typedef struct {
+    int arch;                 /* EVK_ARCH_* */
+    int num_bins;             /* 5 */
+    int base_channels;        /* 32 (unet) / 16 (firenet) */
+    int num_encoders;         /* 3 (unet); ignored for firenet */
+    int num_residual_blocks;  /* 2 */
+    int kernel_size;          /* 5 (unet) / 3 (firenet) */
+    int num_output_channels;  /* 1, or 3 for FlowNet (image = channel 0) */
+    int final_sigmoid;        /* eval.py:143 */
+    int dynamic_decoder;      /* HyperE2VID (unet.py:59-64) */
+    int batch;                /* independent sequences run in lock-step */
+    int height, width;        /* padded input size (multiple of 2^num_encoders) */
+    int precision;            /* 0 = default (tensor-core split-bf16 where applicable), 1 = force fp32 SIMT */
+} evk_model_config;
+
+int evk_model_create(const evk_model_config* cfg, evk_model** out);
+/* One call per state_dict entry, reference names with the wrapper prefix
+ * (unetrecurrent. / unetflow. / net.) stripped; host float32 data. */
+int evk_model_load_tensor(evk_model* m, const char* name, const float* host_data,
+                          const int64_t* shape, int ndim);
+/* Folds eval-mode BatchNorm into the convolutions, repacks and uploads. */
+int evk_model_finalize(evk_model* m, void* stream);
+/* model.reset_states()  (model/model.py:128-130, legacy.py:182-183) */
+int evk_model_reset_states(evk_model* m, void* stream);
+/* model(voxel)['image']: voxel [batch,num_bins,height,width] -> image [batch,1,height,width] */
+int evk_model_forward(evk_model* m, const float* voxel, float* image, void* stream);
+/* Number of recurrent state tensors and their sizes; get/set copy NCHW float32
+ * (model.states property, model/model.py:116-122). index: unet -> 2*i (h), 2*i+1 (c); firenet -> i. */
+int evk_model_num_states(evk_model* m);
+int evk_model_state_shape(evk_model* m, int index, int64_t shape_nchw[4]);
+int evk_model_get_state(evk_model* m, int index, float* out_nchw, void* stream);
+int evk_model_set_state(evk_model* m, int index, const float* in_nchw, void* stream);
+int evk_model_destroy(evk_model* m);
+/* Handle-owned staging buffers: in [batch,num_bins,height,width], out [batch,1,height,width].
+ * Passing these to evk_model_forward skips the device-to-device staging copies. */
+int evk_model_io_buffers(evk_model* m, float** in, float** out);
+/* kernels launched by the last forward (for bench.py's gpu_launches) */
+int evk_model_last_launch_count(evk_model* m);
+/* algorithmic conv FLOPs of one forward (2*Cout*Cin*kh*kw*Hout*Wout summed) */
+double evk_model_flops(evk_model* m);
+
+/* ------------------------------------------------------------ post-process --
+ * post_process_normalization / normalize   reference: eval.py:380-395,
+ * utils/eval_utils.py:15-35.  out = (v - P_qmin) / (P_qmax - P_qmin) with
+ * numpy's linear-interpolated percentiles; apply_exp=1 first takes exp(v)
+ * ('exprobust').  img/out: [n_images, numel] float32 (may alias). */
+int evk_percentile_normalize(const float* img, float* out, int n_images, int numel,
+                             double q_min, double q_max, int apply_exp, void* stream);
+
+/* CropParameters.crop (utils/util.py:58-59): [n,C,Hp,Wp] -> [n,C,H,W] centre crop. */
+int evk_crop(const float* in, float* out, int n, int C, int Hp, int Wp, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------- stage 3 --
+ * MseMetric / SsimMetric .calculate(img, ref)   reference: utils/eval_metrics.py:77-97
+ * (+ the [0,1] clip of EvalMetricsTracker.update :253-255 when clip != 0).
+ * img, ref: [n_images,H,W] float32.  scores: [n_images,2] float64 = (mse, ssim).
+ * SSIM = skimage.structural_similarity(gaussian_weights, sigma 1.5, data_range 1).
+ * H, W must be >= 11. */
+int evk_mse_ssim(const float* img, const float* ref, int n_images, int H, int W, int clip,
+                 double* scores, void* stream);
+
+/* uint8 frame -> float32 / 255  (dataset.py:84) */
+int evk_u8_to_f32(const uint8_t* in, float* out, int64_t numel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVREAL_B200_H */

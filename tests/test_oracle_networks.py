@@ -1,0 +1,53 @@
+"""CPU: the functional network oracle against frames produced by the reference's real nn.Modules."""
+import numpy as np
+import torch
+
+from helpers import golden, weights_of
+from oracle import networks as on
+
+torch.set_num_threads(4)
+
+
+def _run(model, voxels):
+    model.reset_states()
+    return np.stack([model(torch.from_numpy(v)).numpy() for v in voxels])
+
+
+def _check(tag, prefix, make, tol=2e-6):
+    g = golden('networks')
+    _, w = weights_of(g, tag, prefix)
+    got = _run(make(w), g[tag + '.voxels'])
+    ref = g[tag + '.frames']
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= tol * max(1.0, np.max(np.abs(ref))), tag
+
+
+def test_firenet_real_checkpoint():
+    _check('firenet_ckpt', 'net.', lambda w: on.FireNetLegacyOracle(w))
+
+
+def test_firenet_plus_real_checkpoint():
+    _check('firenetplus_ckpt', '', lambda w: on.FireNetOracle(w))
+
+
+def test_e2vid_topology():
+    _check('e2vid_small', 'unetrecurrent.', lambda w: on.UNetRecurrentOracle(w, final_sigmoid=True))
+
+
+def test_flownet_topology():
+    _check('flownet_small', 'unetflow.', lambda w: on.UNetRecurrentOracle(w))
+
+
+def test_hyper_e2vid_topology():
+    _check('hyper_small', 'unetrecurrent.', lambda w: on.UNetRecurrentOracle(w, dynamic_decoder=True))
+
+
+def test_random_weight_builders_have_reference_shapes():
+    w = on.random_unet_weights(seed=0, norm_bn=True)
+    assert tuple(w['encoders.2.recurrent_block.Gates.weight'].shape) == (1024, 512, 3, 3)
+    assert tuple(w['decoders.0.conv2d.weight'].shape) == (128, 256, 5, 5)
+    assert 'encoders.0.conv.conv2d.bias' not in w and 'pred.norm_layer.running_var' in w
+    w = on.random_unet_weights(seed=0, dynamic_decoder=True)
+    assert tuple(w['decoders.0.dynamic_conv.compositional_coefficients'].shape) == (128, 1536, 1, 1)
+    w = on.random_firenet_weights()
+    assert tuple(w['head.recurrent_block.out_gate.weight'].shape) == (16, 32, 3, 3)

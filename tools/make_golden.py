@@ -1,0 +1,365 @@
+"""Generates tests/golden/*.npz by running the REAL reference (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tools/make_golden.py
+Every vector below comes out of the reference's own modules -- utils.event_utils,
+dataset.MemMapDataset, utils.util.CropParameters, eval.normalize_event_tensor,
+model.* (real classes; real FireNet checkpoint, reduced-width random-weight
+instances of the E2VID family so the fixtures stay small) and the real
+eval.eval_method_on_sequence loop driven through the import shims of SURVEY 8c
+(yachalk / pyiqa / ffmpeg stubs, skimage.metrics restated with scipy-equivalent
+code from oracle/metrics.py, CudaTimer -> nullcontext, weights_only=False).
+"""
+import contextlib
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("EVREAL_REFERENCE", "/root/reference")
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+sys.path.insert(0, REF)
+
+from evreal_b200 import synthetic  # noqa: E402  (pure numpy generator, no CUDA needed)
+from oracle import metrics as om  # noqa: E402
+
+
+def install_shims():
+    class _Chalk:
+        def __getattr__(self, _):
+            return self
+
+        def __call__(self, s):
+            return str(s)
+
+    sys.modules['yachalk'] = types.SimpleNamespace(chalk=_Chalk())
+    sys.modules['pyiqa'] = types.SimpleNamespace(list_models=lambda: [])
+    sys.modules['ffmpeg'] = types.ModuleType('ffmpeg')
+    sk = types.ModuleType('skimage')
+    skm = types.ModuleType('skimage.metrics')
+    skm.mean_squared_error = lambda a, b: om.mse_oracle(b, a)
+    skm.structural_similarity = lambda a, b, **kw: om.ssim_oracle(b, a, kw.get('data_range', 1.0))
+    sk.metrics = skm
+    sys.modules['skimage'] = sk
+    sys.modules['skimage.metrics'] = skm
+    _load = torch.load
+    torch.load = lambda *a, **k: _load(*a, **{**k, 'weights_only': False})
+
+
+def gen_events(seed, n, H, W, dur=0.015):
+    g = np.random.default_rng(seed)
+    xs = g.integers(0, W, n)
+    ys = g.integers(0, H, n)
+    ts = np.sort(g.uniform(0, dur, n))
+    ps = g.integers(0, 2, n) * 2.0 - 1.0
+    return (xs.astype(np.float32), ys.astype(np.float32), (ts - ts[0]).astype(np.float32), ps.astype(np.float32))
+
+
+def golden_voxel():
+    from utils.event_utils import events_to_voxel_torch
+    cases = {}
+
+    def add(name, xs, ys, ts, ps, H, W, bins=5):
+        grid = events_to_voxel_torch(*[torch.from_numpy(np.asarray(v, dtype=np.float32)) for v in (xs, ys, ts, ps)],
+                                     bins, sensor_size=(H, W)).numpy()
+        for k, v in (('xs', xs), ('ys', ys), ('ts', ts), ('ps', ps), ('grid', grid)):
+            cases[f'{name}.{k}'] = np.asarray(v, dtype=np.float32)
+        cases[f'{name}.meta'] = np.array([H, W, bins], dtype=np.int64)
+
+    add('small', *gen_events(1, 500, 24, 32), 24, 32)
+    add('cfg1', *gen_events(0, 15000, 180, 240), 180, 240)            # SURVEY A.7 smoke case
+    add('bins3', *gen_events(2, 700, 16, 20), 16, 20, bins=3)
+    add('one_event', [3], [2], [0.0], [1.0], 8, 8)
+    add('two_equal_t', [1, 2], [1, 2], [0.0, 0.0], [1.0, -1.0], 8, 8)  # dt < 1e-9 -> linspace
+    add('three_equal_t', [1, 2, 3], [1, 2, 3], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], 8, 8)
+    add('negative_wrap', [-1, 0, 5], [0, -2, 3], [0.0, 0.5, 1.0], [1.0, 1.0, -1.0], 8, 8)
+    add('same_pixel', np.full(64, 3), np.full(64, 4), np.linspace(0, 1, 64), np.ones(64), 8, 8)
+    np.savez_compressed(os.path.join(OUT, 'voxel.npz'), **cases)
+    print('voxel.npz: cfg1 sum=%.4f abs=%.2f' % (cases['cfg1.grid'].sum(), np.abs(cases['cfg1.grid']).sum()))
+
+
+def golden_glue():
+    """normalize_event_tensor + CropParameters on a few shapes."""
+    import eval as ref_eval
+    from utils.util import CropParameters
+    out = {}
+    for name, (H, W, enc) in {'e2vid_180x240': (180, 240, 3), 'firenet_180x240': (180, 240, 4),
+                              'mvsec_260x346': (260, 346, 3), 'odd_37x53': (37, 53, 2)}.items():
+        cp = CropParameters(W, H, enc)
+        out[f'{name}.meta'] = np.array([H, W, enc, cp.height_crop_size, cp.width_crop_size, cp.padding_top,
+                                        cp.padding_left, cp.iy0, cp.iy1, cp.ix0, cp.ix1], dtype=np.int64)
+    from utils.event_utils import events_to_voxel_torch
+    v = events_to_voxel_torch(*[torch.from_numpy(a) for a in gen_events(3, 4000, 37, 53)], 5, sensor_size=(37, 53))
+    vn = ref_eval.normalize_event_tensor(v[None])
+    cp = CropParameters(53, 37, 2)
+    out['norm.in'] = v.numpy()
+    out['norm.out'] = vn.numpy()
+    out['norm.padded'] = cp.pad(vn).numpy()
+    out['norm.cropped_back'] = cp.crop(cp.pad(vn)).numpy()
+    np.savez_compressed(os.path.join(OUT, 'glue.npz'), **out)
+
+
+def golden_windows(tmp):
+    from dataset import MemMapDataset
+    path = synthetic.write_sequence(os.path.join(tmp, 'winseq'), 32, 40, 20000.0, 1.5, 20.0, seed=5)
+    out = {k: np.load(os.path.join(path, k + '.npy')) for k in
+           ('events_ts', 'events_xy', 'events_p', 'images_ts', 'image_event_indices')}
+    modes = {
+        'between_frames': {'method': 'between_frames'},
+        'k_events': {'method': 'k_events', 'k': 1500, 'sliding_window_w': 0},
+        'k_events_sliding': {'method': 'k_events', 'k': 1500, 'sliding_window_w': 500},
+        't_seconds': {'method': 't_seconds', 't': 0.04, 'sliding_window_t': 0.0},
+        't_seconds_sliding': {'method': 't_seconds', 't': 0.05, 'sliding_window_t': 0.01},
+    }
+    for name, vm in modes.items():
+        ds = MemMapDataset(path, voxel_method=dict(vm), num_bins=5)
+        rows = []
+        for i in range(len(ds)):
+            try:
+                item = ds[i]
+            except ValueError:
+                rows.append([i, -1, -1, 0, 0, 0])       # window past the end of the stream (dataset.py:196-197)
+                continue
+            if vm['method'] == 'between_frames':
+                prev = ds.frames_to_use[i - 1] if i > 0 else 0
+                idx0, idx1 = ds.event_indices[prev][1], ds.event_indices[ds.frames_to_use[i]][1]
+            else:
+                idx0, idx1 = ds.event_indices[i]
+            rows.append([i, idx0, idx1, item['event_count'], item['voxel_timestamp'].item(), item['dt'].item()])
+        out[f'{name}.items'] = np.array(rows, dtype=np.float64)
+        out[f'{name}.table'] = np.array(ds.event_indices, dtype=np.int64)
+        out[f'{name}.len'] = np.array([len(ds)], dtype=np.int64)
+        if vm['method'] != 'between_frames':
+            out[f'{name}.closest_frame'] = np.array(
+                [ds.get_closest_frame_index(r[4]) for r in rows if r[1] >= 0], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, 'windows.npz'), **out)
+
+
+def _run_frames(model, voxels):
+    outs = []
+    model.reset_states()
+    with torch.no_grad():
+        for v in voxels:
+            outs.append(model(v)['image'].clone().numpy())
+    return np.stack(outs)
+
+
+def _small_voxels(seed, frames, N, H, W):
+    from utils.event_utils import events_to_voxel_torch
+    vs = []
+    for f in range(frames):
+        batch = [events_to_voxel_torch(*[torch.from_numpy(a) for a in gen_events(seed * 100 + f * 10 + b, 600, H, W)],
+                                       5, sensor_size=(H, W)) for b in range(N)]
+        vs.append(torch.stack(batch))
+    return vs
+
+
+def _randomize_bn(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(0.1 * torch.randn(m.num_features, generator=g))
+            m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.weight.data.copy_(1.0 + 0.2 * torch.randn(m.num_features, generator=g))
+            m.bias.data.copy_(0.1 * torch.randn(m.num_features, generator=g))
+
+
+def golden_networks():
+    import model as model_arch
+    out = {}
+
+    def save_model(tag, model, voxels, prefix):
+        model.eval()
+        frames = _run_frames(model, voxels)
+        out[f'{tag}.voxels'] = torch.stack(voxels).numpy()
+        out[f'{tag}.frames'] = frames
+        for k, v in model.state_dict().items():
+            if not k.endswith('num_batches_tracked'):
+                out[f'{tag}.w.{k}'] = v.numpy()
+        print(tag, 'frames', frames.shape, 'mean %.5f' % frames.mean())
+
+    # real FireNet checkpoint (37k parameters) on a padded 48x64 input, batch 1, 4 frames
+    ck = torch.load(os.path.join(REF, 'pretrained/FireNet/model.pth'), map_location='cpu')
+    kw = dict(ck['config']['model'])
+    kw['final_activation'] = ''
+    m = model_arch.FireNet_legacy(kw)
+    m.load_state_dict(ck['state_dict'])
+    save_model('firenet_ckpt', m, _small_voxels(1, 4, 1, 48, 64), 'net.')
+
+    # real FireNet+ checkpoint
+    ck = torch.load(os.path.join(REF, 'pretrained/FireNet+/model.pth'), map_location='cpu')
+    m = ck['config'].init_obj('arch', model_arch)
+    m.load_state_dict(ck['state_dict'])
+    save_model('firenetplus_ckpt', m, _small_voxels(2, 3, 2, 40, 56), '')
+
+    # E2VID topology (BN, sigmoid) at base width 8, random weights through the real class, batch 2
+    torch.manual_seed(10)
+    kw = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
+          'base_num_channels': 8, 'num_residual_blocks': 2, 'use_upsample_conv': True, 'norm': 'BN',
+          'final_activation': 'sigmoid'}
+    m = model_arch.E2VIDRecurrent(dict(kw))
+    _randomize_bn(m, 11)
+    save_model('e2vid_small', m, _small_voxels(3, 4, 2, 32, 48), 'unetrecurrent.')
+
+    # E2VID+ topology (FlowNet, no norm, 3 output channels)
+    torch.manual_seed(12)
+    kw = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
+          'base_num_channels': 4, 'num_residual_blocks': 2, 'use_upsample_conv': True, 'norm': 'none',
+          'num_output_channels': 3}
+    m = model_arch.FlowNet(dict(kw))
+    save_model('flownet_small', m, _small_voxels(4, 3, 1, 32, 40), 'unetflow.')
+
+    # HyperE2VID topology (dynamic decoder) at base width 4 (bottleneck 32 channels)
+    torch.manual_seed(13)
+    kw = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'kernel_size': 5,
+          'channel_multiplier': 2, 'num_encoders': 3, 'base_num_channels': 4, 'num_residual_blocks': 2,
+          'use_upsample_conv': True, 'norm': 'none', 'num_output_channels': 1, 'use_dynamic_decoder': True}
+    m = model_arch.E2VIDRecurrent(dict(kw))
+    _randomize_bn(m, 14)
+    save_model('hyper_small', m, _small_voxels(5, 4, 2, 32, 48), 'unetrecurrent.')
+    np.savez_compressed(os.path.join(OUT, 'networks.npz'), **out)
+
+
+def golden_real_checkpoints():
+    """Outputs of the shipped 43 MB checkpoints on the SURVEY A.7 voxel: the weights cannot travel, so only
+    summary statistics + a strided sample are stored; tests/test_oracle_vs_reference.py uses them when the
+    reference tree is present."""
+    import model as model_arch
+    from utils.event_utils import events_to_voxel_torch
+    from utils.util import CropParameters
+    out = {}
+    for name, (H, W) in {'E2VID': (180, 240), 'HyperE2VID': (260, 346), 'E2VID+': (180, 240)}.items():
+        ck = torch.load(os.path.join(REF, f'pretrained/{name}/model.pth'), map_location='cpu')
+        if name == 'E2VID':
+            kw = dict(ck['model'])
+            kw['final_activation'] = 'sigmoid'
+            m = model_arch.E2VIDRecurrent(kw)
+        else:
+            m = ck['config'].init_obj('arch', model_arch)
+        m.load_state_dict(ck['state_dict'])
+        m.eval()
+        v = events_to_voxel_torch(*[torch.from_numpy(a) for a in gen_events(0, 15000, H, W)], 5, sensor_size=(H, W))
+        cp = CropParameters(W, H, 3)
+        with torch.no_grad():
+            frames = [cp.crop(m(cp.pad(v[None]))['image'])[0, 0].numpy() for _ in range(2)]
+        out[f'{name}.stats'] = np.array([[f.min(), f.max(), f.mean()] for f in frames], dtype=np.float64)
+        out[f'{name}.sample'] = np.stack([f[::9, ::11] for f in frames])
+        print(name, out[f'{name}.stats'])
+    np.savez_compressed(os.path.join(OUT, 'real_checkpoints.npz'), **out)
+
+
+def golden_metrics():
+    out = {}
+    yy, xx = np.mgrid[0:180, 0:240]
+    ref = (0.5 + 0.4 * np.sin(xx / 9) * np.cos(yy / 7)).astype(np.float32)
+    img = np.clip(ref + np.random.default_rng(0).normal(0, 0.05, (180, 240)), 0, 1).astype(np.float32)
+    out['a7.ref'], out['a7.img'] = ref, img
+    # independent path: scipy.ndimage.gaussian_filter itself (what scikit-image calls)
+    from scipy.ndimage import gaussian_filter
+
+    def ssim_scipy(x, y):
+        f = lambda a: gaussian_filter(a, 1.5, truncate=3.5, mode='reflect')
+        ux, uy = f(x), f(y)
+        vx, vy, vxy = f(x * x) - ux * ux, f(y * y) - uy * uy, f(x * y) - ux * uy
+        C1, C2 = 0.01 ** 2, 0.03 ** 2
+        S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+        return float(S[5:-5, 5:-5].mean(dtype=np.float64))
+
+    out['a7.scores'] = np.array([np.mean((ref - img) ** 2, dtype=np.float64), ssim_scipy(ref, img)])
+    g = np.random.default_rng(7)
+    pairs = []
+    for i, (H, W) in enumerate([(180, 240), (130, 173), (37, 53), (11, 11), (64, 80)]):
+        a = g.random((H, W)).astype(np.float32)
+        b = np.clip(a + g.normal(0, 0.1 * (i + 1), (H, W)), 0, 1).astype(np.float32)
+        out[f'pair{i}.img'], out[f'pair{i}.ref'] = a, b
+        out[f'pair{i}.scores'] = np.array([np.mean((b - a) ** 2, dtype=np.float64), ssim_scipy(b, a)])
+    # robust normalisation through the reference's own helper
+    from utils.eval_utils import normalize
+    x = (g.random((180, 240)) ** 2).astype(np.float32)
+    out['norm.in'] = x
+    out['norm.robust'] = normalize(x, 1, 99).astype(np.float32)
+    out['norm.standard'] = normalize(x, 0, 100).astype(np.float32)
+    out['norm.exprobust'] = normalize(np.exp(x), 1, 99).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, 'metrics.npz'), **out)
+    print('metrics a7', out['a7.scores'])
+
+
+def golden_eval_loop(tmp):
+    """The REAL eval.eval_method_on_sequence on a small synthetic sequence with the real FireNet checkpoint
+    (event_tensor_normalization on, no post-norm) and with an E2VID-topology model ('robust' post-norm)."""
+    import eval as ref_eval
+    import model as model_arch
+    from dataset import MemMapDataset
+    from torch.utils.data import DataLoader
+    ref_eval.CudaTimer = lambda *_a, **_k: contextlib.nullcontext()
+    ref_eval.tqdm = lambda x, *a, **k: x
+    seq_path = synthetic.write_sequence(os.path.join(tmp, 'evalseq'), 48, 64, 60000.0, 1.0, 20.0, seed=9)
+    out = {k: np.load(os.path.join(seq_path, k + '.npy')) for k in
+           ('events_ts', 'events_xy', 'events_p', 'images', 'images_ts', 'image_event_indices')}
+    eval_config = {'name': 'std', 'save_images': False, 'histeq': 'none', 'eval_infer_all': False, 'ts_tol_ms': 1.0,
+                   'create_video': False}
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        def run(tag, model, method_config, start, end):
+            ds = MemMapDataset(seq_path, num_bins=5, voxel_method={'method': 'between_frames'})
+            sequence = {'name': 'evalseq', 'data_loader': DataLoader(ds), 'start_time_s': start, 'end_time_s': end}
+            # capture per-frame scores by wrapping the tracker factory
+            holder = {}
+            orig = ref_eval.get_eval_metrics_tracker
+
+            def wrapped(*a, **k):
+                holder['t'] = orig(*a, **k)
+                return holder['t']
+            ref_eval.get_eval_metrics_tracker = wrapped
+            n_eval, means = ref_eval.eval_method_on_sequence('SYN', eval_config, tag, model, method_config, sequence,
+                                                             ['mse', 'ssim'])
+            ref_eval.get_eval_metrics_tracker = orig
+            t = holder['t']
+            out[f'{tag}.indices'] = np.array(t.quan_eval_indices, dtype=np.int64)
+            out[f'{tag}.mse'] = np.array(t.metrics[0].scores)
+            out[f'{tag}.ssim'] = np.array(t.metrics[1].scores)
+            out[f'{tag}.summary'] = np.array([n_eval, means['mse'], means['ssim'], start, end])
+            print(tag, n_eval, means)
+
+        ck = torch.load(os.path.join(REF, 'pretrained/FireNet/model.pth'), map_location='cpu')
+        kw = dict(ck['config']['model'])
+        kw['final_activation'] = ''
+        m = model_arch.FireNet_legacy(kw)
+        ref_eval.load_model(m, ck['state_dict'])
+        run('firenet', m, {'event_tensor_normalization': True, 'post_process_norm': 'none'}, 0.2, 0.9)
+
+        torch.manual_seed(10)      # same instance as networks.npz 'e2vid_small'
+        kw = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
+              'base_num_channels': 8, 'num_residual_blocks': 2, 'use_upsample_conv': True, 'norm': 'BN',
+              'final_activation': 'sigmoid'}
+        m = model_arch.E2VIDRecurrent(dict(kw))
+        _randomize_bn(m, 11)
+        m.eval()
+        for p_ in m.parameters():
+            p_.requires_grad = False
+        run('e2vid_small', m, {'event_tensor_normalization': True, 'post_process_norm': 'robust'}, 0.0, 2.0)
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, 'eval_loop.npz'), **out)
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    install_shims()
+    torch.set_num_threads(1)          # single-threaded index_put_ -> bit-reproducible voxel grids
+    with tempfile.TemporaryDirectory() as tmp:
+        golden_voxel()
+        golden_glue()
+        golden_windows(tmp)
+        golden_networks()
+        golden_real_checkpoints()
+        golden_metrics()
+        golden_eval_loop(tmp)
+    for f in sorted(os.listdir(OUT)):
+        print('%8.1f kB  %s' % (os.path.getsize(os.path.join(OUT, f)) / 1e3, f))
