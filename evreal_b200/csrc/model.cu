@@ -480,9 +480,12 @@ static int build_firenet(evk_model* m, bool legacy) {
     return add_pred(B, "pred", r2, nullptr, C, H, W);
 }
 
-static int run_ops(evk_model* m, int par, cudaStream_t st) {
+static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent_t>* ev = nullptr) {
     for (const Op& op : m->ops[par]) {
         int r = EVK_OK;
+        if (ev) {
+            cudaEvent_t e; EVK_CHECK_CUDA(cudaEventCreate(&e)); EVK_CHECK_CUDA(cudaEventRecord(e, st)); ev->push_back(e);
+        }
         switch (op.kind) {
             case OP_HEAD: r = launch_head_conv(op.in, op.w, op.b, op.out, op.N, op.cin, op.H, op.W, op.k, op.cout, st); break;
             case OP_CONV: r = launch_conv(op.cp, m->cfg.precision, st); break;
@@ -492,7 +495,29 @@ static int run_ops(evk_model* m, int par, cudaStream_t st) {
         }
         if (r != EVK_OK) return r;
     }
+    if (ev) {
+        cudaEvent_t e; EVK_CHECK_CUDA(cudaEventCreate(&e)); EVK_CHECK_CUDA(cudaEventRecord(e, st)); ev->push_back(e);
+    }
     return EVK_OK;
+}
+
+static std::string op_desc(const Op& op) {
+    char b[160];
+    switch (op.kind) {
+        case OP_HEAD: snprintf(b, sizeof b, "head conv%dx%d %d->%d @%dx%d", op.k, op.k, op.cin, op.cout, op.H, op.W); break;
+        case OP_CONV: {
+            const ConvParams& p = op.cp;
+            const char* e = p.epi == EPI_LSTM ? "lstm" : p.epi == EPI_GRU_UR ? "gru_ur" : p.epi == EPI_GRU_OUT ? "gru_out" : (p.res ? "linear+res" : "linear");
+            snprintf(b, sizeof b, "conv%dx%d s%d %d+%d->%d %s @%dx%d", p.kh, p.kw, p.stride, p.c1, p.c2, p.cout, e, p.Hout, p.Wout);
+            break;
+        }
+        case OP_UPSAMPLE_ADD: snprintf(b, sizeof b, "upsample2x_add C=%d @%dx%d", op.cin, 2 * op.H, 2 * op.W); break;
+        case OP_PRED: snprintf(b, sizeof b, "pred 1x1 %d->1 @%dx%d", op.cin, op.H, op.W); break;
+        case OP_HYPER_CONTEXT: snprintf(b, sizeof b, "hyper context x0.25"); break;
+        case OP_HYPER_ATOMS: snprintf(b, sizeof b, "hyper atoms A=%d K=%d L=%d @%dx%d", op.hp.A, op.hp.K, op.hp.L, op.hp.h, op.hp.w); break;
+        default: snprintf(b, sizeof b, "hyper dynamic conv C=%d A=%d @%dx%d", op.hp.C, op.hp.A, op.hp.h, op.hp.w); break;
+    }
+    return b;
 }
 
 }  // namespace evk
@@ -592,6 +617,44 @@ int evk_model_forward(evk_model* m, const float* voxel, float* image, void* stre
     if (c.dynamic_decoder) EVK_CHECK_CUDA(cudaMemcpyAsync(m->prev_rec, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
     if (image != m->out_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(image, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
     m->parity ^= 1;
+    return EVK_OK;
+}
+
+int evk_model_profile(evk_model* m, const float* voxel, float* image, void* stream, int max_ops, float* ms, double* flops,
+                      int* n_ops) {
+    EVK_REQUIRE(m && m->finalized, EVK_ERR_STATE, "evk_model_profile: model not finalized");
+    EVK_REQUIRE(voxel && image && ms && flops && n_ops, EVK_ERR_ARG, "evk_model_profile: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const evk_model_config& c = m->cfg;
+    const size_t in_bytes = sizeof(float) * (size_t)c.batch * c.num_bins * c.height * c.width;
+    const size_t out_bytes = sizeof(float) * (size_t)c.batch * c.height * c.width;
+    if (voxel != m->in_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(m->in_buf, voxel, in_bytes, cudaMemcpyDeviceToDevice, st));
+    const int par = m->parity;
+    std::vector<cudaEvent_t> ev;
+    int r = run_ops(m, par, st, &ev);
+    if (c.dynamic_decoder) EVK_CHECK_CUDA(cudaMemcpyAsync(m->prev_rec, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
+    if (image != m->out_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(image, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
+    cudaError_t se = cudaStreamSynchronize(st);
+    const int n = (int)m->ops[par].size();
+    *n_ops = n;
+    if (r == EVK_OK && se == cudaSuccess && (int)ev.size() == n + 1)
+        for (int i = 0; i < n && i < max_ops; ++i) {
+            cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+            flops[i] = m->ops[par][i].flops;
+        }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (r != EVK_OK) return r;
+    EVK_CHECK_CUDA(se);
+    m->last_launches = n;
+    m->parity ^= 1;
+    return EVK_OK;
+}
+
+int evk_model_op_desc(evk_model* m, int index, char* buf, int cap) {
+    EVK_REQUIRE(m && m->finalized && buf && cap > 0 && index >= 0 && index < (int)m->ops[0].size(), EVK_ERR_ARG,
+                "evk_model_op_desc: bad argument");
+    const std::string d = op_desc(m->ops[0][index]);
+    snprintf(buf, (size_t)cap, "%s", d.c_str());
     return EVK_OK;
 }
 

@@ -142,7 +142,6 @@ int voxelize_f32(const float* x, const float* y, const float* t, const float* p,
     EVK_REQUIRE(n > 0, EVK_ERR_ARG, "evk_voxelize: empty window (n=%lld); the reference indexes ts[-1]", (long long)n);
     EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize: bad geometry bins=%d H=%d W=%d", bins, H, W);
     EVK_CHECK_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)bins * H * W, st));
-    if (oob_count) EVK_CHECK_CUDA(cudaMemsetAsync(oob_count, 0, sizeof(int), st));
     VoxGeom g{bins, H, W};
     // all four arrays must share the same 16-byte phase for the vector body
     auto phase = [](const void* q) { return (int)(((uintptr_t)q >> 2) & 3); };
@@ -164,7 +163,6 @@ int voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int64_t
     EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize_raw: bad geometry");
     EVK_REQUIRE(((uintptr_t)xy & 3) == 0 && ((uintptr_t)t & 7) == 0, EVK_ERR_ARG, "evk_voxelize_raw: misaligned arrays");
     EVK_CHECK_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)bins * H * W, st));
-    if (oob_count) EVK_CHECK_CUDA(cudaMemsetAsync(oob_count, 0, sizeof(int), st));
     VoxGeom g{bins, H, W};
     voxelize_raw_kernel<<<vox_grid_blocks(n, 2), kVoxThreads, 0, st>>>(xy, t, pol, n, g, grid, oob_count);
     EVK_CHECK_CUDA(cudaGetLastError());

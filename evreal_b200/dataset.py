@@ -199,7 +199,6 @@ class MemMapDataset(torch.utils.data.Dataset):
         p = np.ascontiguousarray(fh["p"]).astype(np.uint8)
         self._dev_events = tuple(torch.from_numpy(a).pin_memory().to(dev, non_blocking=True) for a in (xy, t, p))
         self.oob_total = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._oob = torch.zeros(1, dtype=torch.int32, device=dev)
         if self.has_images:
             imgs = np.ascontiguousarray(fh["images"][..., 0])
             self._dev_images = torch.from_numpy(imgs).pin_memory().to(dev, non_blocking=True)
@@ -220,8 +219,7 @@ class MemMapDataset(torch.utils.data.Dataset):
             with torch.cuda.device(dev):
                 _lib.check(_lib.load().evk_voxelize_raw(
                     _lib.ptr(xy[idx0:idx1]), _lib.ptr(t[idx0:idx1]), _lib.ptr(p[idx0:idx1]), n, self.num_bins, H, W,
-                    _lib.ptr(grid), _lib.ptr(self._oob), _lib.stream_ptr(dev)))
-                self.oob_total += self._oob        # checked once per sequence (check_bounds())
+                    _lib.ptr(grid), _lib.ptr(self.oob_total), _lib.stream_ptr(dev)))   # checked once per sequence
             return grid
         xs, ys, ts, ps = self.get_events(idx0, idx1)
         ts = (ts - ts[0]).astype(np.float32)
@@ -264,6 +262,24 @@ class MemMapDataset(torch.utils.data.Dataset):
 
     # ------------------------------------------------------------------ loading
     def load_data(self, data_path):
+        if isinstance(data_path, dict):
+            # in-memory sequence in the on-disk layout (synthetic benchmark streams): same keys as the .npy files
+            a = data_path
+            data = {}
+            if all(k in a for k in ('images_ts', 'images', 'image_event_indices')):
+                data["frame_stamps"] = np.asarray(a['images_ts'])
+                data["images"] = a['images']
+                data["image_event_indices"] = np.asarray(a['image_event_indices'])
+                self.has_images = True
+            else:
+                self.has_images = False
+            data["t"] = np.asarray(a['events_ts']).squeeze()
+            data["xy"] = np.asarray(a['events_xy']).squeeze()
+            data["p"] = np.asarray(a['events_p']).squeeze()
+            data['path'] = '<memory>'
+            if self.sensor_resolution is None and 'sensor_resolution' in a:
+                self.sensor_resolution = list(a['sensor_resolution'])
+            return self._finish_load(data, None)
         assert os.path.isdir(data_path), f'{data_path} is not a valid data_path'
         data = {}
         p = lambda name: os.path.join(data_path, name)
@@ -278,6 +294,9 @@ class MemMapDataset(torch.utils.data.Dataset):
         data["xy"] = np.load(p('events_xy.npy'), mmap_mode='r').squeeze()
         data["p"] = np.load(p('events_p.npy'), mmap_mode='r').squeeze()
         data['path'] = data_path
+        return self._finish_load(data, p("metadata.json"))
+
+    def _finish_load(self, data, metadata_path):
         assert (len(data['p']) == len(data['xy']) and len(data['p']) == len(data['t'])), \
             "Number of events, timestamps and coordinates do not match"
         self.t0, self.tk = data['t'][0], data['t'][-1]
@@ -293,8 +312,7 @@ class MemMapDataset(torch.utils.data.Dataset):
         assert (len(self.frame_ts) == self.num_frames), "Number of frames and timestamps do not match"
         self.filehandle = data
         if self.sensor_resolution is None:
-            metadata_path = p("metadata.json")
-            if os.path.exists(metadata_path):
+            if metadata_path is not None and os.path.exists(metadata_path):
                 self.sensor_resolution = read_json(metadata_path)["sensor_resolution"]
             elif self.has_images and self.num_frames > 0:
                 self.sensor_resolution = self.filehandle["images"][0].shape[:2]

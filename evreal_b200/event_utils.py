@@ -43,7 +43,7 @@ def events_to_voxel_torch(xs, ys, ts, ps, num_bins, device=None, sensor_size=(18
         x, y, t, p = (_f32(v, device) for v in (xs, ys, ts, ps))
         H, W = int(sensor_size[0]), int(sensor_size[1])
         grid = torch.empty((num_bins, H, W), dtype=torch.float32, device=device)
-        oob = torch.empty(1, dtype=torch.int32, device=device) if check_bounds else None
+        oob = torch.zeros(1, dtype=torch.int32, device=device) if check_bounds else None
         _lib.check(lib.evk_voxelize(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), n, num_bins, H, W,
                                     _lib.ptr(grid), _lib.ptr(oob) if check_bounds else None, _lib.stream_ptr(device)))
         if check_bounds and int(oob.item()) != 0:
@@ -77,7 +77,7 @@ def events_to_voxel_raw(xy, t, p, num_bins, device=None, sensor_size=(180, 240),
         p = torch.as_tensor(p).to(device=device, dtype=torch.uint8, non_blocking=True).contiguous()
         H, W = int(sensor_size[0]), int(sensor_size[1])
         grid = torch.empty((num_bins, H, W), dtype=torch.float32, device=device)
-        oob = torch.empty(1, dtype=torch.int32, device=device) if check_bounds else None
+        oob = torch.zeros(1, dtype=torch.int32, device=device) if check_bounds else None
         _lib.check(lib.evk_voxelize_raw(_lib.ptr(xy), _lib.ptr(t), _lib.ptr(p), n, num_bins, H, W, _lib.ptr(grid),
                                         _lib.ptr(oob) if check_bounds else None, _lib.stream_ptr(device)))
         if check_bounds and int(oob.item()) != 0:

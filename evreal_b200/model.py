@@ -127,9 +127,43 @@ class _NativeModel:
 
     __call__ = forward
 
+    def forward_into(self, event_tensor, out):
+        """forward() into a caller-owned [N,1,H,W] CUDA buffer (no allocation; the streaming pipeline's path)."""
+        x = event_tensor
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+        N, C, H, W = x.shape
+        assert C == self.num_bins and tuple(out.shape) == (N, 1, H, W) and out.is_contiguous()
+        self._ensure(N, H, W, x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().evk_model_forward(self._handle, _lib.ptr(x), _lib.ptr(out), _lib.stream_ptr(x.device)))
+        if hasattr(self, 'prev_recs'):
+            self.prev_recs = out
+        return out
+
     # ---- introspection used by bench / tests
     def flops_per_forward(self):
         return float(_lib.load().evk_model_flops(self._handle)) if self._handle else 0.0
+
+    def profile_forward(self, event_tensor):
+        """One eager forward with CUDA events around every launch -> [(description, ms, flops), ...]."""
+        x = event_tensor.float().contiguous()
+        N, C, H, W = x.shape
+        self._ensure(N, H, W, x.device)
+        lib = _lib.load()
+        cap = 256
+        ms = (ctypes.c_float * cap)()
+        fl = (ctypes.c_double * cap)()
+        n = ctypes.c_int(0)
+        out = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.evk_model_profile(self._handle, _lib.ptr(x), _lib.ptr(out), _lib.stream_ptr(x.device), cap,
+                                             ms, fl, ctypes.byref(n)))
+        rows = []
+        buf = ctypes.create_string_buffer(160)
+        for i in range(min(n.value, cap)):
+            _lib.check(lib.evk_model_op_desc(self._handle, i, buf, 160))
+            rows.append((buf.value.decode(), float(ms[i]), float(fl[i])))
+        return rows
 
     def last_launch_count(self):
         return int(_lib.load().evk_model_last_launch_count(self._handle)) if self._handle else 0

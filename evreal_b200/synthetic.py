@@ -72,3 +72,100 @@ SHAPES = {
 def hqf_rate(seed):
     """cfg 3: per-sequence rate ~ U(0.5, 2) Mev/s, seeded by the sequence index."""
     return float(np.random.default_rng(1000 + seed).uniform(0.5e6, 2.0e6))
+
+
+# ---------------------------------------------------------------------------
+# Seeded random-initialised weights with the shipped checkpoints' names and shapes (SURVEY A.1).  There is no
+# network for the real checkpoints on the GPU box, so bench.py times these architectures with these weights
+# (same FLOPs, same kernels); the dicts load into the host mirror classes through load_state_dict.
+# ---------------------------------------------------------------------------
+def _conv_w(g, out_c, in_c, k, bias=True, gain=1.0):
+    import torch
+    d = {'weight': torch.from_numpy((g.standard_normal((out_c, in_c, k, k)) * (gain / (in_c * k * k) ** 0.5)).astype(np.float32))}
+    if bias:
+        d['bias'] = torch.from_numpy((g.standard_normal(out_c) * 0.1).astype(np.float32))
+    return d
+
+
+def _bn_w(g, c):
+    import torch
+    f = lambda a: torch.from_numpy(a.astype(np.float32))
+    return {'weight': f(1.0 + 0.2 * g.standard_normal(c)), 'bias': f(0.1 * g.standard_normal(c)),
+            'running_mean': f(0.1 * g.standard_normal(c)), 'running_var': f(0.5 + g.random(c))}
+
+
+def unet_state_dict(seed=0, prefix='unetrecurrent.', base=32, num_encoders=3, num_res=2, k=5, bins=5, norm_bn=False,
+                    num_out=1, dynamic_decoder=False):
+    """E2VID (norm_bn=True) / E2VID+ / SSL-E2VID / HyperE2VID (dynamic_decoder=True) state_dict."""
+    import torch
+    g = np.random.default_rng(seed)
+    w = {}
+
+    def put(pfx, d):
+        for kk, v in d.items():
+            w[prefix + pfx + '.' + kk] = v
+    put('head.conv2d', _conv_w(g, base, bins, k))
+    cin = base
+    for i in range(num_encoders):
+        cout = cin * 2
+        put('encoders.%d.conv.conv2d' % i, _conv_w(g, cout, cin, k, bias=not norm_bn, gain=1.4))
+        if norm_bn:
+            put('encoders.%d.conv.norm_layer' % i, _bn_w(g, cout))
+        put('encoders.%d.recurrent_block.Gates' % i, _conv_w(g, 4 * cout, 2 * cout, 3))
+        cin = cout
+    for j in range(num_res):
+        for n, b in (('conv1', 'bn1'), ('conv2', 'bn2')):
+            put('resblocks.%d.%s' % (j, n), _conv_w(g, cin, cin, 3, bias=not norm_bn))
+            if norm_bn:
+                put('resblocks.%d.%s' % (j, b), _bn_w(g, cin))
+    for i in range(num_encoders):
+        cout = cin // 2
+        if i == 0 and dynamic_decoder:
+            p = 'decoders.0'
+            put(p + '.context_fusion.conv', _conv_w(g, 32, bins + 1, 3))
+            put(p + '.dynamic_atom_generation.bases_net.0', _conv_w(g, 64, 32, 3))
+            put(p + '.dynamic_atom_generation.bases_net.1', _bn_w(g, 64))
+            put(p + '.dynamic_atom_generation.bases_net.3', _conv_w(g, 72, 64, 3))
+            put(p + '.dynamic_atom_generation.bases_net.4', _bn_w(g, 72))
+            w[prefix + p + '.dynamic_atom_generation.bases'] = torch.from_numpy((g.standard_normal((12, k * k)) * 0.3).astype(np.float32))
+            w[prefix + p + '.dynamic_conv.compositional_coefficients'] = torch.from_numpy(
+                (g.standard_normal((cout, cin * 6, 1, 1)) * (1.4 / (cin * 6) ** 0.5)).astype(np.float32))
+            w[prefix + p + '.dynamic_conv.bias'] = torch.from_numpy((g.standard_normal(cout) * 0.1).astype(np.float32))
+        else:
+            put('decoders.%d.conv2d' % i, _conv_w(g, cout, cin, k, bias=not norm_bn, gain=1.4))
+            if norm_bn:
+                put('decoders.%d.norm_layer' % i, _bn_w(g, cout))
+        cin = cout
+    put('pred.conv2d', _conv_w(g, num_out, base, 1, bias=not norm_bn))
+    if norm_bn:
+        put('pred.norm_layer', _bn_w(g, num_out))
+    return w
+
+
+def firenet_state_dict(seed=0, prefix='net.', base=16, bins=5):
+    """pretrained/FireNet (FireNet_legacy) state_dict."""
+    g = np.random.default_rng(seed)
+    w = {}
+
+    def put(pfx, d):
+        for kk, v in d.items():
+            w[prefix + pfx + '.' + kk] = v
+    put('head.conv.conv2d', _conv_w(g, base, bins, 3))
+    for unit in ('head.recurrent_block', 'resblocks.0.recurrent_block'):
+        for gate in ('reset_gate', 'update_gate', 'out_gate'):
+            put(unit + '.' + gate, _conv_w(g, base, 2 * base, 3, gain=1.4))
+    for blk in ('resblocks.0.conv', 'resblocks.1'):
+        for c in ('conv1', 'conv2'):
+            put(blk + '.' + c, _conv_w(g, base, base, 3, gain=1.2))
+    put('pred.conv2d', _conv_w(g, 1, base, 1))
+    return w
+
+
+E2VID_KWARGS = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
+                'base_num_channels': 32, 'num_residual_blocks': 2, 'use_upsample_conv': True, 'norm': 'BN',
+                'final_activation': 'sigmoid'}
+HYPER_KWARGS = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'kernel_size': 5,
+                'channel_multiplier': 2, 'num_encoders': 3, 'base_num_channels': 32, 'num_residual_blocks': 2,
+                'use_upsample_conv': True, 'norm': 'none', 'num_output_channels': 1, 'use_dynamic_decoder': True}
+FIRENET_KWARGS = {'num_bins': 5, 'base_num_channels': 16, 'kernel_size': 3, 'recurrent_block_type': 'convgru',
+                  'num_residual_blocks': 2, 'recurrent_blocks': {'resblock': [0]}}

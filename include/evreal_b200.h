@@ -38,8 +38,9 @@ const char* evk_last_error(void);
  * first event, p in {-1,+1} or any weight).  grid: [num_bins,H,W] float32,
  * zeroed by the call.  Coordinates are truncated toward zero like .long();
  * coordinates in [-W,0) / [-H,0) wrap like python indexing; anything else is
- * skipped and counted in *oob_count (int32 device scalar, may be NULL; the
- * python adapter turns a non-zero count into IndexError like the reference).
+ * skipped and ADDED to *oob_count (int32 device scalar owned and zeroed by the
+ * caller, may be NULL; the python adapter turns a non-zero count into
+ * IndexError like the reference).
  * n == 0 is rejected with EVK_ERR_ARG (the reference indexes ts[-1]).
  */
 int evk_voxelize(const float* x, const float* y, const float* t, const float* p, int64_t n,
@@ -112,6 +113,16 @@ int evk_model_io_buffers(evk_model* m, float** in, float** out);
 int evk_model_last_launch_count(evk_model* m);
 /* algorithmic conv FLOPs of one forward (2*Cout*Cin*kh*kw*Hout*Wout summed) */
 double evk_model_flops(evk_model* m);
+
+/* Eager (graph-less) forward with a CUDA-event pair around every launch: per-launch milliseconds and
+ * algorithmic FLOPs (host arrays of max_ops entries; *n_ops = launches of one forward).  Advances the
+ * recurrent state exactly like evk_model_forward and synchronises the stream.  This is the live
+ * measurement behind bench.py's roofline block; the reference's only counterpart is CudaTimer
+ * (utils/timers.py:11-25) around the whole forward. */
+int evk_model_profile(evk_model* m, const float* voxel, float* image, void* stream, int max_ops, float* host_ms,
+                      double* host_flops, int* n_ops);
+/* Human-readable description of launch `index` of one forward ("conv3x3 s1 128+128->512 lstm @46x60"). */
+int evk_model_op_desc(evk_model* m, int index, char* buf, int cap);
 
 /* ------------------------------------------------------------ post-process --
  * post_process_normalization / normalize   reference: eval.py:380-395,

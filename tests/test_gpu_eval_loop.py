@@ -1,0 +1,132 @@
+"""GPU parity, end to end: evreal_b200.evaluate.eval_method_on_sequence (dataset windowing -> CUDA voxelizer ->
+normalise+pad -> CUDA network -> crop -> percentile norm -> clip -> fused MSE/SSIM) against per-frame scores of
+the REAL eval.eval_method_on_sequence (tests/golden/eval_loop.npz), plus the config/checkpoint plugin surface and
+sequence sharding.
+
+Tolerance (north_star): metric scores within 1e-4 relative; evaluated frame indices bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, weights_of, write_sequence_from_arrays
+
+pytestmark = pytest.mark.gpu
+
+EVAL_CFG = {'name': 'std', 'save_images': False, 'histeq': 'none', 'eval_infer_all': False, 'ts_tol_ms': 1.0,
+            'create_video': False, 'dataset_kwargs': {'num_bins': 5, 'voxel_method': {'method': 'between_frames'}}}
+FIRENET_KW = {'num_bins': 5, 'base_num_channels': 16, 'kernel_size': 3, 'recurrent_block_type': 'convgru',
+              'num_residual_blocks': 2, 'recurrent_blocks': {'resblock': [0]}}
+E2VID_KW = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
+            'base_num_channels': 8, 'num_residual_blocks': 2, 'use_upsample_conv': True, 'norm': 'BN'}
+
+
+def _seq(tmp_path, g, name='evalseq'):
+    arrays = {k: g[k] for k in ('events_ts', 'events_xy', 'events_p', 'images', 'images_ts', 'image_event_indices')}
+    return write_sequence_from_arrays(str(tmp_path / name), arrays, (48, 64))
+
+
+def _run(tmp_path, tag, model, method_config, write_files=False):
+    from evreal_b200 import evaluate as ev
+    g = golden('eval_loop')
+    n_eval, mse, ssim, start, end = g[tag + '.summary']
+    seq = {'name': 'evalseq', 'sequence_path': _seq(tmp_path, g), 'start_time_s': float(start), 'end_time_s': float(end),
+           'dataset_kwargs': dict(EVAL_CFG['dataset_kwargs'])}
+    ev.open_sequence(seq)
+    got_n, means, frames, events = ev.eval_method_on_sequence('SYN', EVAL_CFG, tag, model, method_config, seq,
+                                                              ['mse', 'ssim'], output_root=str(tmp_path / 'out'),
+                                                              write_files=write_files)
+    assert got_n == int(n_eval)
+    assert abs(means['mse'] - mse) <= 1e-4 * mse, (means, mse)
+    assert abs(means['ssim'] - ssim) <= 1e-4 * abs(ssim), (means, ssim)
+    return g, frames, events
+
+
+def test_firenet_real_checkpoint_sequence(tmp_path):
+    from evreal_b200 import FireNet_legacy
+    full, _ = weights_of(golden('networks'), 'firenet_ckpt', 'net.')
+    m = FireNet_legacy(dict(FIRENET_KW)).load_state_dict(full).to('cuda')
+    g, frames, events = _run(tmp_path, 'firenet', m, {'event_tensor_normalization': True, 'post_process_norm': 'none'},
+                             write_files=True)
+    # per-frame score files (utils/eval_utils.py:62-69: '{idx} {score:.5f}')
+    out = tmp_path / 'out' / 'std' / 'SYN' / 'evalseq' / 'firenet'
+    rows = [l.split() for l in open(out / 'mse.txt').read().splitlines()]
+    assert [int(r[0]) for r in rows] == [int(i) for i in g['firenet.indices']]
+    assert np.allclose([float(r[1]) for r in rows], g['firenet.mse'], atol=6e-6)
+    rows = [l.split() for l in open(out / 'ssim.txt').read().splitlines()]
+    assert np.allclose([float(r[1]) for r in rows], g['firenet.ssim'], atol=1e-4)
+    assert len(open(out / 'timestamps.txt').read().splitlines()) == frames
+    assert events > 0
+
+
+def test_e2vid_topology_sequence_with_robust_norm(tmp_path):
+    from evreal_b200 import E2VIDRecurrent
+    full, _ = weights_of(golden('networks'), 'e2vid_small', 'unetrecurrent.')
+    m = E2VIDRecurrent(dict(E2VID_KW, final_activation='sigmoid')).load_state_dict(full).to('cuda')
+    _run(tmp_path, 'e2vid_small', m, {'event_tensor_normalization': True, 'post_process_norm': 'robust'})
+
+
+def test_per_frame_scores_and_images_vs_oracle(tmp_path):
+    """Same loop on the CPU oracle: every frame's image and score, not only the sequence mean."""
+    from evreal_b200 import FireNet_legacy, evaluate as ev
+    from oracle import eval_loop, networks as on
+    g = golden('eval_loop')
+    full, stripped = weights_of(golden('networks'), 'firenet_ckpt', 'net.')
+    arrays = {k: g[k] for k in ('events_ts', 'events_xy', 'events_p', 'images', 'images_ts', 'image_event_indices')}
+    ref = eval_loop.run_sequence(arrays, (48, 64), on.FireNetLegacyOracle(stripped), 4, True, 'none', 0.2, 0.9)
+    m = FireNet_legacy(dict(FIRENET_KW)).load_state_dict(full).to('cuda')
+    seq = {'name': 'evalseq', 'sequence_path': _seq(tmp_path, g), 'start_time_s': 0.2, 'end_time_s': 0.9,
+           'dataset_kwargs': dict(EVAL_CFG['dataset_kwargs'])}
+    images = []
+    ev.eval_method_on_sequence('SYN', EVAL_CFG, 'firenet', m, {'event_tensor_normalization': True,
+                                                               'post_process_norm': 'none'}, seq, ['mse', 'ssim'],
+                               write_files=False, collect_images=images)
+    assert len(images) == len(ref['images'])
+    for a, b in zip(images, ref['images']):
+        assert np.max(np.abs(a.clamp(0, 1).cpu().numpy() - b)) <= 1e-4 * max(np.abs(b).max(), 1e-3)
+
+
+def _write_plugin_tree(root, g, n_seq):
+    """config/{method,eval,dataset}/*.json + a FireNet-dialect checkpoint (eval.py:145-148) + sequences on disk."""
+    full, _ = weights_of(golden('networks'), 'firenet_ckpt', 'net.')
+    os.makedirs(root / 'config' / 'method')
+    os.makedirs(root / 'config' / 'eval')
+    os.makedirs(root / 'config' / 'dataset')
+    os.makedirs(root / 'pretrained' / 'FireNet')
+    torch.save({'config': {'model': dict(FIRENET_KW)}, 'state_dict': full}, root / 'pretrained' / 'FireNet' / 'model.pth')
+    json.dump({'model_name': 'FireNet', 'model_path': str(root / 'pretrained' / 'FireNet' / 'model.pth'),
+               'event_tensor_normalization': True, 'post_process_norm': 'none'},
+              open(root / 'config' / 'method' / 'FireNet.json', 'w'))
+    json.dump({k: v for k, v in EVAL_CFG.items() if k != 'name'}, open(root / 'config' / 'eval' / 'std.json', 'w'))
+    arrays = {k: g[k] for k in ('events_ts', 'events_xy', 'events_p', 'images', 'images_ts', 'image_event_indices')}
+    seqs = {}
+    for i in range(n_seq):
+        a = dict(arrays)
+        n = len(a['events_ts']) - 4000 * i                     # sequences of different lengths / contents
+        a['events_ts'], a['events_xy'], a['events_p'] = a['events_ts'][:n], a['events_xy'][:n], a['events_p'][:n]
+        nf = int(np.searchsorted(a['images_ts'].reshape(-1), a['events_ts'][-1]))
+        a['images'], a['images_ts'], a['image_event_indices'] = a['images'][:nf], a['images_ts'][:nf], a['image_event_indices'][:nf]
+        write_sequence_from_arrays(str(root / 'data' / 'SYN' / ('seq%d' % i)), a, (48, 64))
+        seqs['seq%d' % i] = {'start_time_s': 0.1, 'end_time_s': 0.8}
+    json.dump({'root_path': str(root / 'data' / 'SYN'), 'sequences': seqs}, open(root / 'config' / 'dataset' / 'SYN.json', 'w'))
+
+
+def test_plugin_surface_and_sharded_means(tmp_path):
+    """evaluate() driven by config/*.json + checkpoint, 1 'rank' vs 2 ranks run back to back in one process
+    (the all-reduce itself is covered on CPU by tests/test_dist_gloo.py): dataset means identical."""
+    from evreal_b200 import evaluate as ev
+    g = golden('eval_loop')
+    _write_plugin_tree(tmp_path, g, 3)
+    cfg_root = str(tmp_path / 'config')
+    one = ev.evaluate(['FireNet'], ['std'], ['SYN'], ['mse', 'ssim'], config_root=cfg_root, write_files=False)
+    tr = one['std']['FireNet']['SYN']
+    assert tr.get_count('mse') > 0
+    parts = [ev.evaluate(['FireNet'], ['std'], ['SYN'], ['mse', 'ssim'], config_root=cfg_root, write_files=False,
+                         rank=r, world_size=2)['std']['FireNet']['SYN'] for r in range(2)]
+    for k in ('mse', 'ssim'):
+        total = sum(p.data_dict[k]['total'] for p in parts if k in p.data_dict)
+        count = sum(p.data_dict[k]['count'] for p in parts if k in p.data_dict)
+        assert count == tr.get_count(k)
+        assert abs(total / count - tr.get_average(k)) <= 1e-12 * abs(tr.get_average(k))

@@ -1,0 +1,87 @@
+"""GPU parity: fused clip+MSE+SSIM kernel and the percentile normalisation kernel (through the C ABI) against
+golden values (tests/golden/metrics.npz: scipy.ndimage path = what scikit-image calls; the reference's own
+utils.eval_utils.normalize) and against the CPU oracle.
+
+Tolerance: scores within 1e-4 relative (north_star); in practice the kernel follows scipy's summation order
+(float64 accumulate per 1-D pass, float32 storage) so SSIM agrees to ~1e-7 and MSE to 1e-9 relative."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_survey_a7_known_answer():
+    from evreal_b200.eval_metrics import mse_ssim
+    g = golden('metrics')
+    s = mse_ssim(g['a7.img'], g['a7.ref']).cpu().numpy()[0]
+    assert abs(s[0] - 0.00250339) < 1e-8 and abs(s[1] - 0.7030217) < 2e-6
+    assert abs(s[0] - g['a7.scores'][0]) <= 1e-9 * g['a7.scores'][0]
+    same = mse_ssim(g['a7.ref'], g['a7.ref']).cpu().numpy()[0]
+    assert same[0] == 0.0 and abs(same[1] - 1.0) < 1e-7
+
+
+@pytest.mark.parametrize('i', range(5))
+def test_pairs_match_golden(i):
+    from evreal_b200.eval_metrics import mse_ssim
+    g = golden('metrics')
+    img, ref, want = g['pair%d.img' % i], g['pair%d.ref' % i], g['pair%d.scores' % i]
+    s = mse_ssim(img, ref).cpu().numpy()[0]
+    assert abs(s[0] - want[0]) <= 1e-9 * want[0]
+    assert abs(s[1] - want[1]) <= 1e-5 * abs(want[1]) + 1e-7, (s[1], want[1])
+
+
+def test_batched_and_clip_against_oracle():
+    from evreal_b200.eval_metrics import mse_ssim
+    from oracle import metrics as om
+    g = np.random.default_rng(12)
+    imgs = (g.random((6, 260, 346)) * 1.4 - 0.2).astype(np.float32)       # outside [0,1]: exercises the fused clip
+    refs = g.random((6, 260, 346)).astype(np.float32)
+    got = mse_ssim(torch.from_numpy(imgs).cuda(), torch.from_numpy(refs).cuda(), clip=True).cpu().numpy()
+    for k in range(6):
+        a, b = np.clip(imgs[k], 0, 1), np.clip(refs[k], 0, 1)
+        assert abs(got[k, 0] - om.mse_oracle(a, b)) <= 1e-9
+        assert abs(got[k, 1] - om.ssim_oracle(a, b)) <= 1e-6
+
+
+def test_metric_classes_keep_the_reference_contract():
+    from evreal_b200.eval_metrics import MseMetric, SsimMetric
+    g = golden('metrics')
+    m, s = MseMetric(), SsimMetric()
+    m.update(g['a7.img'], g['a7.ref'])
+    s.update(g['a7.img'], g['a7.ref'])
+    assert m.get_num_scores() == 1 and abs(m.get_last_score() - g['a7.scores'][0]) < 1e-10
+    assert abs(s.get_mean_score() - g['a7.scores'][1]) < 2e-6
+    assert MseMetric().get_mean_score() == -1
+    with pytest.raises(ValueError):
+        m.calculate(np.zeros((8, 8), np.float32), np.zeros((8, 8), np.float32))       # window 11 > image
+    with pytest.raises(ValueError):
+        m.calculate(np.zeros((20, 20), np.float32), np.zeros((20, 21), np.float32))
+
+
+@pytest.mark.parametrize('norm', ['robust', 'standard', 'exprobust'])
+def test_percentile_normalisation_matches_reference_helper(norm):
+    from evreal_b200.eval_utils import post_process_normalization
+    g = golden('metrics')
+    x = torch.from_numpy(g['norm.in']).cuda()
+    got = post_process_normalization(x, norm).cpu().numpy()
+    ref = g['norm.' + norm]
+    tol = 2e-6 if norm == 'exprobust' else 3e-7       # expf on the device vs np.exp: 1 ulp
+    assert np.max(np.abs(got - ref)) <= tol * np.abs(ref).max()
+
+
+def test_percentile_with_duplicates_and_odd_sizes():
+    from evreal_b200.eval_utils import percentile_normalize
+    from oracle import metrics as om
+    g = np.random.default_rng(2)
+    for shape in [(180, 240), (7, 13), (1, 101), (260, 346)]:
+        x = np.round(g.normal(0, 1, shape), 1).astype(np.float32)          # heavy duplicates, negative values
+        got = percentile_normalize(torch.from_numpy(x).cuda(), 1, 99).cpu().numpy()
+        ref = om.robust_normalize_oracle(x, 1, 99)
+        assert np.max(np.abs(got - ref)) <= 3e-7 * np.abs(ref).max(), shape
+    xb = g.random((4, 50, 60)).astype(np.float32)
+    got = percentile_normalize(torch.from_numpy(xb).cuda(), 1, 99, batched=True).cpu().numpy()
+    for k in range(4):
+        assert np.max(np.abs(got[k] - om.robust_normalize_oracle(xb[k], 1, 99))) <= 3e-7 * 1.1
