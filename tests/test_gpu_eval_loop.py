@@ -129,4 +129,4 @@ def test_plugin_surface_and_sharded_means(tmp_path):
         total = sum(p.data_dict[k]['total'] for p in parts if k in p.data_dict)
         count = sum(p.data_dict[k]['count'] for p in parts if k in p.data_dict)
         assert count == tr.get_count(k)
-        assert abs(total / count - tr.get_average(k)) <= 1e-12 * abs(tr.get_average(k))
+        assert abs(total / count - tr.get_average(k)) <= 1e-6 * abs(tr.get_average(k))     # voxelizer atomics: order-dependent ulps

