@@ -1,6 +1,7 @@
 // C ABI entry points (include/evreal_b200.h) for the stateless stages, error
 // reporting, and the conv dispatcher.
 #include <cstdarg>
+#include <vector>
 
 #include "conv.cuh"
 
@@ -24,7 +25,7 @@ int mse_ssim(const float*, const float*, int, int, int, int, double*, cudaStream
 int percentile_normalize(const float*, float*, int, int, double, double, int, cudaStream_t);
 
 int launch_conv(const ConvParams& p, int precision, cudaStream_t st) {
-    (void)precision;
+    if (precision == 0 && p.tc != nullptr) return launch_conv_tc(p, st);
     return launch_conv_simt(p, st);
 }
 
@@ -72,6 +73,60 @@ int evk_percentile_normalize(const float* img, float* out, int n_images, int num
                              int apply_exp, void* stream) {
     EVK_REQUIRE(img && out, EVK_ERR_ARG, "evk_percentile_normalize: null pointer");
     return evk::percentile_normalize(img, out, n_images, numel, q_min, q_max, apply_exp, (cudaStream_t)stream);
+}
+
+int evk_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, const float* w_oihw_host, const float* bias_host, int Cout,
+                    int k, int stride, int pad, int act, const float* res, int precision, float* y, void* stream) {
+    using namespace evk;
+    EVK_REQUIRE(x && w_oihw_host && y, EVK_ERR_ARG, "evk_conv2d_nhwc: null pointer");
+    EVK_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && k > 0 && stride > 0 && pad >= 0 && Cin % 4 == 0 && Cout % 4 == 0,
+                EVK_ERR_ARG, "evk_conv2d_nhwc: bad shape (channels must be multiples of 4)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = k * k * Cin;
+    std::vector<float> wk((size_t)K * Cout), b(Cout, 0.f);
+    for (int n = 0; n < Cout; ++n) {
+        if (bias_host) b[n] = bias_host[n];
+        for (int c = 0; c < Cin; ++c)
+            for (int r = 0; r < k; ++r)
+                for (int q = 0; q < k; ++q)
+                    wk[((size_t)(r * k + q) * Cin + c) * Cout + n] = w_oihw_host[(((size_t)n * Cin + c) * k + r) * k + q];
+    }
+    float *dw = nullptr, *db = nullptr;
+    __nv_bfloat16 *dwt = nullptr, *dxs = nullptr;
+    int rc = EVK_OK;
+    auto cleanup = [&]() { cudaFree(dw); cudaFree(db); cudaFree(dwt); cudaFree(dxs); };
+    EVK_CHECK_CUDA(cudaMalloc(&dw, wk.size() * 4));
+    EVK_CHECK_CUDA(cudaMalloc(&db, b.size() * 4));
+    EVK_CHECK_CUDA(cudaMemcpyAsync(dw, wk.data(), wk.size() * 4, cudaMemcpyHostToDevice, st));
+    EVK_CHECK_CUDA(cudaMemcpyAsync(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice, st));
+    ConvParams p;
+    p.x1 = x; p.c1 = Cin; p.N = N; p.Hin = H; p.Win = W; p.kh = p.kw = k; p.stride = stride; p.pad = pad;
+    p.Hout = (H + 2 * pad - k) / stride + 1; p.Wout = (W + 2 * pad - k) / stride + 1;
+    p.w = dw; p.bias = db; p.cout = Cout; p.epi = EPI_LINEAR; p.act = act; p.res = res; p.y = y;
+    if (precision == 0 && tc_eligible(p)) {
+        std::vector<__nv_bfloat16> wt;
+        p.cout_pad = (Cout + 15) / 16 * 16;
+        pack_weights_tc(wk.data(), K, Cout, p.cout_pad, wt);
+        const int64_t nx = (int64_t)N * H * W * Cin;
+        if (cudaMalloc(&dwt, wt.size() * 2) != cudaSuccess || cudaMalloc(&dxs, (size_t)nx * 4) != cudaSuccess) {
+            cleanup();
+            set_error("evk_conv2d_nhwc: out of device memory");
+            return EVK_ERR_CUDA;
+        }
+        cudaMemcpyAsync(dwt, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice, st);
+        rc = launch_split(x, dxs, nx, st);
+        p.w_tc = dwt; p.x1s = dxs;
+        if (rc == EVK_OK) rc = tc_plan_create(p);
+        if (rc == EVK_OK) rc = launch_conv_tc(p, st);
+    } else {
+        rc = launch_conv_simt(p, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (p.tc) tc_plan_destroy(p.tc);
+    cleanup();
+    if (rc != EVK_OK) return rc;
+    EVK_CHECK_CUDA(e);
+    return EVK_OK;
 }
 
 }  // extern "C"

@@ -6,6 +6,9 @@
 // with k = (r*kw + s)*(c1+c2) + c and torch.cat((x1, x2), 1) expressed as two
 // channel ranges so it is never materialised.
 #pragma once
+#include <cuda_bf16.h>
+#include <vector>
+
 #include "evk_common.cuh"
 
 namespace evk {
@@ -37,7 +40,26 @@ struct ConvParams {
     const float* h_prev = nullptr;                            // GRU_UR / GRU_OUT previous hidden state
     float* u_out = nullptr; float* hr_out = nullptr;          // GRU_UR outputs: update gate, h*reset
     const float* u_in = nullptr;                              // GRU_OUT input: update gate
+    // ---- tensor-core path (conv_tc.cu).  "Split" tensors are two bf16 planes [2][N,H,W,C]: hi = bf16(v),
+    // lo = bf16(v - hi); the three products hi*hi + lo*hi + hi*lo accumulate in fp32 in tensor memory.
+    const __nv_bfloat16* x1s = nullptr;   // split companions of x1 / x2 (required by the TC path)
+    const __nv_bfloat16* x2s = nullptr;
+    __nv_bfloat16* ys = nullptr;          // optional split copy of y (EPI_LINEAR) for a tensor-core consumer
+    __nv_bfloat16* hs_new = nullptr;      // optional split copy of h_new (EPI_LSTM)
+    const __nv_bfloat16* w_tc = nullptr;  // weights [2][cout_pad][K] bf16 (hi, lo), K-major
+    int cout_pad = 0;                     // rows of w_tc (cout rounded up to a multiple of 16)
+    struct TcPlan* tc = nullptr;          // tensor maps + tiling, built once per layer (tc_plan_create)
 };
+
+// ---- tensor-core implicit GEMM (TMA + tcgen05 + TMEM), conv_tc.cu
+bool tc_eligible(const ConvParams& p);
+int tc_plan_create(ConvParams& p);          // fills p.tc; EVK_ERR_ARG when the shape does not qualify
+void tc_plan_destroy(TcPlan* plan);
+int launch_conv_tc(const ConvParams& p, cudaStream_t st);
+// fp32 -> split bf16 planes (elementwise): dst[0..n) = hi, dst[n..2n) = lo
+int launch_split(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st);
+// host: fp32 [K][cout] (K-major rows of the SIMT layout) -> bf16 [2][cout_pad][K]
+void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out);
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);
 // dispatcher: tensor-core split-bf16 kernel when the shape qualifies and precision == 0, else fp32 SIMT
@@ -45,11 +67,11 @@ int launch_conv(const ConvParams& p, int precision, cudaStream_t st);
 
 // head ConvLayer on the NCHW event tensor (Cin = num_bins): NCHW in -> NHWC out, ReLU
 int launch_head_conv(const float* x_nchw, const float* w /*[k*k*cin][cout]*/, const float* bias, float* y_nhwc,
-                     int N, int cin, int H, int W, int k, int cout, cudaStream_t st);
+                     __nv_bfloat16* ys /*optional split copy*/, int N, int cin, int H, int W, int k, int cout, cudaStream_t st);
 // prediction ConvLayer: 1x1 conv on (x [+ skip]) NHWC -> channel 0 only, NCHW [N,1,H,W]; optional sigmoid
 int launch_pred(const float* x, const float* skip, const float* w /*[cin]*/, float bias, float* y, int64_t pixels,
                 int cin, int sigmoid, cudaStream_t st);
 // y[N,2H,2W,C] = bilinear_x2(x + skip), align_corners=False (model/unet.py:130-134 + submodules.py:88)
-int launch_upsample2x_add(const float* x, const float* skip, float* y, int N, int H, int W, int C, cudaStream_t st);
+int launch_upsample2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C, cudaStream_t st);
 
 }  // namespace evk

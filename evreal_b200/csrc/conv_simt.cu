@@ -6,6 +6,7 @@
 // tcgen05 split-bf16 kernels.  Reference semantics: model/submodules.py:8-35
 // (ConvLayer), :152-184 (ResidualBlock), :187-245 (ConvLSTM), :248-287 (ConvGRU).
 #include "conv.cuh"
+#include "tc.cuh"
 
 namespace evk {
 
@@ -133,14 +134,28 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], p.act);
-            *reinterpret_cast<float4*>(p.y + (size_t)m * p.cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.y != nullptr) *reinterpret_cast<float4*>(p.y + (size_t)m * p.cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.ys != nullptr) {
+                __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split_bf16(v[j], hi[j], lo[j]);
+                *reinterpret_cast<uint2*>(p.ys + (size_t)m * p.cout + n) = *reinterpret_cast<uint2*>(hi);
+                *reinterpret_cast<uint2*>(p.ys + (size_t)M * p.cout + (size_t)m * p.cout + n) = *reinterpret_cast<uint2*>(lo);
+            }
         } else if (p.epi == EPI_LSTM) {
             const int C = p.cout >> 2, ch = n >> 2;
             const size_t o = (size_t)m * C + ch;
             const float ig = sigmoidf_(v[0]), fg = sigmoidf_(v[1]), og = sigmoidf_(v[2]), cg = tanhf(v[3]);
             const float cell = __fadd_rn(__fmul_rn(fg, p.c_prev[o]), __fmul_rn(ig, cg));
             p.c_new[o] = cell;
-            p.h_new[o] = og * tanhf(cell);
+            const float hid = og * tanhf(cell);
+            p.h_new[o] = hid;
+            if (p.hs_new != nullptr) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(hid, hi, lo);
+                p.hs_new[o] = hi;
+                p.hs_new[(size_t)M * C + o] = lo;
+            }
         } else if (p.epi == EPI_GRU_UR) {
             const int C = p.cout >> 1, ch = n >> 1;
 #pragma unroll
@@ -188,7 +203,7 @@ int launch_conv_simt(const ConvParams& p, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                 float* __restrict__ y, int cin, int H, int W, int k, int cout) {
+                 float* __restrict__ y, __nv_bfloat16* __restrict__ ys, size_t plane, int cin, int H, int W, int k, int cout) {
     extern __shared__ __align__(16) float smem[];
     const int tw = 16 + k - 1;
     float* wsm = smem;                                  // [k*k*cin][cout]
@@ -232,15 +247,25 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
                 }
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4)
-            if (co0 + j4 * 4 < cout)
-                *reinterpret_cast<float4*>(out + co0 + j4 * 4) =
-                    make_float4(fmaxf(acc[j4 * 4 + 0], 0.f), fmaxf(acc[j4 * 4 + 1], 0.f), fmaxf(acc[j4 * 4 + 2], 0.f),
-                                fmaxf(acc[j4 * 4 + 3], 0.f));
+            if (co0 + j4 * 4 < cout) {
+                const float4 o4 = make_float4(fmaxf(acc[j4 * 4 + 0], 0.f), fmaxf(acc[j4 * 4 + 1], 0.f),
+                                              fmaxf(acc[j4 * 4 + 2], 0.f), fmaxf(acc[j4 * 4 + 3], 0.f));
+                *reinterpret_cast<float4*>(out + co0 + j4 * 4) = o4;
+                if (ys != nullptr) {
+                    const float f[4] = {o4.x, o4.y, o4.z, o4.w};
+                    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_bf16(f[e], hi[e], lo[e]);
+                    const size_t o = (size_t)(out - y) + co0 + j4 * 4;
+                    *reinterpret_cast<uint2*>(ys + o) = *reinterpret_cast<uint2*>(hi);
+                    *reinterpret_cast<uint2*>(ys + plane + o) = *reinterpret_cast<uint2*>(lo);
+                }
+            }
     }
 }
 
-int launch_head_conv(const float* x, const float* w, const float* bias, float* y, int N, int cin, int H, int W, int k,
-                     int cout, cudaStream_t st) {
+int launch_head_conv(const float* x, const float* w, const float* bias, float* y, __nv_bfloat16* ys, int N, int cin, int H,
+                     int W, int k, int cout, cudaStream_t st) {
     EVK_REQUIRE(cout % 4 == 0 && (k == 3 || k == 5 || k == 1 || k == 7), EVK_ERR_ARG, "head_conv: unsupported cout=%d k=%d", cout, k);
     const int tw = 16 + k - 1;
     const size_t smem = sizeof(float) * ((size_t)k * k * cin * cout + (size_t)cin * tw * (tw + 1));
@@ -251,7 +276,7 @@ int launch_head_conv(const float* x, const float* w, const float* bias, float* y
         configured = smem;
     }
     dim3 grid(ceil_div(W, 16), ceil_div(H, 16), N);
-    head_conv_kernel<<<grid, 256, smem, st>>>(x, w, bias, y, cin, H, W, k, cout);
+    head_conv_kernel<<<grid, 256, smem, st>>>(x, w, bias, y, ys, (size_t)N * H * W * cout, cin, H, W, k, cout);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }
@@ -299,8 +324,8 @@ int launch_pred(const float* x, const float* skip, const float* w, float bias, f
 // lerp is applied inside the vertical one like ATen's CPU kernel.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-upsample2x_add_kernel(const float* __restrict__ x, const float* __restrict__ skip, float* __restrict__ y, int N, int H,
-                      int W, int C4) {
+upsample2x_add_kernel(const float* __restrict__ x, const float* __restrict__ skip, float* __restrict__ y,
+                      __nv_bfloat16* __restrict__ ys, int N, int H, int W, int C4) {
     const int Ho = 2 * H, Wo = 2 * W;
     const int64_t total = (int64_t)N * Ho * Wo * C4;
     const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -332,14 +357,23 @@ upsample2x_add_kernel(const float* __restrict__ x, const float* __restrict__ ski
         o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
         o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
         o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-        y4[i] = o;
+        if (y != nullptr) y4[i] = o;
+        if (ys != nullptr) {
+            const float f[4] = {o.x, o.y, o.z, o.w};
+            __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_bf16(f[e], hi[e], lo[e]);
+            *reinterpret_cast<uint2*>(ys + i * 4) = *reinterpret_cast<uint2*>(hi);
+            *reinterpret_cast<uint2*>(ys + total * 4 + i * 4) = *reinterpret_cast<uint2*>(lo);
+        }
     }
 }
 
-int launch_upsample2x_add(const float* x, const float* skip, float* y, int N, int H, int W, int C, cudaStream_t st) {
+int launch_upsample2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C,
+                          cudaStream_t st) {
     EVK_REQUIRE(C % 4 == 0, EVK_ERR_ARG, "upsample2x_add: C=%d must be a multiple of 4", C);
     const int64_t total = (int64_t)N * 4 * H * W * (C / 4);
-    upsample2x_add_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 4736), 256, 0, st>>>(x, skip, y, N, H, W, C / 4);
+    upsample2x_add_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 4736), 256, 0, st>>>(x, skip, y, ys, N, H, W, C / 4);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

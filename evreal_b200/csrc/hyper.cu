@@ -5,6 +5,7 @@
 // neighbourhood is read from a shared-memory halo tile instead and only the
 // [N,h,w,C*A] intermediate that feeds the 1x1 compositional conv is written.
 #include "hyper.cuh"
+#include "tc.cuh"
 
 namespace evk {
 
@@ -95,11 +96,24 @@ __global__ void __launch_bounds__(256) hyper_apply_kernel(const HyperParams p) {
         }
     }
     if (gy < p.h && gx < p.w) {
-        float* o = p.inter + (((size_t)n * p.h + gy) * p.w + gx) * ((size_t)p.C * A) + (size_t)(c0 + lane * 4) * A;
+        const size_t off = (((size_t)n * p.h + gy) * p.w + gx) * ((size_t)p.C * A) + (size_t)(c0 + lane * 4) * A;
+        float* o = p.inter + off;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int a = 0; a < A; ++a) o[c * A + a] = acc[c][a];
+        if (p.inter_s != nullptr) {
+            const size_t plane = (size_t)p.N * p.h * p.w * p.C * A;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    __nv_bfloat16 hi, lo;
+                    split_bf16(acc[c][a], hi, lo);
+                    p.inter_s[off + c * A + a] = hi;
+                    p.inter_s[plane + off + c * A + a] = lo;
+                }
+        }
     }
 }
 

@@ -1,6 +1,8 @@
 // HyperE2VID dynamic decoder pieces that are not plain convolutions.
 // Reference semantics: model/hyper/hyper_dynamic.py:7-92, model/submodules.py:100-127.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "evk_common.cuh"
 
 namespace evk {
@@ -15,6 +17,7 @@ struct HyperParams {
     int h = 0, w = 0, A = 0, K = 0, L = 0, ks = 0;
     // (2) apply: inter[n,y,x,c*A+a] = sum_l atoms[n,y,x,a,l] * xu[n, y+dy(l), x+dx(l), c]   (zero padded)
     const float* xu = nullptr; float* inter = nullptr; int C = 0;
+    __nv_bfloat16* inter_s = nullptr;   // optional split-bf16 copy of inter for the tensor-core 1x1 conv
 };
 
 // which: 0 context, 1 atoms, 2 apply

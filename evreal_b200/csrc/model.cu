@@ -38,6 +38,7 @@ struct Op {
     int N = 0, cin = 0, H = 0, W = 0, k = 0, cout = 0;
     // OP_UPSAMPLE_ADD / OP_PRED
     const float* skip = nullptr;
+    __nv_bfloat16* out_s = nullptr;   // OP_HEAD / OP_UPSAMPLE_ADD: split-bf16 copy of `out` for a tensor-core consumer
     float bias0 = 0.f;
     int sigmoid = 0;
     HyperParams hp;             // OP_HYPER_*
@@ -70,13 +71,25 @@ struct evk_model {
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     bool use_graph = true;
+    std::map<const float*, __nv_bfloat16*> split_of;   // fp32 activation buffer -> its split-bf16 companion
+    std::map<const float*, size_t> buf_elems;          // element count of every activation / state buffer
+    std::vector<TcPlan*> plans;
+    int tc_convs = 0;
 
     float* dalloc(size_t nfloat) {
         void* p = nullptr;
         if (cudaMalloc(&p, nfloat * sizeof(float)) != cudaSuccess) return nullptr;
         cudaMemset(p, 0, nfloat * sizeof(float));
         allocs.push_back(p);
+        buf_elems[(const float*)p] = nfloat;
         return (float*)p;
+    }
+    void* dalloc_bytes(size_t bytes) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, bytes);
+        allocs.push_back(p);
+        return p;
     }
     float* upload(const std::vector<float>& v) {
         float* p = dalloc(v.size());
@@ -157,6 +170,17 @@ struct Builder {
         return conv_packed(pk, x, cin, Hin, Win, stride, pad, act, res, y, cout_out);
     }
 
+    // split-bf16 K-major weights for the tensor-core path (only when the layer shape qualifies)
+    void attach_tc_weights(ConvParams& p, const Packed& pk) {
+        if (m->cfg.precision != 0 || !tc_eligible(p)) return;
+        std::vector<__nv_bfloat16> wt;
+        p.cout_pad = (pk.cout + 15) / 16 * 16;
+        pack_weights_tc(pk.w.data(), pk.kh * pk.kw * pk.cin, pk.cout, p.cout_pad, wt);
+        void* d = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
+        if (d) cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+        p.w_tc = (const __nv_bfloat16*)d;
+    }
+
     int conv_packed(const Packed& pk, const float* x, int cin, int Hin, int Win, int stride, int pad, int act,
                     const float* res, float* y, int* cout_out) {
         Op op; op.kind = OP_CONV;
@@ -167,6 +191,7 @@ struct Builder {
         p.Wout = (Win + 2 * pad - pk.kw) / stride + 1;
         p.w = m->upload(pk.w); p.bias = m->upload(pk.b); p.cout = pk.cout;
         p.epi = EPI_LINEAR; p.act = act; p.res = res; p.y = y;
+        attach_tc_weights(p, pk);
         op.flops = conv_flops(p, pk.cout);
         m->ops[0].push_back(op); m->ops[1].push_back(op);
         if (cout_out) *cout_out = pk.cout;
@@ -196,12 +221,16 @@ static int add_lstm(Builder& B, const std::string& pfx, const float* x, int C, i
     EVK_REQUIRE(pk.cin == 2 * C && pk.kh == 3, EVK_ERR_KEY, "'%s.Gates': unexpected shape", pfx.c_str());
     const float* w = m->upload(pk.w);
     const float* b = m->upload(pk.b);
+    ConvParams wt;   // carries the tensor-core weights shared by both parities
+    wt.c1 = C; wt.c2 = C; wt.stride = 1; wt.cout = 4 * C; wt.epi = EPI_LSTM;
+    B.attach_tc_weights(wt, pk);
     for (int par = 0; par < 2; ++par) {
         Op op; op.kind = OP_CONV;
         ConvParams& p = op.cp;
         p.x1 = x; p.c1 = C; p.x2 = m->states[hs].buf[par]; p.c2 = C;
         p.N = B.N; p.Hin = p.Hout = H; p.Win = p.Wout = W; p.kh = p.kw = 3; p.stride = 1; p.pad = 1;
         p.w = w; p.bias = b; p.cout = 4 * C; p.epi = EPI_LSTM;
+        p.w_tc = wt.w_tc; p.cout_pad = wt.cout_pad;
         p.c_prev = m->states[cs].buf[0]; p.c_new = m->states[cs].buf[0];
         p.h_new = m->states[hs].buf[par ^ 1];
         op.flops = conv_flops(p, 4 * C);
@@ -480,6 +509,57 @@ static int build_firenet(evk_model* m, bool legacy) {
     return add_pred(B, "pred", r2, nullptr, C, H, W);
 }
 
+// Tensor-core wiring: every qualifying convolution gets split-bf16 companions of its inputs (allocated once per
+// fp32 buffer), every producer of such a buffer is told to emit the split copy, and the TMA tensor maps are built.
+static int wire_tc(evk_model* m) {
+    if (m->cfg.precision != 0) return EVK_OK;
+    auto need_split = [&](const float* ptr) -> __nv_bfloat16* {
+        auto it = m->split_of.find(ptr);
+        if (it != m->split_of.end()) return it->second;
+        auto sz = m->buf_elems.find(ptr);
+        if (sz == m->buf_elems.end()) return nullptr;
+        __nv_bfloat16* d = (__nv_bfloat16*)m->dalloc_bytes(sz->second * 2 * sizeof(__nv_bfloat16));
+        m->split_of[ptr] = d;
+        return d;
+    };
+    for (int par = 0; par < 2; ++par)
+        for (Op& op : m->ops[par]) {
+            if (op.kind != OP_CONV || op.cp.w_tc == nullptr || !tc_eligible(op.cp)) continue;
+            op.cp.x1s = need_split(op.cp.x1);
+            if (op.cp.c2) op.cp.x2s = need_split(op.cp.x2);
+            EVK_REQUIRE(op.cp.x1s && (!op.cp.c2 || op.cp.x2s), EVK_ERR_CUDA, "wire_tc: cannot allocate split activations");
+        }
+    auto lookup = [&](const float* ptr) -> __nv_bfloat16* {
+        auto it = m->split_of.find(ptr);
+        return it == m->split_of.end() ? nullptr : it->second;
+    };
+    for (int par = 0; par < 2; ++par)
+        for (Op& op : m->ops[par]) {
+            switch (op.kind) {
+                case OP_HEAD: case OP_UPSAMPLE_ADD: op.out_s = lookup(op.out); break;
+                case OP_CONV:
+                    if (op.cp.epi == EPI_LINEAR) op.cp.ys = lookup(op.cp.y);
+                    if (op.cp.epi == EPI_LSTM) op.cp.hs_new = lookup(op.cp.h_new);
+                    if (op.cp.epi == EPI_GRU_OUT && lookup(op.cp.h_new)) {
+                        set_error("wire_tc: a tensor-core consumer of a ConvGRU state is not supported");
+                        return EVK_ERR_ARG;
+                    }
+                    break;
+                case OP_HYPER_APPLY: op.hp.inter_s = lookup(op.hp.inter); break;
+                default: break;
+            }
+        }
+    for (int par = 0; par < 2; ++par)
+        for (Op& op : m->ops[par]) {
+            if (op.kind != OP_CONV || op.cp.x1s == nullptr) continue;
+            int r = tc_plan_create(op.cp);
+            if (r != EVK_OK) return r;
+            m->plans.push_back(op.cp.tc);
+            if (par == 0) m->tc_convs++;
+        }
+    return EVK_OK;
+}
+
 static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent_t>* ev = nullptr) {
     for (const Op& op : m->ops[par]) {
         int r = EVK_OK;
@@ -487,9 +567,9 @@ static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent
             cudaEvent_t e; EVK_CHECK_CUDA(cudaEventCreate(&e)); EVK_CHECK_CUDA(cudaEventRecord(e, st)); ev->push_back(e);
         }
         switch (op.kind) {
-            case OP_HEAD: r = launch_head_conv(op.in, op.w, op.b, op.out, op.N, op.cin, op.H, op.W, op.k, op.cout, st); break;
+            case OP_HEAD: r = launch_head_conv(op.in, op.w, op.b, op.out, op.out_s, op.N, op.cin, op.H, op.W, op.k, op.cout, st); break;
             case OP_CONV: r = launch_conv(op.cp, m->cfg.precision, st); break;
-            case OP_UPSAMPLE_ADD: r = launch_upsample2x_add(op.in, op.skip, op.out, op.N, op.H, op.W, op.cin, st); break;
+            case OP_UPSAMPLE_ADD: r = launch_upsample2x_add(op.in, op.skip, op.out, op.out_s, op.N, op.H, op.W, op.cin, st); break;
             case OP_PRED: r = launch_pred(op.in, op.skip, op.w, op.bias0, op.out, (int64_t)op.N * op.H * op.W, op.cin, op.sigmoid, st); break;
             default: r = launch_hyper(op.kind - OP_HYPER_CONTEXT, op.hp, st); break;
         }
@@ -508,7 +588,8 @@ static std::string op_desc(const Op& op) {
         case OP_CONV: {
             const ConvParams& p = op.cp;
             const char* e = p.epi == EPI_LSTM ? "lstm" : p.epi == EPI_GRU_UR ? "gru_ur" : p.epi == EPI_GRU_OUT ? "gru_out" : (p.res ? "linear+res" : "linear");
-            snprintf(b, sizeof b, "conv%dx%d s%d %d+%d->%d %s @%dx%d", p.kh, p.kw, p.stride, p.c1, p.c2, p.cout, e, p.Hout, p.Wout);
+            snprintf(b, sizeof b, "conv%dx%d s%d %d+%d->%d %s @%dx%d [%s]", p.kh, p.kw, p.stride, p.c1, p.c2, p.cout, e, p.Hout,
+                     p.Wout, p.tc ? "tcgen05 bf16x3" : "simt fp32");
             break;
         }
         case OP_UPSAMPLE_ADD: snprintf(b, sizeof b, "upsample2x_add C=%d @%dx%d", op.cin, 2 * op.H, 2 * op.W); break;
@@ -564,6 +645,8 @@ int evk_model_finalize(evk_model* m, void* stream) {
     EVK_REQUIRE(m->in_buf && m->out_buf && m->prev_rec, EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
     int r = (c.arch == EVK_ARCH_UNET_RECURRENT) ? build_unet(m) : build_firenet(m, c.arch == EVK_ARCH_FIRENET_LEGACY);
     if (r != EVK_OK) return r;
+    r = wire_tc(m);
+    if (r != EVK_OK) return r;
     for (void* p : m->allocs) EVK_REQUIRE(p != nullptr, EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
     m->flops = 0.0;
     for (const Op& op : m->ops[0]) m->flops += op.flops;
@@ -582,6 +665,10 @@ int evk_model_reset_states(evk_model* m, void* stream) {
         const size_t bytes = sizeof(float) * (size_t)m->cfg.batch * s.H * s.W * s.C;
         EVK_CHECK_CUDA(cudaMemsetAsync(s.buf[0], 0, bytes, st));
         if (s.pingpong) EVK_CHECK_CUDA(cudaMemsetAsync(s.buf[1], 0, bytes, st));
+        for (int k = 0; k < 2; ++k) {
+            auto it = m->split_of.find(s.buf[k]);
+            if (it != m->split_of.end()) EVK_CHECK_CUDA(cudaMemsetAsync(it->second, 0, bytes, st));   // 2 bf16 planes == bytes
+        }
     }
     EVK_CHECK_CUDA(cudaMemsetAsync(m->prev_rec, 0, sizeof(float) * (size_t)m->cfg.batch * m->cfg.height * m->cfg.width, st));
     m->parity = 0;
@@ -682,6 +769,7 @@ int evk_model_destroy(evk_model* m) {
     for (int i = 0; i < 2; ++i)
         if (m->graph[i]) cudaGraphExecDestroy(m->graph[i]);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+    for (TcPlan* pl : m->plans) tc_plan_destroy(pl);
     for (void* p : m->allocs)
         if (p) cudaFree(p);
     delete m;
@@ -731,6 +819,8 @@ int evk_model_set_state(evk_model* m, int index, const float* in_nchw, void* str
     const int64_t total = (int64_t)m->cfg.batch * s.C * s.H * s.W;
     nchw_to_nhwc_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 1184), 256, 0, (cudaStream_t)stream>>>(in_nchw, cur, m->cfg.batch, s.C, s.H * s.W);
     EVK_CHECK_CUDA(cudaGetLastError());
+    auto it = m->split_of.find(cur);
+    if (it != m->split_of.end()) return launch_split(cur, it->second, total, (cudaStream_t)stream);
     return EVK_OK;
 }
 

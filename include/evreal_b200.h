@@ -124,6 +124,15 @@ int evk_model_profile(evk_model* m, const float* voxel, float* image, void* stre
 /* Human-readable description of launch `index` of one forward ("conv3x3 s1 128+128->512 lstm @46x60"). */
 int evk_model_op_desc(evk_model* m, int index, char* buf, int cap);
 
+/* One ConvLayer (model/submodules.py:8-35: conv2d [+ residual] + activation) on NHWC float32 device tensors,
+ * the building block of every network above, exposed for layer-level parity tests and external callers.
+ * x: [N,H,W,Cin]; w: HOST [Cout,Cin,k,k] (torch layout); bias: HOST [Cout] or NULL; res: device [N,Ho,Wo,Cout] or
+ * NULL (added before the activation); act: 0 none, 1 relu, 2 sigmoid, 3 tanh; y: [N,Ho,Wo,Cout].
+ * precision 0 = tcgen05 split-bf16 tensor-core kernel when Cin % 32 == 0, else / precision 1 = fp32 CUDA cores.
+ * Synchronises the stream. */
+int evk_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, const float* w_oihw_host, const float* bias_host, int Cout,
+                    int k, int stride, int pad, int act, const float* res, int precision, float* y, void* stream);
+
 /* ------------------------------------------------------------ post-process --
  * post_process_normalization / normalize   reference: eval.py:380-395,
  * utils/eval_utils.py:15-35.  out = (v - P_qmin) / (P_qmax - P_qmin) with
