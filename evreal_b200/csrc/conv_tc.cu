@@ -117,7 +117,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer
-            const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)a.bn);
+            // Two MMAs per 16-deep K step instead of three: B_hi and B_lo are adjacent in the stage, so
+            //   D[:, 0:2bn]  (+)= A_hi * [B_hi; B_lo]^T      (N = 2*bn: hi*hi | hi*lo)
+            //   D[:, 0:bn]    += A_lo *  B_hi^T
+            // which reads A from shared memory twice instead of three times; the epilogue adds the two halves.
+            const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * a.bn));
+            const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)a.bn);
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % a.stages;
                 const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
@@ -129,10 +134,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     const uint64_t ah = umma_desc_kmajor(sa + k * 32, ROW_BYTES);
                     const uint64_t al = umma_desc_kmajor(sa + A_BYTES + k * 32, ROW_BYTES);
                     const uint64_t bh = umma_desc_kmajor(sa + 2 * A_BYTES + k * 32, ROW_BYTES);
-                    const uint64_t bl = umma_desc_kmajor(sa + 2 * A_BYTES + b_bytes + k * 32, ROW_BYTES);
-                    tc_mma_bf16(tmem_base, al, bh, idesc, (kb | k) != 0 ? 1u : 0u);    // small terms first
-                    tc_mma_bf16(tmem_base, ah, bl, idesc, 1u);
-                    tc_mma_bf16(tmem_base, ah, bh, idesc, 1u);
+                    tc_mma_bf16(tmem_base, ah, bh, idesc2, (kb | k) != 0 ? 1u : 0u);
+                    tc_mma_bf16(tmem_base, al, bh, idesc1, 1u);
                 }
                 tc_commit(bar_empty + 8u * s);      // frees the smem slot when these MMAs retire
             }
@@ -151,15 +154,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         for (int j0 = 0; j0 < a.bn; j0 += 32) {
             uint32_t v[32];
             __syncwarp();                     // tcgen05.ld is .sync.aligned: reconverge after the masked stores
-            tc_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)j0, v);
-            tc_wait_ld();
+            {
+                uint32_t u[32];
+                tc_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)j0, v);
+                tc_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a.bn + j0), u);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+            }
             const int nb = n0 + j0;
             if (!valid || nb >= a.cout) continue;
             if (a.epi == EPI_LINEAR) {
                 const size_t o = pix * a.cout + nb;
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    if (nb + g * 4 >= a.cout) break;
+                    if (nb + g * 4 >= a.cout || j0 + g * 4 >= a.bn) break;
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
                     float f[4] = {__uint_as_float(v[g * 4 + 0]) + b4.x, __uint_as_float(v[g * 4 + 1]) + b4.y,
                                   __uint_as_float(v[g * 4 + 2]) + b4.z, __uint_as_float(v[g * 4 + 3]) + b4.w};
@@ -265,10 +274,22 @@ bool tc_eligible(const ConvParams& p) {
     return true;
 }
 
-static int pick_bn(int cout_pad) {
-    for (int bn = 128; bn >= 16; bn -= 16)
-        if (cout_pad % bn == 0) return bn;
-    return 0;
+// N tile: the divisor of cout_pad (multiple of 16, <= 128 so that [B_hi; B_lo] is one N <= 256 operand) that
+// minimises  waves(CTAs / 148) * (fixed per-CTA cost + K steps * cycles per step), cycles per 16-deep K step from
+// the tcgen05 floor (128*N/256) and the 128 B/clk shared-memory operand read.
+static int pick_bn(int cout_pad, long m_tiles, long k16_steps, int granule) {
+    int best = 0;
+    double best_cost = 0.0;
+    for (int bn = 128; bn >= 16; bn -= 16) {
+        if (cout_pad % bn != 0 || bn % granule != 0) continue;
+        const double mma1 = std::max((double)bn, 32.0 + bn / 2.0);          // N = 2*bn
+        const double mma2 = std::max(bn / 2.0, 32.0 + bn / 4.0);            // N = bn
+        const double per_cta = 8000.0 + (double)k16_steps * (mma1 + mma2) + 40.0 * bn;
+        const long ctas = m_tiles * (cout_pad / bn);
+        const double cost = (double)((ctas + kNumSMs - 1) / kNumSMs) * per_cta;
+        if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    return best;
 }
 
 void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out) {
@@ -289,8 +310,6 @@ int tc_plan_create(ConvParams& p) {
     const int bk = pick_bk(p);
     const int cout_pad = p.cout_pad;
     EVK_REQUIRE(cout_pad >= p.cout && cout_pad % 16 == 0, EVK_ERR_ARG, "conv_tc: cout_pad=%d must be a multiple of 16 >= cout", cout_pad);
-    const int bn = pick_bn(cout_pad);
-    EVK_REQUIRE(bn >= 16, EVK_ERR_ARG, "conv_tc: no N tile for cout_pad=%d", cout_pad);
     // spatial M tile: 128 pixels, least padded area
     const int cand[4][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}};
     int th = 8, tw = 16;
@@ -300,6 +319,9 @@ int tc_plan_create(ConvParams& p) {
         const long area = (long)ceil_div(p.Hout, c[0]) * c[0] * ceil_div(p.Wout, c[1]) * c[1];
         if (best < 0 || area < best) { best = area; th = c[0]; tw = c[1]; }
     }
+    const long m_tiles = (long)ceil_div(p.Hout, th) * ceil_div(p.Wout, tw) * p.N;
+    const int bn = pick_bn(cout_pad, m_tiles, (long)p.kh * p.kw * (p.c1 + p.c2) / 16, p.epi == EPI_LSTM ? 32 : 16);
+    EVK_REQUIRE(bn >= 16, EVK_ERR_ARG, "conv_tc: no N tile for cout_pad=%d", cout_pad);
     TcPlan* pl = new TcPlan();
     pl->bk = bk;
     TcArgs& a = pl->a;
@@ -317,7 +339,7 @@ int tc_plan_create(ConvParams& p) {
     stages = std::max(2, std::min(stages, 6));
     a.stages = stages;
     uint32_t cols = 32;
-    while ((int)cols < bn) cols <<= 1;
+    while ((int)cols < 2 * bn + 16) cols <<= 1;   // two accumulator halves (+ the 32-column read window past a bn%32 tail)
     a.tmem_cols = cols;
     pl->smem = stages * stage_bytes + 1024 + 16 * stages + 64;
     pl->grid = dim3(a.tiles_x * a.tiles_y * p.N, cout_pad / bn);
