@@ -28,9 +28,10 @@ struct TcArgs {
     int N, Hout, Wout, stride, pad, kh, kw;
     int th, tw, tiles_x, tiles_y;
     int chunks1, chunks2;
-    int bn, cout;
+    int bn, n_tiles, m_tiles, cout;
     int epi, act;
     int stages;
+    int acc_stride;         // TMEM columns per accumulator stage
     uint32_t tmem_cols;
     const float* bias;
     const float* res;
@@ -48,8 +49,27 @@ struct TcPlan {
     size_t smem;
 };
 
+constexpr int kTcThreads = 384;      // 12 warps: TMA, MMA, TMEM alloc, (idle), 8 epilogue
+constexpr int kEpiWarps = 8;
+
+// sigmoid / tanh on the SFU (ex2.approx, rcp.approx): absolute error ~2e-7, far inside the 1e-4 parity budget
+__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+__device__ __forceinline__ float fast_act(float v, int act) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(v, 0.0f);
+        case ACT_SIGMOID: return fast_sigmoid(v);
+        case ACT_TANH: return fast_tanh(v);
+        default: return v;
+    }
+}
+
+// Persistent, warp-specialised: every CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  (N tile fastest
+// so CTAs that run concurrently share the activation patch in L2).  The smem ring (TMA -> MMA) runs continuously
+// across tiles; the accumulator is double-buffered in tensor memory so the epilogue of tile i overlaps the MMAs of
+// tile i+1.
 template <int BK>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                const __grid_constant__ CUtensorMap tm_w, const TcArgs a) {
     constexpr uint32_t ROW_BYTES = BK * 2;
@@ -60,18 +80,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
     const uint32_t stage_bytes = 2 * A_BYTES + 2 * b_bytes;
     const uint32_t bar_full = base + (uint32_t)a.stages * stage_bytes;
     const uint32_t bar_empty = bar_full + 8u * a.stages;
-    const uint32_t bar_tmem = bar_empty + 8u * a.stages;
-    const uint32_t slot = bar_tmem + 8u;
+    const uint32_t bar_tfull = bar_empty + 8u * a.stages;     // [2] accumulator ready
+    const uint32_t bar_tempty = bar_tfull + 16u;              // [2] accumulator drained by the epilogue
+    const uint32_t slot = bar_tempty + 16u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int tx_i = tile % a.tiles_x;
-    const int ty_i = (tile / a.tiles_x) % a.tiles_y;
-    const int img = tile / (a.tiles_x * a.tiles_y);
-    const int ox0 = tx_i * a.tw, oy0 = ty_i * a.th;
-    const int n0 = blockIdx.y * a.bn;
     const int chunks = a.chunks1 + a.chunks2;
     const int KB = a.kh * a.kw * chunks;
+    const int total_tiles = a.m_tiles * a.n_tiles;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x1);
@@ -83,7 +100,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             mbar_init(bar_full + 8u * s, 1);
             mbar_init(bar_empty + 8u * s, 1);
         }
-        mbar_init(bar_tmem, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8u * i, 1);
+            mbar_init(bar_tempty + 8u * i, kEpiWarps);
+        }
         mbar_fence_init();
     }
     if (warp == 2) tc_alloc(slot, a.tmem_cols);
@@ -96,124 +116,167 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % a.stages;
-                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
-                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-                mbar_expect_tx(bar_full + 8u * s, stage_bytes);
-                const int tap = kb / chunks, ch = kb - tap * chunks;
-                const int r = tap / a.kw, q = tap - r * a.kw;
-                const int ix0 = ox0 * a.stride - a.pad + q, iy0 = oy0 * a.stride - a.pad + r;
-                const bool first = ch < a.chunks1;
-                const CUtensorMap* m = first ? &tm_x1 : &tm_x2;
-                const int c0 = (first ? ch : ch - a.chunks1) * BK;
-                const uint32_t sa = base + (uint32_t)s * stage_bytes;
-                tma_load_5d(sa, m, bar_full + 8u * s, c0, ix0, iy0, img, 0);
-                tma_load_5d(sa + A_BYTES, m, bar_full + 8u * s, c0, ix0, iy0, img, 1);
-                tma_load_3d(sa + 2 * A_BYTES, &tm_w, bar_full + 8u * s, kb * BK, n0, 0);
-                tma_load_3d(sa + 2 * A_BYTES + b_bytes, &tm_w, bar_full + 8u * s, kb * BK, n0, 1);
+            uint32_t cnt = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+                const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
+                const int oy0 = (rem / a.tiles_x) * a.th, ox0 = (rem % a.tiles_x) * a.tw;
+                const int n0 = nt * a.bn;
+                for (int kb = 0; kb < KB; ++kb, ++cnt) {
+                    const uint32_t s = cnt % (uint32_t)a.stages;
+                    const uint32_t ph = (cnt / (uint32_t)a.stages) & 1u;
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    mbar_expect_tx(bar_full + 8u * s, stage_bytes);
+                    const int tap = kb / chunks, ch = kb - tap * chunks;
+                    const int r = tap / a.kw, q = tap - r * a.kw;
+                    const int ix0 = ox0 * a.stride - a.pad + q, iy0 = oy0 * a.stride - a.pad + r;
+                    const bool first = ch < a.chunks1;
+                    const CUtensorMap* m = first ? &tm_x1 : &tm_x2;
+                    const int c0 = (first ? ch : ch - a.chunks1) * BK;
+                    const uint32_t sa = base + s * stage_bytes;
+                    tma_load_5d(sa, m, bar_full + 8u * s, c0, ix0, iy0, img, 0);
+                    tma_load_5d(sa + A_BYTES, m, bar_full + 8u * s, c0, ix0, iy0, img, 1);
+                    tma_load_3d(sa + 2 * A_BYTES, &tm_w, bar_full + 8u * s, kb * BK, n0, 0);
+                    tma_load_3d(sa + 2 * A_BYTES + b_bytes, &tm_w, bar_full + 8u * s, kb * BK, n0, 1);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ===== MMA issuer
-            // Two MMAs per 16-deep K step instead of three: B_hi and B_lo are adjacent in the stage, so
+            // ===== MMA issuer.  Two MMAs per 16-deep K step: B_hi and B_lo are adjacent in the stage, so
             //   D[:, 0:2bn]  (+)= A_hi * [B_hi; B_lo]^T      (N = 2*bn: hi*hi | hi*lo)
             //   D[:, 0:bn]    += A_lo *  B_hi^T
-            // which reads A from shared memory twice instead of three times; the epilogue adds the two halves.
+            // (A is read from shared memory twice instead of three times; the epilogue adds the two halves.)
             const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * a.bn));
             const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)a.bn);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % a.stages;
-                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
-                mbar_wait(bar_full + 8u * s, ph);
+            uint32_t cnt = 0, it = 0;
+            bool ready = false;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+                mbar_wait(bar_tempty + 8u * as, aph ^ 1u);          // epilogue drained this accumulator stage
                 tc_fence_after();
-                const uint32_t sa = base + (uint32_t)s * stage_bytes;
+                const uint32_t d_tmem = tmem_base + as * (uint32_t)a.acc_stride;
+                for (int kb = 0; kb < KB; ++kb, ++cnt) {
+                    const uint32_t s = cnt % (uint32_t)a.stages;
+                    const uint32_t ph = (cnt / (uint32_t)a.stages) & 1u;
+                    if (!ready) mbar_wait(bar_full + 8u * s, ph);
+                    tc_fence_after();
+                    // poll the NEXT stage now: the round trip of the barrier read overlaps the MMA issue below
+                    const uint32_t s1 = (cnt + 1) % (uint32_t)a.stages;
+                    const uint32_t ph1 = ((cnt + 1) / (uint32_t)a.stages) & 1u;
+                    ready = mbar_try_wait(bar_full + 8u * s1, ph1);
+                    const uint32_t sa = base + s * stage_bytes;
+                    const uint64_t ah = umma_desc_kmajor(sa, ROW_BYTES);
+                    const uint64_t al = umma_desc_kmajor(sa + A_BYTES, ROW_BYTES);
+                    const uint64_t bh = umma_desc_kmajor(sa + 2 * A_BYTES, ROW_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t ah = umma_desc_kmajor(sa + k * 32, ROW_BYTES);
-                    const uint64_t al = umma_desc_kmajor(sa + A_BYTES + k * 32, ROW_BYTES);
-                    const uint64_t bh = umma_desc_kmajor(sa + 2 * A_BYTES + k * 32, ROW_BYTES);
-                    tc_mma_bf16(tmem_base, ah, bh, idesc2, (kb | k) != 0 ? 1u : 0u);
-                    tc_mma_bf16(tmem_base, al, bh, idesc1, 1u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advancing 16 elements (32 B) along K inside the swizzle atom = +2 in the 16-byte address field
+                        tc_mma_bf16(d_tmem, ah + 2 * k, bh + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_bf16(d_tmem, al + 2 * k, bh + 2 * k, idesc1, 1u);
+                    }
+                    tc_commit(bar_empty + 8u * s);      // frees the smem slot when these MMAs retire
                 }
-                tc_commit(bar_empty + 8u * s);      // frees the smem slot when these MMAs retire
+                tc_commit(bar_tfull + 8u * as);         // accumulator complete
             }
-            tc_commit(bar_tmem);                    // accumulator complete
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = accumulator row = output pixel
-        mbar_wait(bar_tmem, 0);
-        tc_fence_after();
-        const int wq = warp - 4;
+        // ===== epilogue: 8 warps; warp (4 + e) owns TMEM lane quadrant e % 4 (its hardware-accessible lanes) and
+        // the 32-column chunks with parity e / 4.  Thread = accumulator row = output pixel.
+        const int e = warp - 4;
+        const int wq = e & 3, half = e >> 2;
         const int row = wq * 32 + lane;
         const int ly = row / a.tw, lx = row - ly * a.tw;
-        const int oy = oy0 + ly, ox = ox0 + lx;
-        const bool valid = oy < a.Hout && ox < a.Wout;
-        const size_t pix = ((size_t)img * a.Hout + oy) * a.Wout + ox;
-        for (int j0 = 0; j0 < a.bn; j0 += 32) {
-            uint32_t v[32];
-            __syncwarp();                     // tcgen05.ld is .sync.aligned: reconverge after the masked stores
-            {
-                uint32_t u[32];
-                tc_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)j0, v);
-                tc_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a.bn + j0), u);
-                tc_wait_ld();
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+            const int nt = t % a.n_tiles, mt = t / a.n_tiles;
+            const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
+            const int oy = (rem / a.tiles_x) * a.th + ly, ox = (rem % a.tiles_x) * a.tw + lx;
+            const int n0 = nt * a.bn;
+            const bool valid = oy < a.Hout && ox < a.Wout;
+            const size_t pix = ((size_t)img * a.Hout + oy) * a.Wout + ox;
+            mbar_wait(bar_tfull + 8u * as, aph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + as * (uint32_t)a.acc_stride + ((uint32_t)(wq * 32) << 16);
+            const int nchunks = (a.bn + 31) / 32;
+            for (int c = half; c < nchunks; c += 2) {
+                const int j0 = c * 32;
+                uint32_t v[32];
+                __syncwarp();                     // tcgen05.ld is .sync.aligned: reconverge after the masked stores
+                {
+                    uint32_t u[32];
+                    tc_ld_32x32(t_row + (uint32_t)j0, v);
+                    tc_ld_32x32(t_row + (uint32_t)(a.bn + j0), u);
+                    tc_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+                }
+                if (c + 2 >= nchunks) {           // last TMEM read of this warp for this tile: release the stage
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8u * as);
+                }
+                const int nb = n0 + j0;
+                if (!valid || nb >= a.cout) continue;
+                if (a.epi == EPI_LINEAR) {
+                    const size_t o = pix * a.cout + nb;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (nb + g * 4 >= a.cout || j0 + g * 4 >= a.bn) break;
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
+                        float f[4] = {__uint_as_float(v[g * 4 + 0]) + b4.x, __uint_as_float(v[g * 4 + 1]) + b4.y,
+                                      __uint_as_float(v[g * 4 + 2]) + b4.z, __uint_as_float(v[g * 4 + 3]) + b4.w};
+                        if (a.res != nullptr) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.res + o + g * 4));
+                            f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) f[i] = fast_act(f[i], a.act);
+                        if (a.y != nullptr) *reinterpret_cast<float4*>(a.y + o + g * 4) = make_float4(f[0], f[1], f[2], f[3]);
+                        if (a.ys != nullptr) {
+                            __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) split_bf16(f[i], hi[i], lo[i]);
+                            *reinterpret_cast<uint2*>(a.ys + o + g * 4) = *reinterpret_cast<uint2*>(hi);
+                            *reinterpret_cast<uint2*>(a.ys + a.ys_plane + o + g * 4) = *reinterpret_cast<uint2*>(lo);
+                        }
+                    }
+                } else {   // EPI_LSTM: packed column = channel*4 + {in, remember, out, cell}
+                    const int C = a.cout >> 2;
+                    const size_t o = pix * C + (nb >> 2);
+                    const float4 cp0 = *reinterpret_cast<const float4*>(a.c_prev + o);
+                    const float4 cp1 = *reinterpret_cast<const float4*>(a.c_prev + o + 4);
+                    const float cprev[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
+                    float cn[8], hn[8];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
+                        const float ig = fast_sigmoid(__uint_as_float(v[g * 4 + 0]) + b4.x);
+                        const float fg = fast_sigmoid(__uint_as_float(v[g * 4 + 1]) + b4.y);
+                        const float og = fast_sigmoid(__uint_as_float(v[g * 4 + 2]) + b4.z);
+                        const float cg = fast_tanh(__uint_as_float(v[g * 4 + 3]) + b4.w);
+                        const float cell = __fadd_rn(__fmul_rn(fg, cprev[g]), __fmul_rn(ig, cg));
+                        cn[g] = cell;
+                        hn[g] = og * fast_tanh(cell);
+                    }
+                    *reinterpret_cast<float4*>(a.c_new + o) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    *reinterpret_cast<float4*>(a.c_new + o + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                    *reinterpret_cast<float4*>(a.h_new + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                    *reinterpret_cast<float4*>(a.h_new + o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                    if (a.hs_new != nullptr) {
+                        __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) split_bf16(hn[i], hi[i], lo[i]);
+                        *reinterpret_cast<uint4*>(a.hs_new + o) = *reinterpret_cast<uint4*>(hi);
+                        *reinterpret_cast<uint4*>(a.hs_new + a.hs_plane + o) = *reinterpret_cast<uint4*>(lo);
+                    }
+                }
             }
-            const int nb = n0 + j0;
-            if (!valid || nb >= a.cout) continue;
-            if (a.epi == EPI_LINEAR) {
-                const size_t o = pix * a.cout + nb;
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    if (nb + g * 4 >= a.cout || j0 + g * 4 >= a.bn) break;
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
-                    float f[4] = {__uint_as_float(v[g * 4 + 0]) + b4.x, __uint_as_float(v[g * 4 + 1]) + b4.y,
-                                  __uint_as_float(v[g * 4 + 2]) + b4.z, __uint_as_float(v[g * 4 + 3]) + b4.w};
-                    if (a.res != nullptr) {
-                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.res + o + g * 4));
-                        f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) f[e] = apply_act(f[e], a.act);
-                    if (a.y != nullptr) *reinterpret_cast<float4*>(a.y + o + g * 4) = make_float4(f[0], f[1], f[2], f[3]);
-                    if (a.ys != nullptr) {
-                        __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) split_bf16(f[e], hi[e], lo[e]);
-                        *reinterpret_cast<uint2*>(a.ys + o + g * 4) = *reinterpret_cast<uint2*>(hi);
-                        *reinterpret_cast<uint2*>(a.ys + a.ys_plane + o + g * 4) = *reinterpret_cast<uint2*>(lo);
-                    }
-                }
-            } else {   // EPI_LSTM: packed column = channel*4 + {in, remember, out, cell}
-                const int C = a.cout >> 2;
-                const int ch0 = nb >> 2;
-                const size_t o = pix * C + ch0;
-                float cn[8], hn[8];
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
-                    const float ig = sigmoidf_(__uint_as_float(v[g * 4 + 0]) + b4.x);
-                    const float fg = sigmoidf_(__uint_as_float(v[g * 4 + 1]) + b4.y);
-                    const float og = sigmoidf_(__uint_as_float(v[g * 4 + 2]) + b4.z);
-                    const float cg = tanhf(__uint_as_float(v[g * 4 + 3]) + b4.w);
-                    const float cell = __fadd_rn(__fmul_rn(fg, a.c_prev[o + g]), __fmul_rn(ig, cg));
-                    cn[g] = cell;
-                    hn[g] = og * tanhf(cell);
-                }
-                *reinterpret_cast<float4*>(a.c_new + o) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                *reinterpret_cast<float4*>(a.c_new + o + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-                *reinterpret_cast<float4*>(a.h_new + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                *reinterpret_cast<float4*>(a.h_new + o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-                if (a.hs_new != nullptr) {
-                    __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) split_bf16(hn[e], hi[e], lo[e]);
-                    *reinterpret_cast<uint4*>(a.hs_new + o) = *reinterpret_cast<uint4*>(hi);
-                    *reinterpret_cast<uint4*>(a.hs_new + a.hs_plane + o) = *reinterpret_cast<uint4*>(lo);
-                }
+            // a warp with no chunk of its parity (bn <= 32 and half == 1) still has to release the stage
+            if (half >= nchunks) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8u * as);
             }
         }
     }
@@ -328,7 +391,7 @@ int tc_plan_create(ConvParams& p) {
     a.N = p.N; a.Hout = p.Hout; a.Wout = p.Wout; a.stride = p.stride; a.pad = p.pad; a.kh = p.kh; a.kw = p.kw;
     a.th = th; a.tw = tw; a.tiles_x = ceil_div(p.Wout, tw); a.tiles_y = ceil_div(p.Hout, th);
     a.chunks1 = p.c1 / bk; a.chunks2 = p.c2 / bk;
-    a.bn = bn; a.cout = p.cout; a.epi = p.epi; a.act = p.act;
+    a.bn = bn; a.n_tiles = cout_pad / bn; a.m_tiles = (int)m_tiles; a.cout = p.cout; a.epi = p.epi; a.act = p.act;
     a.bias = p.bias; a.res = p.res; a.y = p.y; a.ys = p.ys;
     a.ys_plane = (long long)p.N * p.Hout * p.Wout * p.cout;
     a.c_prev = p.c_prev; a.c_new = p.c_new; a.h_new = p.h_new; a.hs_new = p.hs_new;
@@ -338,11 +401,15 @@ int tc_plan_create(ConvParams& p) {
     int stages = (int)((227 * 1024 - 2048) / stage_bytes);
     stages = std::max(2, std::min(stages, 6));
     a.stages = stages;
+    // per accumulator stage: [hi*hi + lo*hi | hi*lo] = 2*bn columns, read in 32-column windows (bn%32 tail -> pad)
+    a.acc_stride = (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;
     uint32_t cols = 32;
-    while ((int)cols < 2 * bn + 16) cols <<= 1;   // two accumulator halves (+ the 32-column read window past a bn%32 tail)
+    while ((int)cols < 2 * a.acc_stride) cols <<= 1;
+    EVK_REQUIRE(cols <= 512, EVK_ERR_ARG, "conv_tc: accumulator does not fit tensor memory (bn=%d)", bn);
     a.tmem_cols = cols;
     pl->smem = stages * stage_bytes + 1024 + 16 * stages + 64;
-    pl->grid = dim3(a.tiles_x * a.tiles_y * p.N, cout_pad / bn);
+    const long total_tiles = m_tiles * (cout_pad / bn);
+    pl->grid = dim3((unsigned)std::min<long>(total_tiles, kNumSMs));
     // activations: [plane, n, y, x, c]
     auto act_map = [&](CUtensorMap* m, const __nv_bfloat16* base, int C) -> int {
         const uint64_t dims[5] = {(uint64_t)C, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)p.N, 2};
@@ -379,9 +446,9 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
     EVK_REQUIRE(p.tc != nullptr, EVK_ERR_STATE, "conv_tc: no plan");
     const TcPlan& pl = *p.tc;
     if (pl.bk == 64)
-        conv_tc_kernel<64><<<pl.grid, 256, pl.smem, st>>>(pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a);
+        conv_tc_kernel<64><<<pl.grid, kTcThreads, pl.smem, st>>>(pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a);
     else
-        conv_tc_kernel<32><<<pl.grid, 256, pl.smem, st>>>(pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a);
+        conv_tc_kernel<32><<<pl.grid, kTcThreads, pl.smem, st>>>(pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }
