@@ -4,18 +4,32 @@
 // Reference semantics: model/submodules.py:8-35 (ConvLayer), :152-184 (ResidualBlock), :187-245 (ConvLSTM),
 // :69-97 (the 5x5 convolution of UpsampleConvLayer).  fp32 parity (1e-4, north_star) rules out single-pass
 // bf16/tf32 operands (2e-3 / 3e-4), so every operand travels as TWO bf16 planes (hi = bf16(v),
-// lo = bf16(v - hi)) and each K step issues three MMAs into the same TMEM accumulator:
+// lo = bf16(v - hi)) and each K step issues three products into the same TMEM accumulator:
 //     D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo          (error ~ 2^-16 relative; measured 4-6e-6 end to end)
 //
-// GEMM view: M = 128 output pixels (a TH x TW spatial patch of one image), N = BN output channels,
-// K = kh*kw*(c1+c2) walked as (tap, channel chunk of BK).  For one K block the A tile is the input patch
-// shifted by the tap offset: ONE tiled TMA load per plane from the 5-D tensor [plane, n, y, x, c] with
-// out-of-bounds zero fill doing the convolution's zero padding (and element strides doing stride 2), landing in
-// shared memory in the 128B-swizzled K-major layout tcgen05.mma consumes.  cat(x, h) is two tensor maps.
+// GEMM view: M = 128 output pixels of one image, N = BN output channels, K = kh*kw*(c1+c2).
 //
-// Warp roles (256 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (thread r owns accumulator row r = one output pixel).
+// The kernel is bound by the L2 -> shared-memory path (measured: the per-tap im2col re-load of round-1 v2 ran at
+// the chip's ~6.3 kB/clk TMA ceiling on every layer), so operand traffic is what the design minimises:
+//
+//  * A (activations), HALO BOXES.  The M tile is 8 pixels along an "atom" axis U by 16 pixels along a "shift" axis V
+//    (U = x, V = y or the transpose, whichever pads the layer less).  8 pixels x BK channels of bf16 are exactly one
+//    swizzle atom (8 rows of the K-major UMMA layout), so ONE tiled TMA load of the box [BK, 8, 16 + kV - 1]
+//    lands (16 + kV - 1) atoms in shared memory, and a kernel tap that shifts the window by j pixels along V is
+//    the SAME data read through a shared-memory descriptor that starts j atoms later -- no re-load.  Only the kU
+//    shifts along U need their own load: kU loads of (16+kV-1) atoms per channel chunk instead of kU*kV loads of
+//    16 atoms (5x5: 100 instead of 400 atoms; 3x3: 54 instead of 144).  Stride 2 = element strides in the box and
+//    one box per parity of the V tap.  Out-of-bounds zero fill is the convolution's zero padding.  cat(x, h) is
+//    two tensor maps.
+//  * B (weights), CLUSTER MULTICAST.  The CTAs of a thread-block cluster work on different M tiles of the same
+//    N tile; each loads 1/cs of the weight tile and multicasts it into every CTA's shared memory.
+//
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles): warp 0 = A producer, warp 3 = B producer,
+// warps 1-2 = MMA issuers (K blocks dealt alternately; warp 2 also allocates TMEM), warps 4-11 = epilogue (thread = accumulator row =
+// output pixel).  Two independent shared-memory rings (A: box stages, B: one tap per stage); the accumulator is
+// double-buffered in tensor memory so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -26,12 +40,20 @@ namespace evk {
 
 struct TcArgs {
     int N, Hout, Wout, stride, pad, kh, kw;
-    int th, tw, tiles_x, tiles_y;
+    int ux;                     // 1: U = x (tile 16 rows x 8 cols), 0: U = y (tile 8 rows x 16 cols)
+    int tiles_u, tiles_v;       // tiles per image along U (8 px) and V (16 px)
+    int ku, kv;                 // kernel extent along U and V
     int chunks1, chunks2;
     int bn, n_tiles, m_tiles, cout;
     int epi, act;
-    int stages;
-    int acc_stride;         // TMEM columns per accumulator stage
+    int a_stages, b_stages;
+    int ar;                     // atoms per A box
+    int n_groups;               // V-tap groups per (chunk, U shift): 1 (stride 1) or 2 (stride 2: even / odd taps)
+    int g_tap0[2], g_ntaps[2], g_step;
+    int cs;                     // cluster size (CTAs sharing one weight tile)
+    int issuers;                // MMA issuer warps (1 or 2); each has its own accumulator of acc_cols TMEM columns
+    int acc_cols;
+    int acc_stride;             // TMEM columns per accumulator stage (= issuers * acc_cols)
     uint32_t tmem_cols;
     const float* bias;
     const float* res;
@@ -39,6 +61,7 @@ struct TcArgs {
     __nv_bfloat16* ys; long long ys_plane;
     const float* c_prev; float* c_new; float* h_new;
     __nv_bfloat16* hs_new; long long hs_plane;
+    unsigned long long* dbg;    // EVK_TC_TIMING: per-CTA clock64 phase counters [grid][8], else nullptr
 };
 
 struct TcPlan {
@@ -49,11 +72,11 @@ struct TcPlan {
     size_t smem;
 };
 
-constexpr int kTcThreads = 384;      // 12 warps: TMA, MMA, TMEM alloc, (idle), 8 epilogue
+constexpr int kTcThreads = 384;      // 12 warps: A producer, MMA, TMEM alloc, B producer, 8 epilogue
 constexpr int kEpiWarps = 8;
 
 // sigmoid / tanh on the SFU (ex2.approx, rcp.approx): absolute error ~2e-7, far inside the 1e-4 parity budget
-__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 __device__ __forceinline__ float fast_act(float v, int act) {
     switch (act) {
@@ -64,31 +87,48 @@ __device__ __forceinline__ float fast_act(float v, int act) {
     }
 }
 
-// Persistent, warp-specialised: every CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  (N tile fastest
-// so CTAs that run concurrently share the activation patch in L2).  The smem ring (TMA -> MMA) runs continuously
-// across tiles; the accumulator is double-buffered in tensor memory so the epilogue of tile i overlaps the MMAs of
-// tile i+1.
-template <int BK>
+struct TileCoord { int nt, img, ou0, ov0; bool dummy; };
+
+__device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int st, int crank) {
+    TileCoord t;
+    t.nt = st % a.n_tiles;
+    int mt = (st / a.n_tiles) * a.cs + crank;
+    t.dummy = mt >= a.m_tiles;            // cluster padding: runs the pipeline (peers multicast into it), stores nothing
+    if (t.dummy) mt = a.m_tiles - 1;
+    const int per_img = a.tiles_u * a.tiles_v;
+    t.img = mt / per_img;
+    const int rem = mt - t.img * per_img;
+    t.ov0 = (rem / a.tiles_u) * 16;
+    t.ou0 = (rem % a.tiles_u) * 8;
+    return t;
+}
+
+template <int BK, bool DBG>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                const __grid_constant__ CUtensorMap tm_w, const TcArgs a) {
     constexpr uint32_t ROW_BYTES = BK * 2;
-    constexpr uint32_t A_BYTES = 128 * ROW_BYTES;
+    constexpr uint32_t ATOM = 8 * ROW_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_bytes = (uint32_t)a.bn * ROW_BYTES;
-    const uint32_t stage_bytes = 2 * A_BYTES + 2 * b_bytes;
-    const uint32_t bar_full = base + (uint32_t)a.stages * stage_bytes;
-    const uint32_t bar_empty = bar_full + 8u * a.stages;
-    const uint32_t bar_tfull = bar_empty + 8u * a.stages;     // [2] accumulator ready
+    const uint32_t a_plane = (uint32_t)a.ar * ATOM, a_stage = 2 * a_plane;
+    const uint32_t b_plane = (uint32_t)a.bn * ROW_BYTES, b_stage = 2 * b_plane;
+    const uint32_t smem_b = base + (uint32_t)a.a_stages * a_stage;
+    const uint32_t bar_fa = smem_b + (uint32_t)a.b_stages * b_stage;
+    const uint32_t bar_ea = bar_fa + 8u * a.a_stages;
+    const uint32_t bar_fb = bar_ea + 8u * a.a_stages;
+    const uint32_t bar_eb = bar_fb + 8u * a.b_stages;
+    const uint32_t bar_tfull = bar_eb + 8u * a.b_stages;      // [2] accumulator ready
     const uint32_t bar_tempty = bar_tfull + 16u;              // [2] accumulator drained by the epilogue
     const uint32_t slot = bar_tempty + 16u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cs = a.cs;
+    const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = blockIdx.x / cs, ncl = gridDim.x / cs;
     const int chunks = a.chunks1 + a.chunks2;
-    const int KB = a.kh * a.kw * chunks;
-    const int total_tiles = a.m_tiles * a.n_tiles;
-    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int n_super = a.n_tiles * ((a.m_tiles + cs - 1) / cs);
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x1);
@@ -96,89 +136,191 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         tma_prefetch_desc(&tm_w);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < a.stages; ++s) {
-            mbar_init(bar_full + 8u * s, 1);
-            mbar_init(bar_empty + 8u * s, 1);
+        for (int s = 0; s < a.a_stages; ++s) {
+            mbar_init(bar_fa + 8u * s, 1);
+            mbar_init(bar_ea + 8u * s, (uint32_t)a.issuers);      // every MMA issuer commits
+        }
+        for (int s = 0; s < a.b_stages; ++s) {
+            mbar_init(bar_fb + 8u * s, 1);
+            mbar_init(bar_eb + 8u * s, (uint32_t)cs);     // every CTA of the cluster must have consumed the slot
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_tfull + 8u * i, 1);
+            mbar_init(bar_tfull + 8u * i, (uint32_t)a.issuers);   // every MMA issuer commits
             mbar_init(bar_tempty + 8u * i, kEpiWarps);
         }
         mbar_fence_init();
     }
     if (warp == 2) tc_alloc(slot, a.tmem_cols);
     tc_fence_before();
-    __syncthreads();
+    if (cs > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
 
+    // The three single-issuer roles run their loops WARP-WIDE (all 32 lanes carry identical values) and predicate only
+    // the issuing instruction with elect.sync: inside an `if (lane == 0)` region ptxas cannot keep descriptors in
+    // uniform registers and wraps every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST waterfall loop (~100+ cycles
+    // each, measured: the tensor pipe ran at ~55% of its floor because of it).
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer
-            uint32_t cnt = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int nt = t % a.n_tiles, mt = t / a.n_tiles;
-                const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
-                const int oy0 = (rem / a.tiles_x) * a.th, ox0 = (rem % a.tiles_x) * a.tw;
-                const int n0 = nt * a.bn;
-                for (int kb = 0; kb < KB; ++kb, ++cnt) {
-                    const uint32_t s = cnt % (uint32_t)a.stages;
-                    const uint32_t ph = (cnt / (uint32_t)a.stages) & 1u;
-                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-                    mbar_expect_tx(bar_full + 8u * s, stage_bytes);
-                    const int tap = kb / chunks, ch = kb - tap * chunks;
-                    const int r = tap / a.kw, q = tap - r * a.kw;
-                    const int ix0 = ox0 * a.stride - a.pad + q, iy0 = oy0 * a.stride - a.pad + r;
-                    const bool first = ch < a.chunks1;
-                    const CUtensorMap* m = first ? &tm_x1 : &tm_x2;
-                    const int c0 = (first ? ch : ch - a.chunks1) * BK;
-                    const uint32_t sa = base + s * stage_bytes;
-                    tma_load_5d(sa, m, bar_full + 8u * s, c0, ix0, iy0, img, 0);
-                    tma_load_5d(sa + A_BYTES, m, bar_full + 8u * s, c0, ix0, iy0, img, 1);
-                    tma_load_3d(sa + 2 * A_BYTES, &tm_w, bar_full + 8u * s, kb * BK, n0, 0);
-                    tma_load_3d(sa + 2 * A_BYTES + b_bytes, &tm_w, bar_full + 8u * s, kb * BK, n0, 1);
-                }
+        // ===== A producer: one halo box (both planes) per (channel chunk, U shift, V-tap group)
+        uint32_t s = 0, ph = 0;
+        long long w_ea = 0;
+        for (int st = cid; st < n_super; st += ncl) {
+            const TileCoord t = tile_coord(a, st, crank);
+            for (int ch = 0; ch < chunks; ++ch) {
+                const bool first = ch < a.chunks1;
+                const CUtensorMap* m = first ? &tm_x1 : &tm_x2;
+                const int c0 = (first ? ch : ch - a.chunks1) * BK;
+                for (int su = 0; su < a.ku; ++su)
+                    for (int g = 0; g < a.n_groups; ++g) {
+                        const long long t0 = DBG ? clock64() : 0;
+                        mbar_wait(bar_ea + 8u * s, ph ^ 1u);
+                        if (DBG) w_ea += clock64() - t0;
+                        const int iu0 = t.ou0 * a.stride - a.pad + su;
+                        const int iv0 = t.ov0 * a.stride - a.pad + a.g_tap0[g];
+                        const uint32_t sa = base + s * a_stage;
+                        if (elect_one()) {
+                            mbar_expect_tx(bar_fa + 8u * s, a_stage);
+                            tma_load_5d(sa, m, bar_fa + 8u * s, c0, iu0, iv0, t.img, 0);
+                            tma_load_5d(sa + a_plane, m, bar_fa + 8u * s, c0, iu0, iv0, t.img, 1);
+                        }
+                        __syncwarp();
+                        if (++s == (uint32_t)a.a_stages) { s = 0; ph ^= 1u; }
+                    }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer.  Two MMAs per 16-deep K step: B_hi and B_lo are adjacent in the stage, so
-            //   D[:, 0:2bn]  (+)= A_hi * [B_hi; B_lo]^T      (N = 2*bn: hi*hi | hi*lo)
-            //   D[:, 0:bn]    += A_lo *  B_hi^T
-            // (A is read from shared memory twice instead of three times; the epilogue adds the two halves.)
-            const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * a.bn));
-            const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)a.bn);
-            uint32_t cnt = 0, it = 0;
-            bool ready = false;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-                const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-                mbar_wait(bar_tempty + 8u * as, aph ^ 1u);          // epilogue drained this accumulator stage
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * (uint32_t)a.acc_stride;
-                for (int kb = 0; kb < KB; ++kb, ++cnt) {
-                    const uint32_t s = cnt % (uint32_t)a.stages;
-                    const uint32_t ph = (cnt / (uint32_t)a.stages) & 1u;
-                    if (!ready) mbar_wait(bar_full + 8u * s, ph);
-                    tc_fence_after();
-                    // poll the NEXT stage now: the round trip of the barrier read overlaps the MMA issue below
-                    const uint32_t s1 = (cnt + 1) % (uint32_t)a.stages;
-                    const uint32_t ph1 = ((cnt + 1) / (uint32_t)a.stages) & 1u;
-                    ready = mbar_try_wait(bar_full + 8u * s1, ph1);
-                    const uint32_t sa = base + s * stage_bytes;
-                    const uint64_t ah = umma_desc_kmajor(sa, ROW_BYTES);
-                    const uint64_t al = umma_desc_kmajor(sa + A_BYTES, ROW_BYTES);
-                    const uint64_t bh = umma_desc_kmajor(sa + 2 * A_BYTES, ROW_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advancing 16 elements (32 B) along K inside the swizzle atom = +2 in the 16-byte address field
-                        tc_mma_bf16(d_tmem, ah + 2 * k, bh + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
-                        tc_mma_bf16(d_tmem, al + 2 * k, bh + 2 * k, idesc1, 1u);
-                    }
-                    tc_commit(bar_empty + 8u * s);      // frees the smem slot when these MMAs retire
-                }
-                tc_commit(bar_tfull + 8u * as);         // accumulator complete
+        if (DBG && lane == 0) a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)w_ea;
+    } else if (warp == 3) {
+        // ===== B producer: one tap x BK channels of the weight tile per stage; with a cluster every CTA loads
+        // 1/cs of the rows and multicasts them to all CTAs (same smem offset, same barrier offset everywhere)
+        const int bnp = a.bn / cs;
+        const int ctot = chunks * BK;
+        uint32_t s = 0, ph = 0;
+        long long w_eb = 0;
+        for (int st = cid; st < n_super; st += ncl) {
+            const TileCoord t = tile_coord(a, st, crank);
+            const int row0 = t.nt * a.bn + crank * bnp;
+            for (int ch = 0; ch < chunks; ++ch)
+                for (int su = 0; su < a.ku; ++su)
+                    for (int g = 0; g < a.n_groups; ++g)
+                        for (int j = 0; j < a.g_ntaps[g]; ++j) {
+                            const long long t0 = DBG ? clock64() : 0;
+                            mbar_wait(bar_eb + 8u * s, ph ^ 1u);
+                            if (DBG) w_eb += clock64() - t0;
+                            const int tv = a.g_tap0[g] + j * a.g_step;
+                            const int tap = a.ux ? tv * a.kw + su : su * a.kw + tv;
+                            const int k0 = tap * ctot + ch * BK;
+                            const uint32_t sb = smem_b + s * b_stage + (uint32_t)(crank * bnp) * ROW_BYTES;
+                            if (elect_one()) {
+                                mbar_expect_tx(bar_fb + 8u * s, b_stage);
+                                if (cs > 1) {
+                                    tma_load_3d_mc(sb, &tm_w, bar_fb + 8u * s, k0, row0, 0, cmask);
+                                    tma_load_3d_mc(sb + b_plane, &tm_w, bar_fb + 8u * s, k0, row0, 1, cmask);
+                                } else {
+                                    tma_load_3d(sb, &tm_w, bar_fb + 8u * s, k0, row0, 0);
+                                    tma_load_3d(sb + b_plane, &tm_w, bar_fb + 8u * s, k0, row0, 1);
+                                }
+                            }
+                            __syncwarp();
+                            if (++s == (uint32_t)a.b_stages) { s = 0; ph ^= 1u; }
+                        }
+        }
+        if (DBG && lane == 0) a.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_eb;
+        // tail: every arrive the peers send to this CTA's empty barriers must land before the CTA exits
+        if (cs > 1) {
+            for (int i = 0; i < a.b_stages; ++i) {       // = the waits of b_stages more (virtual) uses: the previous use of
+                mbar_wait(bar_eb + 8u * s, ph ^ 1u);     //   every slot has been consumed by every CTA of the cluster
+                if (++s == (uint32_t)a.b_stages) { s = 0; ph ^= 1u; }
             }
+        }
+    } else if (warp == 1 || (warp == 2 && a.issuers == 2)) {
+        // ===== MMA issuers (one elected thread per warp).  Per 16-deep K slice two MMAs: B_hi and B_lo are adjacent in
+        // the stage, so
+        //   D[:, 0:2bn]  (+)= A_hi * [B_hi; B_lo]^T      (N = 2*bn: hi*hi | hi*lo)
+        //   D[:, 0:bn]    += A_lo *  B_hi^T
+        // (A is read from shared memory twice instead of three times; the epilogue adds the two halves.)
+        //
+        // Why (up to) two issuers: tcgen05.mma issue is back-pressured -- the issuing thread runs at most ~1-2 MMAs
+        // ahead of the tensor pipe -- so everything a single issuer does between two K blocks (commit, mbarrier poll
+        // ~100 cycles even when complete, descriptors, elect, R2UR) is a pipe bubble: measured 198 / 178 cycles per K
+        // slice at bn = 64 / 32 against a pipe floor of 112 / 94 (tools/microbench/mma_loop_bench.cu).  With the K
+        // blocks of a tile dealt alternately to two issuers, one issuer's inter-block work hides behind the other's
+        // eight MMAs (134 / 122).  Each issuer accumulates into its OWN tensor-memory accumulator (summed by the
+        // epilogue): the interleaving of the two instruction streams in the pipe is timing dependent, and with a
+        // shared accumulator the fp32 summation order -- hence the result bits -- would change from run to run.
+        // bn = 128 keeps one issuer: two accumulators would not fit tensor memory next to the epilogue's double
+        // buffer, and that shape is bound by shared-memory bandwidth, not by issue.
+        const uint32_t role = (uint32_t)(warp - 1);
+        const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * a.bn));
+        const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)a.bn);
+        const uint32_t desc_hi = (uint32_t)(umma_desc_kmajor(0, ROW_BYTES) >> 32);
+        auto mk = [&](uint32_t lo) -> uint64_t { return ((uint64_t)desc_hi << 32) | lo; };
+        auto lo_of = [](uint32_t addr) -> uint32_t { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+        const uint32_t atom16 = ATOM >> 4, a_plane16 = a_plane >> 4;
+        const uint32_t nbs = (uint32_t)a.b_stages;
+        const uint32_t two = a.issuers == 2 ? 1u : 0u;
+        uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0;
+        bool b_ready = false;
+        long long w_te = 0, w_fa = 0, w_fb = 0;
+        const long long t_begin = DBG ? clock64() : 0;
+        for (int st = cid; st < n_super; st += ncl, ++it) {
+            const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+            long long t0 = DBG ? clock64() : 0;
+            mbar_wait(bar_tempty + 8u * as, aph ^ 1u);          // epilogue drained this accumulator stage
+            if (DBG) w_te += clock64() - t0;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * (uint32_t)a.acc_stride + role * (uint32_t)a.acc_cols;
+            uint32_t blk = 0;
+            b_ready = false;      // the poll below looks `issuers` blocks ahead WITHIN a tile; across tiles the distance differs
+            for (int ch = 0; ch < chunks; ++ch)
+                for (int su = 0; su < a.ku; ++su)
+                    for (int g = 0; g < a.n_groups; ++g) {
+                        const int nt_g = a.g_ntaps[g];
+                        uint32_t ah_lo = lo_of(base + sA * a_stage);
+                        t0 = DBG ? clock64() : 0;
+                        mbar_wait(bar_fa + 8u * sA, phA);
+                        if (DBG) w_fa += clock64() - t0;
+                        for (int j = 0; j < nt_g; ++j, ++blk) {
+                            if (two == 0u || (blk & 1u) == role) {
+                                const uint32_t bh_lo = lo_of(smem_b + sB * b_stage);
+                                const uint32_t bar_free = bar_eb + 8u * sB;
+                                if (!b_ready) {
+                                    t0 = DBG ? clock64() : 0;
+                                    mbar_wait(bar_fb + 8u * sB, phB);
+                                    if (DBG) w_fb += clock64() - t0;
+                                }
+                                tc_fence_after();
+                                // this issuer's NEXT block: poll its barrier now, the round trip hides behind the issue
+                                uint32_t s2 = sB + 1u + two, ph2 = phB;
+                                if (s2 >= nbs) { s2 -= nbs; ph2 ^= 1u; }
+                                b_ready = mbar_try_wait(bar_fb + 8u * s2, ph2);
+                                if (elect_one()) {
+#pragma unroll
+                                    for (int k = 0; k < BK / 16; ++k) {
+                                        // +16 elements (32 B) along K inside the swizzle atom = +2 in the 16-byte address field
+                                        tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, (k == 0 && blk == role) ? 0u : 1u);
+                                        tc_mma_bf16(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + 2 * k), idesc1, 1u);
+                                    }
+                                    // frees the weight slot in every CTA of the cluster when these MMAs retire
+                                    if (cs > 1) tc_commit_mc(bar_free, cmask); else tc_commit(bar_free);
+                                }
+                                __syncwarp();
+                            }
+                            if (++sB == nbs) { sB = 0; phB ^= 1u; }
+                            ah_lo += atom16;
+                        }
+                        if (elect_one()) tc_commit(bar_ea + 8u * sA);       // `issuers` arrivals free the activation stage
+                        __syncwarp();
+                        if (++sA == (uint32_t)a.a_stages) { sA = 0; phA ^= 1u; }
+                    }
+            if (elect_one()) tc_commit(bar_tfull + 8u * as);         // `issuers` arrivals: accumulator complete
+            __syncwarp();
+        }
+        if (DBG && lane == 0 && role == 0) {
+            a.dbg[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_begin);
+            a.dbg[blockIdx.x * 8 + 1] = (unsigned long long)w_te;
+            a.dbg[blockIdx.x * 8 + 2] = (unsigned long long)w_fa;
+            a.dbg[blockIdx.x * 8 + 3] = (unsigned long long)w_fb;
         }
     } else if (warp >= 4) {
         // ===== epilogue: 8 warps; warp (4 + e) owns TMEM lane quadrant e % 4 (its hardware-accessible lanes) and
@@ -186,17 +328,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const int e = warp - 4;
         const int wq = e & 3, half = e >> 2;
         const int row = wq * 32 + lane;
-        const int ly = row / a.tw, lx = row - ly * a.tw;
+        const int lu = row & 7, lv = row >> 3;
         uint32_t it = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        long long w_tf = 0;
+        const long long e_begin = DBG ? clock64() : 0;
+        for (int st = cid; st < n_super; st += ncl, ++it) {
             const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-            const int nt = t % a.n_tiles, mt = t / a.n_tiles;
-            const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
-            const int oy = (rem / a.tiles_x) * a.th + ly, ox = (rem % a.tiles_x) * a.tw + lx;
-            const int n0 = nt * a.bn;
-            const bool valid = oy < a.Hout && ox < a.Wout;
-            const size_t pix = ((size_t)img * a.Hout + oy) * a.Wout + ox;
+            const TileCoord t = tile_coord(a, st, crank);
+            const int oy = a.ux ? t.ov0 + lv : t.ou0 + lu;
+            const int ox = a.ux ? t.ou0 + lu : t.ov0 + lv;
+            const int n0 = t.nt * a.bn;
+            const bool valid = !t.dummy && oy < a.Hout && ox < a.Wout;
+            const size_t pix = ((size_t)t.img * a.Hout + oy) * a.Wout + ox;
+            const long long t0 = DBG ? clock64() : 0;
             mbar_wait(bar_tfull + 8u * as, aph);
+            if (DBG) w_tf += clock64() - t0;
             tc_fence_after();
             const uint32_t t_row = tmem_base + as * (uint32_t)a.acc_stride + ((uint32_t)(wq * 32) << 16);
             const int nchunks = (a.bn + 31) / 32;
@@ -211,6 +357,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     tc_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+                    if (a.issuers == 2) {             // second issuer's accumulator (fixed order: deterministic bits)
+                        uint32_t w[32];
+                        tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + j0), u);
+                        tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + a.bn + j0), w);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            v[i] = __float_as_uint(__uint_as_float(v[i]) + (__uint_as_float(u[i]) + __uint_as_float(w[i])));
+                    }
                 }
                 if (c + 2 >= nchunks) {           // last TMEM read of this warp for this tile: release the stage
                     tc_fence_before();
@@ -279,6 +434,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                 if (lane == 0) mbar_arrive(bar_tempty + 8u * as);
             }
         }
+        if (DBG && e == 0 && lane == 0) {
+            a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - e_begin);
+            a.dbg[blockIdx.x * 8 + 7] = (unsigned long long)w_tf;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -337,22 +496,33 @@ bool tc_eligible(const ConvParams& p) {
     return true;
 }
 
-// N tile: the divisor of cout_pad (multiple of 16, <= 128 so that [B_hi; B_lo] is one N <= 256 operand) that
-// minimises  waves(CTAs / 148) * (fixed per-CTA cost + K steps * cycles per step), cycles per 16-deep K step from
-// the tcgen05 floor (128*N/256) and the 128 B/clk shared-memory operand read.
-static int pick_bn(int cout_pad, long m_tiles, long k16_steps, int granule) {
-    int best = 0;
-    double best_cost = 0.0;
-    for (int bn = 128; bn >= 16; bn -= 16) {
-        if (cout_pad % bn != 0 || bn % granule != 0) continue;
-        const double mma1 = std::max((double)bn, 32.0 + bn / 2.0);          // N = 2*bn
-        const double mma2 = std::max(bn / 2.0, 32.0 + bn / 4.0);            // N = bn
-        const double per_cta = 8000.0 + (double)k16_steps * (mma1 + mma2) + 40.0 * bn;
-        const long ctas = m_tiles * (cout_pad / bn);
-        const double cost = (double)((ctas + kNumSMs - 1) / kNumSMs) * per_cta;
-        if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
-    }
-    return best;
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
+// Cost model (cycles) of one layer for a candidate (orientation, N tile, cluster size): waves of co-resident CTAs x
+// per-tile cost, the per-tile cost being the larger of the tcgen05 issue time (floor 128*N/256 per MMA, and the
+// 128 B/clk shared-memory operand read) and the tile's share of the chip-wide L2 -> SM path (~42 B/clk/SM with every
+// SM loading).  EVK_TC_BN / EVK_TC_CS / EVK_TC_UX override the choice (experiments).
+struct TcChoice { int ux, bn, cs; double cost; };
+
+static double tile_cost(int bk, int ku, int kv, int stride, int chunks, int bn, int cs, long ctas, int* ar_out) {
+    const int ngroups = stride == 2 ? 2 : 1;
+    const int max_taps = stride == 2 ? (kv + 1) / 2 : kv;
+    const int ar = 16 + max_taps - 1;
+    if (ar_out) *ar_out = ar;
+    const double k16 = (double)chunks * ku * kv * (bk / 16);
+    const double a_rd = 32.0;                                                 // 128 rows x 32 B per MMA at 128 B/clk
+    const double mma1 = std::max((double)bn, a_rd + bn / 2.0);                // N = 2*bn
+    const double mma2 = std::max(bn / 2.0, a_rd + bn / 4.0);                  // N = bn
+    const double t_mma = k16 * (mma1 + mma2);
+    const double a_bytes = (double)chunks * ku * ngroups * 2.0 * ar * 8 * bk * 2;
+    const double b_bytes = (double)chunks * ku * kv * 2.0 * bn * bk * 2 / cs;
+    const double active = (double)std::min<long>(ctas, kNumSMs);
+    const double t_l2 = (a_bytes + b_bytes) * active / 6300.0;                // chip-wide ceiling shared by the active SMs
+    const double t_epi = 60.0 * bn;
+    return 6000.0 + std::max(std::max(t_mma, t_l2), t_epi);
 }
 
 void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out) {
@@ -367,56 +537,128 @@ void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vect
         }
 }
 
+template <int BK>
+static int max_clusters(int cs, size_t smem) {
+    auto kern = conv_tc_kernel<BK, false>;
+    if (cs <= 1) return kNumSMs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(kNumSMs / cs * cs));
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 int tc_plan_create(ConvParams& p) {
     EVK_REQUIRE(tc_eligible(p), EVK_ERR_ARG, "conv_tc: shape not eligible for the tensor-core path");
     EVK_REQUIRE(p.x1s && p.w_tc && (p.c2 == 0 || p.x2s), EVK_ERR_ARG, "conv_tc: split operands missing");
     const int bk = pick_bk(p);
     const int cout_pad = p.cout_pad;
     EVK_REQUIRE(cout_pad >= p.cout && cout_pad % 16 == 0, EVK_ERR_ARG, "conv_tc: cout_pad=%d must be a multiple of 16 >= cout", cout_pad);
-    // spatial M tile: 128 pixels, least padded area
-    const int cand[4][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}};
-    int th = 8, tw = 16;
-    long best = -1;
-    for (auto& c : cand) {
-        if ((c[1] - 1) * p.stride + 1 > 256) continue;
-        const long area = (long)ceil_div(p.Hout, c[0]) * c[0] * ceil_div(p.Wout, c[1]) * c[1];
-        if (best < 0 || area < best) { best = area; th = c[0]; tw = c[1]; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        const void* kerns[4] = {(const void*)conv_tc_kernel<64, false>, (const void*)conv_tc_kernel<32, false>,
+                                (const void*)conv_tc_kernel<64, true>, (const void*)conv_tc_kernel<32, true>};
+        for (const void* k : kerns) {
+            EVK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            EVK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
+        attr_set = true;
     }
-    const long m_tiles = (long)ceil_div(p.Hout, th) * ceil_div(p.Wout, tw) * p.N;
-    const int bn = pick_bn(cout_pad, m_tiles, (long)p.kh * p.kw * (p.c1 + p.c2) / 16, p.epi == EPI_LSTM ? 32 : 16);
-    EVK_REQUIRE(bn >= 16, EVK_ERR_ARG, "conv_tc: no N tile for cout_pad=%d", cout_pad);
+    const int chunks = (p.c1 + p.c2) / bk;
+    const int granule = p.epi == EPI_LSTM ? 32 : 16;
+    const int f_bn = env_int("EVK_TC_BN", 0), f_cs = env_int("EVK_TC_CS", 0), f_ux = env_int("EVK_TC_UX", -1);
+    TcChoice best = {1, 0, 1, 0.0};
+    for (int ux = 0; ux < 2; ++ux) {
+        if (f_ux >= 0 && ux != f_ux) continue;
+        const int hu = ux ? p.Wout : p.Hout, hv = ux ? p.Hout : p.Wout;
+        const long m_tiles = (long)ceil_div(hu, 8) * ceil_div(hv, 16) * p.N;
+        const int ku = ux ? p.kw : p.kh, kv = ux ? p.kh : p.kw;
+        for (int bn = 128; bn >= 16; bn -= 16) {
+            if (cout_pad % bn != 0 || bn % granule != 0) continue;
+            if (f_bn > 0 && bn != f_bn && cout_pad % f_bn == 0 && f_bn % granule == 0) continue;
+            for (int cs = 1; cs <= 4; cs *= 2) {
+                if ((bn / cs) % 8 != 0 || bn % cs != 0) continue;
+                if (f_cs > 0 && cs != f_cs && (bn / f_cs) % 8 == 0 && f_cs <= 4) continue;
+                const long n_super = (long)(cout_pad / bn) * ((m_tiles + cs - 1) / cs);
+                const long ctas = n_super * cs;
+                const long slots = (long)(kNumSMs / cs) * cs;
+                const long waves = (ctas + slots - 1) / slots;
+                const double cost = (double)waves * tile_cost(bk, ku, kv, p.stride, chunks, bn, cs, ctas, nullptr);
+                if (best.bn == 0 || cost < best.cost) best = {ux, bn, cs, cost};
+            }
+        }
+    }
+    EVK_REQUIRE(best.bn >= 16, EVK_ERR_ARG, "conv_tc: no N tile for cout_pad=%d", cout_pad);
+    const int ux = best.ux, bn = best.bn;
+    int cs = best.cs;
     TcPlan* pl = new TcPlan();
     pl->bk = bk;
     TcArgs& a = pl->a;
     a.N = p.N; a.Hout = p.Hout; a.Wout = p.Wout; a.stride = p.stride; a.pad = p.pad; a.kh = p.kh; a.kw = p.kw;
-    a.th = th; a.tw = tw; a.tiles_x = ceil_div(p.Wout, tw); a.tiles_y = ceil_div(p.Hout, th);
+    a.ux = ux;
+    a.tiles_u = ceil_div(ux ? p.Wout : p.Hout, 8);
+    a.tiles_v = ceil_div(ux ? p.Hout : p.Wout, 16);
+    a.ku = ux ? p.kw : p.kh; a.kv = ux ? p.kh : p.kw;
     a.chunks1 = p.c1 / bk; a.chunks2 = p.c2 / bk;
-    a.bn = bn; a.n_tiles = cout_pad / bn; a.m_tiles = (int)m_tiles; a.cout = p.cout; a.epi = p.epi; a.act = p.act;
+    a.bn = bn; a.n_tiles = cout_pad / bn; a.m_tiles = a.tiles_u * a.tiles_v * p.N; a.cout = p.cout; a.epi = p.epi; a.act = p.act;
+    if (p.stride == 2) {
+        a.n_groups = a.kv > 1 ? 2 : 1; a.g_step = 2;
+        a.g_tap0[0] = 0; a.g_ntaps[0] = (a.kv + 1) / 2;
+        a.g_tap0[1] = 1; a.g_ntaps[1] = a.kv / 2;
+    } else {
+        a.n_groups = 1; a.g_step = 1;
+        a.g_tap0[0] = 0; a.g_ntaps[0] = a.kv;
+        a.g_tap0[1] = 0; a.g_ntaps[1] = 0;
+    }
+    a.ar = 16 + a.g_ntaps[0] - 1;
     a.bias = p.bias; a.res = p.res; a.y = p.y; a.ys = p.ys;
     a.ys_plane = (long long)p.N * p.Hout * p.Wout * p.cout;
     a.c_prev = p.c_prev; a.c_new = p.c_new; a.h_new = p.h_new; a.hs_new = p.hs_new;
     a.hs_plane = (long long)p.N * p.Hout * p.Wout * (p.cout / 4);
+    a.dbg = nullptr;
     const uint32_t row_bytes = bk * 2;
-    const size_t stage_bytes = 2 * (size_t)128 * row_bytes + 2 * (size_t)bn * row_bytes;
-    int stages = (int)((227 * 1024 - 2048) / stage_bytes);
-    stages = std::max(2, std::min(stages, 6));
-    a.stages = stages;
+    const size_t a_stage = 2 * (size_t)a.ar * 8 * row_bytes;
+    const size_t b_stage = 2 * (size_t)bn * row_bytes;
+    const size_t budget = 227 * 1024 - 1024 - 512;
+    int as = 3, bs = (int)((budget - std::min(budget, as * a_stage)) / b_stage);
+    if (bs < 4) { as = 2; bs = (int)((budget - as * a_stage) / b_stage); }
+    bs = std::min(bs, 8);
+    if (bs < 2) { delete pl; EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: tile does not fit shared memory (bn=%d)", bn); }
+    a.a_stages = as; a.b_stages = bs;
     // per accumulator stage: [hi*hi + lo*hi | hi*lo] = 2*bn columns, read in 32-column windows (bn%32 tail -> pad)
-    a.acc_stride = (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;
+    a.acc_cols = (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;
+    const int kb = (a.chunks1 + a.chunks2) * p.kh * p.kw;
+    a.issuers = (4 * a.acc_cols <= 512 && kb >= 2 && env_int("EVK_TC_ISSUERS", 2) == 2) ? 2 : 1;
+    a.acc_stride = a.issuers * a.acc_cols;
     uint32_t cols = 32;
     while ((int)cols < 2 * a.acc_stride) cols <<= 1;
-    EVK_REQUIRE(cols <= 512, EVK_ERR_ARG, "conv_tc: accumulator does not fit tensor memory (bn=%d)", bn);
+    if (cols > 512) { delete pl; EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: accumulator does not fit tensor memory (bn=%d)", bn); }
     a.tmem_cols = cols;
-    pl->smem = stages * stage_bytes + 1024 + 16 * stages + 64;
-    const long total_tiles = m_tiles * (cout_pad / bn);
-    pl->grid = dim3((unsigned)std::min<long>(total_tiles, kNumSMs));
-    // activations: [plane, n, y, x, c]
+    pl->smem = as * a_stage + bs * b_stage + 1024 + 16 * (as + bs) + 64;
+    int ncl = bk == 64 ? max_clusters<64>(cs, pl->smem) : max_clusters<32>(cs, pl->smem);
+    if (ncl == 0 && cs > 1) {          // clusters of this size cannot be scheduled: fall back to independent CTAs
+        cs = 1; ncl = kNumSMs;
+    }
+    a.cs = cs;
+    const long n_super = (long)a.n_tiles * ((a.m_tiles + cs - 1) / cs);
+    pl->grid = dim3((unsigned)(std::min<long>(n_super, ncl) * cs));
+    // activations: [plane, n, V, U, c] (U = atom axis, V = shift axis)
+    const int s = p.stride;
     auto act_map = [&](CUtensorMap* m, const __nv_bfloat16* base, int C) -> int {
-        const uint64_t dims[5] = {(uint64_t)C, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)p.N, 2};
-        const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)p.Win * C * 2, (uint64_t)p.Hin * p.Win * C * 2,
-                                 (uint64_t)p.N * p.Hin * p.Win * C * 2};
-        const uint32_t box[5] = {(uint32_t)bk, (uint32_t)((tw - 1) * p.stride + 1), (uint32_t)((th - 1) * p.stride + 1), 1, 1};
-        const uint32_t es[5] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1, 1};
+        const uint64_t sx = (uint64_t)C * 2, sy = (uint64_t)p.Win * C * 2;
+        const uint64_t dims[5] = {(uint64_t)C, (uint64_t)(ux ? p.Win : p.Hin), (uint64_t)(ux ? p.Hin : p.Win), (uint64_t)p.N, 2};
+        const uint64_t str[4] = {ux ? sx : sy, ux ? sy : sx, (uint64_t)p.Hin * p.Win * C * 2, (uint64_t)p.N * p.Hin * p.Win * C * 2};
+        const uint32_t box[5] = {(uint32_t)bk, (uint32_t)(7 * s + 1), (uint32_t)((a.ar - 1) * s + 1), 1, 1};
+        const uint32_t es[5] = {1, (uint32_t)s, (uint32_t)s, 1, 1};
         return encode_tmap_bf16(m, base, 5, dims, str, box, es, (int)row_bytes);
     };
     int r = act_map(&pl->tm_x1, p.x1s, p.c1);
@@ -425,31 +667,76 @@ int tc_plan_create(ConvParams& p) {
         const uint64_t K = (uint64_t)p.kh * p.kw * (p.c1 + p.c2);
         const uint64_t dims[3] = {K, (uint64_t)cout_pad, 2};
         const uint64_t str[2] = {K * 2, (uint64_t)cout_pad * K * 2};
-        const uint32_t box[3] = {(uint32_t)bk, (uint32_t)bn, 1};
+        const uint32_t box[3] = {(uint32_t)bk, (uint32_t)(bn / cs), 1};
         const uint32_t es[3] = {1, 1, 1};
         r = encode_tmap_bf16(&pl->tm_w, p.w_tc, 3, dims, str, box, es, (int)row_bytes);
     }
     if (r != EVK_OK) { delete pl; return r; }
-    static bool attr_set = false;
-    if (!attr_set) {
-        EVK_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        EVK_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    if (env_int("EVK_TC_VERBOSE", 0))
+        fprintf(stderr, "conv_tc plan: %dx%d s%d %d+%d->%d @%dx%dx%d  ux=%d bn=%d cs=%d issuers=%d stages A%d/B%d ar=%d grid=%u smem=%zu\n", p.kh, p.kw,
+                p.stride, p.c1, p.c2, p.cout, p.N, p.Hout, p.Wout, ux, bn, cs, a.issuers, as, bs, a.ar, pl->grid.x, pl->smem);
     p.tc = pl;
     return EVK_OK;
 }
 
 void tc_plan_destroy(TcPlan* plan) { delete plan; }
 
+// EVK_TC_TIMING=1 (eager launches only, e.g. evk_model_profile): per-CTA clock64 phase counters, averaged and printed
+static int launch_conv_tc_timed(const ConvParams& p, cudaStream_t st);
+
 int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
     EVK_REQUIRE(p.tc != nullptr, EVK_ERR_STATE, "conv_tc: no plan");
+    static const int timing = env_int("EVK_TC_TIMING", 0);
+    if (timing && p.tc->a.dbg == nullptr) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (cap == cudaStreamCaptureStatusNone) return launch_conv_tc_timed(p, st);
+    }
     const TcPlan& pl = *p.tc;
-    if (pl.bk == 64)
-        conv_tc_kernel<64><<<pl.grid, kTcThreads, pl.smem, st>>>(pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a);
-    else
-        conv_tc_kernel<32><<<pl.grid, kTcThreads, pl.smem, st>>>(pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a);
-    EVK_CHECK_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = pl.grid;
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)pl.a.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = pl.a.cs > 1 ? 1 : 0;
+    const bool dbg = pl.a.dbg != nullptr;
+    if (pl.bk == 64) {
+        if (dbg) EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, true>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
+        else EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
+    } else {
+        if (dbg) EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, true>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
+        else EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, false>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
+    }
+    return EVK_OK;
+}
+
+static int launch_conv_tc_timed(const ConvParams& p, cudaStream_t st) {
+    TcPlan& pl = *p.tc;
+    const size_t n = (size_t)pl.grid.x * 8;
+    unsigned long long* d = nullptr;
+    EVK_CHECK_CUDA(cudaMalloc(&d, n * sizeof(unsigned long long)));
+    EVK_CHECK_CUDA(cudaMemsetAsync(d, 0, n * sizeof(unsigned long long), st));
+    pl.a.dbg = d;
+    int r = launch_conv_tc(p, st);
+    pl.a.dbg = nullptr;
+    if (r != EVK_OK) { cudaFree(d); return r; }
+    EVK_CHECK_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> h(n);
+    EVK_CHECK_CUDA(cudaMemcpy(h.data(), d, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    double avg[8] = {0}, mx[8] = {0};
+    for (size_t i = 0; i < n; ++i) { avg[i % 8] += (double)h[i] / pl.grid.x; mx[i % 8] = std::max(mx[i % 8], (double)h[i]); }
+    const TcArgs& a = pl.a;
+    const long n_super = (long)a.n_tiles * ((a.m_tiles + a.cs - 1) / a.cs);
+    const double tiles_per_cta = (double)n_super * a.cs / pl.grid.x;
+    const double k16 = (double)(a.chunks1 + a.chunks2) * a.kh * a.kw * (pl.bk / 16);
+    fprintf(stderr, "TIMING %dx%d s%d c%d->%d @%dx%dx%d bn=%d cs=%d ux=%d grid=%u tiles/cta=%.1f k16/tile=%.0f | mma total %.0f (max %.0f) cyc = %.1f cyc/k16 | "
+            "mma waits: tempty %.0f fullA %.0f fullB %.0f | producers wait: emptyA %.0f emptyB %.0f | epi total %.0f wait tfull %.0f\n",
+            a.kh, a.kw, a.stride, (a.chunks1 + a.chunks2) * pl.bk, a.cout, a.N, a.Hout, a.Wout, a.bn, a.cs, a.ux, pl.grid.x, tiles_per_cta, k16,
+            avg[0], mx[0], avg[0] / (tiles_per_cta * k16), avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
     return EVK_OK;
 }
 
