@@ -48,6 +48,16 @@ struct ConvParams {
     __nv_bfloat16* hs_new = nullptr;      // optional split copy of h_new (EPI_LSTM)
     const __nv_bfloat16* w_tc = nullptr;  // weights [2][cout_pad][K] bf16 (hi, lo), K-major
     int cout_pad = 0;                     // rows of w_tc (cout rounded up to a multiple of 16)
+    // "row-window" input (the Cin <= 8 head convolution on tensor cores): x1s is the packed tensor
+    // [2][N][Hin][Win + 8][8] bf16 (pixel x at padded column x + kw/2, channels >= cin and the pad columns zero) and the
+    // GEMM sees, for every pixel, the 64 contiguous values of the 8 pixels starting there as its "channels" (a TMA
+    // tensor map whose pixel stride, 16 B, is smaller than its 128 B row): the kw taps of one kernel row are ONE K
+    // chunk, so the layer runs as a (kh x 1) convolution with c1 = 64.  kw_packed = the real kw (<= 8).
+    int kw_packed = 0;
+    // prediction layer fused into the epilogue (EPI_LINEAR, cout <= 32, one N tile): out[pix] = act(sum_c w[c] *
+    // (y[pix,c] + skip[pix,c]) + b) -- model/unet.py:136-138; y itself need not be stored
+    const float* pred_w = nullptr; const float* pred_skip = nullptr; float* pred_out = nullptr;
+    float pred_bias = 0.f; int pred_sigmoid = 0;
     struct TcPlan* tc = nullptr;          // tensor maps + tiling, built once per layer (tc_plan_create)
 };
 
@@ -73,5 +83,9 @@ int launch_pred(const float* x, const float* skip, const float* w /*[cin]*/, flo
                 int cin, int sigmoid, cudaStream_t st);
 // y[N,2H,2W,C] = bilinear_x2(x + skip), align_corners=False (model/unet.py:130-134 + submodules.py:88)
 int launch_upsample2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C, cudaStream_t st);
+// NCHW fp32 [N,cin,H,W] (cin <= 8) -> packed split-bf16 row-window tensor [2][N][H][W+8][8], pixel x at column x + left
+int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st);
+// host: head weights [kh*kw*cin][cout] (SIMT layout) -> row-window K layout [kh*64][cout] (k = r*64 + q*8 + c)
+void pack_head_weights_rowwin(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out);
 
 }  // namespace evk

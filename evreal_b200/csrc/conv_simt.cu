@@ -323,57 +323,80 @@ int launch_pred(const float* x, const float* skip, const float* w, float bias, f
 // src = 0.5*(dst+0.5)-0.5 clamped at 0; i1 = min(i0+1, size-1); the horizontal
 // lerp is applied inside the vertical one like ATen's CPU kernel.
 // ---------------------------------------------------------------------------
+// One thread = one INPUT pixel x 8 channels -> the 2x2 output block it maps to: the 3x3 input neighbourhood (x + skip)
+// is read once (9 loads instead of 16 for four independent outputs), every output evaluates ATen's expression
+// hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11) with ATen's source indices / weights (clamped at the borders; a
+// zero-weight tap may come from a clamped duplicate, 0 * finite = 0 either way).
 __global__ void __launch_bounds__(256)
 upsample2x_add_kernel(const float* __restrict__ x, const float* __restrict__ skip, float* __restrict__ y,
-                      __nv_bfloat16* __restrict__ ys, int N, int H, int W, int C4) {
-    const int Ho = 2 * H, Wo = 2 * W;
-    const int64_t total = (int64_t)N * Ho * Wo * C4;
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-    const float4* s4 = reinterpret_cast<const float4*>(skip);
-    float4* y4 = reinterpret_cast<float4*>(y);
+                      __nv_bfloat16* __restrict__ ys, int N, int H, int W, int C8) {
+    const int Ho = 2 * H, Wo = 2 * W, C = C8 * 8;
+    const int64_t total = (int64_t)N * H * W * C8;
+    const int64_t out_elems = (int64_t)N * Ho * Wo * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
-        const int ox = (int)((i / C4) % Wo);
-        const int oy = (int)((i / ((int64_t)C4 * Wo)) % Ho);
-        const int n = (int)(i / ((int64_t)C4 * Wo * Ho));
-        float sy = 0.5f * ((float)oy + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
-        float sx = 0.5f * ((float)ox + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
-        const int y0 = (int)sy, x0 = (int)sx;
-        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-        const float ly = sy - (float)y0, lx = sx - (float)x0;
-        const float hy = 1.f - ly, hx = 1.f - lx;
-        auto at = [&](int yy, int xx) {
-            const size_t o = (((size_t)n * H + yy) * W + xx) * C4 + c;
-            float4 a = __ldg(x4 + o);
-            if (skip) {
-                const float4 b = __ldg(s4 + o);
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
-            return a;
-        };
-        const float4 v00 = at(y0, x0), v01 = at(y0, x1), v10 = at(y1, x0), v11 = at(y1, x1);
-        float4 o;
-        o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
-        o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
-        o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
-        o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-        if (y != nullptr) y4[i] = o;
-        if (ys != nullptr) {
-            const float f[4] = {o.x, o.y, o.z, o.w};
-            __nv_bfloat16 hi[4], lo[4];
+        const int c = (int)(i % C8) * 8;
+        const int ix = (int)((i / C8) % W);
+        const int iy = (int)((i / ((int64_t)C8 * W)) % H);
+        const int n = (int)(i / ((int64_t)C8 * W * H));
+        const int ys3[3] = {max(iy - 1, 0), iy, min(iy + 1, H - 1)};
+        const int xs3[3] = {max(ix - 1, 0), ix, min(ix + 1, W - 1)};
+        float v[3][3][8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_bf16(f[e], hi[e], lo[e]);
-            *reinterpret_cast<uint2*>(ys + i * 4) = *reinterpret_cast<uint2*>(hi);
-            *reinterpret_cast<uint2*>(ys + total * 4 + i * 4) = *reinterpret_cast<uint2*>(lo);
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const size_t o = (((size_t)n * H + ys3[r]) * W + xs3[q]) * C + c;
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + o));
+                const float4 a1 = __ldg(reinterpret_cast<const float4*>(x + o + 4));
+                float t[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                if (skip) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(skip + o));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(skip + o + 4));
+                    t[0] += b0.x; t[1] += b0.y; t[2] += b0.z; t[3] += b0.w;
+                    t[4] += b1.x; t[5] += b1.y; t[6] += b1.z; t[7] += b1.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[r][q][e] = t[e];
+            }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            // output row 2*iy + a: source sy = iy - 0.25 (a = 0; clamped to 0 on the first row) or iy + 0.25 (a = 1)
+            const int r0 = a == 0 ? 0 : 1;                       // index into ys3 of the upper source row
+            const float ly = a == 0 ? (iy == 0 ? 0.f : 0.75f) : 0.25f;
+            const float hy = 1.f - ly;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int q0 = b == 0 ? 0 : 1;
+                const float lx = b == 0 ? (ix == 0 ? 0.f : 0.75f) : 0.25f;
+                const float hx = 1.f - lx;
+                // (first output row / column: ATen's source index is 0 with weight 1, i.e. v[1][.]; ys3[0] == ys3[1] == 0 there)
+                float o8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    o8[e] = hy * (hx * v[r0][q0][e] + lx * v[r0][q0 + 1][e]) + ly * (hx * v[r0 + 1][q0][e] + lx * v[r0 + 1][q0 + 1][e]);
+                const size_t oo = (((size_t)n * Ho + 2 * iy + a) * Wo + 2 * ix + b) * C + c;
+                if (y != nullptr) {
+                    *reinterpret_cast<float4*>(y + oo) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+                    *reinterpret_cast<float4*>(y + oo + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+                }
+                if (ys != nullptr) {
+                    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) split_bf16(o8[e], hi[e], lo[e]);
+                    *reinterpret_cast<uint4*>(ys + oo) = *reinterpret_cast<const uint4*>(hi);
+                    *reinterpret_cast<uint4*>(ys + out_elems + oo) = *reinterpret_cast<const uint4*>(lo);
+                }
+            }
         }
     }
 }
 
 int launch_upsample2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C,
                           cudaStream_t st) {
-    EVK_REQUIRE(C % 4 == 0, EVK_ERR_ARG, "upsample2x_add: C=%d must be a multiple of 4", C);
-    const int64_t total = (int64_t)N * 4 * H * W * (C / 4);
-    upsample2x_add_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 4736), 256, 0, st>>>(x, skip, y, ys, N, H, W, C / 4);
+    EVK_REQUIRE(C % 8 == 0, EVK_ERR_ARG, "upsample2x_add: C=%d must be a multiple of 8", C);
+    EVK_REQUIRE(y != nullptr || ys != nullptr, EVK_ERR_ARG, "upsample2x_add: no output");
+    const int64_t total = (int64_t)N * H * W * (C / 8);
+    upsample2x_add_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 4736), 256, 0, st>>>(x, skip, y, ys, N, H, W, C / 8);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

@@ -39,7 +39,7 @@
 namespace evk {
 
 struct TcArgs {
-    int N, Hout, Wout, stride, pad, kh, kw;
+    int N, Hout, Wout, stride, pad_u, pad_v, kh, kw;
     int ux;                     // 1: U = x (tile 16 rows x 8 cols), 0: U = y (tile 8 rows x 16 cols)
     int tiles_u, tiles_v;       // tiles per image along U (8 px) and V (16 px)
     int ku, kv;                 // kernel extent along U and V
@@ -61,6 +61,7 @@ struct TcArgs {
     __nv_bfloat16* ys; long long ys_plane;
     const float* c_prev; float* c_new; float* h_new;
     __nv_bfloat16* hs_new; long long hs_plane;
+    const float* pred_w; const float* pred_skip; float* pred_out; float pred_bias; int pred_sigmoid;
     unsigned long long* dbg;    // EVK_TC_TIMING: per-CTA clock64 phase counters [grid][8], else nullptr
 };
 
@@ -176,8 +177,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         const long long t0 = DBG ? clock64() : 0;
                         mbar_wait(bar_ea + 8u * s, ph ^ 1u);
                         if (DBG) w_ea += clock64() - t0;
-                        const int iu0 = t.ou0 * a.stride - a.pad + su;
-                        const int iv0 = t.ov0 * a.stride - a.pad + a.g_tap0[g];
+                        const int iu0 = t.ou0 * a.stride - a.pad_u + su;
+                        const int iv0 = t.ov0 * a.stride - a.pad_v + a.g_tap0[g];
                         const uint32_t sa = base + s * a_stage;
                         if (elect_one()) {
                             mbar_expect_tx(bar_fa + 8u * s, a_stage);
@@ -376,6 +377,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                 if (!valid || nb >= a.cout) continue;
                 if (a.epi == EPI_LINEAR) {
                     const size_t o = pix * a.cout + nb;
+                    float pacc = 0.f;
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         if (nb + g * 4 >= a.cout || j0 + g * 4 >= a.bn) break;
@@ -388,6 +390,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) f[i] = fast_act(f[i], a.act);
+                        if (a.pred_out != nullptr) {      // fused 1x1 prediction layer (same summation order as pred_kernel)
+                            const float4 s4 = a.pred_skip ? __ldg(reinterpret_cast<const float4*>(a.pred_skip + o + g * 4))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.pred_w + nb + g * 4));
+                            pacc = fmaf(f[0] + s4.x, w4.x, pacc);
+                            pacc = fmaf(f[1] + s4.y, w4.y, pacc);
+                            pacc = fmaf(f[2] + s4.z, w4.z, pacc);
+                            pacc = fmaf(f[3] + s4.w, w4.w, pacc);
+                        }
                         if (a.y != nullptr) *reinterpret_cast<float4*>(a.y + o + g * 4) = make_float4(f[0], f[1], f[2], f[3]);
                         if (a.ys != nullptr) {
                             __nv_bfloat16 hi[4], lo[4];
@@ -396,6 +407,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             *reinterpret_cast<uint2*>(a.ys + o + g * 4) = *reinterpret_cast<uint2*>(hi);
                             *reinterpret_cast<uint2*>(a.ys + a.ys_plane + o + g * 4) = *reinterpret_cast<uint2*>(lo);
                         }
+                    }
+                    if (a.pred_out != nullptr) {
+                        pacc += a.pred_bias;
+                        a.pred_out[pix] = a.pred_sigmoid ? sigmoidf_(pacc) : pacc;
                     }
                 } else {   // EPI_LSTM: packed column = channel*4 + {in, remember, out, cell}
                     const int C = a.cout >> 2;
@@ -578,12 +593,13 @@ int tc_plan_create(ConvParams& p) {
     const int f_bn = env_int("EVK_TC_BN", 0), f_cs = env_int("EVK_TC_CS", 0), f_ux = env_int("EVK_TC_UX", -1);
     TcChoice best = {1, 0, 1, 0.0};
     for (int ux = 0; ux < 2; ++ux) {
-        if (f_ux >= 0 && ux != f_ux) continue;
+        if (p.kw_packed ? ux != 1 : (f_ux >= 0 && ux != f_ux)) continue;      // row-window input: atoms run along x
         const int hu = ux ? p.Wout : p.Hout, hv = ux ? p.Hout : p.Wout;
         const long m_tiles = (long)ceil_div(hu, 8) * ceil_div(hv, 16) * p.N;
         const int ku = ux ? p.kw : p.kh, kv = ux ? p.kh : p.kw;
         for (int bn = 128; bn >= 16; bn -= 16) {
             if (cout_pad % bn != 0 || bn % granule != 0) continue;
+            if (p.pred_out != nullptr && bn != cout_pad) continue;
             if (f_bn > 0 && bn != f_bn && cout_pad % f_bn == 0 && f_bn % granule == 0) continue;
             for (int cs = 1; cs <= 4; cs *= 2) {
                 if ((bn / cs) % 8 != 0 || bn % cs != 0) continue;
@@ -603,7 +619,7 @@ int tc_plan_create(ConvParams& p) {
     TcPlan* pl = new TcPlan();
     pl->bk = bk;
     TcArgs& a = pl->a;
-    a.N = p.N; a.Hout = p.Hout; a.Wout = p.Wout; a.stride = p.stride; a.pad = p.pad; a.kh = p.kh; a.kw = p.kw;
+    a.N = p.N; a.Hout = p.Hout; a.Wout = p.Wout; a.stride = p.stride; a.pad_u = p.kw_packed ? 0 : p.pad; a.pad_v = p.pad; a.kh = p.kh; a.kw = p.kw;
     a.ux = ux;
     a.tiles_u = ceil_div(ux ? p.Wout : p.Hout, 8);
     a.tiles_v = ceil_div(ux ? p.Hout : p.Wout, 16);
@@ -621,6 +637,11 @@ int tc_plan_create(ConvParams& p) {
     }
     a.ar = 16 + a.g_ntaps[0] - 1;
     a.bias = p.bias; a.res = p.res; a.y = p.y; a.ys = p.ys;
+    a.pred_w = p.pred_w; a.pred_skip = p.pred_skip; a.pred_out = p.pred_out; a.pred_bias = p.pred_bias; a.pred_sigmoid = p.pred_sigmoid;
+    if (p.pred_out != nullptr && (p.epi != EPI_LINEAR || bn < p.cout || bn > 32)) {
+        delete pl;
+        EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: the fused prediction layer needs all %d channels in one 32-column chunk (bn=%d)", p.cout, bn);
+    }
     a.ys_plane = (long long)p.N * p.Hout * p.Wout * p.cout;
     a.c_prev = p.c_prev; a.c_new = p.c_new; a.h_new = p.h_new; a.hs_new = p.hs_new;
     a.hs_plane = (long long)p.N * p.Hout * p.Wout * (p.cout / 4);
@@ -654,6 +675,16 @@ int tc_plan_create(ConvParams& p) {
     // activations: [plane, n, V, U, c] (U = atom axis, V = shift axis)
     const int s = p.stride;
     auto act_map = [&](CUtensorMap* m, const __nv_bfloat16* base, int C) -> int {
+        if (p.kw_packed) {
+            // row-window view of the packed head input [2][N][H][W+8][8]: "channel" dim = the 64 values starting at a
+            // pixel, pixel stride 16 B (rows overlap), so one box row holds the kw taps x 8 channel slots of a kernel row
+            const uint64_t wp = (uint64_t)p.Win + 8;
+            const uint64_t dims[5] = {64, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)p.N, 2};
+            const uint64_t str[4] = {16, wp * 16, (uint64_t)p.Hin * wp * 16, (uint64_t)p.N * p.Hin * wp * 16};
+            const uint32_t box[5] = {64, 8, (uint32_t)a.ar, 1, 1};
+            const uint32_t es[5] = {1, 1, 1, 1, 1};
+            return encode_tmap_bf16(m, base, 5, dims, str, box, es, 128);
+        }
         const uint64_t sx = (uint64_t)C * 2, sy = (uint64_t)p.Win * C * 2;
         const uint64_t dims[5] = {(uint64_t)C, (uint64_t)(ux ? p.Win : p.Hin), (uint64_t)(ux ? p.Hin : p.Win), (uint64_t)p.N, 2};
         const uint64_t str[4] = {ux ? sx : sy, ux ? sy : sx, (uint64_t)p.Hin * p.Win * C * 2, (uint64_t)p.N * p.Hin * p.Win * C * 2};
@@ -738,6 +769,44 @@ static int launch_conv_tc_timed(const ConvParams& p, cudaStream_t st) {
             a.kh, a.kw, a.stride, (a.chunks1 + a.chunks2) * pl.bk, a.cout, a.N, a.Hout, a.Wout, a.bn, a.cs, a.ux, pl.grid.x, tiles_per_cta, k16,
             avg[0], mx[0], avg[0] / (tiles_per_cta * k16), avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
     return EVK_OK;
+}
+
+// ------------------------------------------------------------------ head input: NCHW fp32 -> packed row-window split bf16
+__global__ void __launch_bounds__(256) head_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int cin,
+                                                        int H, int W, int left) {
+    const int64_t total = (int64_t)N * H * W;
+    const int64_t plane = (int64_t)N * H * (W + 8) * 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W);
+        const int yy = (int)((i / W) % H);
+        const int n = (int)(i / ((int64_t)W * H));
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float v = c < cin ? __ldg(x + (((int64_t)n * cin + c) * H + yy) * W + xx) : 0.f;
+            split_bf16(v, hi[c], lo[c]);
+        }
+        const int64_t o = (((int64_t)n * H + yy) * (W + 8) + xx + left) * 8;
+        *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(out + plane + o) = *reinterpret_cast<const uint4*>(lo);
+    }
+}
+
+int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st) {
+    EVK_REQUIRE(x_nchw && packed && cin >= 1 && cin <= 8 && left >= 0 && left <= 7, EVK_ERR_ARG, "head_pack: bad argument");
+    const int64_t total = (int64_t)N * H * W;
+    head_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, 0, st>>>(x_nchw, packed, N, cin, H, W, left);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+void pack_head_weights_rowwin(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out) {
+    out.assign((size_t)kh * 64 * cout, 0.f);
+    for (int r = 0; r < kh; ++r)
+        for (int q = 0; q < kw; ++q)
+            for (int c = 0; c < cin; ++c)
+                for (int n = 0; n < cout; ++n)
+                    out[((size_t)r * 64 + q * 8 + c) * cout + n] = w_kc[((size_t)(r * kw + q) * cin + c) * cout + n];
 }
 
 // ------------------------------------------------------------------ fp32 -> split planes

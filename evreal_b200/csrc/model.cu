@@ -28,7 +28,7 @@ struct HostTensor {
     std::vector<int64_t> shape;
 };
 
-enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY };
+enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HEAD_PACK, OP_NOP };
 
 struct Op {
     OpKind kind;
@@ -303,10 +303,42 @@ static int add_head(Builder& B, const std::string& conv_pfx, const std::string& 
     EVK_REQUIRE(pk.cin == m->cfg.num_bins && pk.cout == cout_expected, EVK_ERR_KEY,
                 "'%s': expected [%d,%d,k,k], checkpoint has [%d,%d,%d,%d]", conv_pfx.c_str(), cout_expected,
                 m->cfg.num_bins, pk.cout, pk.cin, pk.kh, pk.kw);
+    const int H = m->cfg.height, W = m->cfg.width;
+    const double flops = 2.0 * pk.cout * pk.cin * pk.kh * pk.kw * (double)B.N * H * W;
+    if (m->cfg.precision == 0 && pk.cin <= 8 && pk.kw <= 8 && pk.kh == pk.kw && pk.cout % 16 == 0 && getenv("EVK_HEAD_SIMT") == nullptr) {
+        // tensor-core head: pack the NCHW event tensor into the row-window layout (conv.cuh) and run the layer as a
+        // (kh x 1) implicit GEMM with 64 "channels" per kernel row
+        const size_t plane = (size_t)B.N * H * (W + 8) * 8;
+        __nv_bfloat16* packed = (__nv_bfloat16*)m->dalloc_bytes(2 * plane * sizeof(__nv_bfloat16));
+        EVK_REQUIRE(packed != nullptr, EVK_ERR_CUDA, "out of device memory for the packed head input");
+        {
+            Op op; op.kind = OP_HEAD_PACK;
+            op.in = m->in_buf; op.out_s = packed; op.N = B.N; op.cin = pk.cin; op.H = H; op.W = W; op.k = pk.kw;
+            m->ops[0].push_back(op); m->ops[1].push_back(op);
+        }
+        Op op; op.kind = OP_CONV;
+        ConvParams& p = op.cp;
+        p.x1 = nullptr; p.c1 = 64; p.x1s = packed; p.kw_packed = pk.kw;
+        p.N = B.N; p.Hin = p.Hout = H; p.Win = p.Wout = W; p.kh = pk.kh; p.kw = 1; p.stride = 1; p.pad = pk.kh / 2;
+        p.bias = m->upload(pk.b); p.cout = pk.cout; p.epi = EPI_LINEAR; p.act = ACT_RELU; p.y = y;
+        std::vector<float> wr;
+        pack_head_weights_rowwin(pk.w.data(), pk.kh, pk.kw, pk.cin, pk.cout, wr);
+        std::vector<__nv_bfloat16> wt;
+        p.cout_pad = pk.cout;
+        pack_weights_tc(wr.data(), pk.kh * 64, pk.cout, p.cout_pad, wt);
+        void* d = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
+        EVK_REQUIRE(d != nullptr, EVK_ERR_CUDA, "out of device memory for the head weights");
+        cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+        p.w_tc = (const __nv_bfloat16*)d;
+        op.flops = flops;
+        op.cin = pk.cin; op.k = pk.kw;       // real shape, for the description
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+        return EVK_OK;
+    }
     Op op; op.kind = OP_HEAD;
     op.in = m->in_buf; op.w = m->upload(pk.w); op.b = m->upload(pk.b); op.out = y;
-    op.N = B.N; op.cin = pk.cin; op.H = m->cfg.height; op.W = m->cfg.width; op.k = pk.kh; op.cout = pk.cout;
-    op.flops = 2.0 * pk.cout * pk.cin * pk.kh * pk.kw * (double)B.N * op.H * op.W;
+    op.N = B.N; op.cin = pk.cin; op.H = H; op.W = W; op.k = pk.kh; op.cout = pk.cout;
+    op.flops = flops;
     m->ops[0].push_back(op); m->ops[1].push_back(op);
     return EVK_OK;
 }
@@ -525,10 +557,24 @@ static int wire_tc(evk_model* m) {
     for (int par = 0; par < 2; ++par)
         for (Op& op : m->ops[par]) {
             if (op.kind != OP_CONV || op.cp.w_tc == nullptr || !tc_eligible(op.cp)) continue;
-            op.cp.x1s = need_split(op.cp.x1);
+            if (!op.cp.kw_packed) op.cp.x1s = need_split(op.cp.x1);      // (the row-window head brings its own packed input)
             if (op.cp.c2) op.cp.x2s = need_split(op.cp.x2);
             EVK_REQUIRE(op.cp.x1s && (!op.cp.c2 || op.cp.x2s), EVK_ERR_CUDA, "wire_tc: cannot allocate split activations");
         }
+    // prediction layer -> epilogue of the tensor-core convolution that produces its input (the epilogue thread of a
+    // pixel holds all <= 32 channels): saves the launch and the round trip of the full-resolution decoder output
+    if (getenv("EVK_NO_PRED_FUSION") == nullptr)
+        for (int par = 0; par < 2; ++par)
+            for (size_t i = 0; i + 1 < m->ops[par].size(); ++i) {
+                Op& cv = m->ops[par][i];
+                Op& pr = m->ops[par][i + 1];
+                if (cv.kind != OP_CONV || cv.cp.x1s == nullptr || cv.cp.epi != EPI_LINEAR || cv.cp.cout > 32 || cv.cp.cout % 16 != 0) continue;
+                if (pr.kind != OP_PRED || pr.in != cv.cp.y || pr.cin != cv.cp.cout) continue;
+                cv.cp.pred_w = pr.w; cv.cp.pred_skip = pr.skip; cv.cp.pred_out = pr.out;
+                cv.cp.pred_bias = pr.bias0; cv.cp.pred_sigmoid = pr.sigmoid;
+                cv.flops += pr.flops;
+                pr.kind = OP_NOP; pr.flops = 0.0;
+            }
     auto lookup = [&](const float* ptr) -> __nv_bfloat16* {
         auto it = m->split_of.find(ptr);
         return it == m->split_of.end() ? nullptr : it->second;
@@ -549,6 +595,36 @@ static int wire_tc(evk_model* m) {
                 default: break;
             }
         }
+    // fp32 copies that no kernel reads (every consumer takes the split-bf16 companion) are not written at all
+    {
+        std::map<const float*, int> fp32_read;
+        for (const StateBuf& sb : m->states) { fp32_read[sb.buf[0]] = 1; fp32_read[sb.buf[1]] = 1; }
+        fp32_read[m->out_buf] = 1; fp32_read[m->in_buf] = 1; fp32_read[m->prev_rec] = 1;
+        for (int par = 0; par < 2; ++par)
+            for (const Op& op : m->ops[par]) {
+                auto rd = [&](const float* q) { if (q) fp32_read[q] = 1; };
+                switch (op.kind) {
+                    case OP_CONV:
+                        if (op.cp.x1s == nullptr) { rd(op.cp.x1); rd(op.cp.x2); }
+                        rd(op.cp.res); rd(op.cp.c_prev); rd(op.cp.h_prev); rd(op.cp.u_in); rd(op.cp.pred_skip);
+                        break;
+                    case OP_UPSAMPLE_ADD: case OP_PRED: rd(op.in); rd(op.skip); break;
+                    case OP_HYPER_CONTEXT: case OP_HYPER_ATOMS: case OP_HYPER_APPLY:
+                        rd(op.hp.ev_nchw); rd(op.hp.prev); rd(op.hp.ctx); rd(op.hp.coef); rd(op.hp.atoms); rd(op.hp.xu); rd(op.hp.inter);
+                        break;
+                    default: break;
+                }
+            }
+        if (getenv("EVK_KEEP_FP32") == nullptr)
+            for (int par = 0; par < 2; ++par)
+                for (Op& op : m->ops[par]) {
+                    if (op.kind == OP_CONV && op.cp.x1s != nullptr && op.cp.epi == EPI_LINEAR && op.cp.y != nullptr &&
+                        !fp32_read.count(op.cp.y) && (op.cp.ys != nullptr || op.cp.pred_out != nullptr)) {
+                        op.cp.y = nullptr;
+                    }
+                    if (op.kind == OP_UPSAMPLE_ADD && op.out_s != nullptr && !fp32_read.count(op.out)) op.out = nullptr;
+                }
+    }
     for (int par = 0; par < 2; ++par)
         for (Op& op : m->ops[par]) {
             if (op.kind != OP_CONV || op.cp.x1s == nullptr) continue;
@@ -570,6 +646,8 @@ static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent
             case OP_HEAD: r = launch_head_conv(op.in, op.w, op.b, op.out, op.out_s, op.N, op.cin, op.H, op.W, op.k, op.cout, st); break;
             case OP_CONV: r = launch_conv(op.cp, m->cfg.precision, st); break;
             case OP_UPSAMPLE_ADD: r = launch_upsample2x_add(op.in, op.skip, op.out, op.out_s, op.N, op.H, op.W, op.cin, st); break;
+            case OP_NOP: break;
+            case OP_HEAD_PACK: r = launch_head_pack(op.in, op.out_s, op.N, op.cin, op.H, op.W, op.k / 2, st); break;
             case OP_PRED: r = launch_pred(op.in, op.skip, op.w, op.bias0, op.out, (int64_t)op.N * op.H * op.W, op.cin, op.sigmoid, st); break;
             default: r = launch_hyper(op.kind - OP_HYPER_CONTEXT, op.hp, st); break;
         }
@@ -588,12 +666,18 @@ static std::string op_desc(const Op& op) {
         case OP_CONV: {
             const ConvParams& p = op.cp;
             const char* e = p.epi == EPI_LSTM ? "lstm" : p.epi == EPI_GRU_UR ? "gru_ur" : p.epi == EPI_GRU_OUT ? "gru_out" : (p.res ? "linear+res" : "linear");
-            snprintf(b, sizeof b, "conv%dx%d s%d %d+%d->%d %s @%dx%d [%s]", p.kh, p.kw, p.stride, p.c1, p.c2, p.cout, e, p.Hout,
-                     p.Wout, p.tc ? "tcgen05 bf16x3" : "simt fp32");
+            if (p.kw_packed)
+                snprintf(b, sizeof b, "conv%dx%d s1 %d+0->%d head row-window%s @%dx%d [tcgen05 bf16x3]", p.kh, p.kw_packed, op.cin, p.cout,
+                         p.pred_out ? "+pred" : "", p.Hout, p.Wout);
+            else
+                snprintf(b, sizeof b, "conv%dx%d s%d %d+%d->%d %s%s @%dx%d [%s]", p.kh, p.kw, p.stride, p.c1, p.c2, p.cout, e,
+                         p.pred_out ? "+pred" : "", p.Hout, p.Wout, p.tc ? "tcgen05 bf16x3" : "simt fp32");
             break;
         }
         case OP_UPSAMPLE_ADD: snprintf(b, sizeof b, "upsample2x_add C=%d @%dx%d", op.cin, 2 * op.H, 2 * op.W); break;
         case OP_PRED: snprintf(b, sizeof b, "pred 1x1 %d->1 @%dx%d", op.cin, op.H, op.W); break;
+        case OP_NOP: snprintf(b, sizeof b, "(pred 1x1 fused into the previous epilogue)"); break;
+        case OP_HEAD_PACK: snprintf(b, sizeof b, "head pack NCHW -> row-window split bf16 @%dx%d", op.H, op.W); break;
         case OP_HYPER_CONTEXT: snprintf(b, sizeof b, "hyper context x0.25"); break;
         case OP_HYPER_ATOMS: snprintf(b, sizeof b, "hyper atoms A=%d K=%d L=%d @%dx%d", op.hp.A, op.hp.K, op.hp.L, op.hp.h, op.hp.w); break;
         default: snprintf(b, sizeof b, "hyper dynamic conv C=%d A=%d @%dx%d", op.hp.C, op.hp.A, op.hp.h, op.hp.w); break;
@@ -700,7 +784,8 @@ int evk_model_forward(evk_model* m, const float* voxel, float* image, void* stre
         int r = run_ops(m, par, st);
         if (r != EVK_OK) return r;
     }
-    m->last_launches = (int)m->ops[par].size();
+    m->last_launches = 0;
+    for (const Op& op : m->ops[par]) m->last_launches += op.kind != OP_NOP;
     if (c.dynamic_decoder) EVK_CHECK_CUDA(cudaMemcpyAsync(m->prev_rec, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
     if (image != m->out_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(image, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
     m->parity ^= 1;
@@ -732,7 +817,8 @@ int evk_model_profile(evk_model* m, const float* voxel, float* image, void* stre
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     if (r != EVK_OK) return r;
     EVK_CHECK_CUDA(se);
-    m->last_launches = n;
+    m->last_launches = 0;
+    for (const Op& op : m->ops[par]) m->last_launches += op.kind != OP_NOP;
     m->parity ^= 1;
     return EVK_OK;
 }
