@@ -9,10 +9,10 @@ Workload (N=1 and per rank for N>1, weak scaling): BASELINE.json configs[1] -- E
 random weights of the shipped checkpoint's shapes) on synthetic ECD-shape streams: 240x180, 1 Mev/s, 24 Hz frames,
 5 bins, 'between_frames' windows (~41.7k events), normalize_event_tensor on, pad to 184x240, 'robust' percentile
 post-normalisation, clip, MSE + SSIM per frame.  One STEP = frame i of B independent streams run in lock-step
-(SequenceBatch): B voxelizer launches + one batched network forward + one batched metric launch.  `value` = frames/s
+(SequenceBatch): one batched voxelizer launch + one batched network forward + one batched metric launch.  `value` = frames/s
 summed over all ranks with the raw event arrays resident in HBM; `e2e` = the same loop with the event arrays and
 reference frames in pinned HOST memory, every window copied host->device and scores + reconstructed frames copied
-device->host inside the timed region.  Sequences are independent: ranks share nothing and there is no data-path
+device->host inside the timed region (copy streams: the windows of step i+1 are staged while step i computes).  Sequences are independent: ranks share nothing and there is no data-path
 collective (the only collective of the product, one all-reduce of metric sums, runs once after the timed region).
 
 --impl reference: the reference's torch-CPU path for the same config (oracle/eval_loop.py: the same ATen/oneDNN
@@ -260,20 +260,22 @@ def run_ours(args):
         batch.reset()
         idx = 1                                   # item 0 of 'between_frames' is always the empty window
         for _ in range(warm):
-            batch.step(idx)
-            idx = idx % (n_items - 1) + 1
+            nxt = idx % (n_items - 1) + 1
+            batch.step(idx, nxt)
+            idx = nxt
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         sampler = ClockSampler(local) if rank == 0 else None
         launches = events = h2d = d2h = 0
         e0.record()
         for _ in range(k_steps):
-            _, _, n_ev = batch.step(idx)
+            nxt = idx % (n_items - 1) + 1
+            _, _, n_ev = batch.step(idx, nxt)
             launches += batch.launches
             events += n_ev
             h2d += batch.h2d_bytes
             d2h += batch.d2h_bytes
-            idx = idx % (n_items - 1) + 1
+            idx = nxt
         e1.record()
         barrier()
         clocks = sampler.stop() if sampler else None
@@ -302,7 +304,7 @@ def run_ours(args):
     ms_e, events_e, _, h2d, d2h, _ = timed(hosted, K, Wm)
     e2e = {"value": frames / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
            "events_per_s": events_e / (ms_e * 1e-3), "ms_per_step": ms_e / K,
-           "api": "evreal_b200.pipeline.SequenceBatch(resident=False).step -> C ABI (evk_voxelize_raw, evk_normalize_pad, evk_model_forward, evk_crop, evk_percentile_normalize, evk_mse_ssim)"}
+           "api": "evreal_b200.pipeline.SequenceBatch(resident=False).step -> C ABI (evk_stage_windows_h2d, evk_voxelize_raw_batch, evk_normalize_pad, evk_model_forward, evk_crop, evk_percentile_normalize, evk_mse_ssim)"}
     del hosted
     torch.cuda.empty_cache()
 

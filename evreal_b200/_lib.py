@@ -14,6 +14,11 @@ LIB_PATH = os.path.join(_HERE, "libevreal_b200.so")
 EVK_OK, EVK_ERR_ARG, EVK_ERR_CUDA, EVK_ERR_INDEX, EVK_ERR_STATE, EVK_ERR_KEY = 0, -1, -2, -3, -4, -5
 
 
+class EventWindow(ctypes.Structure):
+    """evk_event_window: one raw event window (device or pinned-host pointers)."""
+    _fields_ = [("xy", ctypes.c_void_p), ("t", ctypes.c_void_p), ("pol", ctypes.c_void_p), ("n", ctypes.c_int64)]
+
+
 class ModelConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "arch", "num_bins", "base_channels", "num_encoders", "num_residual_blocks", "kernel_size",
@@ -28,6 +33,10 @@ SIGNATURES = {
     "evk_last_error": (_c.c_char_p, []),
     "evk_voxelize": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "evk_voxelize_raw": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
+    "evk_voxelize_raw_batch": (_i, [_c.POINTER(EventWindow), _i, _i, _i, _i, _vp, _vp, _vp]),
+    "evk_stage_windows_h2d": (_i, [_c.POINTER(EventWindow), _i, _vp, _vp, _vp, _i64, _vp]),
+    "evk_stage_frames_h2d": (_i, [_c.POINTER(_vp), _i, _i64, _vp, _vp]),
+    "evk_u8_to_f32_batch": (_i, [_c.POINTER(_vp), _i, _i64, _vp, _vp]),
     "evk_normalize_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "evk_model_create": (_i, [_c.POINTER(ModelConfig), _c.POINTER(_vp)]),
     "evk_model_load_tensor": (_i, [_vp, _c.c_char_p, _vp, _c.POINTER(_i64), _i]),

@@ -21,6 +21,8 @@ int voxelize_raw(const int16_t*, const double*, const uint8_t*, int64_t, int, in
 int normalize_pad(const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int crop(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int u8_to_f32(const uint8_t*, float*, int64_t, cudaStream_t);
+int voxelize_raw_batch(const evk_event_window*, int, int, int, int, float*, int*, cudaStream_t);
+int u8_to_f32_batch(const uint8_t* const*, int, int64_t, float*, cudaStream_t);
 int mse_ssim(const float*, const float*, int, int, int, int, double*, cudaStream_t);
 int percentile_normalize(const float*, float*, int, int, double, double, int, cudaStream_t);
 
@@ -46,6 +48,40 @@ int evk_voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int
                      float* grid, int* oob_count, void* stream) {
     EVK_REQUIRE(xy && t && pol && grid, EVK_ERR_ARG, "evk_voxelize_raw: null pointer");
     return evk::voxelize_raw(xy, t, pol, n, num_bins, H, W, grid, oob_count, (cudaStream_t)stream);
+}
+
+int evk_voxelize_raw_batch(const evk_event_window* windows, int n_windows, int num_bins, int H, int W, float* grids,
+                           int* oob_count, void* stream) {
+    return evk::voxelize_raw_batch(windows, n_windows, num_bins, H, W, grids, oob_count, (cudaStream_t)stream);
+}
+
+int evk_u8_to_f32_batch(const uint8_t* const* frames, int n_frames, int64_t numel, float* out, void* stream) {
+    return evk::u8_to_f32_batch(frames, n_frames, numel, out, (cudaStream_t)stream);
+}
+
+int evk_stage_windows_h2d(const evk_event_window* host_windows, int n_windows, int16_t* st_xy, double* st_t, uint8_t* st_pol,
+                          int64_t stride_events, void* stream) {
+    EVK_REQUIRE(host_windows && st_xy && st_t && st_pol && n_windows > 0 && stride_events > 0, EVK_ERR_ARG,
+                "evk_stage_windows_h2d: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int b = 0; b < n_windows; ++b) {
+        const evk_event_window& w = host_windows[b];
+        if (w.n <= 0) continue;
+        EVK_REQUIRE(w.n <= stride_events && w.xy && w.t && w.pol, EVK_ERR_ARG, "evk_stage_windows_h2d: window %d (%lld events) does not fit", b, (long long)w.n);
+        EVK_CHECK_CUDA(cudaMemcpyAsync(st_xy + (size_t)b * stride_events * 2, w.xy, (size_t)w.n * 4, cudaMemcpyHostToDevice, st));
+        EVK_CHECK_CUDA(cudaMemcpyAsync(st_t + (size_t)b * stride_events, w.t, (size_t)w.n * 8, cudaMemcpyHostToDevice, st));
+        EVK_CHECK_CUDA(cudaMemcpyAsync(st_pol + (size_t)b * stride_events, w.pol, (size_t)w.n, cudaMemcpyHostToDevice, st));
+    }
+    return EVK_OK;
+}
+
+int evk_stage_frames_h2d(const uint8_t* const* host_frames, int n_frames, int64_t numel, uint8_t* dst, void* stream) {
+    EVK_REQUIRE(host_frames && dst && n_frames > 0 && numel > 0, EVK_ERR_ARG, "evk_stage_frames_h2d: bad argument");
+    for (int b = 0; b < n_frames; ++b) {
+        EVK_REQUIRE(host_frames[b] != nullptr, EVK_ERR_ARG, "evk_stage_frames_h2d: frame %d is null", b);
+        EVK_CHECK_CUDA(cudaMemcpyAsync(dst + (size_t)b * numel, host_frames[b], (size_t)numel, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    }
+    return EVK_OK;
 }
 
 int evk_normalize_pad(const float* in, float* out, int n_samples, int C, int H, int W, int Hp, int Wp, int do_normalize,

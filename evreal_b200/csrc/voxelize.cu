@@ -9,6 +9,8 @@
 // temporal bins, each with one fire-and-forget RED.ADD.F32 into the L2-resident
 // grid (<= 6.1 MB at 5x480x640).  Algorithmic bytes per window:
 // 16*N (f32 SoA) or 13*N (raw int16/f64/u8) + 4*bins*H*W for the grid.
+#include <algorithm>
+
 #include "evk_common.cuh"
 
 namespace evk {
@@ -104,9 +106,9 @@ voxelize_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, co
 }
 
 // Raw on-disk layout: xy int16 pairs, t float64 absolute, pol uint8 {0,1}.
-__global__ void __launch_bounds__(kVoxThreads)
-voxelize_raw_kernel(const int16_t* __restrict__ xy, const double* __restrict__ t, const uint8_t* __restrict__ pol,
-                    int64_t n, VoxGeom g, float* __restrict__ grid, int* __restrict__ oob_count) {
+__device__ __forceinline__ void voxelize_raw_body(const int16_t* __restrict__ xy, const double* __restrict__ t,
+                                                  const uint8_t* __restrict__ pol, int64_t n, VoxGeom g, float* __restrict__ grid,
+                                                  int* __restrict__ oob_count, int64_t tid, int64_t nthreads) {
     const double t0d = __ldg(t);
     TimeNorm tn;
     tn.t0 = 0.0f;   // (t - t[0]).astype(f32)[0] == 0
@@ -115,8 +117,6 @@ voxelize_raw_kernel(const int16_t* __restrict__ xy, const double* __restrict__ t
     tn.degenerate = (double)tn.dt < 1e-9;
     tn.n = n;
     int oob = 0;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int* xy32 = reinterpret_cast<const int*>(xy);   // int16 pairs are 4-byte aligned by construction
     for (int64_t i = tid; i < n; i += nthreads) {
         const int c = __ldcs(xy32 + i);
@@ -127,6 +127,31 @@ voxelize_raw_kernel(const int16_t* __restrict__ xy, const double* __restrict__ t
         scatter_event(xf, yf, tn(tf, i), pf, g, grid, oob);
     }
     if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
+}
+
+__global__ void __launch_bounds__(kVoxThreads)
+voxelize_raw_kernel(const int16_t* __restrict__ xy, const double* __restrict__ t, const uint8_t* __restrict__ pol,
+                    int64_t n, VoxGeom g, float* __restrict__ grid, int* __restrict__ oob_count) {
+    voxelize_raw_body(xy, t, pol, n, g, grid, oob_count, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                      (int64_t)gridDim.x * blockDim.x);
+}
+
+// Several windows (one per sequence of a lock-step batch) in ONE launch: blockIdx.y = window, grids contiguous.
+constexpr int kVoxBatch = 32;
+struct VoxBatch {
+    const int16_t* xy[kVoxBatch];
+    const double* t[kVoxBatch];
+    const uint8_t* pol[kVoxBatch];
+    long long n[kVoxBatch];
+};
+
+__global__ void __launch_bounds__(kVoxThreads)
+voxelize_raw_batch_kernel(const __grid_constant__ VoxBatch wb, VoxGeom g, float* __restrict__ grids, int* __restrict__ oob_count) {
+    const int w = blockIdx.y;
+    const int64_t n = wb.n[w];
+    if (n <= 0) return;                      // empty window: the (pre-zeroed) grid stays zero (dataset.py:59-71)
+    voxelize_raw_body(wb.xy[w], wb.t[w], wb.pol[w], n, g, grids + (size_t)w * g.bins * g.H * g.W, oob_count,
+                      (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 static int vox_grid_blocks(int64_t n, int per_thread) {
@@ -166,6 +191,38 @@ int voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int64_t
     VoxGeom g{bins, H, W};
     voxelize_raw_kernel<<<vox_grid_blocks(n, 2), kVoxThreads, 0, st>>>(xy, t, pol, n, g, grid, oob_count);
     EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+int voxelize_raw_batch(const evk_event_window* windows, int n_windows, int bins, int H, int W, float* grids, int* oob_count,
+                       cudaStream_t st) {
+    EVK_REQUIRE(windows && grids && n_windows > 0, EVK_ERR_ARG, "evk_voxelize_raw_batch: bad argument");
+    EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize_raw_batch: bad geometry");
+    const size_t grid_elems = (size_t)bins * H * W;
+    EVK_CHECK_CUDA(cudaMemsetAsync(grids, 0, sizeof(float) * grid_elems * n_windows, st));
+    VoxGeom g{bins, H, W};
+    for (int w0 = 0; w0 < n_windows; w0 += kVoxBatch) {
+        const int cnt = std::min(kVoxBatch, n_windows - w0);
+        VoxBatch wb;
+        int64_t nmax = 0;
+        for (int i = 0; i < kVoxBatch; ++i) {
+            if (i < cnt) {
+                const evk_event_window& e = windows[w0 + i];
+                EVK_REQUIRE(e.n >= 0 && (e.n == 0 || (e.xy && e.t && e.pol)), EVK_ERR_ARG, "evk_voxelize_raw_batch: window %d is null", w0 + i);
+                EVK_REQUIRE(((uintptr_t)e.xy & 3) == 0 && ((uintptr_t)e.t & 7) == 0, EVK_ERR_ARG, "evk_voxelize_raw_batch: misaligned arrays");
+                wb.xy[i] = e.xy; wb.t[i] = e.t; wb.pol[i] = e.pol; wb.n[i] = e.n;
+                nmax = std::max<int64_t>(nmax, e.n);
+            } else {
+                wb.xy[i] = nullptr; wb.t[i] = nullptr; wb.pol[i] = nullptr; wb.n[i] = 0;
+            }
+        }
+        if (nmax == 0) continue;
+        int64_t bx = ceil_div64(nmax, (int64_t)kVoxThreads * 2);
+        const int64_t cap = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / cnt);
+        bx = std::max<int64_t>(1, std::min(bx, cap));
+        voxelize_raw_batch_kernel<<<dim3((unsigned)bx, (unsigned)cnt), kVoxThreads, 0, st>>>(wb, g, grids + grid_elems * w0, oob_count);
+        EVK_CHECK_CUDA(cudaGetLastError());
+    }
     return EVK_OK;
 }
 
@@ -290,6 +347,32 @@ int crop(const float* in, float* out, int n, int C, int Hp, int Wp, int H, int W
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = __fdiv_rn((float)in[i], 255.0f);
+}
+
+constexpr int kU8Batch = 64;
+struct U8Batch { const uint8_t* src[kU8Batch]; };
+
+__global__ void __launch_bounds__(256) u8_to_f32_batch_kernel(const __grid_constant__ U8Batch b, float* __restrict__ out, int64_t n) {
+    const uint8_t* in = b.src[blockIdx.y];
+    float* o = out + (size_t)blockIdx.y * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        o[i] = __fdiv_rn((float)in[i], 255.0f);
+}
+
+int u8_to_f32_batch(const uint8_t* const* frames, int n_frames, int64_t numel, float* out, cudaStream_t st) {
+    EVK_REQUIRE(frames && out && n_frames > 0 && numel > 0, EVK_ERR_ARG, "evk_u8_to_f32_batch: bad argument");
+    for (int f0 = 0; f0 < n_frames; f0 += kU8Batch) {
+        const int cnt = std::min(kU8Batch, n_frames - f0);
+        U8Batch b;
+        for (int i = 0; i < kU8Batch; ++i) {
+            b.src[i] = i < cnt ? frames[f0 + i] : nullptr;
+            EVK_REQUIRE(i >= cnt || b.src[i] != nullptr, EVK_ERR_ARG, "evk_u8_to_f32_batch: frame %d is null", f0 + i);
+        }
+        const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(numel, 256 * 4), kNumSMs * 8 / cnt));
+        u8_to_f32_batch_kernel<<<dim3(bx, (unsigned)cnt), 256, 0, st>>>(b, out + (size_t)f0 * numel, numel);
+        EVK_CHECK_CUDA(cudaGetLastError());
+    }
+    return EVK_OK;
 }
 
 int u8_to_f32(const uint8_t* in, float* out, int64_t n, cudaStream_t st) {

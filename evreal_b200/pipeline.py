@@ -2,18 +2,22 @@
 
 The reference evaluates one sequence at a time with batch 1 (eval.py:189-246, DataLoader defaults at
 eval.py:72).  Sequences are independent (state reset per sequence, eval.py:197) and frames inside one are
-strictly serial, so the B200 form of the loop runs frame ``i`` of B sequences together: one voxelizer launch
-per window, then ONE batched normalise+pad, network forward, crop, percentile normalisation and fused MSE/SSIM
+strictly serial, so the B200 form of the loop runs frame ``i`` of B sequences together: ONE voxelizer launch for
+the B windows, then ONE batched normalise+pad, network forward, crop, percentile normalisation and fused MSE/SSIM
 launch for all B.  Per-sample arithmetic is unchanged (normalize_event_tensor statistics are per sample), so
 every sequence gets the frames and scores it would get alone (tests/test_gpu_pipeline.py).
 
 Two input modes:
   * ``resident=True``  -- raw event arrays (int16 xy, float64 t, uint8 p) and reference frames are uploaded once
     and every window is voxelized from HBM (bench.py ``value``);
-  * ``resident=False`` -- the arrays stay in pinned HOST memory; each step copies its windows (13 B/event) and
-    reference frames host->device inside the step and reads scores + reconstructed frames back (bench.py ``e2e``).
+  * ``resident=False`` -- the arrays stay in pinned HOST memory; every step's windows (13 B/event) and reference
+    frames are copied host->device and scores + reconstructed frames are read back (bench.py ``e2e``).  The copies
+    run on their own streams: the windows of step i+1 are staged (double-buffered) while step i computes, and the
+    results of step i travel back while step i+1 runs, so PCIe time hides behind the network.
 All device buffers are allocated once; a step allocates nothing.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -22,6 +26,8 @@ from .util import CropParameters
 
 
 class SequenceBatch:
+    RING = 4          # result slots (device + pinned host) in flight
+
     def __init__(self, model, datasets, event_tensor_normalization=False, post_process_norm='none', resident=True,
                  device=None, compute_metrics=True):
         _lib.require_cuda()
@@ -51,20 +57,31 @@ class SequenceBatch:
         self.padded = torch.empty((B, self.bins, self.Hp, self.Wp), **f32)
         self.recon_p = torch.empty((B, 1, self.Hp, self.Wp), **f32)
         self.recon = torch.empty((B, 1, H, W), **f32)
-        self.image = torch.empty((B, 1, H, W), **f32)
         self.ref = torch.zeros((B, H, W), **f32)
-        self.scores = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+        # results rotate through RING device slots so that the device->host copy of step i (own stream) never races
+        # the kernels of step i+1
+        self.image_ring = torch.empty((self.RING, B, 1, H, W), **f32)
+        self.scores_ring = torch.zeros((self.RING, B, 2), dtype=torch.float64, device=dev)
+        self.scores = self.scores_ring[0]
+        self.image = self.image_ring[0]
         self.oob_total = torch.zeros(1, dtype=torch.int32, device=dev)
         self.launches = 0            # kernels launched by the last step (bench.py gpu_launches)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self._src = []
+        self._nstep = 0
+        # window tables (start, end, frame index) of every item, once: dataset.py:104-130 via MemMapDataset.window
+        n_items = len(self)
+        self._win = np.zeros((B, n_items, 3), dtype=np.int64)
         max_win = 1
-        for ds in self.datasets:
-            for i in range(len(ds)):
-                i0, i1, _ = ds.window(i)
-                max_win = max(max_win, int(i1) - int(i0))
-        for ds in self.datasets:
+        for b, ds in enumerate(self.datasets):
+            for i in range(n_items):
+                i0, i1, fi = ds.window(i)
+                self._win[b, i] = (int(i0), max(int(i1), int(i0)), int(fi) if fi is not None else 0)
+            max_win = max(max_win, int((self._win[b, :, 1] - self._win[b, :, 0]).max()))
+        self.max_win = max_win
+        self._src = []
+        self._base = np.zeros((B, 4), dtype=np.int64)      # raw base addresses (xy, t, p, images) of every sequence
+        for b, ds in enumerate(self.datasets):
             fh = ds.filehandle
             xy = torch.from_numpy(np.ascontiguousarray(fh["xy"], dtype=np.int16)).pin_memory()
             t = torch.from_numpy(np.ascontiguousarray(fh["t"], dtype=np.float64)).pin_memory()
@@ -74,18 +91,26 @@ class SequenceBatch:
                 xy, t, p = (a.to(dev, non_blocking=True) for a in (xy, t, p))
                 im = im.to(dev, non_blocking=True) if im is not None else None
             self._src.append((xy, t, p, im))
+            self._base[b] = (xy.data_ptr(), t.data_ptr(), p.data_ptr(), im.data_ptr() if im is not None else 0)
+        self._windows = (_lib.EventWindow * B)()
+        self._frames = (ctypes.c_void_p * B)()
         if not resident:
-            # per-stream staging (windows are copied host->device every step); t first so it stays 8-byte aligned
-            self.st_xy = torch.empty((B, max_win, 2), dtype=torch.int16, device=dev)
-            self.st_t = torch.empty((B, max_win), dtype=torch.float64, device=dev)
-            self.st_p = torch.empty((B, max_win), dtype=torch.uint8, device=dev)
-            self.st_im = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
-            # results land in a ring of pinned host slots; a slot is reused only after its copy completed
-            self.ring = 4
-            self.host_scores = torch.empty((self.ring, B, 2), dtype=torch.float64).pin_memory()
-            self.host_image = torch.empty((self.ring, B, 1, H, W), dtype=torch.float32).pin_memory()
-            self._slot_done = [None] * self.ring
-            self._nstep = 0
+            # double-buffered device staging: slot s is filled by the copy stream while slot s^1 is being voxelized
+            self.st_xy = torch.empty((2, B, max_win, 2), dtype=torch.int16, device=dev)
+            self.st_t = torch.empty((2, B, max_win), dtype=torch.float64, device=dev)
+            self.st_p = torch.empty((2, B, max_win), dtype=torch.uint8, device=dev)
+            self.st_im = torch.empty((2, B, H, W), dtype=torch.uint8, device=dev)
+            self.host_scores = torch.empty((self.RING, B, 2), dtype=torch.float64).pin_memory()
+            self.host_image = torch.empty((self.RING, B, 1, H, W), dtype=torch.float32).pin_memory()
+            self.copy_stream = torch.cuda.Stream(dev)
+            self.d2h_stream = torch.cuda.Stream(dev)
+            self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [None, None]                 # recorded on the compute stream after a slot was voxelized
+            self._d2h_done = [None] * self.RING
+            self._staged = [None, None]                   # item index held (or in flight) in each staging slot
+            self._last_slot = 1
+            self._host_windows = (_lib.EventWindow * B)()
+            self._host_frames = (ctypes.c_void_p * B)()
         torch.cuda.synchronize(dev)
 
     def __len__(self):
@@ -95,44 +120,87 @@ class SequenceBatch:
         self.model.reset_states()
         self.oob_total.zero_()
 
-    def step(self, idx):
+    # ------------------------------------------------------------------ host-mode staging
+    def _stage(self, idx, slot):
+        """Issue the host->device copies of item ``idx`` into staging slot ``slot`` on the copy stream."""
+        B, lib = self.B, self.lib
+        if self._consumed[slot] is not None:
+            self.copy_stream.wait_event(self._consumed[slot])      # the kernels that read this slot have finished
+        win = self._win[:, idx]
+        hw = self._host_windows
+        for b in range(B):
+            i0, i1 = int(win[b, 0]), int(win[b, 1])
+            w = hw[b]
+            w.xy = int(self._base[b, 0]) + i0 * 4
+            w.t = int(self._base[b, 1]) + i0 * 8
+            w.pol = int(self._base[b, 2]) + i0
+            w.n = i1 - i0
+        cs = ctypes.c_void_p(self.copy_stream.cuda_stream)
+        _lib.check(lib.evk_stage_windows_h2d(hw, B, _lib.ptr(self.st_xy[slot]), _lib.ptr(self.st_t[slot]),
+                                             _lib.ptr(self.st_p[slot]), self.max_win, cs))
+        if self.compute_metrics:
+            hf = self._host_frames
+            for b in range(B):
+                hf[b] = int(self._base[b, 3]) + int(win[b, 2]) * self.H * self.W
+            _lib.check(lib.evk_stage_frames_h2d(hf, B, self.H * self.W, _lib.ptr(self.st_im[slot]), cs))
+        self._h2d_done[slot].record(self.copy_stream)
+        self._staged[slot] = idx
+
+    def step(self, idx, next_idx=None):
         """Frame ``idx`` of every sequence.  Returns (scores [B,2] float64 (mse, ssim), image [B,1,H,W], n_events).
-        In host mode the returned tensors are pinned host tensors (valid after the returned event / a sync)."""
+        In host mode the returned tensors are pinned host tensors, valid after ``self.result_event`` (or a device
+        synchronize); ``next_idx`` (default idx + 1) is the item whose windows are staged while this one computes."""
         lib, dev, B = self.lib, self.dev, self.B
-        st = _lib.stream_ptr(dev)
+        main = torch.cuda.current_stream(dev)
+        st = ctypes.c_void_p(main.cuda_stream)
         launches = 0
         h2d = d2h = 0
-        n_events = 0
+        win = self._win[:, idx]
+        n_events = int((win[:, 1] - win[:, 0]).sum())
+        ring = self._nstep % self.RING
+        self._nstep += 1
         with torch.cuda.device(dev):
-            for b, ds in enumerate(self.datasets):
-                i0, i1, frame_index = ds.window(idx)
-                i0, i1 = int(i0), int(i1)
-                n = max(i1 - i0, 0)
-                n_events += n
-                xy, t, p, im = self._src[b]
-                if n > 0:
-                    if self.resident:
-                        wxy, wt, wp = xy[i0:i1], t[i0:i1], p[i0:i1]
-                    else:
-                        wxy, wt, wp = self.st_xy[b, :n], self.st_t[b, :n], self.st_p[b, :n]
-                        wxy.copy_(xy[i0:i1], non_blocking=True)
-                        wt.copy_(t[i0:i1], non_blocking=True)
-                        wp.copy_(p[i0:i1], non_blocking=True)
-                        h2d += n * 13
-                    _lib.check(lib.evk_voxelize_raw(_lib.ptr(wxy), _lib.ptr(wt), _lib.ptr(wp), n, self.bins, self.H,
-                                                    self.W, _lib.ptr(self.voxel[b]), _lib.ptr(self.oob_total), st))
-                    launches += 1
-                else:
-                    self.voxel[b].zero_()          # empty window -> zeros grid (dataset.py:59-71)
-                if self.compute_metrics:
-                    if self.resident:
-                        src = im[frame_index]
-                    else:
-                        src = self.st_im[b]
-                        src.copy_(im[frame_index], non_blocking=True)
-                        h2d += src.numel()
-                    _lib.check(lib.evk_u8_to_f32(_lib.ptr(src), _lib.ptr(self.ref[b]), src.numel(), st))
-                    launches += 1
+            ws, fr = self._windows, self._frames
+            if self.resident:
+                for b in range(B):
+                    i0, i1 = int(win[b, 0]), int(win[b, 1])
+                    w = ws[b]
+                    w.xy = int(self._base[b, 0]) + i0 * 4
+                    w.t = int(self._base[b, 1]) + i0 * 8
+                    w.pol = int(self._base[b, 2]) + i0
+                    w.n = i1 - i0
+                    fr[b] = int(self._base[b, 3]) + int(win[b, 2]) * self.H * self.W
+            else:
+                slot = 0 if self._staged[0] == idx else (1 if self._staged[1] == idx else None)
+                if slot is None:                      # first step / non-sequential access: stage now
+                    slot = self._last_slot ^ 1
+                    self._stage(idx, slot)
+                self._last_slot = slot
+                main.wait_event(self._h2d_done[slot])
+                xy0, t0, p0, im0 = (self.st_xy[slot].data_ptr(), self.st_t[slot].data_ptr(), self.st_p[slot].data_ptr(),
+                                    self.st_im[slot].data_ptr())
+                for b in range(B):
+                    w = ws[b]
+                    w.xy = xy0 + b * self.max_win * 4
+                    w.t = t0 + b * self.max_win * 8
+                    w.pol = p0 + b * self.max_win
+                    w.n = int(win[b, 1] - win[b, 0])
+                    fr[b] = im0 + b * self.H * self.W
+                h2d += n_events * 13 + (B * self.H * self.W if self.compute_metrics else 0)
+            # empty windows -> zeros grid (dataset.py:59-71) is part of the batched call
+            _lib.check(lib.evk_voxelize_raw_batch(ws, B, self.bins, self.H, self.W, _lib.ptr(self.voxel),
+                                                  _lib.ptr(self.oob_total), st))
+            launches += 1 if n_events > 0 else 0
+            if self.compute_metrics:
+                _lib.check(lib.evk_u8_to_f32_batch(fr, B, self.H * self.W, _lib.ptr(self.ref), st))
+                launches += 1
+            if not self.resident:
+                if self._consumed[slot] is None:
+                    self._consumed[slot] = torch.cuda.Event()
+                self._consumed[slot].record(main)
+                nxt = idx + 1 if next_idx is None else next_idx
+                if 0 <= nxt < self._win.shape[1] and self._staged[slot ^ 1] != nxt:
+                    self._stage(nxt, slot ^ 1)        # overlaps everything below
             _lib.check(lib.evk_normalize_pad(_lib.ptr(self.voxel), _lib.ptr(self.padded), B, self.bins, self.H, self.W,
                                              self.Hp, self.Wp, int(self.normalize), st))
             launches += 2 if self.normalize else 1
@@ -140,33 +208,44 @@ class SequenceBatch:
             launches += self.model.last_launch_count()
             _lib.check(lib.evk_crop(_lib.ptr(out), _lib.ptr(self.recon), B, 1, self.Hp, self.Wp, self.H, self.W, st))
             launches += 1
-            image = self.recon
+            if not self.resident and self._d2h_done[ring] is not None:
+                main.wait_event(self._d2h_done[ring])             # slot's previous results have left the device
+            image = self.image_ring[ring]
+            scores = self.scores_ring[ring]
             if self.post != 'none':
                 q = (0.0, 100.0) if self.post == 'standard' else (1.0, 99.0)
-                _lib.check(lib.evk_percentile_normalize(_lib.ptr(self.recon), _lib.ptr(self.image), B, self.H * self.W,
+                _lib.check(lib.evk_percentile_normalize(_lib.ptr(self.recon), _lib.ptr(image), B, self.H * self.W,
                                                         q[0], q[1], int(self.post == 'exprobust'), st))
                 launches += 1
-                image = self.image
+            else:
+                image = self.recon
             if self.compute_metrics:
                 # clip of EvalMetricsTracker.update (utils/eval_metrics.py:253-255) fused into the metric kernel
                 _lib.check(lib.evk_mse_ssim(_lib.ptr(image), _lib.ptr(self.ref), B, self.H, self.W, 1,
-                                            _lib.ptr(self.scores), st))
+                                            _lib.ptr(scores), st))
                 launches += 2
-            scores = self.scores
+            self.scores, self.image = scores, image
             if not self.resident:
-                slot = self._nstep % self.ring
-                self._nstep += 1
-                if self._slot_done[slot] is not None:
-                    self._slot_done[slot].synchronize()
-                else:
-                    self._slot_done[slot] = torch.cuda.Event()
-                self.host_scores[slot].copy_(self.scores, non_blocking=True)
-                self.host_image[slot].copy_(image, non_blocking=True)
-                self._slot_done[slot].record()
-                d2h += self.scores.numel() * 8 + image.numel() * 4
-                scores, image = self.host_scores[slot], self.host_image[slot]
+                done = torch.cuda.Event()
+                done.record(main)
+                self.d2h_stream.wait_event(done)
+                with torch.cuda.stream(self.d2h_stream):
+                    self.host_scores[ring].copy_(scores, non_blocking=True)
+                    self.host_image[ring].copy_(image, non_blocking=True)
+                if self._d2h_done[ring] is None:
+                    self._d2h_done[ring] = torch.cuda.Event()
+                self._d2h_done[ring].record(self.d2h_stream)
+                self.result_event = self._d2h_done[ring]
+                d2h += scores.numel() * 8 + image.numel() * 4
+                scores, image = self.host_scores[ring], self.host_image[ring]
         self.launches, self.h2d_bytes, self.d2h_bytes = launches, h2d, d2h
         return scores, image, n_events
+
+    def finish(self):
+        """Wait for every copy in flight (host mode)."""
+        if not self.resident:
+            self.copy_stream.synchronize()
+            self.d2h_stream.synchronize()
 
     def check_bounds(self):
         n = int(self.oob_total.item())

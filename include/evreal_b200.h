@@ -53,6 +53,27 @@ int evk_voxelize(const float* x, const float* y, const float* t, const float* p,
 int evk_voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int64_t n,
                      int num_bins, int H, int W, float* grid, int* oob_count, void* stream);
 
+/* The same for several windows in ONE launch (frame i of a lock-step batch of independent sequences: eval.py:197
+ * resets state per sequence, so sequences are independent units).  windows: HOST array of device pointers / sizes;
+ * grids: [n_windows, num_bins, H, W] float32, zeroed by the call.  A window with n == 0 yields the zeros grid, as
+ * MemMapDataset.__getitem__ does for empty windows (dataset.py:59-71). */
+typedef struct evk_event_window {
+    const int16_t* xy;
+    const double* t;
+    const uint8_t* pol;
+    int64_t n;
+} evk_event_window;
+int evk_voxelize_raw_batch(const evk_event_window* windows, int n_windows, int num_bins, int H, int W,
+                           float* grids, int* oob_count, void* stream);
+
+/* Host-buffer ingest (the DataLoader's role, eval.py:72 / dataset.py:222-228): copies the raw windows of a lock-step
+ * batch from (pinned) HOST arrays into per-sequence device staging rows of stride_events events, asynchronously on
+ * `stream`; window b lands at st_xy + b*stride_events*2, st_t + b*stride_events, st_pol + b*stride_events. */
+int evk_stage_windows_h2d(const evk_event_window* host_windows, int n_windows, int16_t* st_xy, double* st_t,
+                          uint8_t* st_pol, int64_t stride_events, void* stream);
+/* n_frames uint8 reference frames (HOST array of host pointers, numel bytes each) -> dst [n_frames, numel] on the device */
+int evk_stage_frames_h2d(const uint8_t* const* host_frames, int n_frames, int64_t numel, uint8_t* dst, void* stream);
+
 /* normalize_event_tensor(event_tensor)   reference: eval.py:398-410
  * in/out: [n_samples, numel] float32 (may alias).  Statistics are per sample
  * over non-zero entries.  Optionally fuses CropParameters.pad
@@ -155,6 +176,8 @@ int evk_mse_ssim(const float* img, const float* ref, int n_images, int H, int W,
 
 /* uint8 frame -> float32 / 255  (dataset.py:84) */
 int evk_u8_to_f32(const uint8_t* in, float* out, int64_t numel, void* stream);
+/* n_frames frames of numel bytes each (HOST array of device pointers) -> out [n_frames, numel] float32, one launch */
+int evk_u8_to_f32_batch(const uint8_t* const* frames, int n_frames, int64_t numel, float* out, void* stream);
 
 #ifdef __cplusplus
 }
