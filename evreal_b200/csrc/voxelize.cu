@@ -6,9 +6,13 @@
 //
 // HBM-bound integer/float scatter: every event is read exactly once with
 // 128-bit loads (4 events per thread per array) and contributes to at most two
-// temporal bins, each with one fire-and-forget RED.ADD.F32 into the L2-resident
-// grid (<= 6.1 MB at 5x480x640).  Algorithmic bytes per window:
-// 16*N (f32 SoA) or 13*N (raw int16/f64/u8) + 4*bins*H*W for the grid.
+// ADJACENT temporal bins.  The scatter target is a pixel-interleaved scratch grid
+// [H][W][G][4] (G = (bins-1)/3 + 1 groups of four slots; group g holds bins 3g..3g+3, so every adjacent pair of
+// bins shares one aligned 16-byte group) and each event is ONE fire-and-forget RED.ADD.V4.F32 into it: the L2
+// reduction units are request-rate bound (~83 requests/clk measured, tools/microbench/red_bench.cu) and a v4
+// request costs the same as a scalar one, so this halves the scatter time of the two-scalar-reds form.  A gather
+// pass then writes the reference's planar [bins,H,W] layout (bin 3g = slot 0 of group g + slot 3 of group g-1).
+// Algorithmic bytes per window: 16*N (f32 SoA) or 13*N (raw int16/f64/u8) + 4*bins*H*W for the grid.
 #include <algorithm>
 
 #include "evk_common.cuh"
@@ -19,13 +23,15 @@ constexpr int kVoxThreads = 256;
 
 struct VoxGeom {
     int bins, H, W;
+    int groups;     // 16-byte slot groups per pixel in the scratch grid
 };
+static inline int vox_groups(int bins) { return (bins - 1) / 3 + 1; }
 
 // One event's contribution.  tn is the normalised time in [0, bins-1]; only
 // floor(tn) and floor(tn)+1 can have weight max(0, 1-|tn-b|) > 0, so the
 // reference's five passes collapse to two adds with identical float values.
 __device__ __forceinline__ void scatter_event(float xf, float yf, float tn, float pol, const VoxGeom g,
-                                              float* __restrict__ grid, int& oob) {
+                                              float* __restrict__ scratch, int& oob) {
     int xi = (int)xf;   // truncation toward zero == tensor.long()
     int yi = (int)yf;
     if (xi < 0) xi += g.W;   // python-style wrap of negative indices (index_put_)
@@ -36,14 +42,38 @@ __device__ __forceinline__ void scatter_event(float xf, float yf, float tn, floa
     }
     const float fb = floorf(tn);
     const int b0 = (int)fb;
-    float* cell = grid + (size_t)yi * g.W + xi;
-    const size_t plane = (size_t)g.H * g.W;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int b = b0 + k;
-        if (b < 0 || b >= g.bins) continue;
-        const float w = 1.0f - fabsf(tn - (float)b);
-        if (w > 0.0f) atomicAdd(cell + (size_t)b * plane, pol * w);
+    if (b0 < -1 || b0 >= g.bins) return;              // no bin within distance 1 (cannot happen for sorted windows)
+    const int grp = max(b0, 0) / 3;
+    // the reference's per-bin weight max(0, 1 - |tn - b|) for the two bins that can be non-zero (same float values)
+    const float w0 = 1.0f - fabsf(tn - (float)b0), w1 = 1.0f - fabsf(tn - (float)(b0 + 1));
+    const float c0 = (b0 >= 0 && w0 > 0.0f) ? pol * w0 : 0.0f;
+    const float c1 = (b0 + 1 < g.bins && w1 > 0.0f) ? pol * w1 : 0.0f;
+    const int o = b0 - 3 * grp;                       // slot of bin b0 in its group: -1 (b0 == -1), 0, 1 or 2
+    const float v0 = o == 0 ? c0 : (o == -1 ? c1 : 0.0f);
+    const float v1 = o == 1 ? c0 : (o == 0 ? c1 : 0.0f);
+    const float v2 = o == 2 ? c0 : (o == 1 ? c1 : 0.0f);
+    const float v3 = o == 2 ? c1 : 0.0f;
+    float* cell = scratch + (((size_t)yi * g.W + xi) * g.groups + grp) * 4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+}
+
+// scratch [n][H*W][G][4] -> planar [n][bins][H*W]
+__global__ void __launch_bounds__(256) voxel_gather_kernel(const float* __restrict__ scratch, float* __restrict__ grid, VoxGeom g,
+                                                           int64_t pixels, int n_grids) {
+    const int64_t total = pixels * n_grids;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = i / pixels, pix = i - w * pixels;
+        const float4* src = reinterpret_cast<const float4*>(scratch) + i * g.groups;
+        float* dst = grid + (size_t)w * g.bins * pixels + pix;
+        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int gi = 0; gi < g.groups; ++gi) {
+            const float4 c = __ldcs(src + gi);
+            const int b = 3 * gi;
+            if (b < g.bins) dst[(size_t)b * pixels] = gi > 0 ? c.x + prev.w : c.x;
+            if (b + 1 < g.bins) dst[(size_t)(b + 1) * pixels] = c.y;
+            if (b + 2 < g.bins) dst[(size_t)(b + 2) * pixels] = c.z;
+            prev = c;
+        }
     }
 }
 
@@ -150,7 +180,7 @@ voxelize_raw_batch_kernel(const __grid_constant__ VoxBatch wb, VoxGeom g, float*
     const int w = blockIdx.y;
     const int64_t n = wb.n[w];
     if (n <= 0) return;                      // empty window: the (pre-zeroed) grid stays zero (dataset.py:59-71)
-    voxelize_raw_body(wb.xy[w], wb.t[w], wb.pol[w], n, g, grids + (size_t)w * g.bins * g.H * g.W, oob_count,
+    voxelize_raw_body(wb.xy[w], wb.t[w], wb.pol[w], n, g, grids + (size_t)w * 4 * g.groups * g.H * g.W, oob_count,
                       (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
@@ -162,24 +192,54 @@ static int vox_grid_blocks(int64_t n, int per_thread) {
     return (int)blocks;
 }
 
+// stream-ordered scratch (no library-global state): allocate + zero, ... scatter ..., gather into the planar grid + free
+static int vox_scratch_begin(float** scratch, const VoxGeom& g, int n_grids, cudaStream_t st) {
+    const size_t bytes = sizeof(float) * 4 * g.groups * (size_t)g.H * g.W * n_grids;
+    // keep freed blocks in the device's default pool (the default release threshold of 0 hands them back to the driver
+    // at every synchronisation point, which turns each call into a real allocation: measured 100+ us)
+    static bool pool_ready[64] = {false};
+    int dev = 0;
+    EVK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+        cudaMemPool_t pool;
+        EVK_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        EVK_CHECK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_ready[dev] = true;
+    }
+    EVK_CHECK_CUDA(cudaMallocAsync((void**)scratch, bytes, st));
+    EVK_CHECK_CUDA(cudaMemsetAsync(*scratch, 0, bytes, st));
+    return EVK_OK;
+}
+static int vox_scratch_end(float* scratch, float* grid, const VoxGeom& g, int n_grids, cudaStream_t st) {
+    const int64_t pixels = (int64_t)g.H * g.W;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(pixels * n_grids, 256), (int64_t)kNumSMs * 8);
+    voxel_gather_kernel<<<blocks, 256, 0, st>>>(scratch, grid, g, pixels, n_grids);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    EVK_CHECK_CUDA(cudaFreeAsync(scratch, st));
+    return EVK_OK;
+}
+
 int voxelize_f32(const float* x, const float* y, const float* t, const float* p, int64_t n, int bins, int H, int W,
                  float* grid, int* oob_count, cudaStream_t st) {
     EVK_REQUIRE(n > 0, EVK_ERR_ARG, "evk_voxelize: empty window (n=%lld); the reference indexes ts[-1]", (long long)n);
     EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize: bad geometry bins=%d H=%d W=%d", bins, H, W);
-    EVK_CHECK_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)bins * H * W, st));
-    VoxGeom g{bins, H, W};
+    VoxGeom g{bins, H, W, vox_groups(bins)};
+    float* scratch = nullptr;
+    int r = vox_scratch_begin(&scratch, g, 1, st);
+    if (r != EVK_OK) return r;
     // all four arrays must share the same 16-byte phase for the vector body
     auto phase = [](const void* q) { return (int)(((uintptr_t)q >> 2) & 3); };
     const bool same = phase(x) == phase(y) && phase(y) == phase(t) && phase(t) == phase(p) &&
                       (((uintptr_t)x | (uintptr_t)y | (uintptr_t)t | (uintptr_t)p) & 3) == 0;
     if (same && n >= 64) {
         int64_t head = (4 - phase(x)) & 3;
-        voxelize_f32_kernel<true><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, grid, oob_count);
+        voxelize_f32_kernel<true><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, scratch, oob_count);
     } else {
-        voxelize_f32_kernel<false><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, grid, oob_count);
+        voxelize_f32_kernel<false><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, scratch, oob_count);
     }
     EVK_CHECK_CUDA(cudaGetLastError());
-    return EVK_OK;
+    return vox_scratch_end(scratch, grid, g, 1, st);
 }
 
 int voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int64_t n, int bins, int H, int W,
@@ -187,20 +247,24 @@ int voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int64_t
     EVK_REQUIRE(n > 0, EVK_ERR_ARG, "evk_voxelize_raw: empty window");
     EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize_raw: bad geometry");
     EVK_REQUIRE(((uintptr_t)xy & 3) == 0 && ((uintptr_t)t & 7) == 0, EVK_ERR_ARG, "evk_voxelize_raw: misaligned arrays");
-    EVK_CHECK_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)bins * H * W, st));
-    VoxGeom g{bins, H, W};
-    voxelize_raw_kernel<<<vox_grid_blocks(n, 2), kVoxThreads, 0, st>>>(xy, t, pol, n, g, grid, oob_count);
+    VoxGeom g{bins, H, W, vox_groups(bins)};
+    float* scratch = nullptr;
+    int r = vox_scratch_begin(&scratch, g, 1, st);
+    if (r != EVK_OK) return r;
+    voxelize_raw_kernel<<<vox_grid_blocks(n, 2), kVoxThreads, 0, st>>>(xy, t, pol, n, g, scratch, oob_count);
     EVK_CHECK_CUDA(cudaGetLastError());
-    return EVK_OK;
+    return vox_scratch_end(scratch, grid, g, 1, st);
 }
 
 int voxelize_raw_batch(const evk_event_window* windows, int n_windows, int bins, int H, int W, float* grids, int* oob_count,
                        cudaStream_t st) {
     EVK_REQUIRE(windows && grids && n_windows > 0, EVK_ERR_ARG, "evk_voxelize_raw_batch: bad argument");
     EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize_raw_batch: bad geometry");
-    const size_t grid_elems = (size_t)bins * H * W;
-    EVK_CHECK_CUDA(cudaMemsetAsync(grids, 0, sizeof(float) * grid_elems * n_windows, st));
-    VoxGeom g{bins, H, W};
+    VoxGeom g{bins, H, W, vox_groups(bins)};
+    const size_t scratch_elems = (size_t)4 * g.groups * H * W;
+    float* scratch = nullptr;
+    int r = vox_scratch_begin(&scratch, g, n_windows, st);
+    if (r != EVK_OK) return r;
     for (int w0 = 0; w0 < n_windows; w0 += kVoxBatch) {
         const int cnt = std::min(kVoxBatch, n_windows - w0);
         VoxBatch wb;
@@ -220,10 +284,10 @@ int voxelize_raw_batch(const evk_event_window* windows, int n_windows, int bins,
         int64_t bx = ceil_div64(nmax, (int64_t)kVoxThreads * 2);
         const int64_t cap = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / cnt);
         bx = std::max<int64_t>(1, std::min(bx, cap));
-        voxelize_raw_batch_kernel<<<dim3((unsigned)bx, (unsigned)cnt), kVoxThreads, 0, st>>>(wb, g, grids + grid_elems * w0, oob_count);
+        voxelize_raw_batch_kernel<<<dim3((unsigned)bx, (unsigned)cnt), kVoxThreads, 0, st>>>(wb, g, scratch + scratch_elems * w0, oob_count);
         EVK_CHECK_CUDA(cudaGetLastError());
     }
-    return EVK_OK;
+    return vox_scratch_end(scratch, grids, g, n_windows, st);
 }
 
 // ---------------------------------------------------------------------------
