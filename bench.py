@@ -46,7 +46,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -60,7 +60,7 @@ class ClockSampler:
             sel = ["-i", str(device_index)]
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"] + sel, stdout=self.file, stderr=subprocess.DEVNULL)
+                                          "-lms", "50"] + sel, stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -349,9 +349,9 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=8, help="independent streams run in lock-step per GPU")
+    ap.add_argument("--batch", type=int, default=24, help="independent streams run in lock-step per GPU (24 measured best: r01 profiles)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=100, help="bounded CPU-baseline sample (frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

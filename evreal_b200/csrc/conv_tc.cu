@@ -51,9 +51,11 @@ struct TcArgs {
     int n_groups;               // V-tap groups per (chunk, U shift): 1 (stride 1) or 2 (stride 2: even / odd taps)
     int g_tap0[2], g_ntaps[2], g_step;
     int cs;                     // cluster size (CTAs sharing one weight tile)
-    int issuers;                // MMA issuer warps (1 or 2); each has its own accumulator of acc_cols TMEM columns
+    int issuers;                // MMA issuer warps (1 or 2)
+    int own_acc;                // 1: every issuer has its own accumulator of acc_cols columns (free-running, summed by the
+                                //    epilogue); 0: shared accumulator, strict block order by handshake
     int acc_cols;
-    int acc_stride;             // TMEM columns per accumulator stage (= issuers * acc_cols)
+    int acc_stride;             // TMEM columns per accumulator stage (= acc_cols, or 2 * acc_cols with own_acc)
     uint32_t tmem_cols;
     const float* bias;
     const float* res;
@@ -62,6 +64,7 @@ struct TcArgs {
     const float* c_prev; float* c_new; float* h_new;
     __nv_bfloat16* hs_new; long long hs_plane;
     const float* pred_w; const float* pred_skip; float* pred_out; float pred_bias; int pred_sigmoid;
+    int exp;                    // DBG kernels only (EVK_TC_EXP bit mask): 1 skip weight loads, 2 skip activation loads, 4 skip epilogue stores
     unsigned long long* dbg;    // EVK_TC_TIMING: per-CTA clock64 phase counters [grid][8], else nullptr
 };
 
@@ -181,9 +184,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         const int iv0 = t.ov0 * a.stride - a.pad_v + a.g_tap0[g];
                         const uint32_t sa = base + s * a_stage;
                         if (elect_one()) {
-                            mbar_expect_tx(bar_fa + 8u * s, a_stage);
-                            tma_load_5d(sa, m, bar_fa + 8u * s, c0, iu0, iv0, t.img, 0);
-                            tma_load_5d(sa + a_plane, m, bar_fa + 8u * s, c0, iu0, iv0, t.img, 1);
+                            if (DBG && (a.exp & 2)) {
+                                mbar_arrive(bar_fa + 8u * s);
+                            } else {
+                                mbar_expect_tx(bar_fa + 8u * s, a_stage);
+                                tma_load_5d(sa, m, bar_fa + 8u * s, c0, iu0, iv0, t.img, 0);
+                                tma_load_5d(sa + a_plane, m, bar_fa + 8u * s, c0, iu0, iv0, t.img, 1);
+                            }
                         }
                         __syncwarp();
                         if (++s == (uint32_t)a.a_stages) { s = 0; ph ^= 1u; }
@@ -212,7 +219,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             const int tap = a.ux ? tv * a.kw + su : su * a.kw + tv;
                             const int k0 = tap * ctot + ch * BK;
                             const uint32_t sb = smem_b + s * b_stage + (uint32_t)(crank * bnp) * ROW_BYTES;
-                            if (elect_one()) {
+                            if (DBG && (a.exp & 1)) {
+                                if (elect_one()) mbar_arrive(bar_fb + 8u * s);
+                            } else if (elect_one()) {
                                 mbar_expect_tx(bar_fb + 8u * s, b_stage);
                                 if (cs > 1) {
                                     tma_load_3d_mc(sb, &tm_w, bar_fb + 8u * s, k0, row0, 0, cmask);
@@ -241,16 +250,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         //   D[:, 0:bn]    += A_lo *  B_hi^T
         // (A is read from shared memory twice instead of three times; the epilogue adds the two halves.)
         //
-        // Why (up to) two issuers: tcgen05.mma issue is back-pressured -- the issuing thread runs at most ~1-2 MMAs
-        // ahead of the tensor pipe -- so everything a single issuer does between two K blocks (commit, mbarrier poll
-        // ~100 cycles even when complete, descriptors, elect, R2UR) is a pipe bubble: measured 198 / 178 cycles per K
-        // slice at bn = 64 / 32 against a pipe floor of 112 / 94 (tools/microbench/mma_loop_bench.cu).  With the K
-        // blocks of a tile dealt alternately to two issuers, one issuer's inter-block work hides behind the other's
-        // eight MMAs (134 / 122).  Each issuer accumulates into its OWN tensor-memory accumulator (summed by the
-        // epilogue): the interleaving of the two instruction streams in the pipe is timing dependent, and with a
-        // shared accumulator the fp32 summation order -- hence the result bits -- would change from run to run.
-        // bn = 128 keeps one issuer: two accumulators would not fit tensor memory next to the epilogue's double
-        // buffer, and that shape is bound by shared-memory bandwidth, not by issue.
+        // Why two issuers: tcgen05.mma issue is back-pressured -- the issuing thread runs at most ~1-2 MMAs ahead of the
+        // tensor pipe -- so everything a single issuer does between two K blocks (commit, mbarrier poll ~100 cycles even
+        // when complete, descriptors, elect, R2UR) is a pipe bubble: measured 283 / 198 / 178 cycles per K slice at
+        // bn = 128 / 64 / 32 against a pipe floor of 192 / 112 / 94 -- with all loads and stores disabled, i.e. not a
+        // memory effect (EVK_TC_EXP; tools/microbench/mma_loop_bench.cu).  The K blocks of a tile are dealt alternately
+        // to two issuer warps that accumulate into the SAME tensor-memory accumulator in STRICT block order: issuer r
+        // prepares block b (barrier wait, fence, descriptors), then waits on named barrier 1+r for the other issuer's
+        // "block b-1 issued" signal, issues its eight MMAs and signals barrier 2-r.  Only the ~30-cycle handshake sits
+        // between two blocks (192 / 143 / 132 cycles per slice in the microbenchmark), and because the pipe executes
+        // in issue order the fp32 summation order -- hence every output bit -- is the same from run to run.
+        // Small N tiles (bn <= 64), whose MMAs are too short to cover even the handshake, run the two issuers FREE
+        // (no handshake) into one accumulator EACH, summed in fixed order by the epilogue -- equally deterministic,
+        // 134 / 122 cycles per slice; bn = 128 cannot afford two accumulators next to the epilogue's double buffer.
+        // Barriers that guard data read by both issuers' MMAs (A stage free, accumulator complete) count two commits.
         const uint32_t role = (uint32_t)(warp - 1);
         const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * a.bn));
         const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)a.bn);
@@ -260,6 +273,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const uint32_t atom16 = ATOM >> 4, a_plane16 = a_plane >> 4;
         const uint32_t nbs = (uint32_t)a.b_stages;
         const uint32_t two = a.issuers == 2 ? 1u : 0u;
+        const bool own = a.own_acc != 0;
+        const uint32_t first_blk = own ? role : 0u;      // the block whose first MMA initialises the accumulator
+        const uint32_t kb_total = (uint32_t)(chunks * a.ku * (a.g_ntaps[0] + (a.n_groups > 1 ? a.g_ntaps[1] : 0)));
         uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0;
         bool b_ready = false;
         long long w_te = 0, w_fa = 0, w_fb = 0;
@@ -270,7 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             mbar_wait(bar_tempty + 8u * as, aph ^ 1u);          // epilogue drained this accumulator stage
             if (DBG) w_te += clock64() - t0;
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * (uint32_t)a.acc_stride + role * (uint32_t)a.acc_cols;
+            const uint32_t d_tmem = tmem_base + as * (uint32_t)a.acc_stride + (own ? role * (uint32_t)a.acc_cols : 0u);
             uint32_t blk = 0;
             b_ready = false;      // the poll below looks `issuers` blocks ahead WITHIN a tile; across tiles the distance differs
             for (int ch = 0; ch < chunks; ++ch)
@@ -295,17 +311,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                 uint32_t s2 = sB + 1u + two, ph2 = phB;
                                 if (s2 >= nbs) { s2 -= nbs; ph2 ^= 1u; }
                                 b_ready = mbar_try_wait(bar_fb + 8u * s2, ph2);
+                                if (two && !own && blk > 0) {     // my turn: the other issuer has issued block blk - 1
+                                    if (role) asm volatile("bar.sync 2, 64;" ::: "memory"); else asm volatile("bar.sync 1, 64;" ::: "memory");
+                                }
                                 if (elect_one()) {
 #pragma unroll
                                     for (int k = 0; k < BK / 16; ++k) {
                                         // +16 elements (32 B) along K inside the swizzle atom = +2 in the 16-byte address field
-                                        tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, (k == 0 && blk == role) ? 0u : 1u);
+                                        tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, (k == 0 && blk == first_blk) ? 0u : 1u);
                                         tc_mma_bf16(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + 2 * k), idesc1, 1u);
                                     }
                                     // frees the weight slot in every CTA of the cluster when these MMAs retire
                                     if (cs > 1) tc_commit_mc(bar_free, cmask); else tc_commit(bar_free);
                                 }
                                 __syncwarp();
+                                if (two && !own && blk + 1 < kb_total) {  // hand the turn to the other issuer
+                                    if (role) asm volatile("bar.arrive 1, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory");
+                                }
                             }
                             if (++sB == nbs) { sB = 0; phB ^= 1u; }
                             ah_lo += atom16;
@@ -358,7 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     tc_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-                    if (a.issuers == 2) {             // second issuer's accumulator (fixed order: deterministic bits)
+                    if (a.own_acc) {                  // second issuer's accumulator (fixed order: deterministic bits)
                         uint32_t w[32];
                         tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + j0), u);
                         tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + a.bn + j0), w);
@@ -374,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     if (lane == 0) mbar_arrive(bar_tempty + 8u * as);
                 }
                 const int nb = n0 + j0;
-                if (!valid || nb >= a.cout) continue;
+                if (!valid || nb >= a.cout || (DBG && (a.exp & 4))) continue;
                 if (a.epi == EPI_LINEAR) {
                     const size_t o = pix * a.cout + nb;
                     float pacc = 0.f;
@@ -646,6 +668,7 @@ int tc_plan_create(ConvParams& p) {
     a.c_prev = p.c_prev; a.c_new = p.c_new; a.h_new = p.h_new; a.hs_new = p.hs_new;
     a.hs_plane = (long long)p.N * p.Hout * p.Wout * (p.cout / 4);
     a.dbg = nullptr;
+    a.exp = env_int("EVK_TC_EXP", 0);
     const uint32_t row_bytes = bk * 2;
     const size_t a_stage = 2 * (size_t)a.ar * 8 * row_bytes;
     const size_t b_stage = 2 * (size_t)bn * row_bytes;
@@ -658,8 +681,9 @@ int tc_plan_create(ConvParams& p) {
     // per accumulator stage: [hi*hi + lo*hi | hi*lo] = 2*bn columns, read in 32-column windows (bn%32 tail -> pad)
     a.acc_cols = (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;
     const int kb = (a.chunks1 + a.chunks2) * p.kh * p.kw;
-    a.issuers = (4 * a.acc_cols <= 512 && kb >= 2 && env_int("EVK_TC_ISSUERS", 2) == 2) ? 2 : 1;
-    a.acc_stride = a.issuers * a.acc_cols;
+    a.issuers = (kb >= 2 && env_int("EVK_TC_ISSUERS", 2) == 2) ? 2 : 1;
+    a.own_acc = (a.issuers == 2 && 4 * a.acc_cols <= 512 && env_int("EVK_TC_OWN_ACC", 1)) ? 1 : 0;
+    a.acc_stride = a.own_acc ? 2 * a.acc_cols : a.acc_cols;
     uint32_t cols = 32;
     while ((int)cols < 2 * a.acc_stride) cols <<= 1;
     if (cols > 512) { delete pl; EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: accumulator does not fit tensor memory (bn=%d)", bn); }

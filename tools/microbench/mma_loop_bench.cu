@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256, 1) loop_bench(Args a, long long* out) {
     const uint32_t smem_b = base + (uint32_t)a.a_stages * a_stage;
     const uint32_t bar_fa = smem_u32(&bars[0]), bar_ea = smem_u32(&bars[8]), bar_fb = smem_u32(&bars[16]), bar_eb = smem_u32(&bars[24]);
     const uint32_t bar_done = smem_u32(&bars[39]);
-    if (warp == 0 || (VARIANT >= 6 && warp >= 2 && warp < 1 + a.ni)) {
+    if (warp == 0 || (VARIANT >= 6 && warp >= 2 && warp < 1 + (VARIANT == 8 ? 2 : a.ni))) {
         const int role = warp == 0 ? 0 : warp - 1;
         const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * a.bn));
         const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)a.bn);
@@ -216,6 +216,43 @@ __global__ void __launch_bounds__(256, 1) loop_bench(Args a, long long* out) {
                 }
             }
             (void)b_ready;
+        } else if (VARIANT == 8) {
+            // ---- two issuers, ONE accumulator, strict block order enforced by a named-barrier handshake (deterministic
+            // summation order): issuer r waits on barrier 1+r before block b > 0 and signals barrier 1+(1-r) after
+            // issuing block b when a block b+1 follows
+            const int KB = a.groups * a.ntaps;
+            for (int t = 0; t < a.tiles; ++t) {
+                uint32_t blk = 0;
+                for (int grp = 0; grp < a.groups; ++grp) {
+                    uint32_t ah_lo = lo_of(base + sA * a_stage);
+                    mbar_wait(bar_fa + 8u * sA, 1);
+                    for (int j = 0; j < a.ntaps; ++j, ++blk) {
+                        const uint32_t bh_lo = lo_of(smem_b + sB * b_stage);
+                        const uint32_t bar_free = bar_eb + 8u * sB;
+                        const bool mine = (blk & 1u) == (uint32_t)role;
+                        if (mine) {
+                            mbar_wait(bar_fb + 8u * sB, 1);
+                            tc_fence_after();
+                            if (blk > 0) { if (role) asm volatile("bar.sync 2, 64;" ::: "memory"); else asm volatile("bar.sync 1, 64;" ::: "memory"); }
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k) {
+                                    tc_mma_bf16(tmem_base, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, (k == 0 && blk == 0) ? 0u : 1u);
+                                    tc_mma_bf16(tmem_base, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + 2 * k), idesc1, 1u);
+                                }
+                                tc_commit(bar_free);
+                            }
+                            __syncwarp();
+                            if ((int)blk + 1 < KB) { if (role) asm volatile("bar.arrive 1, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory"); }
+                        }
+                        if (++sB == (uint32_t)a.b_stages) sB = 0;
+                        ah_lo += atom16;
+                    }
+                    if (elect_one()) tc_commit(bar_ea + 8u * sA);
+                    __syncwarp();
+                    if (++sA == (uint32_t)a.a_stages) sA = 0;
+                }
+            }
         } else if (VARIANT == 3) {
             // ---- same operands every block (no ring), elect + commit: isolates the effect of rotating smem addresses
             for (int t = 0; t < a.tiles; ++t)
@@ -266,18 +303,10 @@ int main() {
     cudaMalloc(&d, 296 * sizeof(long long));
     for (int bn : {128, 64, 32}) {
         Args a = {bn, 2, 4, 18, 3, 6, 18, 20, 2};
-        run<0>("V0 conv_tc loop (warp-wide, elect, waits pass immediately)", a, d);
-        run<1>("V1 one elected thread runs the loop", a, d);
-        run<2>("V2 warp-wide, elect, no barrier waits", a, d);
-        run<3>("V3 warp-wide, elect, fixed operands", a, d);
-        run<4>("V4 fused K-block asm + embedded polls, warp-wide + shfl", a, d);
-        run<5>("V5 fused K-block asm + embedded polls, one thread", a, d);
-        run<6>("V6 two issuer warps alternate blocks, no waits", a, d);
-        run<7>("V7 two issuer warps alternate blocks, with waits", a, d);
-        a.ni = 3; run<7>("V7 THREE issuer warps, with waits", a, d);
-        a.ni = 4; run<7>("V7 FOUR issuer warps, with waits", a, d);
-        a.ntaps = 5; a.b_stages = bn > 64 ? 4 : 8; run<7>("V7 FOUR issuer warps, with waits, 5 taps, 8 B stages", a, d);
-        a.ni = 2; run<7>("V7 TWO issuer warps, with waits, 5 taps, 8 B stages", a, d);
+        run<0>("V0 conv_tc loop, one issuer (waits pass immediately)", a, d);
+        run<6>("V6 two issuers alternate blocks, shared accumulator, no waits (order not deterministic)", a, d);
+        run<7>("V7 two issuers alternate blocks, with waits (order not deterministic)", a, d);
+        run<8>("V8 two issuers, strict order via named-barrier handshake, with waits", a, d);
     }
     return 0;
 }

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=8)
+    ap.add_argument('--batch', type=int, default=24)
     ap.add_argument('--model', default='e2vid', choices=['e2vid', 'firenet', 'hyper'])
     ap.add_argument('--voxel-only', action='store_true', help='cfg 5 voxelizer launches only (640x480, 4M events)')
     args = ap.parse_args()
