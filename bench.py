@@ -249,6 +249,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU implementation (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device('cuda', local))
     import evreal_b200 as evk
     from evreal_b200 import _lib, synthetic

@@ -174,6 +174,22 @@ int evk_crop(const float* in, float* out, int n, int C, int Hp, int Wp, int H, i
 int evk_mse_ssim(const float* img, const float* ref, int n_images, int H, int W, int clip,
                  double* scores, void* stream);
 
+/* LPIPS   reference: utils/eval_metrics.py:100-156 (PyIqaMetricFactory: `pyiqa.create_metric('lpips')` on frames
+ * repeated to 3 channels by cv2torch(num_ch=3), utils/eval_utils.py:46-54, in queues of 4).  pyiqa and its weights are
+ * a third-party dependency absent from the reference tree: this is the published LPIPS v0.1 algorithm on the same
+ * convolution kernels, with weights supplied by the caller under the lpips / pyiqa state_dict names
+ * ("net.slice{s}.{i}.weight|bias" or torchvision "features.{i}.*", "lin{k}.model.1.weight" or "lins.{k}...").
+ * backbone: 0 = AlexNet (pyiqa 'lpips'), 1 = VGG16 ('lpips-vgg').  batch = pairs per call (the reference queues 4).
+ * img, ref: [n, H, W] float32 grey frames in [0,1] on the device; scores: [n] float64 on the device. */
+typedef struct evk_lpips evk_lpips;
+int evk_lpips_create(int backbone, int batch, int H, int W, int precision, evk_lpips** out);
+int evk_lpips_load_tensor(evk_lpips* l, const char* name, const float* host_data, const int64_t* shape, int ndim);
+int evk_lpips_finalize(evk_lpips* l);
+int evk_lpips_forward(evk_lpips* l, const float* img, const float* ref, int n, double* scores, void* stream);
+double evk_lpips_flops(evk_lpips* l);
+int evk_lpips_num_tc_layers(evk_lpips* l);
+int evk_lpips_destroy(evk_lpips* l);
+
 /* uint8 frame -> float32 / 255  (dataset.py:84) */
 int evk_u8_to_f32(const uint8_t* in, float* out, int64_t numel, void* stream);
 /* n_frames frames of numel bytes each (HOST array of device pointers) -> out [n_frames, numel] float32, one launch */
