@@ -45,7 +45,8 @@ struct ConvParams {
     const __nv_bfloat16* x1s = nullptr;   // split companions of x1 / x2 (required by the TC path)
     const __nv_bfloat16* x2s = nullptr;
     __nv_bfloat16* ys = nullptr;          // optional split copy of y (EPI_LINEAR) for a tensor-core consumer
-    __nv_bfloat16* hs_new = nullptr;      // optional split copy of h_new (EPI_LSTM)
+    __nv_bfloat16* hs_new = nullptr;      // optional split copy of h_new (EPI_LSTM, EPI_GRU_OUT)
+    __nv_bfloat16* hrs_out = nullptr;     // optional split copy of hr_out (EPI_GRU_UR)
     const __nv_bfloat16* w_tc = nullptr;  // weights [2][cout_pad][K] bf16 (hi, lo), K-major
     int cout_pad = 0;                     // rows of w_tc (cout rounded up to a multiple of 16)
     // "row-window" input (the Cin <= 8 head convolution on tensor cores): x1s is the packed tensor

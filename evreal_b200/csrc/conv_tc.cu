@@ -63,6 +63,7 @@ struct TcArgs {
     __nv_bfloat16* ys; long long ys_plane;
     const float* c_prev; float* c_new; float* h_new;
     __nv_bfloat16* hs_new; long long hs_plane;
+    const float* h_prev; const float* u_in; float* u_out; float* hr_out; __nv_bfloat16* hrs_out;   // ConvGRU epilogues
     const float* pred_w; const float* pred_skip; float* pred_out; float pred_bias; int pred_sigmoid;
     int exp;                    // DBG kernels only (EVK_TC_EXP bit mask): 1 skip weight loads, 2 skip activation loads, 4 skip epilogue stores
     unsigned long long* dbg;    // EVK_TC_TIMING: per-CTA clock64 phase counters [grid][8], else nullptr
@@ -263,6 +264,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         // Small N tiles (bn <= 64), whose MMAs are too short to cover even the handshake, run the two issuers FREE
         // (no handshake) into one accumulator EACH, summed in fixed order by the epilogue -- equally deterministic,
         // 134 / 122 cycles per slice; bn = 128 cannot afford two accumulators next to the epilogue's double buffer.
+        // Free-running issuers deal the blocks by the GLOBAL block count (continuous across tiles) over an EVEN number
+        // of weight stages, so that a ring slot is always consumed by the same issuer: mbarrier waits are parity
+        // based, and an issuer that runs ahead must never wait for use n of a slot whose use n-1 the OTHER issuer has
+        // not seen complete yet (the parity test would pass on the stale phase).
         // Barriers that guard data read by both issuers' MMAs (A stage free, accumulator complete) count two commits.
         const uint32_t role = (uint32_t)(warp - 1);
         const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * a.bn));
@@ -274,9 +279,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const uint32_t nbs = (uint32_t)a.b_stages;
         const uint32_t two = a.issuers == 2 ? 1u : 0u;
         const bool own = a.own_acc != 0;
-        const uint32_t first_blk = own ? role : 0u;      // the block whose first MMA initialises the accumulator
         const uint32_t kb_total = (uint32_t)(chunks * a.ku * (a.g_ntaps[0] + (a.n_groups > 1 ? a.g_ntaps[1] : 0)));
-        uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0;
+        uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0, gblk = 0;
         bool b_ready = false;
         long long w_te = 0, w_fa = 0, w_fb = 0;
         const long long t_begin = DBG ? clock64() : 0;
@@ -288,7 +292,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * (uint32_t)a.acc_stride + (own ? role * (uint32_t)a.acc_cols : 0u);
             uint32_t blk = 0;
-            b_ready = false;      // the poll below looks `issuers` blocks ahead WITHIN a tile; across tiles the distance differs
+            bool fresh = true;                // the next MMA of this issuer initialises its accumulator
+            if (!own) b_ready = false;        // strict mode deals blocks per tile: the look-ahead distance differs across tiles
             for (int ch = 0; ch < chunks; ++ch)
                 for (int su = 0; su < a.ku; ++su)
                     for (int g = 0; g < a.n_groups; ++g) {
@@ -297,8 +302,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         t0 = DBG ? clock64() : 0;
                         mbar_wait(bar_fa + 8u * sA, phA);
                         if (DBG) w_fa += clock64() - t0;
-                        for (int j = 0; j < nt_g; ++j, ++blk) {
-                            if (two == 0u || (blk & 1u) == role) {
+                        for (int j = 0; j < nt_g; ++j, ++blk, ++gblk) {
+                            if (two == 0u || ((own ? gblk : blk) & 1u) == role) {
                                 const uint32_t bh_lo = lo_of(smem_b + sB * b_stage);
                                 const uint32_t bar_free = bar_eb + 8u * sB;
                                 if (!b_ready) {
@@ -318,13 +323,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
 #pragma unroll
                                     for (int k = 0; k < BK / 16; ++k) {
                                         // +16 elements (32 B) along K inside the swizzle atom = +2 in the 16-byte address field
-                                        tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, (k == 0 && blk == first_blk) ? 0u : 1u);
+                                        tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, (k == 0 && (own ? fresh : blk == 0u)) ? 0u : 1u);
                                         tc_mma_bf16(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + 2 * k), idesc1, 1u);
                                     }
                                     // frees the weight slot in every CTA of the cluster when these MMAs retire
                                     if (cs > 1) tc_commit_mc(bar_free, cmask); else tc_commit(bar_free);
                                 }
                                 __syncwarp();
+                                fresh = false;
                                 if (two && !own && blk + 1 < kb_total) {  // hand the turn to the other issuer
                                     if (role) asm volatile("bar.arrive 1, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory");
                                 }
@@ -434,6 +440,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         pacc += a.pred_bias;
                         a.pred_out[pix] = a.pred_sigmoid ? sigmoidf_(pacc) : pacc;
                     }
+                } else if (a.epi == EPI_GRU_UR) {   // packed column = channel*2 + {update, reset} (model/submodules.py:281-282)
+                    const int C = a.cout >> 1;
+                    const size_t o = pix * C + (nb >> 1);
+                    float hr[16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (nb + g * 8 >= a.cout || j0 + g * 8 >= a.bn) break;
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 8));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 8 + 4));
+                        const float4 hp = *reinterpret_cast<const float4*>(a.h_prev + o + g * 4);
+                        const float u0 = sigmoidf_(__uint_as_float(v[g * 8 + 0]) + b0.x), r0 = sigmoidf_(__uint_as_float(v[g * 8 + 1]) + b0.y);
+                        const float u1 = sigmoidf_(__uint_as_float(v[g * 8 + 2]) + b0.z), r1 = sigmoidf_(__uint_as_float(v[g * 8 + 3]) + b0.w);
+                        const float u2 = sigmoidf_(__uint_as_float(v[g * 8 + 4]) + b1.x), r2 = sigmoidf_(__uint_as_float(v[g * 8 + 5]) + b1.y);
+                        const float u3 = sigmoidf_(__uint_as_float(v[g * 8 + 6]) + b1.z), r3 = sigmoidf_(__uint_as_float(v[g * 8 + 7]) + b1.w);
+                        *reinterpret_cast<float4*>(a.u_out + o + g * 4) = make_float4(u0, u1, u2, u3);
+                        hr[g * 4 + 0] = hp.x * r0; hr[g * 4 + 1] = hp.y * r1; hr[g * 4 + 2] = hp.z * r2; hr[g * 4 + 3] = hp.w * r3;
+                        *reinterpret_cast<float4*>(a.hr_out + o + g * 4) = make_float4(hr[g * 4 + 0], hr[g * 4 + 1], hr[g * 4 + 2], hr[g * 4 + 3]);
+                        if (a.hrs_out != nullptr) {
+                            __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) split_bf16(hr[g * 4 + i], hi[i], lo[i]);
+                            *reinterpret_cast<uint2*>(a.hrs_out + o + g * 4) = *reinterpret_cast<uint2*>(hi);
+                            *reinterpret_cast<uint2*>(a.hrs_out + a.hs_plane + o + g * 4) = *reinterpret_cast<uint2*>(lo);
+                        }
+                    }
+                } else if (a.epi == EPI_GRU_OUT) {  // h' = h (1 - u) + tanh(.) u (model/submodules.py:283-285)
+                    const size_t o = pix * a.cout + nb;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (nb + g * 4 >= a.cout || j0 + g * 4 >= a.bn) break;
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
+                        const float4 u4 = *reinterpret_cast<const float4*>(a.u_in + o + g * 4);
+                        const float4 h4 = *reinterpret_cast<const float4*>(a.h_prev + o + g * 4);
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, uu[4] = {u4.x, u4.y, u4.z, u4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
+                        float hn[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float cand = tanhf(__uint_as_float(v[g * 4 + i]) + bb[i]);
+                            hn[i] = __fadd_rn(__fmul_rn(hh[i], __fsub_rn(1.0f, uu[i])), __fmul_rn(cand, uu[i]));
+                        }
+                        *reinterpret_cast<float4*>(a.h_new + o + g * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                        if (a.hs_new != nullptr) {
+                            __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) split_bf16(hn[i], hi[i], lo[i]);
+                            *reinterpret_cast<uint2*>(a.hs_new + o + g * 4) = *reinterpret_cast<uint2*>(hi);
+                            *reinterpret_cast<uint2*>(a.hs_new + a.hs_plane + o + g * 4) = *reinterpret_cast<uint2*>(lo);
+                        }
+                    }
                 } else {   // EPI_LSTM: packed column = channel*4 + {in, remember, out, cell}
                     const int C = a.cout >> 2;
                     const size_t o = pix * C + (nb >> 2);
@@ -513,6 +568,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 static int pick_bk(const ConvParams& p) {
     if (p.c1 % 64 == 0 && p.c2 % 64 == 0) return 64;
     if (p.c1 % 32 == 0 && p.c2 % 32 == 0) return 32;
+    if (p.c1 % 16 == 0 && p.c2 % 16 == 0) return 16;     // FireNet's 16-channel stack: one 16-deep slice per K block
     return 0;
 }
 
@@ -525,11 +581,11 @@ bool tc_eligible(const ConvParams& p) {
         if (e && e[0] == '0') g_tc_stride2 = false;
         env_read = true;
     }
-    if (p.epi != EPI_LINEAR && p.epi != EPI_LSTM) return false;
     if (pick_bk(p) == 0 || p.c1 == 0) return false;
     if (p.stride != 1 && !(p.stride == 2 && g_tc_stride2)) return false;
     if (p.cout % 4 != 0) return false;
     if (p.epi == EPI_LSTM && p.cout % 32 != 0) return false;
+    if (p.epi == EPI_GRU_UR && p.cout % 8 != 0) return false;
     return true;
 }
 
@@ -539,10 +595,18 @@ static int env_int(const char* name, int dflt) {
 }
 
 // Cost model (cycles) of one layer for a candidate (orientation, N tile, cluster size): waves of co-resident CTAs x
-// per-tile cost, the per-tile cost being the larger of the tcgen05 issue time (floor 128*N/256 per MMA, and the
-// 128 B/clk shared-memory operand read) and the tile's share of the chip-wide L2 -> SM path (~42 B/clk/SM with every
-// SM loading).  EVK_TC_BN / EVK_TC_CS / EVK_TC_UX override the choice (experiments).
+// per-tile cost.  Per 16-deep K slice the kernel is bound by MMA issue: measured in-kernel cycles per
+// slice as a function of the N tile (two issuers; tools/tc_experiment.py with EVK_TC_TIMING=1), next to the tile's share
+// of the chip-wide L2 -> SM path (~42 B/clk/SM with every SM loading), which only binds for small tiles of wide layers.
+// EVK_TC_BN / EVK_TC_CS / EVK_TC_UX override the choice (experiments).
 struct TcChoice { int ux, bn, cs; double cost; };
+
+static double slice_cycles(int bn) {
+    // measured: bn 128 -> 235, 64 -> 150, 32 -> 140 (the N <= 64 MMAs cost >= 50 cycles each: the A-operand read)
+    if (bn >= 128) return 235.0;
+    if (bn >= 64) return 150.0 + (bn - 64) * (235.0 - 150.0) / 64.0;
+    return 130.0 + bn * (150.0 - 130.0) / 64.0;
+}
 
 static double tile_cost(int bk, int ku, int kv, int stride, int chunks, int bn, int cs, long ctas, int* ar_out) {
     const int ngroups = stride == 2 ? 2 : 1;
@@ -550,16 +614,13 @@ static double tile_cost(int bk, int ku, int kv, int stride, int chunks, int bn, 
     const int ar = 16 + max_taps - 1;
     if (ar_out) *ar_out = ar;
     const double k16 = (double)chunks * ku * kv * (bk / 16);
-    const double a_rd = 32.0;                                                 // 128 rows x 32 B per MMA at 128 B/clk
-    const double mma1 = std::max((double)bn, a_rd + bn / 2.0);                // N = 2*bn
-    const double mma2 = std::max(bn / 2.0, a_rd + bn / 4.0);                  // N = bn
-    const double t_mma = k16 * (mma1 + mma2);
+    const double t_mma = k16 * slice_cycles(bn);
     const double a_bytes = (double)chunks * ku * ngroups * 2.0 * ar * 8 * bk * 2;
     const double b_bytes = (double)chunks * ku * kv * 2.0 * bn * bk * 2 / cs;
     const double active = (double)std::min<long>(ctas, kNumSMs);
     const double t_l2 = (a_bytes + b_bytes) * active / 6300.0;                // chip-wide ceiling shared by the active SMs
-    const double t_epi = 60.0 * bn;
-    return 6000.0 + std::max(std::max(t_mma, t_l2), t_epi);
+    const double t_epi = 60.0 * bn;                                           // epilogue of the previous tile (overlapped)
+    return 5000.0 + std::max(std::max(t_mma, t_l2), t_epi);
 }
 
 void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out) {
@@ -602,8 +663,9 @@ int tc_plan_create(ConvParams& p) {
     EVK_REQUIRE(cout_pad >= p.cout && cout_pad % 16 == 0, EVK_ERR_ARG, "conv_tc: cout_pad=%d must be a multiple of 16 >= cout", cout_pad);
     static bool attr_set = false;
     if (!attr_set) {
-        const void* kerns[4] = {(const void*)conv_tc_kernel<64, false>, (const void*)conv_tc_kernel<32, false>,
-                                (const void*)conv_tc_kernel<64, true>, (const void*)conv_tc_kernel<32, true>};
+        const void* kerns[6] = {(const void*)conv_tc_kernel<64, false>, (const void*)conv_tc_kernel<32, false>,
+                                (const void*)conv_tc_kernel<64, true>, (const void*)conv_tc_kernel<32, true>,
+                                (const void*)conv_tc_kernel<16, false>, (const void*)conv_tc_kernel<16, true>};
         for (const void* k : kerns) {
             EVK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             EVK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -666,7 +728,9 @@ int tc_plan_create(ConvParams& p) {
     }
     a.ys_plane = (long long)p.N * p.Hout * p.Wout * p.cout;
     a.c_prev = p.c_prev; a.c_new = p.c_new; a.h_new = p.h_new; a.hs_new = p.hs_new;
-    a.hs_plane = (long long)p.N * p.Hout * p.Wout * (p.cout / 4);
+    a.h_prev = p.h_prev; a.u_in = p.u_in; a.u_out = p.u_out; a.hr_out = p.hr_out; a.hrs_out = p.hrs_out;
+    // plane stride of the split copy of the recurrent output: hidden channels = cout/4 (LSTM), cout/2 (GRU u,r), cout (GRU out)
+    a.hs_plane = (long long)p.N * p.Hout * p.Wout * (p.epi == EPI_LSTM ? p.cout / 4 : p.epi == EPI_GRU_UR ? p.cout / 2 : p.cout);
     a.dbg = nullptr;
     a.exp = env_int("EVK_TC_EXP", 0);
     const uint32_t row_bytes = bk * 2;
@@ -684,12 +748,15 @@ int tc_plan_create(ConvParams& p) {
     a.issuers = (kb >= 2 && env_int("EVK_TC_ISSUERS", 2) == 2) ? 2 : 1;
     a.own_acc = (a.issuers == 2 && 4 * a.acc_cols <= 512 && env_int("EVK_TC_OWN_ACC", 1)) ? 1 : 0;
     a.acc_stride = a.own_acc ? 2 * a.acc_cols : a.acc_cols;
+    if (a.own_acc && (a.b_stages & 1)) {      // free-running issuers need a slot to belong to one issuer (see the kernel)
+        a.b_stages -= 1; bs -= 1;
+    }
     uint32_t cols = 32;
     while ((int)cols < 2 * a.acc_stride) cols <<= 1;
     if (cols > 512) { delete pl; EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: accumulator does not fit tensor memory (bn=%d)", bn); }
     a.tmem_cols = cols;
     pl->smem = as * a_stage + bs * b_stage + 1024 + 16 * (as + bs) + 64;
-    int ncl = bk == 64 ? max_clusters<64>(cs, pl->smem) : max_clusters<32>(cs, pl->smem);
+    int ncl = bk == 64 ? max_clusters<64>(cs, pl->smem) : bk == 32 ? max_clusters<32>(cs, pl->smem) : max_clusters<16>(cs, pl->smem);
     if (ncl == 0 && cs > 1) {          // clusters of this size cannot be scheduled: fall back to independent CTAs
         cs = 1; ncl = kNumSMs;
     }
@@ -761,9 +828,12 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
     if (pl.bk == 64) {
         if (dbg) EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, true>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
         else EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
-    } else {
+    } else if (pl.bk == 32) {
         if (dbg) EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, true>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
         else EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, false>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
+    } else {
+        if (dbg) EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, true>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
+        else EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<16, false>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
     }
     return EVK_OK;
 }

@@ -97,22 +97,28 @@ __global__ void __launch_bounds__(256) hyper_apply_kernel(const HyperParams p) {
     }
     if (gy < p.h && gx < p.w) {
         const size_t off = (((size_t)n * p.h + gy) * p.w + gx) * ((size_t)p.C * A) + (size_t)(c0 + lane * 4) * A;
-        float* o = p.inter + off;
+        // the thread's 4 channels x A atoms are 4*A contiguous values of the [.., C*A] pixel record: vector stores
+        float vals[4 * A];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int a = 0; a < A; ++a) o[c * A + a] = acc[c][a];
+            for (int a = 0; a < A; ++a) vals[c * A + a] = acc[c][a];
+        static_assert((4 * A) % 8 == 0, "vector stores need 4*A to be a multiple of 8");
+        if (p.inter != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4 * A; q += 4)
+                *reinterpret_cast<float4*>(p.inter + off + q) = make_float4(vals[q], vals[q + 1], vals[q + 2], vals[q + 3]);
+        }
         if (p.inter_s != nullptr) {
             const size_t plane = (size_t)p.N * p.h * p.w * p.C * A;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int q = 0; q < 4 * A; q += 8) {
+                __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    __nv_bfloat16 hi, lo;
-                    split_bf16(acc[c][a], hi, lo);
-                    p.inter_s[off + c * A + a] = hi;
-                    p.inter_s[plane + off + c * A + a] = lo;
-                }
+                for (int e = 0; e < 8; ++e) split_bf16(vals[q + e], hi[e], lo[e]);
+                *reinterpret_cast<uint4*>(p.inter_s + off + q) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(p.inter_s + plane + off + q) = *reinterpret_cast<const uint4*>(lo);
+            }
         }
     }
 }

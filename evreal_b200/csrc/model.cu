@@ -270,6 +270,10 @@ static int add_gru(Builder& B, const std::string& pfx, const float* x, int C, in
         p.kh = p.kw = k; p.stride = 1; p.pad = k / 2;
         p.w = m->upload(w); p.bias = m->upload(b); p.cout = 2 * C; p.epi = EPI_GRU_UR;
         p.h_prev = h; p.u_out = u_buf; p.hr_out = hr_buf;
+        {
+            Packed pk2; pk2.w = w; pk2.b = b; pk2.cout = 2 * C; pk2.cin = cin; pk2.kh = k; pk2.kw = k;
+            B.attach_tc_weights(p, pk2);
+        }
         op.flops = conv_flops(p, 2 * C);
         m->ops[0].push_back(op); m->ops[1].push_back(op);
     }
@@ -283,6 +287,7 @@ static int add_gru(Builder& B, const std::string& pfx, const float* x, int C, in
         p.kh = p.kw = k; p.stride = 1; p.pad = k / 2;
         p.w = m->upload(pk.w); p.bias = m->upload(pk.b); p.cout = C; p.epi = EPI_GRU_OUT;
         p.h_prev = h; p.u_in = u_buf; p.h_new = h;
+        B.attach_tc_weights(p, pk);
         op.flops = conv_flops(p, C);
         m->ops[0].push_back(op); m->ops[1].push_back(op);
     }
@@ -586,8 +591,11 @@ static int wire_tc(evk_model* m) {
                 case OP_CONV:
                     if (op.cp.epi == EPI_LINEAR) op.cp.ys = lookup(op.cp.y);
                     if (op.cp.epi == EPI_LSTM) op.cp.hs_new = lookup(op.cp.h_new);
-                    if (op.cp.epi == EPI_GRU_OUT && lookup(op.cp.h_new)) {
-                        set_error("wire_tc: a tensor-core consumer of a ConvGRU state is not supported");
+                    if (op.cp.epi == EPI_GRU_OUT) op.cp.hs_new = lookup(op.cp.h_new);
+                    if (op.cp.epi == EPI_GRU_UR) op.cp.hrs_out = lookup(op.cp.hr_out);
+                    if ((op.cp.hs_new || op.cp.hrs_out) && op.cp.x1s == nullptr) {
+                        // the fp32 CUDA-core kernel does not write split copies: a tensor-core consumer needs a tensor-core producer
+                        set_error("wire_tc: ConvGRU on the CUDA-core path feeds a tensor-core convolution (unsupported channel mix)");
                         return EVK_ERR_ARG;
                     }
                     break;
@@ -610,7 +618,7 @@ static int wire_tc(evk_model* m) {
                         break;
                     case OP_UPSAMPLE_ADD: case OP_PRED: rd(op.in); rd(op.skip); break;
                     case OP_HYPER_CONTEXT: case OP_HYPER_ATOMS: case OP_HYPER_APPLY:
-                        rd(op.hp.ev_nchw); rd(op.hp.prev); rd(op.hp.ctx); rd(op.hp.coef); rd(op.hp.atoms); rd(op.hp.xu); rd(op.hp.inter);
+                        rd(op.hp.ev_nchw); rd(op.hp.prev); rd(op.hp.coef); rd(op.hp.atoms); rd(op.hp.xu);   // (ctx / inter are outputs here)
                         break;
                     default: break;
                 }
@@ -623,6 +631,7 @@ static int wire_tc(evk_model* m) {
                         op.cp.y = nullptr;
                     }
                     if (op.kind == OP_UPSAMPLE_ADD && op.out_s != nullptr && !fp32_read.count(op.out)) op.out = nullptr;
+                    if (op.kind == OP_HYPER_APPLY && op.hp.inter_s != nullptr && !fp32_read.count(op.hp.inter)) op.hp.inter = nullptr;
                 }
     }
     for (int par = 0; par < 2; ++par)
