@@ -47,6 +47,7 @@ struct TcArgs {
     int bn, n_tiles, m_tiles, cout;
     int epi, act;
     int a_stages, b_stages;
+    int tpb;                    // taps per K block (= per weight stage): 1, or all taps of a V group when they fit in 40 KB
     int ar;                     // atoms per A box
     int n_groups;               // V-tap groups per (chunk, U shift): 1 (stride 1) or 2 (stride 2: even / odd taps)
     int g_tap0[2], g_ntaps[2], g_step;
@@ -117,7 +118,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_plane = (uint32_t)a.ar * ATOM, a_stage = 2 * a_plane;
-    const uint32_t b_plane = (uint32_t)a.bn * ROW_BYTES, b_stage = 2 * b_plane;
+    const uint32_t b_plane = (uint32_t)a.bn * ROW_BYTES, b_tap = 2 * b_plane, b_stage = (uint32_t)a.tpb * b_tap;
     const uint32_t smem_b = base + (uint32_t)a.a_stages * a_stage;
     const uint32_t bar_fa = smem_b + (uint32_t)a.b_stages * b_stage;
     const uint32_t bar_ea = bar_fa + 8u * a.a_stages;
@@ -200,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         }
         if (DBG && lane == 0) a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)w_ea;
     } else if (warp == 3) {
-        // ===== B producer: one tap x BK channels of the weight tile per stage; with a cluster every CTA loads
+        // ===== B producer: one K block (tpb taps x BK channels of the weight tile) per stage; with a cluster every CTA loads
         // 1/cs of the rows and multicasts them to all CTAs (same smem offset, same barrier offset everywhere)
         const int bnp = a.bn / cs;
         const int ctot = chunks * BK;
@@ -212,24 +213,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             for (int ch = 0; ch < chunks; ++ch)
                 for (int su = 0; su < a.ku; ++su)
                     for (int g = 0; g < a.n_groups; ++g)
-                        for (int j = 0; j < a.g_ntaps[g]; ++j) {
+                        for (int j0 = 0; j0 < a.g_ntaps[g]; j0 += a.tpb) {
+                            const int ntb = min(a.tpb, a.g_ntaps[g] - j0);       // taps in this K block
                             const long long t0 = DBG ? clock64() : 0;
                             mbar_wait(bar_eb + 8u * s, ph ^ 1u);
                             if (DBG) w_eb += clock64() - t0;
-                            const int tv = a.g_tap0[g] + j * a.g_step;
-                            const int tap = a.ux ? tv * a.kw + su : su * a.kw + tv;
-                            const int k0 = tap * ctot + ch * BK;
                             const uint32_t sb = smem_b + s * b_stage + (uint32_t)(crank * bnp) * ROW_BYTES;
                             if (DBG && (a.exp & 1)) {
                                 if (elect_one()) mbar_arrive(bar_fb + 8u * s);
                             } else if (elect_one()) {
-                                mbar_expect_tx(bar_fb + 8u * s, b_stage);
-                                if (cs > 1) {
-                                    tma_load_3d_mc(sb, &tm_w, bar_fb + 8u * s, k0, row0, 0, cmask);
-                                    tma_load_3d_mc(sb + b_plane, &tm_w, bar_fb + 8u * s, k0, row0, 1, cmask);
-                                } else {
-                                    tma_load_3d(sb, &tm_w, bar_fb + 8u * s, k0, row0, 0);
-                                    tma_load_3d(sb + b_plane, &tm_w, bar_fb + 8u * s, k0, row0, 1);
+                                mbar_expect_tx(bar_fb + 8u * s, (uint32_t)ntb * b_tap);
+                                for (int jj = 0; jj < ntb; ++jj) {
+                                    const int tv = a.g_tap0[g] + (j0 + jj) * a.g_step;
+                                    const int tap = a.ux ? tv * a.kw + su : su * a.kw + tv;
+                                    const int k0 = tap * ctot + ch * BK;
+                                    const uint32_t dst = sb + (uint32_t)jj * b_tap;
+                                    if (cs > 1) {
+                                        tma_load_3d_mc(dst, &tm_w, bar_fb + 8u * s, k0, row0, 0, cmask);
+                                        tma_load_3d_mc(dst + b_plane, &tm_w, bar_fb + 8u * s, k0, row0, 1, cmask);
+                                    } else {
+                                        tma_load_3d(dst, &tm_w, bar_fb + 8u * s, k0, row0, 0);
+                                        tma_load_3d(dst + b_plane, &tm_w, bar_fb + 8u * s, k0, row0, 1);
+                                    }
                                 }
                             }
                             __syncwarp();
@@ -275,11 +280,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const uint32_t desc_hi = (uint32_t)(umma_desc_kmajor(0, ROW_BYTES) >> 32);
         auto mk = [&](uint32_t lo) -> uint64_t { return ((uint64_t)desc_hi << 32) | lo; };
         auto lo_of = [](uint32_t addr) -> uint32_t { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
-        const uint32_t atom16 = ATOM >> 4, a_plane16 = a_plane >> 4;
+        const uint32_t atom16 = ATOM >> 4, a_plane16 = a_plane >> 4, btap16 = b_tap >> 4;
         const uint32_t nbs = (uint32_t)a.b_stages;
         const uint32_t two = a.issuers == 2 ? 1u : 0u;
         const bool own = a.own_acc != 0;
-        const uint32_t kb_total = (uint32_t)(chunks * a.ku * (a.g_ntaps[0] + (a.n_groups > 1 ? a.g_ntaps[1] : 0)));
+        const uint32_t kb_total = (uint32_t)(chunks * a.ku * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0)));
         uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0, gblk = 0;
         bool b_ready = false;
         long long w_te = 0, w_fa = 0, w_fb = 0;
@@ -302,7 +307,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         t0 = DBG ? clock64() : 0;
                         mbar_wait(bar_fa + 8u * sA, phA);
                         if (DBG) w_fa += clock64() - t0;
-                        for (int j = 0; j < nt_g; ++j, ++blk, ++gblk) {
+                        for (int j0 = 0; j0 < nt_g; j0 += a.tpb, ++blk, ++gblk) {
+                            const int ntb = min(a.tpb, nt_g - j0);               // taps in this K block
                             if (two == 0u || ((own ? gblk : blk) & 1u) == role) {
                                 const uint32_t bh_lo = lo_of(smem_b + sB * b_stage);
                                 const uint32_t bar_free = bar_eb + 8u * sB;
@@ -320,11 +326,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                     if (role) asm volatile("bar.sync 2, 64;" ::: "memory"); else asm volatile("bar.sync 1, 64;" ::: "memory");
                                 }
                                 if (elect_one()) {
+                                    const uint32_t acc0 = (own ? fresh : blk == 0u) ? 0u : 1u;
+                                    if (a.tpb == 1) {             // (kept separate: no loop-carried state on the hot single-tap path)
 #pragma unroll
-                                    for (int k = 0; k < BK / 16; ++k) {
-                                        // +16 elements (32 B) along K inside the swizzle atom = +2 in the 16-byte address field
-                                        tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, (k == 0 && (own ? fresh : blk == 0u)) ? 0u : 1u);
-                                        tc_mma_bf16(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + 2 * k), idesc1, 1u);
+                                        for (int k = 0; k < BK / 16; ++k) {
+                                            // +16 elements (32 B) along K inside the swizzle atom = +2 in the 16-byte address field
+                                            tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, k == 0 ? acc0 : 1u);
+                                            tc_mma_bf16(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + 2 * k), idesc1, 1u);
+                                        }
+                                    } else {
+                                        uint32_t al = ah_lo, bl = bh_lo, acc = acc0;
+                                        for (int jj = 0; jj < ntb; ++jj, al += atom16, bl += btap16) {
+#pragma unroll
+                                            for (int k = 0; k < BK / 16; ++k) {
+                                                tc_mma_bf16(d_tmem, mk(al + 2 * k), mk(bl + 2 * k), idesc2, acc);
+                                                acc = 1u;
+                                                tc_mma_bf16(d_tmem, mk(al + a_plane16 + 2 * k), mk(bl + 2 * k), idesc1, 1u);
+                                            }
+                                        }
                                     }
                                     // frees the weight slot in every CTA of the cluster when these MMAs retire
                                     if (cs > 1) tc_commit_mc(bar_free, cmask); else tc_commit(bar_free);
@@ -336,7 +355,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                 }
                             }
                             if (++sB == nbs) { sB = 0; phB ^= 1u; }
-                            ah_lo += atom16;
+                            ah_lo += (uint32_t)ntb * atom16;
                         }
                         if (elect_one()) tc_commit(bar_ea + 8u * sA);       // `issuers` arrivals free the activation stage
                         __syncwarp();
@@ -735,7 +754,18 @@ int tc_plan_create(ConvParams& p) {
     a.exp = env_int("EVK_TC_EXP", 0);
     const uint32_t row_bytes = bk * 2;
     const size_t a_stage = 2 * (size_t)a.ar * 8 * row_bytes;
-    const size_t b_stage = 2 * (size_t)bn * row_bytes;
+    const size_t b_tap = 2 * (size_t)bn * row_bytes;
+    // several taps per K block when the weights are small: fewer barrier round trips per MMA (the per-block issue
+    // overhead is ~100+ cycles, a 16-deep slice of a small tile ~50-100)
+    a.tpb = 1;
+    {
+        const int blocks_all = (a.chunks1 + a.chunks2) * a.ku * a.n_groups;      // K blocks per tile if a block takes a whole group
+        // measured: pays for the one-slice blocks of 16-channel layers (FireNet +13%); with BK >= 32 the larger stages
+        // leave too few of them in flight (the last decoder of E2VID lost 40%), so those keep one tap per block
+        const size_t limit = env_int("EVK_TC_TPB", 0) > 1 ? 40 * 1024 : 8 * 1024;
+        if (a.g_ntaps[0] * b_tap <= limit && blocks_all >= 3 && env_int("EVK_TC_TPB", 0) != 1) a.tpb = a.g_ntaps[0];
+    }
+    const size_t b_stage = (size_t)a.tpb * b_tap;
     const size_t budget = 227 * 1024 - 1024 - 512;
     int as = 3, bs = (int)((budget - std::min(budget, as * a_stage)) / b_stage);
     if (bs < 4) { as = 2; bs = (int)((budget - as * a_stage) / b_stage); }
@@ -744,7 +774,7 @@ int tc_plan_create(ConvParams& p) {
     a.a_stages = as; a.b_stages = bs;
     // per accumulator stage: [hi*hi + lo*hi | hi*lo] = 2*bn columns, read in 32-column windows (bn%32 tail -> pad)
     a.acc_cols = (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;
-    const int kb = (a.chunks1 + a.chunks2) * p.kh * p.kw;
+    const int kb = (a.chunks1 + a.chunks2) * a.ku * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0));
     a.issuers = (kb >= 2 && env_int("EVK_TC_ISSUERS", 2) == 2) ? 2 : 1;
     a.own_acc = (a.issuers == 2 && 4 * a.acc_cols <= 512 && env_int("EVK_TC_OWN_ACC", 1)) ? 1 : 0;
     a.acc_stride = a.own_acc ? 2 * a.acc_cols : a.acc_cols;
@@ -795,8 +825,8 @@ int tc_plan_create(ConvParams& p) {
     }
     if (r != EVK_OK) { delete pl; return r; }
     if (env_int("EVK_TC_VERBOSE", 0))
-        fprintf(stderr, "conv_tc plan: %dx%d s%d %d+%d->%d @%dx%dx%d  ux=%d bn=%d cs=%d issuers=%d stages A%d/B%d ar=%d grid=%u smem=%zu\n", p.kh, p.kw,
-                p.stride, p.c1, p.c2, p.cout, p.N, p.Hout, p.Wout, ux, bn, cs, a.issuers, as, bs, a.ar, pl->grid.x, pl->smem);
+        fprintf(stderr, "conv_tc plan: %dx%d s%d %d+%d->%d @%dx%dx%d  ux=%d bn=%d cs=%d issuers=%d tpb=%d stages A%d/B%d ar=%d grid=%u smem=%zu\n", p.kh, p.kw,
+                p.stride, p.c1, p.c2, p.cout, p.N, p.Hout, p.Wout, ux, bn, cs, a.issuers, a.tpb, as, bs, a.ar, pl->grid.x, pl->smem);
     p.tc = pl;
     return EVK_OK;
 }

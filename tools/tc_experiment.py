@@ -6,8 +6,16 @@ import torch
 import evreal_b200 as evk
 from evreal_b200 import synthetic
 batch = int(os.environ.get('BATCH', '8'))
-model = evk.E2VIDRecurrent(dict(synthetic.E2VID_KWARGS)).load_state_dict(synthetic.unet_state_dict(0, norm_bn=True)).to('cuda')
-x = torch.randn(batch, 5, 184, 240, device='cuda')
+which = os.environ.get('MODEL', 'e2vid')
+if which == 'firenet':
+    model = evk.FireNet_legacy(dict(synthetic.FIRENET_KWARGS)).load_state_dict(synthetic.firenet_state_dict(0)).to('cuda')
+    x = torch.randn(batch, 5, 192, 240, device='cuda')
+elif which == 'hyper':
+    model = evk.E2VIDRecurrent(dict(synthetic.HYPER_KWARGS)).load_state_dict(synthetic.unet_state_dict(0, dynamic_decoder=True)).to('cuda')
+    x = torch.randn(batch, 5, 264, 352, device='cuda')
+else:
+    model = evk.E2VIDRecurrent(dict(synthetic.E2VID_KWARGS)).load_state_dict(synthetic.unet_state_dict(0, norm_bn=True)).to('cuda')
+    x = torch.randn(batch, 5, 184, 240, device='cuda')
 agg = {}
 frames = int(os.environ.get('FRAMES', '6'))
 for f in range(frames):
