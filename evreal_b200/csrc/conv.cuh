@@ -84,6 +84,8 @@ int launch_pred(const float* x, const float* skip, const float* w /*[cin]*/, flo
                 int cin, int sigmoid, cudaStream_t st);
 // y[N,2H,2W,C] = bilinear_x2(x + skip), align_corners=False (model/unet.py:130-134 + submodules.py:88)
 int launch_upsample2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C, cudaStream_t st);
+// y[N,2H,2W,C]: (x + skip) at the even positions, zero elsewhere (ConvTranspose2d stride 2 as a stride-1 convolution)
+int launch_zero_insert2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C, cudaStream_t st);
 // NCHW fp32 [N,cin,H,W] (cin <= 8) -> packed split-bf16 row-window tensor [2][N][H][W+8][8], pixel x at column x + left
 int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st);
 // host: head weights [kh*kw*cin][cout] (SIMT layout) -> row-window K layout [kh*64][cout] (k = r*64 + q*8 + c)

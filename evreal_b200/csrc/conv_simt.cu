@@ -391,6 +391,48 @@ upsample2x_add_kernel(const float* __restrict__ x, const float* __restrict__ ski
     }
 }
 
+// y[N,2H,2W,C]: y[2i,2j] = x[i,j] + skip[i,j], zero elsewhere -- the zero-insertion that turns ConvTranspose2d(k, stride 2,
+// padding p, output_padding 1) into a stride-1 convolution with the flipped kernel and padding k-1-p (the extra zero
+// row / column at the bottom / right is the output_padding).  model/submodules.py:38-66, model/unet.py:130-134.
+__global__ void __launch_bounds__(256)
+zero_insert2x_add_kernel(const float* __restrict__ x, const float* __restrict__ skip, float* __restrict__ y,
+                         __nv_bfloat16* __restrict__ ys, int N, int H, int W, int C4) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    const int64_t total = (int64_t)N * Ho * Wo * C4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const int ox = (int)((i / C4) % Wo);
+        const int oy = (int)((i / ((int64_t)C4 * Wo)) % Ho);
+        const int n = (int)(i / ((int64_t)C4 * Wo * Ho));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (((ox | oy) & 1) == 0) {
+            const size_t o = (((size_t)n * H + (oy >> 1)) * W + (ox >> 1)) * C4 + c;
+            v = __ldg(reinterpret_cast<const float4*>(x) + o);
+            if (skip) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(skip) + o);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+        }
+        if (y != nullptr) reinterpret_cast<float4*>(y)[i] = v;
+        if (ys != nullptr) {
+            const float f[4] = {v.x, v.y, v.z, v.w};
+            __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_bf16(f[e], hi[e], lo[e]);
+            *reinterpret_cast<uint2*>(ys + i * 4) = *reinterpret_cast<uint2*>(hi);
+            *reinterpret_cast<uint2*>(ys + total * 4 + i * 4) = *reinterpret_cast<uint2*>(lo);
+        }
+    }
+}
+
+int launch_zero_insert2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C, cudaStream_t st) {
+    EVK_REQUIRE(C % 4 == 0 && (y != nullptr || ys != nullptr), EVK_ERR_ARG, "zero_insert2x_add: bad argument (C=%d)", C);
+    const int64_t total = (int64_t)N * 4 * H * W * (C / 4);
+    zero_insert2x_add_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 4736), 256, 0, st>>>(x, skip, y, ys, N, H, W, C / 4);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
 int launch_upsample2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C,
                           cudaStream_t st) {
     EVK_REQUIRE(C % 8 == 0, EVK_ERR_ARG, "upsample2x_add: C=%d must be a multiple of 8", C);

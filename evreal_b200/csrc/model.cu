@@ -28,7 +28,7 @@ struct HostTensor {
     std::vector<int64_t> shape;
 };
 
-enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HEAD_PACK, OP_NOP };
+enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HEAD_PACK, OP_NOP, OP_ZERO_INSERT_ADD };
 
 struct Op {
     OpKind kind;
@@ -114,11 +114,13 @@ struct Packed {
 // Folds an optional eval-mode BatchNorm (prefix bn) and an optional bias into
 // one conv (float64 arithmetic), and permutes output channels: packed channel
 // n takes reference channel perm[n].
+// transposed: the tensor is a ConvTranspose2d weight [Cin, Cout, kh, kw]; the packed result is the equivalent stride-1
+// convolution on the zero-inserted input: Wc[co][ci][r][q] = Wt[ci][co][kh-1-r][kw-1-q].
 static int pack_conv(const evk_model* m, const std::string& wname, const std::string& bname, const std::string& bn,
-                     const std::vector<int>* perm, Packed& out) {
+                     const std::vector<int>* perm, Packed& out, bool transposed = false) {
     const HostTensor* w = m->find(wname);
     EVK_REQUIRE(w && w->shape.size() == 4, EVK_ERR_KEY, "missing weight tensor '%s'", wname.c_str());
-    const int co = (int)w->shape[0], ci = (int)w->shape[1], kh = (int)w->shape[2], kw = (int)w->shape[3];
+    const int co = (int)w->shape[transposed ? 1 : 0], ci = (int)w->shape[transposed ? 0 : 1], kh = (int)w->shape[2], kw = (int)w->shape[3];
     const HostTensor* bias = bname.empty() ? nullptr : m->find(bname);
     const HostTensor *g = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr;
     if (!bn.empty() && m->find(bn + ".running_mean")) {
@@ -142,7 +144,9 @@ static int pack_conv(const evk_model* m, const std::string& wname, const std::st
         for (int c = 0; c < ci; ++c)
             for (int y = 0; y < kh; ++y)
                 for (int x = 0; x < kw; ++x) {
-                    const double v = (double)w->data[(((size_t)r * ci + c) * kh + y) * kw + x] * scale;
+                    const double wv = transposed ? (double)w->data[(((size_t)c * co + r) * kh + (kh - 1 - y)) * kw + (kw - 1 - x)]
+                                                 : (double)w->data[(((size_t)r * ci + c) * kh + y) * kw + x];
+                    const double v = wv * scale;
                     out.w[((size_t)(y * kw + x) * ci + c) * cop + n] = (float)v;
                 }
     }
@@ -162,9 +166,9 @@ struct Builder {
 
     // generic ConvLayer-like op appended to both parities
     int conv(const std::string& wname, const std::string& bname, const std::string& bn, const float* x, int cin, int Hin,
-             int Win, int stride, int pad, int act, const float* res, float* y, int* cout_out) {
+             int Win, int stride, int pad, int act, const float* res, float* y, int* cout_out, bool transposed = false) {
         Packed pk;
-        int r = pack_conv(m, wname, bname, bn, nullptr, pk);
+        int r = pack_conv(m, wname, bname, bn, nullptr, pk, transposed);
         if (r != EVK_OK) return r;
         EVK_REQUIRE(pk.cin == cin, EVK_ERR_KEY, "'%s': expected %d input channels, checkpoint has %d", wname.c_str(), cin, pk.cin);
         return conv_packed(pk, x, cin, Hin, Win, stride, pad, act, res, y, cout_out);
@@ -474,9 +478,10 @@ static int build_unet(evk_model* m) {
         const int e = E - 1 - i;
         const std::string pfx = "decoders." + std::to_string(i);
         const float* skip = m->states[hstate[e]].buf[1];   // placeholder, fixed per parity below
+        const bool tconv = m->find(pfx + ".transposed_conv2d.weight") != nullptr;     // use_upsample_conv=False
         float* up = B.act(2 * H, 2 * W, C);
         {
-            Op op; op.kind = OP_UPSAMPLE_ADD;
+            Op op; op.kind = tconv ? OP_ZERO_INSERT_ADD : OP_UPSAMPLE_ADD;
             op.in = x; op.skip = skip; op.out = up; op.N = B.N; op.H = H; op.W = W; op.cin = C;
             m->ops[0].push_back(op); m->ops[1].push_back(op);
         }
@@ -487,11 +492,16 @@ static int build_unet(evk_model* m) {
             x = y;
         } else {
             float* y = B.act(2 * H, 2 * W, C / 2);
-            EVK_REQUIRE(m->find(pfx + ".conv2d.weight") != nullptr, EVK_ERR_KEY,
-                        "'%s.conv2d.weight' missing (transposed-conv decoders are not supported: every shipped "
-                        "checkpoint uses use_upsample_conv=True)", pfx.c_str());
-            r = B.conv(pfx + ".conv2d.weight", pfx + ".conv2d.bias", pfx + ".norm_layer", up, C, 2 * H, 2 * W, 1, k / 2,
-                       ACT_RELU, nullptr, y, nullptr);
+            if (tconv) {
+                // TransposedConvLayer (model/submodules.py:38-66): ConvTranspose2d(k, stride 2, padding k/2, output_padding 1)
+                // == stride-1 convolution of the zero-inserted map with the flipped kernel, padding k - 1 - k/2
+                r = B.conv(pfx + ".transposed_conv2d.weight", pfx + ".transposed_conv2d.bias", pfx + ".norm_layer", up, C, 2 * H, 2 * W, 1,
+                           k - 1 - k / 2, ACT_RELU, nullptr, y, nullptr, true);
+            } else {
+                EVK_REQUIRE(m->find(pfx + ".conv2d.weight") != nullptr, EVK_ERR_KEY, "'%s.conv2d.weight' / '.transposed_conv2d.weight' missing", pfx.c_str());
+                r = B.conv(pfx + ".conv2d.weight", pfx + ".conv2d.bias", pfx + ".norm_layer", up, C, 2 * H, 2 * W, 1, k / 2,
+                           ACT_RELU, nullptr, y, nullptr);
+            }
             if (r != EVK_OK) return r;
             x = y;
         }
@@ -507,7 +517,7 @@ static int build_unet(evk_model* m) {
             auto fix = [&](const float*& p) { if (p == s.buf[1]) p = s.buf[0]; };
             if (op.kind == OP_CONV && op.cp.epi == EPI_LSTM) { fix(op.cp.x1); continue; }   // x2/h_new already per parity
             if (op.kind == OP_CONV) { fix(op.cp.x1); fix(op.cp.res); }
-            if (op.kind == OP_UPSAMPLE_ADD || op.kind == OP_PRED) { fix(op.in); fix(op.skip); }
+            if (op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD || op.kind == OP_PRED) { fix(op.in); fix(op.skip); }
         }
     }
     return EVK_OK;
@@ -587,7 +597,7 @@ static int wire_tc(evk_model* m) {
     for (int par = 0; par < 2; ++par)
         for (Op& op : m->ops[par]) {
             switch (op.kind) {
-                case OP_HEAD: case OP_UPSAMPLE_ADD: op.out_s = lookup(op.out); break;
+                case OP_HEAD: case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: op.out_s = lookup(op.out); break;
                 case OP_CONV:
                     if (op.cp.epi == EPI_LINEAR) op.cp.ys = lookup(op.cp.y);
                     if (op.cp.epi == EPI_LSTM) op.cp.hs_new = lookup(op.cp.h_new);
@@ -616,7 +626,7 @@ static int wire_tc(evk_model* m) {
                         if (op.cp.x1s == nullptr) { rd(op.cp.x1); rd(op.cp.x2); }
                         rd(op.cp.res); rd(op.cp.c_prev); rd(op.cp.h_prev); rd(op.cp.u_in); rd(op.cp.pred_skip);
                         break;
-                    case OP_UPSAMPLE_ADD: case OP_PRED: rd(op.in); rd(op.skip); break;
+                    case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_PRED: rd(op.in); rd(op.skip); break;
                     case OP_HYPER_CONTEXT: case OP_HYPER_ATOMS: case OP_HYPER_APPLY:
                         rd(op.hp.ev_nchw); rd(op.hp.prev); rd(op.hp.coef); rd(op.hp.atoms); rd(op.hp.xu);   // (ctx / inter are outputs here)
                         break;
@@ -630,7 +640,7 @@ static int wire_tc(evk_model* m) {
                         !fp32_read.count(op.cp.y) && (op.cp.ys != nullptr || op.cp.pred_out != nullptr)) {
                         op.cp.y = nullptr;
                     }
-                    if (op.kind == OP_UPSAMPLE_ADD && op.out_s != nullptr && !fp32_read.count(op.out)) op.out = nullptr;
+                    if ((op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD) && op.out_s != nullptr && !fp32_read.count(op.out)) op.out = nullptr;
                     if (op.kind == OP_HYPER_APPLY && op.hp.inter_s != nullptr && !fp32_read.count(op.hp.inter)) op.hp.inter = nullptr;
                 }
     }
@@ -655,6 +665,7 @@ static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent
             case OP_HEAD: r = launch_head_conv(op.in, op.w, op.b, op.out, op.out_s, op.N, op.cin, op.H, op.W, op.k, op.cout, st); break;
             case OP_CONV: r = launch_conv(op.cp, m->cfg.precision, st); break;
             case OP_UPSAMPLE_ADD: r = launch_upsample2x_add(op.in, op.skip, op.out, op.out_s, op.N, op.H, op.W, op.cin, st); break;
+            case OP_ZERO_INSERT_ADD: r = launch_zero_insert2x_add(op.in, op.skip, op.out, op.out_s, op.N, op.H, op.W, op.cin, st); break;
             case OP_NOP: break;
             case OP_HEAD_PACK: r = launch_head_pack(op.in, op.out_s, op.N, op.cin, op.H, op.W, op.k / 2, st); break;
             case OP_PRED: r = launch_pred(op.in, op.skip, op.w, op.bias0, op.out, (int64_t)op.N * op.H * op.W, op.cin, op.sigmoid, st); break;
@@ -684,6 +695,7 @@ static std::string op_desc(const Op& op) {
             break;
         }
         case OP_UPSAMPLE_ADD: snprintf(b, sizeof b, "upsample2x_add C=%d @%dx%d", op.cin, 2 * op.H, 2 * op.W); break;
+        case OP_ZERO_INSERT_ADD: snprintf(b, sizeof b, "zero_insert2x_add C=%d @%dx%d", op.cin, 2 * op.H, 2 * op.W); break;
         case OP_PRED: snprintf(b, sizeof b, "pred 1x1 %d->1 @%dx%d", op.cin, op.H, op.W); break;
         case OP_NOP: snprintf(b, sizeof b, "(pred 1x1 fused into the previous epilogue)"); break;
         case OP_HEAD_PACK: snprintf(b, sizeof b, "head pack NCHW -> row-window split bf16 @%dx%d", op.H, op.W); break;

@@ -211,9 +211,6 @@ class _UNetFamily(_NativeModel):
         if kw.get('recurrent_block_type', 'convlstm') != 'convlstm':
             raise _lib.EvkError("UNetRecurrent with recurrent_block_type=%r is not built (all shipped checkpoints use "
                                 "convlstm)" % kw.get('recurrent_block_type'))
-        if not kw.get('use_upsample_conv', True):
-            raise _lib.EvkError("use_upsample_conv=False (TransposedConvLayer) is not built: every shipped checkpoint "
-                                "uses UpsampleConvLayer")
         if kw.get('channel_multiplier', 2) != 2:
             raise _lib.EvkError("channel_multiplier != 2 is not built")
 

@@ -74,6 +74,18 @@ def test_e2vid_topology_bn_sigmoid_batch2(precision):
     _assert_close(_frames(m, g['e2vid_small.voxels']), g['e2vid_small.frames'], 'e2vid_small')
 
 
+@pytest.mark.parametrize('precision', [0, 1])
+def test_transposed_conv_decoders(precision):
+    """use_upsample_conv=False: TransposedConvLayer decoders (model/submodules.py:38-66) as zero insertion + flipped
+    stride-1 convolution; frames of the real reference class with BN, batch 2, 3 recurrent steps."""
+    from evreal_b200 import E2VIDRecurrent
+    g = golden('networks')
+    full, _ = weights_of(g, 'e2vid_tconv', 'unetrecurrent.')
+    m = _load(E2VIDRecurrent(dict(E2VID_KW, use_upsample_conv=False, base_num_channels=8, norm='BN', final_activation='sigmoid')), full)
+    m.precision = precision
+    _assert_close(_frames(m, g['e2vid_tconv.voxels']), g['e2vid_tconv.frames'], 'e2vid_tconv')
+
+
 def test_flownet_topology_image_channel():
     from evreal_b200 import FlowNet
     g = golden('networks')

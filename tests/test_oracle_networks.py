@@ -34,6 +34,10 @@ def test_e2vid_topology():
     _check('e2vid_small', 'unetrecurrent.', lambda w: on.UNetRecurrentOracle(w, final_sigmoid=True))
 
 
+def test_transposed_conv_decoder_topology():
+    _check('e2vid_tconv', 'unetrecurrent.', lambda w: on.UNetRecurrentOracle(w, final_sigmoid=True, upsample_conv_decoder=False))
+
+
 def test_flownet_topology():
     _check('flownet_small', 'unetflow.', lambda w: on.UNetRecurrentOracle(w))
 

@@ -222,6 +222,16 @@ def golden_networks():
     m = model_arch.E2VIDRecurrent(dict(kw))
     _randomize_bn(m, 14)
     save_model('hyper_small', m, _small_voxels(5, 4, 2, 32, 48), 'unetrecurrent.')
+
+    # TransposedConvLayer decoders (use_upsample_conv=False; model/submodules.py:38-66) -- no shipped checkpoint uses
+    # them, so random weights through the real class: once with BN, once without
+    torch.manual_seed(15)
+    kw = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
+          'base_num_channels': 8, 'num_residual_blocks': 2, 'use_upsample_conv': False, 'norm': 'BN',
+          'final_activation': 'sigmoid'}
+    m = model_arch.E2VIDRecurrent(dict(kw))
+    _randomize_bn(m, 16)
+    save_model('e2vid_tconv', m, _small_voxels(6, 3, 2, 32, 48), 'unetrecurrent.')
     np.savez_compressed(os.path.join(OUT, 'networks.npz'), **out)
 
 
