@@ -1,6 +1,7 @@
 // C ABI entry points (include/evreal_b200.h) for the stateless stages, error
 // reporting, and the conv dispatcher.
 #include <cstdarg>
+#include <cstdlib>
 #include <vector>
 
 #include "conv.cuh"
@@ -141,8 +142,16 @@ int evk_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, const float* w
     p.w = dw; p.bias = db; p.cout = Cout; p.epi = EPI_LINEAR; p.act = act; p.res = res; p.y = y;
     if (precision == 0 && tc_eligible(p)) {
         std::vector<__nv_bfloat16> wt;
-        p.cout_pad = (Cout + 15) / 16 * 16;
-        pack_weights_tc(wk.data(), K, Cout, p.cout_pad, wt);
+        if (Cout == 32 && stride == 1 && p.Hout % 2 == 0 && res == nullptr && getenv("EVK_NO_ROW_PAIR") == nullptr) {
+            std::vector<float> w2;          // same rule as the network builder (model.cu): row-pair form of the last decoder
+            pack_weights_row_pair(wk.data(), k, k, Cin, Cout, w2);
+            p.row_pair = 1;
+            p.cout_pad = 2 * Cout;
+            pack_weights_tc(w2.data(), (k + 1) * k * Cin, 2 * Cout, p.cout_pad, wt);
+        } else {
+            p.cout_pad = (Cout + 15) / 16 * 16;
+            pack_weights_tc(wk.data(), K, Cout, p.cout_pad, wt);
+        }
         const int64_t nx = (int64_t)N * H * W * Cin;
         if (cudaMalloc(&dwt, wt.size() * 2) != cudaSuccess || cudaMalloc(&dxs, (size_t)nx * 4) != cudaSuccess) {
             cleanup();

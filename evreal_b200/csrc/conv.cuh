@@ -55,6 +55,11 @@ struct ConvParams {
     // tensor map whose pixel stride, 16 B, is smaller than its 128 B row): the kw taps of one kernel row are ONE K
     // chunk, so the layer runs as a (kh x 1) convolution with c1 = 64.  kw_packed = the real kw (<= 8).
     int kw_packed = 0;
+    // "row pair" form of a stride-1 layer with cout == 32 (the last decoder): the GEMM computes output rows 2y and 2y+1
+    // together as N = 64 columns of a (kh+1) x kw convolution with vertical stride 2 (weights of row 2y+1 shifted one tap
+    // down) -- an MMA with N <= 64 costs the same ~50 cycles as one with N = 32, so this halves the MMA count per
+    // output pixel at 6/5 of the taps.  w_tc then holds the stacked weights [2][64][(kh+1)*kw*cin] (pack_weights_row_pair).
+    int row_pair = 0;
     // prediction layer fused into the epilogue (EPI_LINEAR, cout <= 32, one N tile): out[pix] = act(sum_c w[c] *
     // (y[pix,c] + skip[pix,c]) + b) -- model/unet.py:136-138; y itself need not be stored
     const float* pred_w = nullptr; const float* pred_skip = nullptr; float* pred_out = nullptr;
@@ -71,6 +76,9 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st);
 int launch_split(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st);
 // host: fp32 [K][cout] (K-major rows of the SIMT layout) -> bf16 [2][cout_pad][K]
 void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out);
+
+// host: fp32 [kh*kw*cin][cout] -> row-pair weights [ (kh+1)*kw*cin ][2*cout] (see ConvParams::row_pair)
+void pack_weights_row_pair(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out);
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);
 // dispatcher: tensor-core split-bf16 kernel when the shape qualifies and precision == 0, else fp32 SIMT

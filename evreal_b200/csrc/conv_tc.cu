@@ -39,7 +39,9 @@
 namespace evk {
 
 struct TcArgs {
-    int N, Hout, Wout, stride, pad_u, pad_v, kh, kw;
+    int N, Hout, Wout, su, sv, pad_u, pad_v, kh, kw;       // Hout counts row PAIRS in row-pair mode; su / sv = stride along U / V
+    int cw;                     // epilogue chunk width in accumulator columns: 32, or 16 for a 32-column linear tile (both halves of the epilogue warps get work)
+    int rp, creal, hreal;       // row-pair mode, real channel count / output height (addressing)
     int ux;                     // 1: U = x (tile 16 rows x 8 cols), 0: U = y (tile 8 rows x 16 cols)
     int tiles_u, tiles_v;       // tiles per image along U (8 px) and V (16 px)
     int ku, kv;                 // kernel extent along U and V
@@ -182,8 +184,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         const long long t0 = DBG ? clock64() : 0;
                         mbar_wait(bar_ea + 8u * s, ph ^ 1u);
                         if (DBG) w_ea += clock64() - t0;
-                        const int iu0 = t.ou0 * a.stride - a.pad_u + su;
-                        const int iv0 = t.ov0 * a.stride - a.pad_v + a.g_tap0[g];
+                        const int iu0 = t.ou0 * a.su - a.pad_u + su;
+                        const int iv0 = t.ov0 * a.sv - a.pad_v + a.g_tap0[g];
                         const uint32_t sa = base + s * a_stage;
                         if (elect_one()) {
                             if (DBG && (a.exp & 2)) {
@@ -393,22 +395,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             if (DBG) w_tf += clock64() - t0;
             tc_fence_after();
             const uint32_t t_row = tmem_base + as * (uint32_t)a.acc_stride + ((uint32_t)(wq * 32) << 16);
-            const int nchunks = (a.bn + 31) / 32;
+            const int cw = a.cw;
+            const int nchunks = (a.bn + cw - 1) / cw;
             for (int c = half; c < nchunks; c += 2) {
-                const int j0 = c * 32;
+                const int j0 = c * cw;
                 uint32_t v[32];
                 __syncwarp();                     // tcgen05.ld is .sync.aligned: reconverge after the masked stores
                 {
                     uint32_t u[32];
-                    tc_ld_32x32(t_row + (uint32_t)j0, v);
-                    tc_ld_32x32(t_row + (uint32_t)(a.bn + j0), u);
+                    if (cw == 32) {
+                        tc_ld_32x32(t_row + (uint32_t)j0, v);
+                        tc_ld_32x32(t_row + (uint32_t)(a.bn + j0), u);
+                    } else {
+#pragma unroll
+                        for (int i = 16; i < 32; ++i) { v[i] = 0u; u[i] = 0u; }
+                        tc_ld_32x16(t_row + (uint32_t)j0, v);
+                        tc_ld_32x16(t_row + (uint32_t)(a.bn + j0), u);
+                    }
                     tc_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
                     if (a.own_acc) {                  // second issuer's accumulator (fixed order: deterministic bits)
                         uint32_t w[32];
-                        tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + j0), u);
-                        tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + a.bn + j0), w);
+                        if (cw == 32) {
+                            tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + j0), u);
+                            tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + a.bn + j0), w);
+                        } else {
+#pragma unroll
+                            for (int i = 16; i < 32; ++i) w[i] = 0u;
+                            tc_ld_32x16(t_row + (uint32_t)(a.acc_cols + j0), u);
+                            tc_ld_32x16(t_row + (uint32_t)(a.acc_cols + a.bn + j0), w);
+                        }
                         tc_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
@@ -423,12 +440,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                 const int nb = n0 + j0;
                 if (!valid || nb >= a.cout || (DBG && (a.exp & 4))) continue;
                 if (a.epi == EPI_LINEAR) {
-                    const size_t o = pix * a.cout + nb;
+                    // row-pair mode: columns [0, C) are output row 2*oy, columns [C, 2C) row 2*oy + 1
+                    const int rowsel = (a.rp && nb >= a.creal) ? 1 : 0;
+                    const int nbr = nb - rowsel * a.creal;
+                    const size_t pixl = a.rp ? ((size_t)t.img * a.hreal + 2 * oy + rowsel) * a.Wout + ox : pix;
+                    const size_t o = pixl * a.creal + nbr;
                     float pacc = 0.f;
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
-                        if (nb + g * 4 >= a.cout || j0 + g * 4 >= a.bn) break;
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
+                        if (nb + g * 4 >= a.cout || j0 + g * 4 >= a.bn || g * 4 >= cw) break;
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nbr + g * 4));
                         float f[4] = {__uint_as_float(v[g * 4 + 0]) + b4.x, __uint_as_float(v[g * 4 + 1]) + b4.y,
                                       __uint_as_float(v[g * 4 + 2]) + b4.z, __uint_as_float(v[g * 4 + 3]) + b4.w};
                         if (a.res != nullptr) {
@@ -440,7 +461,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         if (a.pred_out != nullptr) {      // fused 1x1 prediction layer (same summation order as pred_kernel)
                             const float4 s4 = a.pred_skip ? __ldg(reinterpret_cast<const float4*>(a.pred_skip + o + g * 4))
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.pred_w + nb + g * 4));
+                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.pred_w + nbr + g * 4));
                             pacc = fmaf(f[0] + s4.x, w4.x, pacc);
                             pacc = fmaf(f[1] + s4.y, w4.y, pacc);
                             pacc = fmaf(f[2] + s4.z, w4.z, pacc);
@@ -457,7 +478,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     }
                     if (a.pred_out != nullptr) {
                         pacc += a.pred_bias;
-                        a.pred_out[pix] = a.pred_sigmoid ? sigmoidf_(pacc) : pacc;
+                        a.pred_out[pixl] = a.pred_sigmoid ? sigmoidf_(pacc) : pacc;
                     }
                 } else if (a.epi == EPI_GRU_UR) {   // packed column = channel*2 + {update, reset} (model/submodules.py:281-282)
                     const int C = a.cout >> 1;
@@ -679,7 +700,12 @@ int tc_plan_create(ConvParams& p) {
     EVK_REQUIRE(p.x1s && p.w_tc && (p.c2 == 0 || p.x2s), EVK_ERR_ARG, "conv_tc: split operands missing");
     const int bk = pick_bk(p);
     const int cout_pad = p.cout_pad;
-    EVK_REQUIRE(cout_pad >= p.cout && cout_pad % 16 == 0, EVK_ERR_ARG, "conv_tc: cout_pad=%d must be a multiple of 16 >= cout", cout_pad);
+    const bool rp = p.row_pair != 0;
+    EVK_REQUIRE(!rp || (p.epi == EPI_LINEAR && p.stride == 1 && p.cout == 32 && cout_pad == 64 && p.Hout % 2 == 0 && p.res == nullptr &&
+                        !p.kw_packed), EVK_ERR_ARG, "conv_tc: row-pair mode needs a stride-1 linear layer with cout 32 and an even height");
+    const int e_kh = rp ? p.kh + 1 : p.kh, e_hout = rp ? p.Hout / 2 : p.Hout, e_cout = rp ? 2 * p.cout : p.cout;
+    const int s_y = rp ? 2 : p.stride, s_x = p.stride;
+    EVK_REQUIRE(cout_pad >= e_cout && cout_pad % 16 == 0, EVK_ERR_ARG, "conv_tc: cout_pad=%d must be a multiple of 16 >= cout", cout_pad);
     static bool attr_set = false;
     if (!attr_set) {
         const void* kerns[6] = {(const void*)conv_tc_kernel<64, false>, (const void*)conv_tc_kernel<32, false>,
@@ -696,13 +722,13 @@ int tc_plan_create(ConvParams& p) {
     const int f_bn = env_int("EVK_TC_BN", 0), f_cs = env_int("EVK_TC_CS", 0), f_ux = env_int("EVK_TC_UX", -1);
     TcChoice best = {1, 0, 1, 0.0};
     for (int ux = 0; ux < 2; ++ux) {
-        if (p.kw_packed ? ux != 1 : (f_ux >= 0 && ux != f_ux)) continue;      // row-window input: atoms run along x
-        const int hu = ux ? p.Wout : p.Hout, hv = ux ? p.Hout : p.Wout;
+        if (p.kw_packed ? ux != 1 : rp ? ux != 0 : (f_ux >= 0 && ux != f_ux)) continue;   // row-window input: atoms along x; row pairs: along y
+        const int hu = ux ? p.Wout : e_hout, hv = ux ? e_hout : p.Wout;
         const long m_tiles = (long)ceil_div(hu, 8) * ceil_div(hv, 16) * p.N;
-        const int ku = ux ? p.kw : p.kh, kv = ux ? p.kh : p.kw;
+        const int ku = ux ? p.kw : e_kh, kv = ux ? e_kh : p.kw;
         for (int bn = 128; bn >= 16; bn -= 16) {
             if (cout_pad % bn != 0 || bn % granule != 0) continue;
-            if (p.pred_out != nullptr && bn != cout_pad) continue;
+            if ((p.pred_out != nullptr || rp) && bn != cout_pad) continue;
             if (f_bn > 0 && bn != f_bn && cout_pad % f_bn == 0 && f_bn % granule == 0) continue;
             for (int cs = 1; cs <= 4; cs *= 2) {
                 if ((bn / cs) % 8 != 0 || bn % cs != 0) continue;
@@ -711,7 +737,7 @@ int tc_plan_create(ConvParams& p) {
                 const long ctas = n_super * cs;
                 const long slots = (long)(kNumSMs / cs) * cs;
                 const long waves = (ctas + slots - 1) / slots;
-                const double cost = (double)waves * tile_cost(bk, ku, kv, p.stride, chunks, bn, cs, ctas, nullptr);
+                const double cost = (double)waves * tile_cost(bk, ku, kv, ux ? s_y : s_x, chunks, bn, cs, ctas, nullptr);
                 if (best.bn == 0 || cost < best.cost) best = {ux, bn, cs, cost};
             }
         }
@@ -722,14 +748,17 @@ int tc_plan_create(ConvParams& p) {
     TcPlan* pl = new TcPlan();
     pl->bk = bk;
     TcArgs& a = pl->a;
-    a.N = p.N; a.Hout = p.Hout; a.Wout = p.Wout; a.stride = p.stride; a.pad_u = p.kw_packed ? 0 : p.pad; a.pad_v = p.pad; a.kh = p.kh; a.kw = p.kw;
+    a.N = p.N; a.Hout = e_hout; a.Wout = p.Wout; a.pad_u = p.kw_packed ? 0 : p.pad; a.pad_v = p.pad; a.kh = e_kh; a.kw = p.kw;
+    a.su = ux ? s_x : s_y; a.sv = ux ? s_y : s_x;
+    a.rp = rp ? 1 : 0; a.creal = p.cout; a.hreal = p.Hout;
+    a.cw = (p.epi == EPI_LINEAR && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
     a.ux = ux;
-    a.tiles_u = ceil_div(ux ? p.Wout : p.Hout, 8);
-    a.tiles_v = ceil_div(ux ? p.Hout : p.Wout, 16);
-    a.ku = ux ? p.kw : p.kh; a.kv = ux ? p.kh : p.kw;
+    a.tiles_u = ceil_div(ux ? p.Wout : e_hout, 8);
+    a.tiles_v = ceil_div(ux ? e_hout : p.Wout, 16);
+    a.ku = ux ? p.kw : e_kh; a.kv = ux ? e_kh : p.kw;
     a.chunks1 = p.c1 / bk; a.chunks2 = p.c2 / bk;
-    a.bn = bn; a.n_tiles = cout_pad / bn; a.m_tiles = a.tiles_u * a.tiles_v * p.N; a.cout = p.cout; a.epi = p.epi; a.act = p.act;
-    if (p.stride == 2) {
+    a.bn = bn; a.n_tiles = cout_pad / bn; a.m_tiles = a.tiles_u * a.tiles_v * p.N; a.cout = e_cout; a.epi = p.epi; a.act = p.act;
+    if (a.sv == 2) {
         a.n_groups = a.kv > 1 ? 2 : 1; a.g_step = 2;
         a.g_tap0[0] = 0; a.g_ntaps[0] = (a.kv + 1) / 2;
         a.g_tap0[1] = 1; a.g_ntaps[1] = a.kv / 2;
@@ -741,7 +770,7 @@ int tc_plan_create(ConvParams& p) {
     a.ar = 16 + a.g_ntaps[0] - 1;
     a.bias = p.bias; a.res = p.res; a.y = p.y; a.ys = p.ys;
     a.pred_w = p.pred_w; a.pred_skip = p.pred_skip; a.pred_out = p.pred_out; a.pred_bias = p.pred_bias; a.pred_sigmoid = p.pred_sigmoid;
-    if (p.pred_out != nullptr && (p.epi != EPI_LINEAR || bn < p.cout || bn > 32)) {
+    if (p.pred_out != nullptr && (p.epi != EPI_LINEAR || bn < e_cout || p.cout > 32)) {
         delete pl;
         EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: the fused prediction layer needs all %d channels in one 32-column chunk (bn=%d)", p.cout, bn);
     }
@@ -794,7 +823,7 @@ int tc_plan_create(ConvParams& p) {
     const long n_super = (long)a.n_tiles * ((a.m_tiles + cs - 1) / cs);
     pl->grid = dim3((unsigned)(std::min<long>(n_super, ncl) * cs));
     // activations: [plane, n, V, U, c] (U = atom axis, V = shift axis)
-    const int s = p.stride;
+    const int su = a.su, sv = a.sv;
     auto act_map = [&](CUtensorMap* m, const __nv_bfloat16* base, int C) -> int {
         if (p.kw_packed) {
             // row-window view of the packed head input [2][N][H][W+8][8]: "channel" dim = the 64 values starting at a
@@ -809,14 +838,14 @@ int tc_plan_create(ConvParams& p) {
         const uint64_t sx = (uint64_t)C * 2, sy = (uint64_t)p.Win * C * 2;
         const uint64_t dims[5] = {(uint64_t)C, (uint64_t)(ux ? p.Win : p.Hin), (uint64_t)(ux ? p.Hin : p.Win), (uint64_t)p.N, 2};
         const uint64_t str[4] = {ux ? sx : sy, ux ? sy : sx, (uint64_t)p.Hin * p.Win * C * 2, (uint64_t)p.N * p.Hin * p.Win * C * 2};
-        const uint32_t box[5] = {(uint32_t)bk, (uint32_t)(7 * s + 1), (uint32_t)((a.ar - 1) * s + 1), 1, 1};
-        const uint32_t es[5] = {1, (uint32_t)s, (uint32_t)s, 1, 1};
+        const uint32_t box[5] = {(uint32_t)bk, (uint32_t)(7 * su + 1), (uint32_t)((a.ar - 1) * sv + 1), 1, 1};
+        const uint32_t es[5] = {1, (uint32_t)su, (uint32_t)sv, 1, 1};
         return encode_tmap_bf16(m, base, 5, dims, str, box, es, (int)row_bytes);
     };
     int r = act_map(&pl->tm_x1, p.x1s, p.c1);
     if (r == EVK_OK) r = p.c2 ? act_map(&pl->tm_x2, p.x2s, p.c2) : act_map(&pl->tm_x2, p.x1s, p.c1);
     if (r == EVK_OK) {
-        const uint64_t K = (uint64_t)p.kh * p.kw * (p.c1 + p.c2);
+        const uint64_t K = (uint64_t)e_kh * p.kw * (p.c1 + p.c2);
         const uint64_t dims[3] = {K, (uint64_t)cout_pad, 2};
         const uint64_t str[2] = {K * 2, (uint64_t)cout_pad * K * 2};
         const uint32_t box[3] = {(uint32_t)bk, (uint32_t)(bn / cs), 1};
@@ -890,7 +919,7 @@ static int launch_conv_tc_timed(const ConvParams& p, cudaStream_t st) {
     const double k16 = (double)(a.chunks1 + a.chunks2) * a.kh * a.kw * (pl.bk / 16);
     fprintf(stderr, "TIMING %dx%d s%d c%d->%d @%dx%dx%d bn=%d cs=%d ux=%d grid=%u tiles/cta=%.1f k16/tile=%.0f | mma total %.0f (max %.0f) cyc = %.1f cyc/k16 | "
             "mma waits: tempty %.0f fullA %.0f fullB %.0f | producers wait: emptyA %.0f emptyB %.0f | epi total %.0f wait tfull %.0f\n",
-            a.kh, a.kw, a.stride, (a.chunks1 + a.chunks2) * pl.bk, a.cout, a.N, a.Hout, a.Wout, a.bn, a.cs, a.ux, pl.grid.x, tiles_per_cta, k16,
+            a.kh, a.kw, a.su > a.sv ? a.su : a.sv, (a.chunks1 + a.chunks2) * pl.bk, a.cout, a.N, a.Hout, a.Wout, a.bn, a.cs, a.ux, pl.grid.x, tiles_per_cta, k16,
             avg[0], mx[0], avg[0] / (tiles_per_cta * k16), avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
     return EVK_OK;
 }
@@ -922,6 +951,18 @@ int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin,
     head_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, 0, st>>>(x_nchw, packed, N, cin, H, W, left);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
+}
+
+void pack_weights_row_pair(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out) {
+    out.assign((size_t)(kh + 1) * kw * cin * 2 * cout, 0.f);
+    for (int r = 0; r <= kh; ++r)
+        for (int q = 0; q < kw; ++q)
+            for (int c = 0; c < cin; ++c)
+                for (int n = 0; n < cout; ++n) {
+                    const size_t dst = ((size_t)(r * kw + q) * cin + c) * (2 * cout);
+                    if (r < kh) out[dst + n] = w_kc[((size_t)(r * kw + q) * cin + c) * cout + n];                  // row 2y: tap r
+                    if (r >= 1) out[dst + cout + n] = w_kc[((size_t)((r - 1) * kw + q) * cin + c) * cout + n];     // row 2y+1: tap r-1
+                }
 }
 
 void pack_head_weights_rowwin(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out) {

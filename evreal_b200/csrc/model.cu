@@ -178,8 +178,18 @@ struct Builder {
     void attach_tc_weights(ConvParams& p, const Packed& pk) {
         if (m->cfg.precision != 0 || !tc_eligible(p)) return;
         std::vector<__nv_bfloat16> wt;
-        p.cout_pad = (pk.cout + 15) / 16 * 16;
-        pack_weights_tc(pk.w.data(), pk.kh * pk.kw * pk.cin, pk.cout, p.cout_pad, wt);
+        if (p.epi == EPI_LINEAR && pk.cout == 32 && p.stride == 1 && p.Hout > 0 && p.Hout % 2 == 0 && p.res == nullptr && !p.kw_packed &&
+            getenv("EVK_NO_ROW_PAIR") == nullptr) {
+            // last decoder: two output rows per GEMM row (conv.cuh, ConvParams::row_pair)
+            std::vector<float> w2;
+            pack_weights_row_pair(pk.w.data(), pk.kh, pk.kw, pk.cin, pk.cout, w2);
+            p.row_pair = 1;
+            p.cout_pad = 2 * pk.cout;
+            pack_weights_tc(w2.data(), (pk.kh + 1) * pk.kw * pk.cin, 2 * pk.cout, p.cout_pad, wt);
+        } else {
+            p.cout_pad = (pk.cout + 15) / 16 * 16;
+            pack_weights_tc(pk.w.data(), pk.kh * pk.kw * pk.cin, pk.cout, p.cout_pad, wt);
+        }
         void* d = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
         if (d) cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
         p.w_tc = (const __nv_bfloat16*)d;
