@@ -9,8 +9,7 @@
 //
 // GEMM view: M = 128 output pixels of one image, N = BN output channels, K = kh*kw*(c1+c2).
 //
-// The kernel is bound by the L2 -> shared-memory path (measured: the per-tap im2col re-load of round-1 v2 ran at
-// the chip's ~6.3 kB/clk TMA ceiling on every layer), so operand traffic is what the design minimises:
+// Operand traffic (the per-tap im2col re-load of the first version ran at the chip's ~6.3 kB/clk L2 -> SM ceiling):
 //
 //  * A (activations), HALO BOXES.  The M tile is 8 pixels along an "atom" axis U by 16 pixels along a "shift" axis V
 //    (U = x, V = y or the transpose, whichever pads the layer less).  8 pixels x BK channels of bf16 are exactly one
@@ -24,10 +23,13 @@
 //  * B (weights), CLUSTER MULTICAST.  The CTAs of a thread-block cluster work on different M tiles of the same
 //    N tile; each loads 1/cs of the weight tile and multicasts it into every CTA's shared memory.
 //
+// With the loads out of the way the kernel is bound by tcgen05.mma ISSUE (see the MMA issuer section below): two
+// issuer warps, and shapes that keep every MMA at N >= 64 where possible (row-pair mode for cout = 32).
+//
 // Warp roles (384 threads, 1 CTA/SM, persistent over tiles): warp 0 = A producer, warp 3 = B producer,
-// warps 1-2 = MMA issuers (K blocks dealt alternately; warp 2 also allocates TMEM), warps 4-11 = epilogue (thread = accumulator row =
-// output pixel).  Two independent shared-memory rings (A: box stages, B: one tap per stage); the accumulator is
-// double-buffered in tensor memory so the epilogue of tile i overlaps the MMAs of tile i+1.
+// warps 1-2 = MMA issuers (K blocks dealt alternately; warp 2 also allocates TMEM), warps 4-11 = epilogue
+// (thread = accumulator row = output pixel).  Two independent shared-memory rings (A: box stages, B: one K block per
+// stage); the accumulator is double-buffered in tensor memory so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

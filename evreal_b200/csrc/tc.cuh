@@ -129,64 +129,6 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// One K block of the split-bf16 scheme as ONE asm statement: KS 16-deep slices x { A_hi*[B_hi;B_lo] (N = 2bn),
-// A_lo*B_hi (N = bn) }, then the commit that frees the weight slot -- with the readiness polls of the NEXT block's
-// barriers embedded after the first slice, so that their round trip (~100+ cycles even when the phase is already
-// complete; measured with tools/microbench/mma_loop_bench.cu) overlaps the issue of the remaining MMAs instead of
-// sitting between two K blocks as a tensor-pipe bubble.  Descriptor low words advance by 2 (= 32 bytes >> 4) per
-// slice.  mask == 0: CTA-local commit, else cluster multicast.  Returns bit 0 = next weight barrier complete,
-// bit 1 = next activation barrier complete.
-#define EVK_MMA_HEAD                                                        \
-    "{\n\t"                                                                 \
-    ".reg .pred pacc, pone, pb, pa, pm;\n\t"                                \
-    ".reg .b64 da, dl, db;\n\t"                                             \
-    ".reg .b32 rb, ra;\n\t"                                                 \
-    "setp.ne.b32 pacc, %8, 0;\n\t"                                          \
-    "setp.eq.b32 pone, %8, %8;\n\t"                                         \
-    "setp.ne.b16 pm, %10, 0;\n\t"                                           \
-    "mov.b64 da, {%2, %1};\n\t"                                             \
-    "mov.b64 dl, {%3, %1};\n\t"                                             \
-    "mov.b64 db, {%4, %1};\n\t"                                             \
-    "tcgen05.mma.cta_group::1.kind::f16 [%5], da, db, %6, pacc;\n\t"        \
-    "tcgen05.mma.cta_group::1.kind::f16 [%5], dl, db, %7, pone;\n\t"        \
-    "mbarrier.try_wait.parity.shared::cta.b64 pb, [%11], %12;\n\t"          \
-    "mbarrier.try_wait.parity.shared::cta.b64 pa, [%13], %14;\n\t"
-#define EVK_MMA_SLICE                                                       \
-    "add.s64 da, da, 2;\n\t"                                                \
-    "add.s64 dl, dl, 2;\n\t"                                                \
-    "add.s64 db, db, 2;\n\t"                                                \
-    "tcgen05.mma.cta_group::1.kind::f16 [%5], da, db, %6, pone;\n\t"        \
-    "tcgen05.mma.cta_group::1.kind::f16 [%5], dl, db, %7, pone;\n\t"
-#define EVK_MMA_TAIL                                                                                                   \
-    "@pm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%9], %10;\n\t"      \
-    "@!pm tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"                             \
-    "selp.u32 rb, 1, 0, pb;\n\t"                                                                                       \
-    "selp.u32 ra, 2, 0, pa;\n\t"                                                                                       \
-    "or.b32 %0, rb, ra;\n\t"                                                                                           \
-    "}"
-#define EVK_MMA_OPERANDS                                                                                                 \
-    : "=r"(ready)                                                                                                        \
-    : "r"(desc_hi), "r"(ah_lo), "r"(al_lo), "r"(bh_lo), "r"(d_tmem), "r"(idesc2), "r"(idesc1), "r"(accumulate),          \
-      "r"(commit_bar), "h"(mask), "r"(next_b_bar), "r"(next_b_parity), "r"(next_a_bar), "r"(next_a_parity)               \
-    : "memory"
-template <int KS>
-__device__ __forceinline__ uint32_t tc_mma_block(uint32_t d_tmem, uint32_t desc_hi, uint32_t ah_lo, uint32_t al_lo, uint32_t bh_lo,
-                                                 uint32_t idesc2, uint32_t idesc1, uint32_t accumulate, uint32_t commit_bar,
-                                                 uint16_t mask, uint32_t next_b_bar, uint32_t next_b_parity,
-                                                 uint32_t next_a_bar, uint32_t next_a_parity) {
-    static_assert(KS == 2 || KS == 4, "K block = 2 or 4 slices of 16");
-    uint32_t ready;
-    if constexpr (KS == 4)
-        asm volatile(EVK_MMA_HEAD EVK_MMA_SLICE EVK_MMA_SLICE EVK_MMA_SLICE EVK_MMA_TAIL EVK_MMA_OPERANDS);
-    else
-        asm volatile(EVK_MMA_HEAD EVK_MMA_SLICE EVK_MMA_TAIL EVK_MMA_OPERANDS);
-    return ready;
-}
-#undef EVK_MMA_HEAD
-#undef EVK_MMA_SLICE
-#undef EVK_MMA_TAIL
-#undef EVK_MMA_OPERANDS
-
 // 32 lanes x 32 columns of fp32 accumulators: thread i of the warp receives lane (base+i), columns col..col+31
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
