@@ -60,6 +60,16 @@ struct ConvParams {
     // down) -- an MMA with N <= 64 costs the same ~50 cycles as one with N = 32, so this halves the MMA count per
     // output pixel at 6/5 of the taps.  w_tc then holds the stacked weights [2][64][(kh+1)*kw*cin] (pack_weights_row_pair).
     int row_pair = 0;
+    // "phase-stacked" form of UpsampleConvLayer (poly.cu): the GEMM runs on the replicate-padded LOW-resolution map
+    // (x1s = [2][N][Hin][Win][c1], Hin = H + 4, pad = 0, Hout x Wout = H x W) with N = 4 * cout composite columns
+    // (column block a*2+b = output phase); the epilogue writes column block (a, b) of GEMM row (i, j) to output pixel
+    // (2i+a, 2j+b) of the [N, 2*Hout, 2*Wout, cout] result and adds the border corrections (minus the excess of the taps
+    // that fall outside the upsampled map) on the two outermost rows / columns before the activation.
+    // w_tc = pack_weights_phase4 -> pack_weights_tc, cout_pad = 4*cout.  2 = one row phase per N tile (bn = 2*cout), the
+    // all-zero tap row of each skipped.
+    int phase4 = 0;
+    const float* ring_h = nullptr;        // [2 (top, bottom)][N][2*Wout][4*cout]: column block l = output row {0, 1, Ho-2, Ho-1}
+    const float* ring_v = nullptr;        // [2 (left, right)][N][2*Hout][4*cout]: column block l = output column {0, 1, Wo-2, Wo-1}
     // prediction layer fused into the epilogue (EPI_LINEAR, cout <= 32, one N tile): out[pix] = act(sum_c w[c] *
     // (y[pix,c] + skip[pix,c]) + b) -- model/unet.py:136-138; y itself need not be stored
     const float* pred_w = nullptr; const float* pred_skip = nullptr; float* pred_out = nullptr;
@@ -79,6 +89,16 @@ void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vect
 
 // host: fp32 [kh*kw*cin][cout] -> row-pair weights [ (kh+1)*kw*cin ][2*cout] (see ConvParams::row_pair)
 void pack_weights_row_pair(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out);
+
+// ---- phase-stacked decoder (poly.cu)
+// host: fp32 [25*cin][cout] -> composite phase weights [25*cin][4*cout] (column = (a*2+b)*cout + n)
+void pack_weights_phase4(const float* w_kc, int cin, int cout, std::vector<float>& out);
+// host: NEGATED pre-summed out-of-bounds tap weights of the two border-line convolutions, [2][5*cin][4*cout]
+void pack_weights_ring(const float* w_kc, int cin, int cout, std::vector<float>& out);
+// out[2][N][H+4][W+4][C] = split_bf16(x + skip), replicate padding of 2
+int launch_add_pad_split(const float* x, const float* skip, __nv_bfloat16* out, int N, int H, int W, int C, cudaStream_t st);
+// u_ext just outside the four borders as split-bf16 line images [2][2N][2W+4][C] (horizontal) / [2][2N][2H+4][C] (vertical)
+int launch_ring_lines(const __nv_bfloat16* xp, __nv_bfloat16* lines_h, __nv_bfloat16* lines_v, int N, int H, int W, int C, cudaStream_t st);
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);
 // dispatcher: tensor-core split-bf16 kernel when the shape qualifies and precision == 0, else fp32 SIMT

@@ -44,6 +44,8 @@ struct TcArgs {
     int N, Hout, Wout, su, sv, pad_u, pad_v, kh, kw;       // Hout counts row PAIRS in row-pair mode; su / sv = stride along U / V
     int cw;                     // epilogue chunk width in accumulator columns: 32, or 16 for a 32-column linear tile (both halves of the epilogue warps get work)
     int rp, creal, hreal;       // row-pair mode, real channel count / output height (addressing)
+    int ps, wreal;              // phase-stacked mode (ConvParams::phase4): column block a*2+b -> output pixel (2oy+a, 2ox+b); output width
+    const float* ring_h; const float* ring_v;   // phase-stacked mode: border corrections (ConvParams), added before the activation
     int ux;                     // 1: U = x (tile 16 rows x 8 cols), 0: U = y (tile 8 rows x 16 cols)
     int tiles_u, tiles_v;       // tiles per image along U (8 px) and V (16 px)
     int ku, kv;                 // kernel extent along U and V
@@ -113,6 +115,13 @@ __device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int st, int cra
     return t;
 }
 
+// Phase-pair mode (a.ps == 2, U = y): N tile nt holds the two column phases of ROW phase nt, whose composite 5x5 kernel
+// has an all-zero first (row phase 1) or last (row phase 0) tap row -- that U shift is skipped by all three pipeline roles.
+__device__ __forceinline__ void su_range(const TcArgs& a, int nt, int& su0, int& su1) {
+    su0 = 0; su1 = a.ku;
+    if (a.ps == 2) { if (nt == 0) su1 = a.ku - 1; else su0 = 1; }
+}
+
 template <int BK, bool DBG>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
@@ -177,11 +186,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         long long w_ea = 0;
         for (int st = cid; st < n_super; st += ncl) {
             const TileCoord t = tile_coord(a, st, crank);
+            int su0, su1;
+            su_range(a, t.nt, su0, su1);
             for (int ch = 0; ch < chunks; ++ch) {
                 const bool first = ch < a.chunks1;
                 const CUtensorMap* m = first ? &tm_x1 : &tm_x2;
                 const int c0 = (first ? ch : ch - a.chunks1) * BK;
-                for (int su = 0; su < a.ku; ++su)
+                for (int su = su0; su < su1; ++su)
                     for (int g = 0; g < a.n_groups; ++g) {
                         const long long t0 = DBG ? clock64() : 0;
                         mbar_wait(bar_ea + 8u * s, ph ^ 1u);
@@ -214,8 +225,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         for (int st = cid; st < n_super; st += ncl) {
             const TileCoord t = tile_coord(a, st, crank);
             const int row0 = t.nt * a.bn + crank * bnp;
+            int su0, su1;
+            su_range(a, t.nt, su0, su1);
             for (int ch = 0; ch < chunks; ++ch)
-                for (int su = 0; su < a.ku; ++su)
+                for (int su = su0; su < su1; ++su)
                     for (int g = 0; g < a.n_groups; ++g)
                         for (int j0 = 0; j0 < a.g_ntaps[g]; j0 += a.tpb) {
                             const int ntb = min(a.tpb, a.g_ntaps[g] - j0);       // taps in this K block
@@ -288,7 +301,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const uint32_t nbs = (uint32_t)a.b_stages;
         const uint32_t two = a.issuers == 2 ? 1u : 0u;
         const bool own = a.own_acc != 0;
-        const uint32_t kb_total = (uint32_t)(chunks * a.ku * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0)));
+        const uint32_t kb_total = (uint32_t)(chunks * (a.ps == 2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0)));
         uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0, gblk = 0;
         bool b_ready = false;
         long long w_te = 0, w_fa = 0, w_fb = 0;
@@ -303,8 +316,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             uint32_t blk = 0;
             bool fresh = true;                // the next MMA of this issuer initialises its accumulator
             if (!own) b_ready = false;        // strict mode deals blocks per tile: the look-ahead distance differs across tiles
+            int su0, su1;
+            su_range(a, st % a.n_tiles, su0, su1);
             for (int ch = 0; ch < chunks; ++ch)
-                for (int su = 0; su < a.ku; ++su)
+                for (int su = su0; su < su1; ++su)
                     for (int g = 0; g < a.n_groups; ++g) {
                         const int nt_g = a.g_ntaps[g];
                         uint32_t ah_lo = lo_of(base + sA * a_stage);
@@ -443,9 +458,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                 if (!valid || nb >= a.cout || (DBG && (a.exp & 4))) continue;
                 if (a.epi == EPI_LINEAR) {
                     // row-pair mode: columns [0, C) are output row 2*oy, columns [C, 2C) row 2*oy + 1
-                    const int rowsel = (a.rp && nb >= a.creal) ? 1 : 0;
-                    const int nbr = nb - rowsel * a.creal;
-                    const size_t pixl = a.rp ? ((size_t)t.img * a.hreal + 2 * oy + rowsel) * a.Wout + ox : pix;
+                    // phase-stacked mode: column block ph = a*2+b of GEMM row (oy, ox) is output pixel (2oy+a, 2ox+b)
+                    int nbr = nb;
+                    size_t pixl = pix;
+                    const float* ringh = nullptr;
+                    const float* ringv = nullptr;
+                    if (a.rp) {
+                        const int rowsel = nb >= a.creal ? 1 : 0;
+                        nbr = nb - rowsel * a.creal;
+                        pixl = ((size_t)t.img * a.hreal + 2 * oy + rowsel) * a.Wout + ox;
+                    } else if (a.ps) {
+                        const int ph = nb / a.creal;
+                        nbr = nb - ph * a.creal;
+                        const int Y = 2 * oy + (ph >> 1), X = 2 * ox + (ph & 1);
+                        pixl = ((size_t)t.img * a.hreal + Y) * a.wreal + X;
+                        if (Y < 2 || Y >= a.hreal - 2) {          // border line l = {0, 1, Ho-2, Ho-1} -> column block l
+                            const int side = Y < 2 ? 0 : 1, l = Y < 2 ? Y : Y - a.hreal + 4;
+                            ringh = a.ring_h + (((size_t)(side * a.N + t.img) * a.wreal + X) * 4 + l) * a.creal + nbr;
+                        }
+                        if (X < 2 || X >= a.wreal - 2) {
+                            const int side = X < 2 ? 0 : 1, l = X < 2 ? X : X - a.wreal + 4;
+                            ringv = a.ring_v + (((size_t)(side * a.N + t.img) * a.hreal + Y) * 4 + l) * a.creal + nbr;
+                        }
+                    }
                     const size_t o = pixl * a.creal + nbr;
                     float pacc = 0.f;
 #pragma unroll
@@ -456,6 +491,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                       __uint_as_float(v[g * 4 + 2]) + b4.z, __uint_as_float(v[g * 4 + 3]) + b4.w};
                         if (a.res != nullptr) {
                             const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.res + o + g * 4));
+                            f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
+                        }
+                        if (ringh != nullptr) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(ringh + g * 4));
+                            f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
+                        }
+                        if (ringv != nullptr) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(ringv + g * 4));
                             f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
                         }
 #pragma unroll
@@ -703,9 +746,13 @@ int tc_plan_create(ConvParams& p) {
     const int bk = pick_bk(p);
     const int cout_pad = p.cout_pad;
     const bool rp = p.row_pair != 0;
+    const bool ps = p.phase4 != 0, ps2 = p.phase4 == 2;
+    EVK_REQUIRE(!ps || (!rp && p.epi == EPI_LINEAR && p.stride == 1 && p.pad == 0 && p.kh == 5 && p.kw == 5 && p.cout % 32 == 0 &&
+                        cout_pad == 4 * p.cout && p.res == nullptr && p.ring_h != nullptr && p.ring_v != nullptr && !p.kw_packed), EVK_ERR_ARG,
+                "conv_tc: phase-stacked mode needs a 5x5 stride-1 unpadded linear layer with cout %% 32 == 0 and a ring buffer");
     EVK_REQUIRE(!rp || (p.epi == EPI_LINEAR && p.stride == 1 && p.cout == 32 && cout_pad == 64 && p.Hout % 2 == 0 && p.res == nullptr &&
                         !p.kw_packed), EVK_ERR_ARG, "conv_tc: row-pair mode needs a stride-1 linear layer with cout 32 and an even height");
-    const int e_kh = rp ? p.kh + 1 : p.kh, e_hout = rp ? p.Hout / 2 : p.Hout, e_cout = rp ? 2 * p.cout : p.cout;
+    const int e_kh = rp ? p.kh + 1 : p.kh, e_hout = rp ? p.Hout / 2 : p.Hout, e_cout = rp ? 2 * p.cout : ps ? 4 * p.cout : p.cout;
     const int s_y = rp ? 2 : p.stride, s_x = p.stride;
     EVK_REQUIRE(cout_pad >= e_cout && cout_pad % 16 == 0, EVK_ERR_ARG, "conv_tc: cout_pad=%d must be a multiple of 16 >= cout", cout_pad);
     static bool attr_set = false;
@@ -724,13 +771,15 @@ int tc_plan_create(ConvParams& p) {
     const int f_bn = env_int("EVK_TC_BN", 0), f_cs = env_int("EVK_TC_CS", 0), f_ux = env_int("EVK_TC_UX", -1);
     TcChoice best = {1, 0, 1, 0.0};
     for (int ux = 0; ux < 2; ++ux) {
-        if (p.kw_packed ? ux != 1 : rp ? ux != 0 : (f_ux >= 0 && ux != f_ux)) continue;   // row-window input: atoms along x; row pairs: along y
+        if (p.kw_packed ? ux != 1 : (rp || ps2) ? ux != 0 : (f_ux >= 0 && ux != f_ux)) continue;   // row-window input: atoms along x; row pairs / phase pairs: along y
         const int hu = ux ? p.Wout : e_hout, hv = ux ? e_hout : p.Wout;
         const long m_tiles = (long)ceil_div(hu, 8) * ceil_div(hv, 16) * p.N;
         const int ku = ux ? p.kw : e_kh, kv = ux ? e_kh : p.kw;
         for (int bn = 128; bn >= 16; bn -= 16) {
             if (cout_pad % bn != 0 || bn % granule != 0) continue;
             if ((p.pred_out != nullptr || rp) && bn != cout_pad) continue;
+            if (ps && bn % 32 != 0) continue;             // a 32-column epilogue chunk must not straddle two phases
+            if (ps2 && bn != 2 * p.cout) continue;        // phase pairs: one row phase per N tile
             if (f_bn > 0 && bn != f_bn && cout_pad % f_bn == 0 && f_bn % granule == 0) continue;
             for (int cs = 1; cs <= 4; cs *= 2) {
                 if ((bn / cs) % 8 != 0 || bn % cs != 0) continue;
@@ -739,7 +788,7 @@ int tc_plan_create(ConvParams& p) {
                 const long ctas = n_super * cs;
                 const long slots = (long)(kNumSMs / cs) * cs;
                 const long waves = (ctas + slots - 1) / slots;
-                const double cost = (double)waves * tile_cost(bk, ku, kv, ux ? s_y : s_x, chunks, bn, cs, ctas, nullptr);
+                const double cost = (double)waves * tile_cost(bk, ps2 ? ku - 1 : ku, kv, ux ? s_y : s_x, chunks, bn, cs, ctas, nullptr);
                 if (best.bn == 0 || cost < best.cost) best = {ux, bn, cs, cost};
             }
         }
@@ -752,7 +801,9 @@ int tc_plan_create(ConvParams& p) {
     TcArgs& a = pl->a;
     a.N = p.N; a.Hout = e_hout; a.Wout = p.Wout; a.pad_u = p.kw_packed ? 0 : p.pad; a.pad_v = p.pad; a.kh = e_kh; a.kw = p.kw;
     a.su = ux ? s_x : s_y; a.sv = ux ? s_y : s_x;
-    a.rp = rp ? 1 : 0; a.creal = p.cout; a.hreal = p.Hout;
+    a.rp = rp ? 1 : 0; a.creal = p.cout; a.hreal = ps ? 2 * p.Hout : p.Hout;
+    a.ps = p.phase4; a.wreal = ps ? 2 * p.Wout : p.Wout;
+    a.ring_h = p.ring_h; a.ring_v = p.ring_v;
     a.cw = (p.epi == EPI_LINEAR && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
     a.ux = ux;
     a.tiles_u = ceil_div(ux ? p.Wout : e_hout, 8);
@@ -776,7 +827,7 @@ int tc_plan_create(ConvParams& p) {
         delete pl;
         EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: the fused prediction layer needs all %d channels in one 32-column chunk (bn=%d)", p.cout, bn);
     }
-    a.ys_plane = (long long)p.N * p.Hout * p.Wout * p.cout;
+    a.ys_plane = (long long)p.N * p.Hout * p.Wout * p.cout * (ps ? 4 : 1);
     a.c_prev = p.c_prev; a.c_new = p.c_new; a.h_new = p.h_new; a.hs_new = p.hs_new;
     a.h_prev = p.h_prev; a.u_in = p.u_in; a.u_out = p.u_out; a.hr_out = p.hr_out; a.hrs_out = p.hrs_out;
     // plane stride of the split copy of the recurrent output: hidden channels = cout/4 (LSTM), cout/2 (GRU u,r), cout (GRU out)
@@ -805,7 +856,7 @@ int tc_plan_create(ConvParams& p) {
     a.a_stages = as; a.b_stages = bs;
     // per accumulator stage: [hi*hi + lo*hi | hi*lo] = 2*bn columns, read in 32-column windows (bn%32 tail -> pad)
     a.acc_cols = (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;
-    const int kb = (a.chunks1 + a.chunks2) * a.ku * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0));
+    const int kb = (a.chunks1 + a.chunks2) * (ps2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0));
     a.issuers = (kb >= 2 && env_int("EVK_TC_ISSUERS", 2) == 2) ? 2 : 1;
     a.own_acc = (a.issuers == 2 && 4 * a.acc_cols <= 512 && env_int("EVK_TC_OWN_ACC", 1)) ? 1 : 0;
     a.acc_stride = a.own_acc ? 2 * a.acc_cols : a.acc_cols;

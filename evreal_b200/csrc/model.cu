@@ -28,7 +28,7 @@ struct HostTensor {
     std::vector<int64_t> shape;
 };
 
-enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HEAD_PACK, OP_NOP, OP_ZERO_INSERT_ADD };
+enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HEAD_PACK, OP_NOP, OP_ZERO_INSERT_ADD, OP_ADD_PAD, OP_RING_LINES };
 
 struct Op {
     OpKind kind;
@@ -39,6 +39,8 @@ struct Op {
     // OP_UPSAMPLE_ADD / OP_PRED
     const float* skip = nullptr;
     __nv_bfloat16* out_s = nullptr;   // OP_HEAD / OP_UPSAMPLE_ADD: split-bf16 copy of `out` for a tensor-core consumer
+    __nv_bfloat16* lines_h = nullptr; __nv_bfloat16* lines_v = nullptr;   // OP_RING_LINES outputs
+    int ring_line = 0;                // OP_CONV: 1 / 2 = horizontal / vertical border-line convolution of a phase-stacked decoder
     float bias0 = 0.f;
     int sigmoid = 0;
     HyperParams hp;             // OP_HYPER_*
@@ -378,6 +380,79 @@ static int add_pred(Builder& B, const std::string& pfx, const float* x, const fl
     return EVK_OK;
 }
 
+// UpsampleConvLayer in phase-stacked form (poly.cu): (x + skip) -> replicate-padded split planes, border-ring
+// correction, then ONE 5x5 convolution on the low-resolution map with N = 4 * cout whose epilogue scatters the phases.
+static int add_poly_decoder(Builder& B, const std::string& pfx, const float* x, const float* skip, int C, int H, int W, float* y) {
+    evk_model* m = B.m;
+    Packed pk;
+    int r = pack_conv(m, pfx + ".conv2d.weight", pfx + ".conv2d.bias", pfx + ".norm_layer", nullptr, pk);
+    if (r != EVK_OK) return r;
+    EVK_REQUIRE(pk.cin == C && pk.kh == 5 && pk.kw == 5, EVK_ERR_KEY, "'%s': unexpected decoder shape", pfx.c_str());
+    const int Co = pk.cout, N = B.N;
+    const size_t plane = (size_t)N * (H + 4) * (W + 4) * C;
+    __nv_bfloat16* xp = (__nv_bfloat16*)m->dalloc_bytes(2 * plane * sizeof(__nv_bfloat16));
+    // border corrections: u_ext lines just outside the four borders -> two 1x5 tensor-core convolutions (poly.cu)
+    const int Ho = 2 * H, Wo = 2 * W, R = 2 * N;
+    __nv_bfloat16* lines[2] = {(__nv_bfloat16*)m->dalloc_bytes((size_t)2 * R * (Wo + 4) * C * sizeof(__nv_bfloat16)),
+                               (__nv_bfloat16*)m->dalloc_bytes((size_t)2 * R * (Ho + 4) * C * sizeof(__nv_bfloat16))};
+    float* ring[2] = {m->dalloc((size_t)R * Wo * 4 * Co), m->dalloc((size_t)R * Ho * 4 * Co)};
+    EVK_REQUIRE(xp && lines[0] && lines[1] && ring[0] && ring[1], EVK_ERR_CUDA, "out of device memory for the phase-stacked decoder");
+    {
+        Op op; op.kind = OP_ADD_PAD;
+        op.in = x; op.skip = skip; op.out_s = xp; op.N = N; op.H = H; op.W = W; op.cin = C;
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+    }
+    {
+        Op op; op.kind = OP_RING_LINES;
+        op.out_s = xp; op.lines_h = lines[0]; op.lines_v = lines[1]; op.N = N; op.H = H; op.W = W; op.cin = C;
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+    }
+    {
+        std::vector<float> wr;
+        pack_weights_ring(pk.w.data(), C, Co, wr);
+        const float* zero_bias = m->upload(std::vector<float>((size_t)4 * Co, 0.f));
+        EVK_REQUIRE(zero_bias != nullptr, EVK_ERR_CUDA, "out of device memory for the ring bias");
+        for (int v = 0; v < 2; ++v) {
+            const int L = v ? Ho : Wo;
+            Op op; op.kind = OP_CONV;
+            ConvParams& p = op.cp;
+            p.x1 = nullptr; p.c1 = C; p.x1s = lines[v];
+            p.N = 1; p.Hin = p.Hout = R; p.Win = L + 4; p.Wout = L; p.kh = 1; p.kw = 5; p.stride = 1; p.pad = 0;
+            p.bias = zero_bias; p.cout = 4 * Co; p.epi = EPI_LINEAR; p.act = ACT_NONE; p.y = ring[v];
+            std::vector<__nv_bfloat16> wt;
+            p.cout_pad = 4 * Co;
+            pack_weights_tc(wr.data() + (size_t)v * 5 * C * 4 * Co, 5 * C, 4 * Co, p.cout_pad, wt);
+            void* d = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
+            EVK_REQUIRE(d != nullptr, EVK_ERR_CUDA, "out of device memory for the ring weights");
+            cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+            p.w_tc = (const __nv_bfloat16*)d;
+            EVK_REQUIRE(tc_eligible(p), EVK_ERR_ARG, "'%s': border-line convolution is not eligible for the tensor-core path", pfx.c_str());
+            op.flops = 0.0;                       // overhead of this formulation, not the reference's arithmetic
+            op.ring_line = 1 + v;
+            m->ops[0].push_back(op); m->ops[1].push_back(op);
+        }
+    }
+    Op op; op.kind = OP_CONV;
+    ConvParams& p = op.cp;
+    p.x1 = nullptr; p.c1 = C; p.x1s = xp; p.phase4 = Co == 32 ? 1 : 2; p.ring_h = ring[0]; p.ring_v = ring[1];    // 4 phases in one N tile, or one row phase per tile
+    p.N = N; p.Hin = H + 4; p.Win = W + 4; p.Hout = H; p.Wout = W; p.kh = 5; p.kw = 5; p.stride = 1; p.pad = 0;
+    p.bias = m->upload(pk.b); p.cout = Co; p.epi = EPI_LINEAR; p.act = ACT_RELU; p.y = y;
+    std::vector<float> wc;
+    pack_weights_phase4(pk.w.data(), C, Co, wc);
+    std::vector<__nv_bfloat16> wt;
+    p.cout_pad = 4 * Co;
+    pack_weights_tc(wc.data(), 25 * C, 4 * Co, p.cout_pad, wt);
+    void* d = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
+    EVK_REQUIRE(d != nullptr, EVK_ERR_CUDA, "out of device memory for the phase-stacked weights");
+    cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+    p.w_tc = (const __nv_bfloat16*)d;
+    EVK_REQUIRE(tc_eligible(p), EVK_ERR_ARG, "'%s': phase-stacked decoder is not eligible for the tensor-core path", pfx.c_str());
+    op.flops = 2.0 * Co * C * 25.0 * (double)N * (2 * H) * (2 * W);      // the reference's arithmetic (no credit for the zeros)
+    op.cin = C; op.H = 2 * H; op.W = 2 * W;
+    m->ops[0].push_back(op); m->ops[1].push_back(op);
+    return EVK_OK;
+}
+
 // DynamicUpsampleLayer after the shared x2 upsample (model/submodules.py:120-127):
 // context fusion -> atom generation -> per-pixel dynamic conv -> 1x1 compositional conv -> ReLU.
 static int add_hyper_decoder(Builder& B, const std::string& pfx, const float* xu, int C, int h, int w, float* y) {
@@ -489,6 +564,16 @@ static int build_unet(evk_model* m) {
         const std::string pfx = "decoders." + std::to_string(i);
         const float* skip = m->states[hstate[e]].buf[1];   // placeholder, fixed per parity below
         const bool tconv = m->find(pfx + ".transposed_conv2d.weight") != nullptr;     // use_upsample_conv=False
+        // last decoder(s) with cout = 32: four output phases stacked along N on the low-resolution map (poly.cu)
+        static const int poly_max_c = getenv("EVK_POLY_MAX_C") ? atoi(getenv("EVK_POLY_MAX_C")) : 128;
+        if (!tconv && !(i == 0 && c.dynamic_decoder) && c.precision == 0 && k == 5 && (C == 64 || C == 128) && C <= poly_max_c &&
+            H >= 2 && W >= 2 && getenv("EVK_NO_POLY") == nullptr) {
+            float* y = B.act(2 * H, 2 * W, C / 2);
+            r = add_poly_decoder(B, pfx, x, skip, C, H, W, y);
+            if (r != EVK_OK) return r;
+            x = y; C /= 2; H *= 2; W *= 2;
+            continue;
+        }
         float* up = B.act(2 * H, 2 * W, C);
         {
             Op op; op.kind = tconv ? OP_ZERO_INSERT_ADD : OP_UPSAMPLE_ADD;
@@ -527,7 +612,7 @@ static int build_unet(evk_model* m) {
             auto fix = [&](const float*& p) { if (p == s.buf[1]) p = s.buf[0]; };
             if (op.kind == OP_CONV && op.cp.epi == EPI_LSTM) { fix(op.cp.x1); continue; }   // x2/h_new already per parity
             if (op.kind == OP_CONV) { fix(op.cp.x1); fix(op.cp.res); }
-            if (op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD || op.kind == OP_PRED) { fix(op.in); fix(op.skip); }
+            if (op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD || op.kind == OP_PRED || op.kind == OP_ADD_PAD) { fix(op.in); fix(op.skip); }
         }
     }
     return EVK_OK;
@@ -582,7 +667,7 @@ static int wire_tc(evk_model* m) {
     for (int par = 0; par < 2; ++par)
         for (Op& op : m->ops[par]) {
             if (op.kind != OP_CONV || op.cp.w_tc == nullptr || !tc_eligible(op.cp)) continue;
-            if (!op.cp.kw_packed) op.cp.x1s = need_split(op.cp.x1);      // (the row-window head brings its own packed input)
+            if (op.cp.x1 != nullptr) op.cp.x1s = need_split(op.cp.x1);   // (the row-window head and the phase-stacked decoder ops bring their own packed input)
             if (op.cp.c2) op.cp.x2s = need_split(op.cp.x2);
             EVK_REQUIRE(op.cp.x1s && (!op.cp.c2 || op.cp.x2s), EVK_ERR_CUDA, "wire_tc: cannot allocate split activations");
         }
@@ -636,7 +721,7 @@ static int wire_tc(evk_model* m) {
                         if (op.cp.x1s == nullptr) { rd(op.cp.x1); rd(op.cp.x2); }
                         rd(op.cp.res); rd(op.cp.c_prev); rd(op.cp.h_prev); rd(op.cp.u_in); rd(op.cp.pred_skip);
                         break;
-                    case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_PRED: rd(op.in); rd(op.skip); break;
+                    case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_PRED: case OP_ADD_PAD: rd(op.in); rd(op.skip); break;
                     case OP_HYPER_CONTEXT: case OP_HYPER_ATOMS: case OP_HYPER_APPLY:
                         rd(op.hp.ev_nchw); rd(op.hp.prev); rd(op.hp.coef); rd(op.hp.atoms); rd(op.hp.xu);   // (ctx / inter are outputs here)
                         break;
@@ -677,6 +762,8 @@ static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent
             case OP_UPSAMPLE_ADD: r = launch_upsample2x_add(op.in, op.skip, op.out, op.out_s, op.N, op.H, op.W, op.cin, st); break;
             case OP_ZERO_INSERT_ADD: r = launch_zero_insert2x_add(op.in, op.skip, op.out, op.out_s, op.N, op.H, op.W, op.cin, st); break;
             case OP_NOP: break;
+            case OP_ADD_PAD: r = launch_add_pad_split(op.in, op.skip, op.out_s, op.N, op.H, op.W, op.cin, st); break;
+            case OP_RING_LINES: r = launch_ring_lines(op.out_s, op.lines_h, op.lines_v, op.N, op.H, op.W, op.cin, st); break;
             case OP_HEAD_PACK: r = launch_head_pack(op.in, op.out_s, op.N, op.cin, op.H, op.W, op.k / 2, st); break;
             case OP_PRED: r = launch_pred(op.in, op.skip, op.w, op.bias0, op.out, (int64_t)op.N * op.H * op.W, op.cin, op.sigmoid, st); break;
             default: r = launch_hyper(op.kind - OP_HYPER_CONTEXT, op.hp, st); break;
@@ -699,6 +786,12 @@ static std::string op_desc(const Op& op) {
             if (p.kw_packed)
                 snprintf(b, sizeof b, "conv%dx%d s1 %d+0->%d head row-window%s @%dx%d [tcgen05 bf16x3]", p.kh, p.kw_packed, op.cin, p.cout,
                          p.pred_out ? "+pred" : "", p.Hout, p.Wout);
+            else if (op.ring_line)
+                snprintf(b, sizeof b, "conv1x5 %d->4x%d %s border correction of the next layer @%dx%d lines [tcgen05 bf16x3]", p.c1, p.cout / 4,
+                         op.ring_line == 1 ? "horizontal" : "vertical", p.Hout, p.Wout);
+            else if (p.phase4)
+                snprintf(b, sizeof b, "conv5x5 s1 %d+0->%d linear%s @%dx%d as 4 stacked phases (N=%d%s) on %dx%d [tcgen05 bf16x3]", p.c1, p.cout,
+                         p.pred_out ? "+pred" : "", 2 * p.Hout, 2 * p.Wout, 4 * p.cout, p.phase4 == 2 ? ", 4 of 5 tap rows per tile" : "", p.Hout, p.Wout);
             else
                 snprintf(b, sizeof b, "conv%dx%d s%d %d+%d->%d %s%s @%dx%d [%s]", p.kh, p.kw, p.stride, p.c1, p.c2, p.cout, e,
                          p.pred_out ? "+pred" : "", p.Hout, p.Wout, p.tc ? "tcgen05 bf16x3" : "simt fp32");
@@ -708,6 +801,8 @@ static std::string op_desc(const Op& op) {
         case OP_ZERO_INSERT_ADD: snprintf(b, sizeof b, "zero_insert2x_add C=%d @%dx%d", op.cin, 2 * op.H, 2 * op.W); break;
         case OP_PRED: snprintf(b, sizeof b, "pred 1x1 %d->1 @%dx%d", op.cin, op.H, op.W); break;
         case OP_NOP: snprintf(b, sizeof b, "(pred 1x1 fused into the previous epilogue)"); break;
+        case OP_ADD_PAD: snprintf(b, sizeof b, "add + replicate pad -> split bf16 C=%d @%dx%d", op.cin, op.H, op.W); break;
+        case OP_RING_LINES: snprintf(b, sizeof b, "border lines of u_ext -> split bf16 C=%d @%dx%d", op.cin, 2 * op.H, 2 * op.W); break;
         case OP_HEAD_PACK: snprintf(b, sizeof b, "head pack NCHW -> row-window split bf16 @%dx%d", op.H, op.W); break;
         case OP_HYPER_CONTEXT: snprintf(b, sizeof b, "hyper context x0.25"); break;
         case OP_HYPER_ATOMS: snprintf(b, sizeof b, "hyper atoms A=%d K=%d L=%d @%dx%d", op.hp.A, op.hp.K, op.hp.L, op.hp.h, op.hp.w); break;

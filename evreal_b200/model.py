@@ -165,6 +165,19 @@ class _NativeModel:
             rows.append((buf.value.decode(), float(ms[i]), float(fl[i])))
         return rows
 
+    def op_descriptions(self):
+        """Descriptions of the launches of one forward (after the first forward built the device program)."""
+        if not self._handle:
+            return []
+        lib = _lib.load()
+        buf = ctypes.create_string_buffer(160)
+        rows = []
+        for i in range(256):
+            if lib.evk_model_op_desc(self._handle, i, buf, 160) != 0:
+                break
+            rows.append(buf.value.decode())
+        return rows
+
     def last_launch_count(self):
         return int(_lib.load().evk_model_last_launch_count(self._handle)) if self._handle else 0
 

@@ -86,6 +86,24 @@ def test_transposed_conv_decoders(precision):
     _assert_close(_frames(m, g['e2vid_tconv.voxels']), g['e2vid_tconv.frames'], 'e2vid_tconv')
 
 
+@pytest.mark.parametrize('poly', [True, False])
+@pytest.mark.parametrize('tag,norm,act', [('e2vid_b32', 'BN', 'sigmoid'), ('e2vid_b32_nonorm', 'none', '')])
+def test_e2vid_base32_phase_stacked_decoder(tag, norm, act, poly, monkeypatch):
+    """Shipped width (last decoder 64 -> 32) through the real reference class, one encoder, sizes that are not tile
+    multiples (30x44, 18x26), batch 2, 3 recurrent frames: the last decoder runs as four stacked phases on the
+    low-resolution map plus the border-ring correction (poly.cu); EVK_NO_POLY=1 is the upsample + 5x5 form."""
+    from evreal_b200 import E2VIDRecurrent
+    if not poly:
+        monkeypatch.setenv('EVK_NO_POLY', '1')
+    g = golden('networks_base32')
+    full, _ = weights_of(g, tag, 'unetrecurrent.')
+    m = _load(E2VIDRecurrent(dict(E2VID_KW, num_encoders=1, num_residual_blocks=1, base_num_channels=32, norm=norm,
+                                  final_activation=act)), full)
+    _assert_close(_frames(m, g[tag + '.voxels']), g[tag + '.frames'], tag)
+    descs = m.op_descriptions()
+    assert any('stacked phases' in d for d in descs) == poly, descs
+
+
 def test_flownet_topology_image_channel():
     from evreal_b200 import FlowNet
     g = golden('networks')
@@ -114,6 +132,24 @@ def _voxels(seed, frames, N, H, W, n_ev):
              for b_ in range(N)]
         out.append(torch.stack(b).numpy())
     return out
+
+
+@pytest.mark.parametrize('norm_bn', [True, False])
+def test_e2vid_two_encoders_phase_pair_decoder_vs_oracle(norm_bn):
+    """Two encoders at the shipped width: decoders 128 -> 64 (one row phase per N tile, 4 of 5 tap rows) and 64 -> 32
+    (four phases in one tile) both in phase-stacked form, sizes that are not tile multiples (36x52), batch 2, 3 frames."""
+    from evreal_b200 import E2VIDRecurrent
+    from oracle import networks as on
+    w = on.random_unet_weights(seed=9, num_encoders=2, num_res=1, norm_bn=norm_bn)
+    m = _load(E2VIDRecurrent(dict(E2VID_KW, num_encoders=2, num_residual_blocks=1, base_num_channels=32,
+                                  norm='BN' if norm_bn else 'none', final_activation='sigmoid' if norm_bn else '')),
+              {'unetrecurrent.' + k: v for k, v in w.items()})
+    vox = _voxels(90, 3, 2, 36, 52, 900)
+    oracle = on.UNetRecurrentOracle(w, 2, 1, final_sigmoid=norm_bn)
+    ref = np.stack([oracle(torch.from_numpy(v)).numpy() for v in vox])
+    _assert_close(_frames(m, vox), ref, 'e2vid_two_encoders')
+    descs = m.op_descriptions()
+    assert sum('stacked phases' in d for d in descs) == 2 and sum('tap rows per tile' in d for d in descs) == 1, descs
 
 
 @pytest.mark.parametrize('precision', [0, 1])

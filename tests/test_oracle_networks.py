@@ -13,8 +13,8 @@ def _run(model, voxels):
     return np.stack([model(torch.from_numpy(v)).numpy() for v in voxels])
 
 
-def _check(tag, prefix, make, tol=2e-6):
-    g = golden('networks')
+def _check(tag, prefix, make, tol=2e-6, file='networks'):
+    g = golden(file)
     _, w = weights_of(g, tag, prefix)
     got = _run(make(w), g[tag + '.voxels'])
     ref = g[tag + '.frames']
@@ -36,6 +36,12 @@ def test_e2vid_topology():
 
 def test_transposed_conv_decoder_topology():
     _check('e2vid_tconv', 'unetrecurrent.', lambda w: on.UNetRecurrentOracle(w, final_sigmoid=True, upsample_conv_decoder=False))
+
+
+def test_e2vid_base32_one_encoder():
+    """shipped width (last decoder 64 -> 32), one encoder: the fixture that pins the phase-stacked decoder (poly.cu)"""
+    _check('e2vid_b32', 'unetrecurrent.', lambda w: on.UNetRecurrentOracle(w, 1, 1, final_sigmoid=True), file='networks_base32')
+    _check('e2vid_b32_nonorm', 'unetrecurrent.', lambda w: on.UNetRecurrentOracle(w, 1, 1), file='networks_base32')
 
 
 def test_flownet_topology():

@@ -235,6 +235,30 @@ def golden_networks():
     np.savez_compressed(os.path.join(OUT, 'networks.npz'), **out)
 
 
+def golden_networks_base32():
+    """E2VID family at the SHIPPED width (base 32, last decoder 64 -> 32: the phase-stacked decoder of poly.cu) but with one
+    encoder / one residual block so the fixture stays ~2 MB; sizes that are not multiples of the 8x16 GEMM tile."""
+    import model as model_arch
+    out = {}
+    for tag, seed, norm, act, H, W in (('e2vid_b32', 20, 'BN', 'sigmoid', 30, 44), ('e2vid_b32_nonorm', 22, 'none', '', 18, 26)):
+        torch.manual_seed(seed)
+        kw = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 1,
+              'base_num_channels': 32, 'num_residual_blocks': 1, 'use_upsample_conv': True, 'norm': norm,
+              'final_activation': act}
+        m = model_arch.E2VIDRecurrent(dict(kw))
+        _randomize_bn(m, seed + 1)
+        m.eval()
+        voxels = _small_voxels(seed, 3, 2, H, W)
+        frames = _run_frames(m, voxels)
+        out[f'{tag}.voxels'] = torch.stack(voxels).numpy()
+        out[f'{tag}.frames'] = frames
+        for k, v in m.state_dict().items():
+            if not k.endswith('num_batches_tracked'):
+                out[f'{tag}.w.{k}'] = v.numpy()
+        print(tag, 'frames', frames.shape, 'mean %.5f' % frames.mean())
+    np.savez_compressed(os.path.join(OUT, 'networks_base32.npz'), **out)
+
+
 def golden_real_checkpoints():
     """Outputs of the shipped 43 MB checkpoints on the SURVEY A.7 voxel: the weights cannot travel, so only
     summary statistics + a strided sample are stored; tests/test_oracle_vs_reference.py uses them when the
@@ -363,11 +387,15 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     install_shims()
     torch.set_num_threads(1)          # single-threaded index_put_ -> bit-reproducible voxel grids
+    if '--only-base32' in sys.argv:   # added later; leaves the other fixtures untouched
+        golden_networks_base32()
+        sys.exit(0)
     with tempfile.TemporaryDirectory() as tmp:
         golden_voxel()
         golden_glue()
         golden_windows(tmp)
         golden_networks()
+        golden_networks_base32()
         golden_real_checkpoints()
         golden_metrics()
         golden_eval_loop(tmp)
