@@ -55,6 +55,11 @@ struct ConvParams {
     // tensor map whose pixel stride, 16 B, is smaller than its 128 B row): the kw taps of one kernel row are ONE K
     // chunk, so the layer runs as a (kh x 1) convolution with c1 = 64.  kw_packed = the real kw (<= 8).
     int kw_packed = 0;
+    // kw_group = G > 1: one GEMM row computes G consecutive output pixels (G + kw - 1 <= 8: their taps all lie in the same
+    // 8-pixel window) as G * cout packed columns -- the output [N,H,W,cout] is the same memory as [N,H,W/G,G*cout], so
+    // the layer is an ordinary one on a W/G-wide image (Win = Wout = W/G, cout = G * real cout, bias repeated G times)
+    // whose window rows are G pixels apart.  MMAs G times wider, G times fewer tiles.
+    int kw_group = 0;
     // "row pair" form of a stride-1 layer with cout == 32 (the last decoder): the GEMM computes output rows 2y and 2y+1
     // together as N = 64 columns of a (kh+1) x kw convolution with vertical stride 2 (weights of row 2y+1 shifted one tap
     // down) -- an MMA with N <= 64 costs the same ~50 cycles as one with N = 32, so this halves the MMA count per
@@ -116,7 +121,8 @@ int launch_upsample2x_add(const float* x, const float* skip, float* y, __nv_bflo
 int launch_zero_insert2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C, cudaStream_t st);
 // NCHW fp32 [N,cin,H,W] (cin <= 8) -> packed split-bf16 row-window tensor [2][N][H][W+8][8], pixel x at column x + left
 int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st);
-// host: head weights [kh*kw*cin][cout] (SIMT layout) -> row-window K layout [kh*64][cout] (k = r*64 + q*8 + c)
-void pack_head_weights_rowwin(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out);
+// host: head weights [kh*kw*cin][cout] (SIMT layout) -> row-window K layout [kh*64][group*cout] (k = r*64 + slot*8 + c,
+// output pixel g of a group reads tap q from window slot g + q)
+void pack_head_weights_rowwin(const float* w_kc, int kh, int kw, int cin, int cout, int group, std::vector<float>& out);
 
 }  // namespace evk

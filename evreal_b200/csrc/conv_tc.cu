@@ -44,6 +44,7 @@ struct TcArgs {
     int N, Hout, Wout, su, sv, pad_u, pad_v, kh, kw;       // Hout counts row PAIRS in row-pair mode; su / sv = stride along U / V
     int cw;                     // epilogue chunk width in accumulator columns: 32, or 16 for a 32-column linear tile (both halves of the epilogue warps get work)
     int rp, creal, hreal;       // row-pair mode, real channel count / output height (addressing)
+    int wide;                   // EPI_LINEAR: 256-bit stores (real and packed channel counts are multiples of 16)
     int ps, wreal;              // phase-stacked mode (ConvParams::phase4): column block a*2+b -> output pixel (2oy+a, 2ox+b); output width
     const float* ring_h; const float* ring_v;   // phase-stacked mode: border corrections (ConvParams), added before the activation
     int ux;                     // 1: U = x (tile 16 rows x 8 cols), 0: U = y (tile 8 rows x 16 cols)
@@ -97,6 +98,14 @@ __device__ __forceinline__ float fast_act(float v, int act) {
         case ACT_TANH: return fast_tanh(v);
         default: return v;
     }
+}
+
+// 256-bit global stores (sm_100+): one full 32-byte sector per lane and instruction.  The epilogue thread owns one output
+// pixel (= one row of channels), so its lanes never share a sector: with 8 / 16-byte stores the store path moves a
+// quarter / half sector per request and small-K layers (head, first encoder) ran at the L1 store request rate.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
 struct TileCoord { int nt, img, ou0, ov0; bool dummy; };
@@ -482,6 +491,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         }
                     }
                     const size_t o = pixl * a.creal + nbr;
+                    const bool wide = a.wide != 0;     // channel counts are multiples of 16: every 8 fp32 / 16 bf16 run is one aligned sector
                     float pacc = 0.f;
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
@@ -511,6 +521,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             pacc = fmaf(f[1] + s4.y, w4.y, pacc);
                             pacc = fmaf(f[2] + s4.z, w4.z, pacc);
                             pacc = fmaf(f[3] + s4.w, w4.w, pacc);
+                        }
+                        if (wide) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[g * 4 + i] = __float_as_uint(f[i]);
+                            if ((g & 1) && a.y != nullptr) st_global_v8(a.y + o + (g - 1) * 4, &v[(g - 1) * 4]);
+                            if ((g & 3) == 3 && a.ys != nullptr) {
+                                uint32_t hw[8], lw[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    __nv_bfloat16 h0, l0, h1, l1;
+                                    split_bf16(__uint_as_float(v[(g - 3) * 4 + 2 * i]), h0, l0);
+                                    split_bf16(__uint_as_float(v[(g - 3) * 4 + 2 * i + 1]), h1, l1);
+                                    hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                    lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                }
+                                st_global_v8(a.ys + o + (g - 3) * 4, hw);
+                                st_global_v8(a.ys + a.ys_plane + o + (g - 3) * 4, lw);
+                            }
+                            continue;
                         }
                         if (a.y != nullptr) *reinterpret_cast<float4*>(a.y + o + g * 4) = make_float4(f[0], f[1], f[2], f[3]);
                         if (a.ys != nullptr) {
@@ -804,6 +833,7 @@ int tc_plan_create(ConvParams& p) {
     a.rp = rp ? 1 : 0; a.creal = p.cout; a.hreal = ps ? 2 * p.Hout : p.Hout;
     a.ps = p.phase4; a.wreal = ps ? 2 * p.Wout : p.Wout;
     a.ring_h = p.ring_h; a.ring_v = p.ring_v;
+    a.wide = (p.epi == EPI_LINEAR && p.cout % 16 == 0 && env_int("EVK_TC_WIDE_ST", 1)) ? 1 : 0;
     a.cw = (p.epi == EPI_LINEAR && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
     a.ux = ux;
     a.tiles_u = ceil_div(ux ? p.Wout : e_hout, 8);
@@ -881,9 +911,11 @@ int tc_plan_create(ConvParams& p) {
         if (p.kw_packed) {
             // row-window view of the packed head input [2][N][H][W+8][8]: "channel" dim = the 64 values starting at a
             // pixel, pixel stride 16 B (rows overlap), so one box row holds the kw taps x 8 channel slots of a kernel row
-            const uint64_t wp = (uint64_t)p.Win + 8;
+            // (kw_group = G > 1: GEMM row = G consecutive output pixels, so rows are G pixels = 16*G bytes apart)
+            const uint64_t G = (uint64_t)(p.kw_group > 1 ? p.kw_group : 1);
+            const uint64_t wp = (uint64_t)p.Win * G + 8;
             const uint64_t dims[5] = {64, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)p.N, 2};
-            const uint64_t str[4] = {16, wp * 16, (uint64_t)p.Hin * wp * 16, (uint64_t)p.N * p.Hin * wp * 16};
+            const uint64_t str[4] = {16 * G, wp * 16, (uint64_t)p.Hin * wp * 16, (uint64_t)p.N * p.Hin * wp * 16};
             const uint32_t box[5] = {64, 8, (uint32_t)a.ar, 1, 1};
             const uint32_t es[5] = {1, 1, 1, 1, 1};
             return encode_tmap_bf16(m, base, 5, dims, str, box, es, 128);
@@ -1018,13 +1050,14 @@ void pack_weights_row_pair(const float* w_kc, int kh, int kw, int cin, int cout,
                 }
 }
 
-void pack_head_weights_rowwin(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out) {
-    out.assign((size_t)kh * 64 * cout, 0.f);
+void pack_head_weights_rowwin(const float* w_kc, int kh, int kw, int cin, int cout, int group, std::vector<float>& out) {
+    out.assign((size_t)kh * 64 * group * cout, 0.f);
     for (int r = 0; r < kh; ++r)
-        for (int q = 0; q < kw; ++q)
-            for (int c = 0; c < cin; ++c)
-                for (int n = 0; n < cout; ++n)
-                    out[((size_t)r * 64 + q * 8 + c) * cout + n] = w_kc[((size_t)(r * kw + q) * cin + c) * cout + n];
+        for (int g = 0; g < group; ++g)              // output pixel g of the group sees tap q in window slot g + q
+            for (int q = 0; q < kw; ++q)
+                for (int c = 0; c < cin; ++c)
+                    for (int n = 0; n < cout; ++n)
+                        out[((size_t)r * 64 + (g + q) * 8 + c) * (group * cout) + g * cout + n] = w_kc[((size_t)(r * kw + q) * cin + c) * cout + n];
 }
 
 // ------------------------------------------------------------------ fp32 -> split planes

@@ -337,16 +337,23 @@ static int add_head(Builder& B, const std::string& conv_pfx, const std::string& 
             op.in = m->in_buf; op.out_s = packed; op.N = B.N; op.cin = pk.cin; op.H = H; op.W = W; op.k = pk.kw;
             m->ops[0].push_back(op); m->ops[1].push_back(op);
         }
+        // G consecutive output pixels per GEMM row (conv.cuh, ConvParams::kw_group): N = G * cout columns per MMA
+        int G = 1;
+        if (getenv("EVK_HEAD_GROUP") == nullptr || atoi(getenv("EVK_HEAD_GROUP")) > 1)
+            for (int g = 4; g >= 2; g /= 2)
+                if (W % g == 0 && g + pk.kw - 1 <= 8 && g * pk.cout <= 128) { G = g; break; }
         Op op; op.kind = OP_CONV;
         ConvParams& p = op.cp;
-        p.x1 = nullptr; p.c1 = 64; p.x1s = packed; p.kw_packed = pk.kw;
-        p.N = B.N; p.Hin = p.Hout = H; p.Win = p.Wout = W; p.kh = pk.kh; p.kw = 1; p.stride = 1; p.pad = pk.kh / 2;
-        p.bias = m->upload(pk.b); p.cout = pk.cout; p.epi = EPI_LINEAR; p.act = ACT_RELU; p.y = y;
+        p.x1 = nullptr; p.c1 = 64; p.x1s = packed; p.kw_packed = pk.kw; p.kw_group = G;
+        p.N = B.N; p.Hin = p.Hout = H; p.Win = p.Wout = W / G; p.kh = pk.kh; p.kw = 1; p.stride = 1; p.pad = pk.kh / 2;
+        std::vector<float> bg((size_t)G * pk.cout);
+        for (int g = 0; g < G; ++g) std::copy(pk.b.begin(), pk.b.end(), bg.begin() + (size_t)g * pk.cout);
+        p.bias = m->upload(bg); p.cout = G * pk.cout; p.epi = EPI_LINEAR; p.act = ACT_RELU; p.y = y;
         std::vector<float> wr;
-        pack_head_weights_rowwin(pk.w.data(), pk.kh, pk.kw, pk.cin, pk.cout, wr);
+        pack_head_weights_rowwin(pk.w.data(), pk.kh, pk.kw, pk.cin, pk.cout, G, wr);
         std::vector<__nv_bfloat16> wt;
-        p.cout_pad = pk.cout;
-        pack_weights_tc(wr.data(), pk.kh * 64, pk.cout, p.cout_pad, wt);
+        p.cout_pad = G * pk.cout;
+        pack_weights_tc(wr.data(), pk.kh * 64, G * pk.cout, p.cout_pad, wt);
         void* d = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
         EVK_REQUIRE(d != nullptr, EVK_ERR_CUDA, "out of device memory for the head weights");
         cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
@@ -784,8 +791,9 @@ static std::string op_desc(const Op& op) {
             const ConvParams& p = op.cp;
             const char* e = p.epi == EPI_LSTM ? "lstm" : p.epi == EPI_GRU_UR ? "gru_ur" : p.epi == EPI_GRU_OUT ? "gru_out" : (p.res ? "linear+res" : "linear");
             if (p.kw_packed)
-                snprintf(b, sizeof b, "conv%dx%d s1 %d+0->%d head row-window%s @%dx%d [tcgen05 bf16x3]", p.kh, p.kw_packed, op.cin, p.cout,
-                         p.pred_out ? "+pred" : "", p.Hout, p.Wout);
+                snprintf(b, sizeof b, "conv%dx%d s1 %d+0->%d head row-window%s @%dx%d, %d pixels per GEMM row (N=%d) [tcgen05 bf16x3]", p.kh, p.kw_packed,
+                         op.cin, p.cout / (p.kw_group > 1 ? p.kw_group : 1), p.pred_out ? "+pred" : "", p.Hout, p.Wout * (p.kw_group > 1 ? p.kw_group : 1),
+                         p.kw_group > 1 ? p.kw_group : 1, p.cout);
             else if (op.ring_line)
                 snprintf(b, sizeof b, "conv1x5 %d->4x%d %s border correction of the next layer @%dx%d lines [tcgen05 bf16x3]", p.c1, p.cout / 4,
                          op.ring_line == 1 ? "horizontal" : "vertical", p.Hout, p.Wout);
