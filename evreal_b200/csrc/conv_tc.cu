@@ -44,6 +44,8 @@ struct TcArgs {
     int N, Hout, Wout, su, sv, pad_u, pad_v, kh, kw;       // Hout counts row PAIRS in row-pair mode; su / sv = stride along U / V
     int cw;                     // epilogue chunk width in accumulator columns: 32, or 16 for a 32-column linear tile (both halves of the epilogue warps get work)
     int rp, creal, hreal;       // row-pair mode, real channel count / output height (addressing)
+    int fastlin;                // EPI_LINEAR, wide, 32-column chunks, no row-pair / phase / prediction: straight-line epilogue
+    float act_floor;            // fastlin: lower clamp of the activation (0 for ReLU, -inf for none)
     int wide;                   // EPI_LINEAR: 256-bit stores (real and packed channel counts are multiples of 16)
     int ps, wreal;              // phase-stacked mode (ConvParams::phase4): column block a*2+b -> output pixel (2oy+a, 2ox+b); output width
     const float* ring_h; const float* ring_v;   // phase-stacked mode: border corrections (ConvParams), added before the activation
@@ -158,6 +160,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
     const int n_super = a.n_tiles * ((a.m_tiles + cs - 1) / cs);
     const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
 
+    // programmatic dependent launch: the next kernel of the stream may start its prologue on SMs this grid has left
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x1);
         if (a.chunks2) tma_prefetch_desc(&tm_x2);
@@ -184,6 +188,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+    // ... and this grid touches global memory only after the previous kernel has completed (no-op without the launch attribute)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // The three single-issuer roles run their loops WARP-WIDE (all 32 lanes carry identical values) and predicate only
     // the issuing instruction with elect.sync: inside an `if (lane == 0)` region ptxas cannot keep descriptors in
@@ -465,7 +471,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                 }
                 const int nb = n0 + j0;
                 if (!valid || nb >= a.cout || (DBG && (a.exp & 4))) continue;
-                if (a.epi == EPI_LINEAR) {
+                if (a.epi == EPI_LINEAR && a.fastlin && cw == 32) {
+                    // Straight-line form of the common case (bias [+ residual] -> ReLU / none -> fp32 and / or split-bf16 stores,
+                    // channel counts multiples of 32): no per-group branches, all loads issued up front.  The generic path below
+                    // costs ~760 instructions per 32x32 chunk at ~9 cycles each with two epilogue warps per scheduler -- 3x the MMA
+                    // time of a 20-slice tile (head), and it is the un-overlapped tail of every layer's last tile.
+                    const size_t o = pix * a.creal + nb;
+                    float4 b4[8], r4[8];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) b4[g] = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
+                    if (a.res != nullptr) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) r4[g] = __ldg(reinterpret_cast<const float4*>(a.res + o + g * 4));
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) r4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    const float fl = a.act_floor;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        v[g * 4 + 0] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 0]) + b4[g].x + r4[g].x, fl));
+                        v[g * 4 + 1] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 1]) + b4[g].y + r4[g].y, fl));
+                        v[g * 4 + 2] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 2]) + b4[g].z + r4[g].z, fl));
+                        v[g * 4 + 3] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 3]) + b4[g].w + r4[g].w, fl));
+                    }
+                    if (a.y != nullptr) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) st_global_v8(a.y + o + g * 8, &v[g * 8]);
+                    }
+                    if (a.ys != nullptr) {
+                        uint32_t hw[16], lw[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(__uint_as_float(v[2 * i]), h0, l0);
+                            split_bf16(__uint_as_float(v[2 * i + 1]), h1, l1);
+                            hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        st_global_v8(a.ys + o, hw);
+                        st_global_v8(a.ys + o + 16, hw + 8);
+                        st_global_v8(a.ys + a.ys_plane + o, lw);
+                        st_global_v8(a.ys + a.ys_plane + o + 16, lw + 8);
+                    }
+                } else if (a.epi == EPI_LINEAR) {
                     // row-pair mode: columns [0, C) are output row 2*oy, columns [C, 2C) row 2*oy + 1
                     // phase-stacked mode: column block ph = a*2+b of GEMM row (oy, ox) is output pixel (2oy+a, 2ox+b)
                     int nbr = nb;
@@ -834,6 +883,9 @@ int tc_plan_create(ConvParams& p) {
     a.ps = p.phase4; a.wreal = ps ? 2 * p.Wout : p.Wout;
     a.ring_h = p.ring_h; a.ring_v = p.ring_v;
     a.wide = (p.epi == EPI_LINEAR && p.cout % 16 == 0 && env_int("EVK_TC_WIDE_ST", 1)) ? 1 : 0;
+    a.fastlin = (a.wide && !rp && !ps && p.pred_out == nullptr && p.cout % 32 == 0 && bn % 32 == 0 && (p.act == ACT_RELU || p.act == ACT_NONE) &&
+                 env_int("EVK_TC_FASTLIN", 1)) ? 1 : 0;
+    a.act_floor = p.act == ACT_RELU ? 0.0f : -INFINITY;
     a.cw = (p.epi == EPI_LINEAR && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
     a.ux = ux;
     a.tiles_u = ceil_div(ux ? p.Wout : e_hout, 8);
@@ -964,10 +1016,20 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
     cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)pl.a.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = pl.a.cs > 1 ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pl.a.cs > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = (unsigned)pl.a.cs; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    static const int pdl = env_int("EVK_TC_PDL", 1);
+    if (pdl) {        // prologue (barriers, tensor memory, descriptor prefetch) overlaps the tail of the previous kernel
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = (unsigned)na;
     const bool dbg = pl.a.dbg != nullptr;
     if (pl.bk == 64) {
         if (dbg) EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, true>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
