@@ -79,6 +79,9 @@ struct ConvParams {
     // (y[pix,c] + skip[pix,c]) + b) -- model/unet.py:136-138; y itself need not be stored
     const float* pred_w = nullptr; const float* pred_skip = nullptr; float* pred_out = nullptr;
     float pred_bias = 0.f; int pred_sigmoid = 0;
+    // skip operand of the fused prediction layer as split-bf16 planes (hi + lo = the value to 2^-17): when set it replaces
+    // pred_skip, and the producer of the skip tensor (the head) need not write its fp32 copy at all
+    const __nv_bfloat16* pred_skip_s = nullptr; long long pred_skip_plane = 0;
     struct TcPlan* tc = nullptr;          // tensor maps + tiling, built once per layer (tc_plan_create)
 };
 

@@ -44,6 +44,7 @@ struct TcArgs {
     int N, Hout, Wout, su, sv, pad_u, pad_v, kh, kw;       // Hout counts row PAIRS in row-pair mode; su / sv = stride along U / V
     int cw;                     // epilogue chunk width in accumulator columns: 32, or 16 for a 32-column linear tile (both halves of the epilogue warps get work)
     int rp, creal, hreal;       // row-pair mode, real channel count / output height (addressing)
+    int fastps;                 // phase-stacked last decoder (cout 32, ReLU, fused prediction layer, no tensor output): straight-line epilogue
     int fastlin;                // EPI_LINEAR, wide, 32-column chunks, no row-pair / phase / prediction: straight-line epilogue
     float act_floor;            // fastlin: lower clamp of the activation (0 for ReLU, -inf for none)
     int wide;                   // EPI_LINEAR: 256-bit stores (real and packed channel counts are multiples of 16)
@@ -75,6 +76,7 @@ struct TcArgs {
     __nv_bfloat16* hs_new; long long hs_plane;
     const float* h_prev; const float* u_in; float* u_out; float* hr_out; __nv_bfloat16* hrs_out;   // ConvGRU epilogues
     const float* pred_w; const float* pred_skip; float* pred_out; float pred_bias; int pred_sigmoid;
+    const __nv_bfloat16* pred_skip_s; long long pred_skip_plane;
     int exp;                    // DBG kernels only (EVK_TC_EXP bit mask): 1 skip weight loads, 2 skip activation loads, 4 skip epilogue stores
     unsigned long long* dbg;    // EVK_TC_TIMING: per-CTA clock64 phase counters [grid][8], else nullptr
 };
@@ -128,9 +130,16 @@ __device__ __forceinline__ TileCoord tile_coord(const TcArgs& a, int st, int cra
 
 // Phase-pair mode (a.ps == 2, U = y): N tile nt holds the two column phases of ROW phase nt, whose composite 5x5 kernel
 // has an all-zero first (row phase 1) or last (row phase 0) tap row -- that U shift is skipped by all three pipeline roles.
+// Single-phase mode (a.ps == 3, bn = cout): N tile nt is output phase nt = a*2+b; the zero tap COLUMN of column phase b is
+// skipped as well (first / last V tap of every box), 16 of 25 taps per tile.
 __device__ __forceinline__ void su_range(const TcArgs& a, int nt, int& su0, int& su1) {
     su0 = 0; su1 = a.ku;
     if (a.ps == 2) { if (nt == 0) su1 = a.ku - 1; else su0 = 1; }
+    if (a.ps == 3) { if ((nt >> 1) == 0) su1 = a.ku - 1; else su0 = 1; }
+}
+__device__ __forceinline__ void tv_range(const TcArgs& a, int nt, int ntaps, int& tv0, int& tv1) {
+    tv0 = 0; tv1 = ntaps;
+    if (a.ps == 3) { if ((nt & 1) == 0) tv1 = ntaps - 1; else tv0 = 1; }
 }
 
 template <int BK, bool DBG>
@@ -244,9 +253,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             su_range(a, t.nt, su0, su1);
             for (int ch = 0; ch < chunks; ++ch)
                 for (int su = su0; su < su1; ++su)
-                    for (int g = 0; g < a.n_groups; ++g)
-                        for (int j0 = 0; j0 < a.g_ntaps[g]; j0 += a.tpb) {
-                            const int ntb = min(a.tpb, a.g_ntaps[g] - j0);       // taps in this K block
+                    for (int g = 0; g < a.n_groups; ++g) {
+                        int tv0, tv1;
+                        tv_range(a, t.nt, a.g_ntaps[g], tv0, tv1);
+                        for (int j0 = tv0; j0 < tv1; j0 += a.tpb) {
+                            const int ntb = min(a.tpb, tv1 - j0);       // taps in this K block
                             const long long t0 = DBG ? clock64() : 0;
                             mbar_wait(bar_eb + 8u * s, ph ^ 1u);
                             if (DBG) w_eb += clock64() - t0;
@@ -272,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             __syncwarp();
                             if (++s == (uint32_t)a.b_stages) { s = 0; ph ^= 1u; }
                         }
+                    }
         }
         if (DBG && lane == 0) a.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_eb;
         // tail: every arrive the peers send to this CTA's empty barriers must land before the CTA exits
@@ -316,7 +328,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const uint32_t nbs = (uint32_t)a.b_stages;
         const uint32_t two = a.issuers == 2 ? 1u : 0u;
         const bool own = a.own_acc != 0;
-        const uint32_t kb_total = (uint32_t)(chunks * (a.ps == 2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0)));
+        const uint32_t kb_total = a.ps == 3 ? (uint32_t)(chunks * (a.ku - 1) * (a.kv - 1)) : (uint32_t)(chunks * (a.ps == 2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0)));
         uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0, gblk = 0;
         bool b_ready = false;
         long long w_te = 0, w_fa = 0, w_fb = 0;
@@ -332,7 +344,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             bool fresh = true;                // the next MMA of this issuer initialises its accumulator
             if (!own) b_ready = false;        // strict mode deals blocks per tile: the look-ahead distance differs across tiles
             int su0, su1;
-            su_range(a, st % a.n_tiles, su0, su1);
+            const int nt_tile = st % a.n_tiles;
+            su_range(a, nt_tile, su0, su1);
             for (int ch = 0; ch < chunks; ++ch)
                 for (int su = su0; su < su1; ++su)
                     for (int g = 0; g < a.n_groups; ++g) {
@@ -341,8 +354,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         t0 = DBG ? clock64() : 0;
                         mbar_wait(bar_fa + 8u * sA, phA);
                         if (DBG) w_fa += clock64() - t0;
-                        for (int j0 = 0; j0 < nt_g; j0 += a.tpb, ++blk, ++gblk) {
-                            const int ntb = min(a.tpb, nt_g - j0);               // taps in this K block
+                        int tv0, tv1;
+                        tv_range(a, nt_tile, nt_g, tv0, tv1);
+                        ah_lo += (uint32_t)tv0 * atom16;
+                        for (int j0 = tv0; j0 < tv1; j0 += a.tpb, ++blk, ++gblk) {
+                            const int ntb = min(a.tpb, tv1 - j0);               // taps in this K block
                             if (two == 0u || ((own ? gblk : blk) & 1u) == role) {
                                 const uint32_t bh_lo = lo_of(smem_b + sB * b_stage);
                                 const uint32_t bar_free = bar_eb + 8u * sB;
@@ -514,6 +530,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         st_global_v8(a.ys + a.ys_plane + o, lw);
                         st_global_v8(a.ys + a.ys_plane + o + 16, lw + 8);
                     }
+                } else if (a.epi == EPI_LINEAR && a.fastps) {
+                    // Straight-line form of the last decoder's epilogue (four stacked phases of 32 channels, one phase per chunk;
+                    // ReLU, then the fused 1x1 prediction layer; nothing but the image is stored): all loads up front, same
+                    // summation order as the generic path below.
+                    const int ph = nb >> 5;
+                    const int Y = 2 * oy + (ph >> 1), X = 2 * ox + (ph & 1);
+                    const size_t pixl = ((size_t)t.img * a.hreal + Y) * a.wreal + X;
+                    const size_t o = pixl * 32;
+                    const float* rh = nullptr;
+                    const float* rv = nullptr;
+                    if (Y < 2 || Y >= a.hreal - 2) {          // border corrections (poly.cu), two outermost rows / columns only
+                        const int side = Y < 2 ? 0 : 1, l = Y < 2 ? Y : Y - a.hreal + 4;
+                        rh = a.ring_h + (((size_t)(side * a.N + t.img) * a.wreal + X) * 4 + l) * 32;
+                    }
+                    if (X < 2 || X >= a.wreal - 2) {
+                        const int side = X < 2 ? 0 : 1, l = X < 2 ? X : X - a.wreal + 4;
+                        rv = a.ring_v + (((size_t)(side * a.N + t.img) * a.hreal + Y) * 4 + l) * 32;
+                    }
+                    float pacc = 0.f;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {          // 16 channels at a time (register budget)
+                        float4 b4[4], w4[4], s4[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            b4[g] = __ldg(reinterpret_cast<const float4*>(a.bias + hf * 16 + g * 4));
+                            w4[g] = __ldg(reinterpret_cast<const float4*>(a.pred_w + hf * 16 + g * 4));
+                        }
+                        if (a.pred_skip_s != nullptr) {          // hi + lo planes of the skip tensor, 8 channels per 16-byte load
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(a.pred_skip_s + o + hf * 16 + q * 8));
+                                const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(a.pred_skip_s + a.pred_skip_plane + o + hf * 16 + q * 8));
+                                const uint32_t hh[4] = {h4.x, h4.y, h4.z, h4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w};
+                                float e[8];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    e[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+                                    e[2 * i + 1] = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
+                                }
+                                s4[2 * q] = make_float4(e[0], e[1], e[2], e[3]);
+                                s4[2 * q + 1] = make_float4(e[4], e[5], e[6], e[7]);
+                            }
+                        } else if (a.pred_skip != nullptr) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) s4[g] = __ldg(reinterpret_cast<const float4*>(a.pred_skip + o + hf * 16 + g * 4));
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) s4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        if (rh != nullptr) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rh + hf * 16 + g * 4));
+                                b4[g].x += r4.x; b4[g].y += r4.y; b4[g].z += r4.z; b4[g].w += r4.w;
+                            }
+                        }
+                        if (rv != nullptr) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv + hf * 16 + g * 4));
+                                b4[g].x += r4.x; b4[g].y += r4.y; b4[g].z += r4.z; b4[g].w += r4.w;
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int c = hf * 16 + g * 4;
+                            const float f0 = fmaxf(__uint_as_float(v[c + 0]) + b4[g].x, 0.f), f1 = fmaxf(__uint_as_float(v[c + 1]) + b4[g].y, 0.f);
+                            const float f2 = fmaxf(__uint_as_float(v[c + 2]) + b4[g].z, 0.f), f3 = fmaxf(__uint_as_float(v[c + 3]) + b4[g].w, 0.f);
+                            pacc = fmaf(f0 + s4[g].x, w4[g].x, pacc);
+                            pacc = fmaf(f1 + s4[g].y, w4[g].y, pacc);
+                            pacc = fmaf(f2 + s4[g].z, w4[g].z, pacc);
+                            pacc = fmaf(f3 + s4[g].w, w4[g].w, pacc);
+                        }
+                    }
+                    pacc += a.pred_bias;
+                    a.pred_out[pixl] = a.pred_sigmoid ? sigmoidf_(pacc) : pacc;
                 } else if (a.epi == EPI_LINEAR) {
                     // row-pair mode: columns [0, C) are output row 2*oy, columns [C, 2C) row 2*oy + 1
                     // phase-stacked mode: column block ph = a*2+b of GEMM row (oy, ox) is output pixel (2oy+a, 2ox+b)
@@ -563,8 +655,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 4; ++i) f[i] = fast_act(f[i], a.act);
                         if (a.pred_out != nullptr) {      // fused 1x1 prediction layer (same summation order as pred_kernel)
-                            const float4 s4 = a.pred_skip ? __ldg(reinterpret_cast<const float4*>(a.pred_skip + o + g * 4))
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (a.pred_skip_s != nullptr) {          // hi + lo planes of the skip tensor
+                                const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(a.pred_skip_s + o + g * 4));
+                                const uint2 l2 = __ldg(reinterpret_cast<const uint2*>(a.pred_skip_s + a.pred_skip_plane + o + g * 4));
+                                s4.x = __uint_as_float(h2.x << 16) + __uint_as_float(l2.x << 16);
+                                s4.y = __uint_as_float(h2.x & 0xffff0000u) + __uint_as_float(l2.x & 0xffff0000u);
+                                s4.z = __uint_as_float(h2.y << 16) + __uint_as_float(l2.y << 16);
+                                s4.w = __uint_as_float(h2.y & 0xffff0000u) + __uint_as_float(l2.y & 0xffff0000u);
+                            } else if (a.pred_skip != nullptr) {
+                                s4 = __ldg(reinterpret_cast<const float4*>(a.pred_skip + o + g * 4));
+                            }
                             const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.pred_w + nbr + g * 4));
                             pacc = fmaf(f[0] + s4.x, w4.x, pacc);
                             pacc = fmaf(f[1] + s4.y, w4.y, pacc);
@@ -824,7 +925,7 @@ int tc_plan_create(ConvParams& p) {
     const int bk = pick_bk(p);
     const int cout_pad = p.cout_pad;
     const bool rp = p.row_pair != 0;
-    const bool ps = p.phase4 != 0, ps2 = p.phase4 == 2;
+    const bool ps = p.phase4 != 0, ps2 = p.phase4 >= 2, ps3 = p.phase4 == 3;   // (ps2: a tap row is skipped per tile -> U = y)
     EVK_REQUIRE(!ps || (!rp && p.epi == EPI_LINEAR && p.stride == 1 && p.pad == 0 && p.kh == 5 && p.kw == 5 && p.cout % 32 == 0 &&
                         cout_pad == 4 * p.cout && p.res == nullptr && p.ring_h != nullptr && p.ring_v != nullptr && !p.kw_packed), EVK_ERR_ARG,
                 "conv_tc: phase-stacked mode needs a 5x5 stride-1 unpadded linear layer with cout %% 32 == 0 and a ring buffer");
@@ -857,7 +958,7 @@ int tc_plan_create(ConvParams& p) {
             if (cout_pad % bn != 0 || bn % granule != 0) continue;
             if ((p.pred_out != nullptr || rp) && bn != cout_pad) continue;
             if (ps && bn % 32 != 0) continue;             // a 32-column epilogue chunk must not straddle two phases
-            if (ps2 && bn != 2 * p.cout) continue;        // phase pairs: one row phase per N tile
+            if (ps2 && bn != (ps3 ? 1 : 2) * p.cout) continue;        // phase pairs: one row phase per N tile; single phases: one per tile
             if (f_bn > 0 && bn != f_bn && cout_pad % f_bn == 0 && f_bn % granule == 0) continue;
             for (int cs = 1; cs <= 4; cs *= 2) {
                 if ((bn / cs) % 8 != 0 || bn % cs != 0) continue;
@@ -866,7 +967,7 @@ int tc_plan_create(ConvParams& p) {
                 const long ctas = n_super * cs;
                 const long slots = (long)(kNumSMs / cs) * cs;
                 const long waves = (ctas + slots - 1) / slots;
-                const double cost = (double)waves * tile_cost(bk, ps2 ? ku - 1 : ku, kv, ux ? s_y : s_x, chunks, bn, cs, ctas, nullptr);
+                const double cost = (double)waves * tile_cost(bk, ps2 ? ku - 1 : ku, ps3 ? kv - 1 : kv, ux ? s_y : s_x, chunks, bn, cs, ctas, nullptr);
                 if (best.bn == 0 || cost < best.cost) best = {ux, bn, cs, cost};
             }
         }
@@ -886,6 +987,8 @@ int tc_plan_create(ConvParams& p) {
     a.fastlin = (a.wide && !rp && !ps && p.pred_out == nullptr && p.cout % 32 == 0 && bn % 32 == 0 && (p.act == ACT_RELU || p.act == ACT_NONE) &&
                  env_int("EVK_TC_FASTLIN", 1)) ? 1 : 0;
     a.act_floor = p.act == ACT_RELU ? 0.0f : -INFINITY;
+    a.fastps = (p.phase4 == 1 && p.cout == 32 && bn == 128 && p.pred_out != nullptr && p.y == nullptr && p.ys == nullptr && p.act == ACT_RELU &&
+                env_int("EVK_TC_FASTPS", 1)) ? 1 : 0;
     a.cw = (p.epi == EPI_LINEAR && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
     a.ux = ux;
     a.tiles_u = ceil_div(ux ? p.Wout : e_hout, 8);
@@ -904,6 +1007,7 @@ int tc_plan_create(ConvParams& p) {
     }
     a.ar = 16 + a.g_ntaps[0] - 1;
     a.bias = p.bias; a.res = p.res; a.y = p.y; a.ys = p.ys;
+    a.pred_skip_s = p.pred_skip_s; a.pred_skip_plane = p.pred_skip_plane;
     a.pred_w = p.pred_w; a.pred_skip = p.pred_skip; a.pred_out = p.pred_out; a.pred_bias = p.pred_bias; a.pred_sigmoid = p.pred_sigmoid;
     if (p.pred_out != nullptr && (p.epi != EPI_LINEAR || bn < e_cout || p.cout > 32)) {
         delete pl;
@@ -929,6 +1033,7 @@ int tc_plan_create(ConvParams& p) {
         const size_t limit = env_int("EVK_TC_TPB", 0) > 1 ? 40 * 1024 : 8 * 1024;
         if (a.g_ntaps[0] * b_tap <= limit && blocks_all >= 3 && env_int("EVK_TC_TPB", 0) != 1) a.tpb = a.g_ntaps[0];
     }
+    if (ps3) a.tpb = 1;             // the per-tile tap range is applied tap by tap
     const size_t b_stage = (size_t)a.tpb * b_tap;
     const size_t budget = 227 * 1024 - 1024 - 512;
     int as = 3, bs = (int)((budget - std::min(budget, as * a_stage)) / b_stage);
@@ -938,7 +1043,7 @@ int tc_plan_create(ConvParams& p) {
     a.a_stages = as; a.b_stages = bs;
     // per accumulator stage: [hi*hi + lo*hi | hi*lo] = 2*bn columns, read in 32-column windows (bn%32 tail -> pad)
     a.acc_cols = (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;
-    const int kb = (a.chunks1 + a.chunks2) * (ps2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0));
+    const int kb = ps3 ? (a.chunks1 + a.chunks2) * (a.ku - 1) * (a.kv - 1) : (a.chunks1 + a.chunks2) * (ps2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0));
     a.issuers = (kb >= 2 && env_int("EVK_TC_ISSUERS", 2) == 2) ? 2 : 1;
     a.own_acc = (a.issuers == 2 && 4 * a.acc_cols <= 512 && env_int("EVK_TC_OWN_ACC", 1)) ? 1 : 0;
     a.acc_stride = a.own_acc ? 2 * a.acc_cols : a.acc_cols;

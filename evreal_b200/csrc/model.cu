@@ -441,7 +441,7 @@ static int add_poly_decoder(Builder& B, const std::string& pfx, const float* x, 
     }
     Op op; op.kind = OP_CONV;
     ConvParams& p = op.cp;
-    p.x1 = nullptr; p.c1 = C; p.x1s = xp; p.phase4 = Co == 32 ? 1 : 2; p.ring_h = ring[0]; p.ring_v = ring[1];    // 4 phases in one N tile, or one row phase per tile
+    p.x1 = nullptr; p.c1 = C; p.x1s = xp; p.phase4 = Co == 32 ? 1 : Co == 64 ? 2 : 3; p.ring_h = ring[0]; p.ring_v = ring[1];    // 4 phases in one N tile, one row phase per tile, or one phase per tile
     p.N = N; p.Hin = H + 4; p.Win = W + 4; p.Hout = H; p.Wout = W; p.kh = 5; p.kw = 5; p.stride = 1; p.pad = 0;
     p.bias = m->upload(pk.b); p.cout = Co; p.epi = EPI_LINEAR; p.act = ACT_RELU; p.y = y;
     std::vector<float> wc;
@@ -572,8 +572,8 @@ static int build_unet(evk_model* m) {
         const float* skip = m->states[hstate[e]].buf[1];   // placeholder, fixed per parity below
         const bool tconv = m->find(pfx + ".transposed_conv2d.weight") != nullptr;     // use_upsample_conv=False
         // last decoder(s) with cout = 32: four output phases stacked along N on the low-resolution map (poly.cu)
-        static const int poly_max_c = getenv("EVK_POLY_MAX_C") ? atoi(getenv("EVK_POLY_MAX_C")) : 128;
-        if (!tconv && !(i == 0 && c.dynamic_decoder) && c.precision == 0 && k == 5 && (C == 64 || C == 128) && C <= poly_max_c &&
+        static const int poly_max_c = getenv("EVK_POLY_MAX_C") ? atoi(getenv("EVK_POLY_MAX_C")) : 256;
+        if (!tconv && !(i == 0 && c.dynamic_decoder) && c.precision == 0 && k == 5 && (C == 64 || C == 128 || C == 256) && C <= poly_max_c &&
             H >= 2 && W >= 2 && getenv("EVK_NO_POLY") == nullptr) {
             float* y = B.act(2 * H, 2 * W, C / 2);
             r = add_poly_decoder(B, pfx, x, skip, C, H, W, y);
@@ -715,6 +715,18 @@ static int wire_tc(evk_model* m) {
                 default: break;
             }
         }
+    // the fused prediction layer reads its skip operand (the head output) from the split planes when they exist: the
+    // head is bound by its output stores (HBM writes), and this drops its fp32 copy
+    if (getenv("EVK_PRED_SKIP_FP32") == nullptr)
+        for (int par = 0; par < 2; ++par)
+            for (Op& op : m->ops[par]) {
+                if (op.kind != OP_CONV || op.cp.pred_out == nullptr || op.cp.pred_skip == nullptr || op.cp.x1s == nullptr) continue;
+                __nv_bfloat16* sp = lookup(op.cp.pred_skip);
+                auto sz = m->buf_elems.find(op.cp.pred_skip);
+                if (sp == nullptr || sz == m->buf_elems.end()) continue;
+                op.cp.pred_skip_s = sp; op.cp.pred_skip_plane = (long long)sz->second;
+                op.cp.pred_skip = nullptr;
+            }
     // fp32 copies that no kernel reads (every consumer takes the split-bf16 companion) are not written at all
     {
         std::map<const float*, int> fp32_read;
@@ -799,7 +811,7 @@ static std::string op_desc(const Op& op) {
                          op.ring_line == 1 ? "horizontal" : "vertical", p.Hout, p.Wout);
             else if (p.phase4)
                 snprintf(b, sizeof b, "conv5x5 s1 %d+0->%d linear%s @%dx%d as 4 stacked phases (N=%d%s) on %dx%d [tcgen05 bf16x3]", p.c1, p.cout,
-                         p.pred_out ? "+pred" : "", 2 * p.Hout, 2 * p.Wout, 4 * p.cout, p.phase4 == 2 ? ", 4 of 5 tap rows per tile" : "", p.Hout, p.Wout);
+                         p.pred_out ? "+pred" : "", 2 * p.Hout, 2 * p.Wout, 4 * p.cout, p.phase4 == 2 ? ", 4 of 5 tap rows per tile" : p.phase4 == 3 ? ", 4x4 of 5x5 taps per tile" : "", p.Hout, p.Wout);
             else
                 snprintf(b, sizeof b, "conv%dx%d s%d %d+%d->%d %s%s @%dx%d [%s]", p.kh, p.kw, p.stride, p.c1, p.c2, p.cout, e,
                          p.pred_out ? "+pred" : "", p.Hout, p.Wout, p.tc ? "tcgen05 bf16x3" : "simt fp32");

@@ -152,6 +152,22 @@ def test_e2vid_two_encoders_phase_pair_decoder_vs_oracle(norm_bn):
     assert sum('stacked phases' in d for d in descs) == 2 and sum('tap rows per tile' in d for d in descs) == 1, descs
 
 
+def test_e2vid_three_encoders_all_decoders_phase_stacked_vs_oracle():
+    """Shipped E2VID shape at a small size that is not a tile multiple (40x56, batch 2, 3 frames, no norm): decoder 256 -> 128
+    runs one output phase per N tile (4x4 of the 5x5 composite taps), 128 -> 64 one row phase per tile, 64 -> 32 all four."""
+    from evreal_b200 import E2VIDRecurrent
+    from oracle import networks as on
+    w = on.random_unet_weights(seed=11, num_encoders=3, num_res=2, norm_bn=False)
+    m = _load(E2VIDRecurrent(dict(E2VID_KW, base_num_channels=32, norm='none', final_activation='')),
+              {'unetrecurrent.' + k: v for k, v in w.items()})
+    vox = _voxels(95, 3, 2, 40, 56, 1200)
+    oracle = on.UNetRecurrentOracle(w)
+    ref = np.stack([oracle(torch.from_numpy(v)).numpy() for v in vox])
+    _assert_close(_frames(m, vox), ref, 'e2vid_three_encoders')
+    descs = m.op_descriptions()
+    assert sum('stacked phases' in d for d in descs) == 3 and sum('4x4 of 5x5' in d for d in descs) == 1, descs
+
+
 @pytest.mark.parametrize('precision', [0, 1])
 def test_e2vid_full_size_vs_oracle(precision):
     """BASELINE cfg 2 shape: E2VID (BN, sigmoid, base 32) at 240x180 padded to 184x240, 5 recurrent frames."""
