@@ -354,7 +354,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=24, help="independent streams run in lock-step per GPU (24 measured best: r01 profiles)")
+    ap.add_argument("--batch", type=int, default=36, help="independent streams run in lock-step per GPU (36 measured best of 24..49: profiles/r01_batch_sweep_v7.txt)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=100, help="bounded CPU-baseline sample (frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
