@@ -96,11 +96,12 @@ class ClockSampler:
 def make_streams(n_streams, seed0, duration):
     from evreal_b200 import synthetic
     from evreal_b200.dataset import MemMapDataset
-    out = []
-    for b in range(n_streams):
-        arrays = synthetic.make_stream(H, W, RATE, duration, FPS, seed=seed0 + b)
-        out.append((arrays, MemMapDataset(arrays, num_bins=5, voxel_method={'method': 'between_frames'}, resident=False)))
-    return out
+    from concurrent.futures import ThreadPoolExecutor
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workers = max(1, min(n_streams, (os.cpu_count() or 1) // max(world, 1)))     # numpy's generators and sort release the GIL
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        arrs = list(pool.map(lambda b: synthetic.make_stream(H, W, RATE, duration, FPS, seed=seed0 + b), range(n_streams)))
+    return [(a, MemMapDataset(a, num_bins=5, voxel_method={'method': 'between_frames'}, resident=False)) for a in arrs]
 
 
 def e2vid_weights():

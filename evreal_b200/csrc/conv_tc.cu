@@ -710,7 +710,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     float hr[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        if (nb + g * 8 >= a.cout || j0 + g * 8 >= a.bn) break;
+                        if (nb + g * 8 >= a.cout || j0 + g * 8 >= a.bn || g * 8 >= cw) break;
                         const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 8));
                         const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 8 + 4));
                         const float4 hp = *reinterpret_cast<const float4*>(a.h_prev + o + g * 4);
@@ -733,7 +733,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     const size_t o = pix * a.cout + nb;
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
-                        if (nb + g * 4 >= a.cout || j0 + g * 4 >= a.bn) break;
+                        if (nb + g * 4 >= a.cout || j0 + g * 4 >= a.bn || g * 4 >= cw) break;
                         const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
                         const float4 u4 = *reinterpret_cast<const float4*>(a.u_in + o + g * 4);
                         const float4 h4 = *reinterpret_cast<const float4*>(a.h_prev + o + g * 4);
@@ -989,7 +989,8 @@ int tc_plan_create(ConvParams& p) {
     a.act_floor = p.act == ACT_RELU ? 0.0f : -INFINITY;
     a.fastps = (p.phase4 == 1 && p.cout == 32 && bn == 128 && p.pred_out != nullptr && p.y == nullptr && p.ys == nullptr && p.act == ACT_RELU &&
                 env_int("EVK_TC_FASTPS", 1)) ? 1 : 0;
-    a.cw = (p.epi == EPI_LINEAR && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
+    // 16-column chunks for 32-column tiles: both halves of the epilogue warps get a chunk (linear, ConvGRU)
+    a.cw = ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_UR || p.epi == EPI_GRU_OUT) && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
     a.ux = ux;
     a.tiles_u = ceil_div(ux ? p.Wout : e_hout, 8);
     a.tiles_v = ceil_div(ux ? e_hout : p.Wout, 16);
@@ -1030,7 +1031,8 @@ int tc_plan_create(ConvParams& p) {
         const int blocks_all = (a.chunks1 + a.chunks2) * a.ku * a.n_groups;      // K blocks per tile if a block takes a whole group
         // measured: pays for the one-slice blocks of 16-channel layers (FireNet +13%); with BK >= 32 the larger stages
         // leave too few of them in flight (the last decoder of E2VID lost 40%), so those keep one tap per block
-        const size_t limit = env_int("EVK_TC_TPB", 0) > 1 ? 40 * 1024 : 8 * 1024;
+        // (32-channel layers -- the first encoder: two-slice blocks cost 327 cycles per slice of issue time, -13 % with a tap group per block)
+        const size_t limit = env_int("EVK_TC_TPB", 0) > 1 ? 40 * 1024 : bk <= 32 ? 24 * 1024 : 8 * 1024;
         if (a.g_ntaps[0] * b_tap <= limit && blocks_all >= 3 && env_int("EVK_TC_TPB", 0) != 1) a.tpb = a.g_ntaps[0];
     }
     if (ps3) a.tpb = 1;             // the per-tile tap range is applied tap by tap
