@@ -454,11 +454,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     if (cw == 32) {
                         tc_ld_32x32(t_row + (uint32_t)j0, v);
                         tc_ld_32x32(t_row + (uint32_t)(a.bn + j0), u);
-                    } else {
+                    } else if (cw == 16) {
 #pragma unroll
                         for (int i = 16; i < 32; ++i) { v[i] = 0u; u[i] = 0u; }
                         tc_ld_32x16(t_row + (uint32_t)j0, v);
                         tc_ld_32x16(t_row + (uint32_t)(a.bn + j0), u);
+                    } else {
+#pragma unroll
+                        for (int i = 8; i < 32; ++i) { v[i] = 0u; u[i] = 0u; }
+                        tc_ld_32x8(t_row + (uint32_t)j0, v);
+                        tc_ld_32x8(t_row + (uint32_t)(a.bn + j0), u);
                     }
                     tc_wait_ld();
 #pragma unroll
@@ -468,11 +473,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         if (cw == 32) {
                             tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + j0), u);
                             tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + a.bn + j0), w);
-                        } else {
+                        } else if (cw == 16) {
 #pragma unroll
                             for (int i = 16; i < 32; ++i) w[i] = 0u;
                             tc_ld_32x16(t_row + (uint32_t)(a.acc_cols + j0), u);
                             tc_ld_32x16(t_row + (uint32_t)(a.acc_cols + a.bn + j0), w);
+                        } else {
+#pragma unroll
+                            for (int i = 8; i < 32; ++i) w[i] = 0u;
+                            tc_ld_32x8(t_row + (uint32_t)(a.acc_cols + j0), u);
+                            tc_ld_32x8(t_row + (uint32_t)(a.acc_cols + a.bn + j0), w);
                         }
                         tc_wait_ld();
 #pragma unroll
@@ -983,14 +993,16 @@ int tc_plan_create(ConvParams& p) {
     a.rp = rp ? 1 : 0; a.creal = p.cout; a.hreal = ps ? 2 * p.Hout : p.Hout;
     a.ps = p.phase4; a.wreal = ps ? 2 * p.Wout : p.Wout;
     a.ring_h = p.ring_h; a.ring_v = p.ring_v;
-    a.wide = (p.epi == EPI_LINEAR && p.cout % 16 == 0 && env_int("EVK_TC_WIDE_ST", 1)) ? 1 : 0;
+    // 16-column chunks for 32-column tiles: both halves of the epilogue warps get a chunk (linear, ConvGRU)
+    a.cw = ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_UR || p.epi == EPI_GRU_OUT) && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
+    // ... and 8-column chunks for 16-column tiles (FireNet's 16-channel layers)
+    if ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_OUT) && bn == 16 && p.pred_out == nullptr && env_int("EVK_TC_CW8", 1)) a.cw = 8;
+    a.wide = (p.epi == EPI_LINEAR && p.cout % 16 == 0 && a.cw >= 16 && env_int("EVK_TC_WIDE_ST", 1)) ? 1 : 0;
     a.fastlin = (a.wide && !rp && !ps && p.pred_out == nullptr && p.cout % 32 == 0 && bn % 32 == 0 && (p.act == ACT_RELU || p.act == ACT_NONE) &&
                  env_int("EVK_TC_FASTLIN", 1)) ? 1 : 0;
     a.act_floor = p.act == ACT_RELU ? 0.0f : -INFINITY;
     a.fastps = (p.phase4 == 1 && p.cout == 32 && bn == 128 && p.pred_out != nullptr && p.y == nullptr && p.ys == nullptr && p.act == ACT_RELU &&
                 env_int("EVK_TC_FASTPS", 1)) ? 1 : 0;
-    // 16-column chunks for 32-column tiles: both halves of the epilogue warps get a chunk (linear, ConvGRU)
-    a.cw = ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_UR || p.epi == EPI_GRU_OUT) && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
     a.ux = ux;
     a.tiles_u = ceil_div(ux ? p.Wout : e_hout, 8);
     a.tiles_v = ceil_div(ux ? e_hout : p.Wout, 16);
