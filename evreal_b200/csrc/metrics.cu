@@ -225,17 +225,34 @@ percentile_normalize_kernel(const float* __restrict__ img, float* __restrict__ o
             hist[(tgt * kSelWarps) * 256 + bin] = c;
         }
         __syncthreads();
-        if (tid < 2) {
-            const unsigned int* h = hist + (tid * kSelWarps) * 256;
-            unsigned int r = s_rank[tid], acc = 0;
-            int b = 0;
-            for (; b < 256; ++b) {
-                if (acc + h[b] > r) break;
-                acc += h[b];
+        if (warp < 2) {
+            // warp t finds the bin holding rank r of target t: lane l owns bins 8l..8l+7 (a serial scan of 256 bins by one
+            // thread cost ~8k cycles per pass)
+            const unsigned int* h = hist + (warp * kSelWarps) * 256;
+            const int l = tid & 31;
+            unsigned int c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = h[8 * l + j]; sum += c[j]; }
+            unsigned int incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (l >= off) incl += t;
             }
-            if (b > 255) b = 255;
-            s_rank[tid] = r - acc;
-            s_prefix[tid] |= ((unsigned int)b << shift);
+            const unsigned int r = s_rank[warp];
+            unsigned int acc = incl - sum;                         // elements in the bins before this lane's
+            const bool mine = (acc <= r && r < incl) || (l == 31 && r >= incl);
+            __syncwarp();
+            if (mine) {
+                int b = 0;
+                for (; b < 8; ++b) {
+                    if (acc + c[b] > r) break;
+                    acc += c[b];
+                }
+                if (b > 7) { b = 7; }
+                s_rank[warp] = r - acc;
+                s_prefix[warp] |= ((unsigned int)(8 * l + b) << shift);
+            }
         }
         __syncthreads();
     }

@@ -373,7 +373,8 @@ int normalize_pad(const float* in, float* out, int n_samples, int C, int H, int 
         EVK_CHECK_CUDA(cudaMallocAsync(&stats, sizeof(EvStats) * n_samples, st));
         EVK_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(EvStats) * n_samples, st));
         const int64_t numel = (int64_t)C * H * W;
-        dim3 grid((unsigned)std::min<int64_t>(ceil_div64(numel, 256 * 4), 256), n_samples);
+        // few blocks per sample: every block ends in three contended float64 atomics on the sample's record
+        dim3 grid((unsigned)std::min<int64_t>(ceil_div64(numel, 256 * 4), n_samples >= 8 ? 32 : 128), n_samples);
         event_stats_kernel<<<grid, 256, 0, st>>>(in, numel, stats);
         EVK_CHECK_CUDA(cudaGetLastError());
     }
