@@ -249,10 +249,12 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU implementation (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout (file descriptor 1, from C) whatever
+    # NCCL_DEBUG says, so everything until the final print goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device('cuda', local))
     import evreal_b200 as evk
     from evreal_b200 import _lib, synthetic
@@ -346,6 +348,9 @@ def run_ours(args):
                        "weights": "seeded random, shapes of pretrained/E2VID (10.7 M parameters)"},
             "e2e": e2e, "gpu_launches": launches, "roofline": net, "voxelizer": voxel, "cpu_baseline": cpu, "clocks": clocks,
             "last_step_scores_mse_ssim": [[float(a), float(b)] for a, b in last_scores[:2]]}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     print(json.dumps(line))
     return 0
 
