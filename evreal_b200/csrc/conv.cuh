@@ -60,6 +60,13 @@ struct ConvParams {
     // the layer is an ordinary one on a W/G-wide image (Win = Wout = W/G, cout = G * real cout, bias repeated G times)
     // whose window rows are G pixels apart.  MMAs G times wider, G times fewer tiles.
     int kw_group = 0;
+    // "window" mode for 16-channel layers (FireNet): the same row-window K layout over ordinary activations.  x1s / x2s are
+    // ROW-PADDED split tensors [2][N][Hin][win_wp][win_c] (pixel x at padded column x + kw_packed/2, pad columns zero), 64 / win_c
+    // pixels make one 128-byte K row (a 32-byte K row -- BK = 16, 32-byte swizzle -- costs ~3x per MMA), and kw_group
+    // output pixels share a window (kw_group + kw_packed - 1 <= 64 / win_c).  c1 (and c2) = 64; weights from pack_weights_window.
+    int win_c = 0, win_wp = 0;
+    // split OUTPUTS (ys / hs_new / hrs_out) written row-padded for window-mode consumers: padded width, channels per pixel, left pad
+    int s_wp = 0, s_c = 0, s_left = 0;
     // "row pair" form of a stride-1 layer with cout == 32 (the last decoder): the GEMM computes output rows 2y and 2y+1
     // together as N = 64 columns of a (kh+1) x kw convolution with vertical stride 2 (weights of row 2y+1 shifted one tap
     // down) -- an MMA with N <= 64 costs the same ~50 cycles as one with N = 32, so this halves the MMA count per
@@ -124,6 +131,11 @@ int launch_upsample2x_add(const float* x, const float* skip, float* y, __nv_bflo
 int launch_zero_insert2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C, cudaStream_t st);
 // NCHW fp32 [N,cin,H,W] (cin <= 8) -> packed split-bf16 row-window tensor [2][N][H][W+8][8], pixel x at column x + left
 int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st);
+// host: [kh*kw*cin][cout] (cin = T tensors of c_tensor channels) -> window K layout [kh*T*64][group*cout]
+// (k = r*64*T + t*64 + slot*c_tensor + c; output pixel g of a group reads tap q from window slot g + q)
+void pack_weights_window(const float* w_kc, int kh, int kw, int cin, int c_tensor, int cout, int group, std::vector<float>& out);
+// fp32 [rows][W][C] -> split planes in the row-padded layout [2][rows][wp][C] (pixel x at column x + left; pads untouched)
+int launch_split_padded(const float* src, __nv_bfloat16* dst, int64_t rows, int W, int C, int wp, int left, cudaStream_t st);
 // host: head weights [kh*kw*cin][cout] (SIMT layout) -> row-window K layout [kh*64][group*cout] (k = r*64 + slot*8 + c,
 // output pixel g of a group reads tap q from window slot g + q)
 void pack_head_weights_rowwin(const float* w_kc, int kh, int kw, int cin, int cout, int group, std::vector<float>& out);

@@ -44,6 +44,8 @@ struct TcArgs {
     int N, Hout, Wout, su, sv, pad_u, pad_v, kh, kw;       // Hout counts row PAIRS in row-pair mode; su / sv = stride along U / V
     int cw;                     // epilogue chunk width in accumulator columns: 32, or 16 for a 32-column linear tile (both halves of the epilogue warps get work)
     int rp, creal, hreal;       // row-pair mode, real channel count / output height (addressing)
+    int s_pitch, s_grp, s_off;  // split OUTPUT tensors with padded rows (window-mode consumers, ConvParams::s_wp): elements per padded
+                                // row, per GEMM row and of the left padding; 0 = dense [N,H,W,C]
     int fastps;                 // phase-stacked last decoder (cout 32, ReLU, fused prediction layer, no tensor output): straight-line epilogue
     int fastlin;                // EPI_LINEAR, wide, 32-column chunks, no row-pair / phase / prediction: straight-line epilogue
     float act_floor;            // fastlin: lower clamp of the activation (0 for ReLU, -inf for none)
@@ -438,6 +440,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             const int n0 = t.nt * a.bn;
             const bool valid = !t.dummy && oy < a.Hout && ox < a.Wout;
             const size_t pix = ((size_t)t.img * a.Hout + oy) * a.Wout + ox;
+            // split outputs in a row-padded layout: offset of this GEMM row's record relative to its dense offset pix * s_grp
+            const long long sd = a.s_pitch ? (long long)((size_t)t.img * a.Hout + oy) * (a.s_pitch - a.Wout * a.s_grp) + a.s_off : 0;
             const long long t0 = DBG ? clock64() : 0;
             mbar_wait(bar_tfull + 8u * as, aph);
             if (DBG) w_tf += clock64() - t0;
@@ -535,10 +539,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                             lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                         }
-                        st_global_v8(a.ys + o, hw);
-                        st_global_v8(a.ys + o + 16, hw + 8);
-                        st_global_v8(a.ys + a.ys_plane + o, lw);
-                        st_global_v8(a.ys + a.ys_plane + o + 16, lw + 8);
+                        st_global_v8(a.ys + sd + o, hw);
+                        st_global_v8(a.ys + sd + o + 16, hw + 8);
+                        st_global_v8(a.ys + a.ys_plane + sd + o, lw);
+                        st_global_v8(a.ys + a.ys_plane + sd + o + 16, lw + 8);
                     }
                 } else if (a.epi == EPI_LINEAR && a.fastps) {
                     // Straight-line form of the last decoder's epilogue (four stacked phases of 32 channels, one phase per chunk;
@@ -696,8 +700,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                     hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                                     lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                                 }
-                                st_global_v8(a.ys + o + (g - 3) * 4, hw);
-                                st_global_v8(a.ys + a.ys_plane + o + (g - 3) * 4, lw);
+                                st_global_v8(a.ys + sd + o + (g - 3) * 4, hw);
+                                st_global_v8(a.ys + a.ys_plane + sd + o + (g - 3) * 4, lw);
                             }
                             continue;
                         }
@@ -706,8 +710,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) split_bf16(f[i], hi[i], lo[i]);
-                            *reinterpret_cast<uint2*>(a.ys + o + g * 4) = *reinterpret_cast<uint2*>(hi);
-                            *reinterpret_cast<uint2*>(a.ys + a.ys_plane + o + g * 4) = *reinterpret_cast<uint2*>(lo);
+                            *reinterpret_cast<uint2*>(a.ys + sd + o + g * 4) = *reinterpret_cast<uint2*>(hi);
+                            *reinterpret_cast<uint2*>(a.ys + a.ys_plane + sd + o + g * 4) = *reinterpret_cast<uint2*>(lo);
                         }
                     }
                     if (a.pred_out != nullptr) {
@@ -735,8 +739,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) split_bf16(hr[g * 4 + i], hi[i], lo[i]);
-                            *reinterpret_cast<uint2*>(a.hrs_out + o + g * 4) = *reinterpret_cast<uint2*>(hi);
-                            *reinterpret_cast<uint2*>(a.hrs_out + a.hs_plane + o + g * 4) = *reinterpret_cast<uint2*>(lo);
+                            *reinterpret_cast<uint2*>(a.hrs_out + sd + o + g * 4) = *reinterpret_cast<uint2*>(hi);
+                            *reinterpret_cast<uint2*>(a.hrs_out + a.hs_plane + sd + o + g * 4) = *reinterpret_cast<uint2*>(lo);
                         }
                     }
                 } else if (a.epi == EPI_GRU_OUT) {  // h' = h (1 - u) + tanh(.) u (model/submodules.py:283-285)
@@ -759,8 +763,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) split_bf16(hn[i], hi[i], lo[i]);
-                            *reinterpret_cast<uint2*>(a.hs_new + o + g * 4) = *reinterpret_cast<uint2*>(hi);
-                            *reinterpret_cast<uint2*>(a.hs_new + a.hs_plane + o + g * 4) = *reinterpret_cast<uint2*>(lo);
+                            *reinterpret_cast<uint2*>(a.hs_new + sd + o + g * 4) = *reinterpret_cast<uint2*>(hi);
+                            *reinterpret_cast<uint2*>(a.hs_new + a.hs_plane + sd + o + g * 4) = *reinterpret_cast<uint2*>(lo);
                         }
                     }
                 } else {   // EPI_LSTM: packed column = channel*4 + {in, remember, out, cell}
@@ -1027,10 +1031,17 @@ int tc_plan_create(ConvParams& p) {
         EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: the fused prediction layer needs all %d channels in one 32-column chunk (bn=%d)", p.cout, bn);
     }
     a.ys_plane = (long long)p.N * p.Hout * p.Wout * p.cout * (ps ? 4 : 1);
+    a.s_pitch = 0; a.s_grp = 0; a.s_off = 0;
     a.c_prev = p.c_prev; a.c_new = p.c_new; a.h_new = p.h_new; a.hs_new = p.hs_new;
     a.h_prev = p.h_prev; a.u_in = p.u_in; a.u_out = p.u_out; a.hr_out = p.hr_out; a.hrs_out = p.hrs_out;
     // plane stride of the split copy of the recurrent output: hidden channels = cout/4 (LSTM), cout/2 (GRU u,r), cout (GRU out)
     a.hs_plane = (long long)p.N * p.Hout * p.Wout * (p.epi == EPI_LSTM ? p.cout / 4 : p.epi == EPI_GRU_UR ? p.cout / 2 : p.cout);
+    if (p.s_wp > 0) {          // row-padded split outputs: s_c channels per pixel, pixel x at padded column x + s_left
+        if (rp || ps || p.epi == EPI_LSTM) { delete pl; EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: padded split outputs are not built for this epilogue"); }
+        a.s_grp = p.epi == EPI_GRU_UR ? p.cout / 2 : p.cout;                  // split elements per GEMM row
+        a.s_pitch = p.s_wp * p.s_c; a.s_off = p.s_left * p.s_c;
+        a.ys_plane = a.hs_plane = (long long)p.N * p.Hout * a.s_pitch;
+    }
     a.dbg = nullptr;
     a.exp = env_int("EVK_TC_EXP", 0);
     const uint32_t row_bytes = bk * 2;
@@ -1083,10 +1094,12 @@ int tc_plan_create(ConvParams& p) {
             // row-window view of the packed head input [2][N][H][W+8][8]: "channel" dim = the 64 values starting at a
             // pixel, pixel stride 16 B (rows overlap), so one box row holds the kw taps x 8 channel slots of a kernel row
             // (kw_group = G > 1: GEMM row = G consecutive output pixels, so rows are G pixels = 16*G bytes apart)
+            // (window mode, win_c > 0: the same view of a row-padded [N][H][win_wp][win_c] activation tensor, 2 * win_c bytes per pixel)
             const uint64_t G = (uint64_t)(p.kw_group > 1 ? p.kw_group : 1);
-            const uint64_t wp = (uint64_t)p.Win * G + 8;
+            const uint64_t pxb = p.win_c > 0 ? (uint64_t)p.win_c * 2 : 16;
+            const uint64_t wp = p.win_c > 0 ? (uint64_t)p.win_wp : (uint64_t)p.Win * G + 8;
             const uint64_t dims[5] = {64, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)p.N, 2};
-            const uint64_t str[4] = {16 * G, wp * 16, (uint64_t)p.Hin * wp * 16, (uint64_t)p.N * p.Hin * wp * 16};
+            const uint64_t str[4] = {pxb * G, wp * pxb, (uint64_t)p.Hin * wp * pxb, (uint64_t)p.N * p.Hin * wp * pxb};
             const uint32_t box[5] = {64, 8, (uint32_t)a.ar, 1, 1};
             const uint32_t es[5] = {1, 1, 1, 1, 1};
             return encode_tmap_bf16(m, base, 5, dims, str, box, es, 128);
@@ -1231,6 +1244,22 @@ void pack_weights_row_pair(const float* w_kc, int kh, int kw, int cin, int cout,
                 }
 }
 
+void pack_weights_window(const float* w_kc, int kh, int kw, int cin, int c_tensor, int cout, int group, std::vector<float>& out) {
+    const int T = cin / c_tensor, slots = 64 / c_tensor;
+    out.assign((size_t)kh * 64 * T * group * cout, 0.f);
+    for (int r = 0; r < kh; ++r)
+        for (int g = 0; g < group; ++g)              // output pixel g of the group reads tap q from window slot g + q
+            for (int q = 0; q < kw; ++q) {
+                if (g + q >= slots) continue;
+                for (int c = 0; c < cin; ++c) {
+                    const int t = c / c_tensor, cc = c % c_tensor;
+                    for (int n = 0; n < cout; ++n)
+                        out[((size_t)r * 64 * T + t * 64 + (g + q) * c_tensor + cc) * (group * cout) + g * cout + n] =
+                            w_kc[((size_t)(r * kw + q) * cin + c) * cout + n];
+                }
+            }
+}
+
 void pack_head_weights_rowwin(const float* w_kc, int kh, int kw, int cin, int cout, int group, std::vector<float>& out) {
     out.assign((size_t)kh * 64 * group * cout, 0.f);
     for (int r = 0; r < kh; ++r)
@@ -1254,6 +1283,28 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ sr
 int launch_split(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st) {
     EVK_REQUIRE(src && dst && n > 0, EVK_ERR_ARG, "split: bad argument");
     split_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 2368), 256, 0, st>>>(src, dst, n);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+__global__ void __launch_bounds__(256) split_padded_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows,
+                                                           int W, int C, int wp, int left) {
+    const int64_t n = rows * W * C, plane = rows * (int64_t)wp * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int x = (int)((i / C) % W);
+        const int64_t r = i / ((int64_t)C * W);
+        __nv_bfloat16 hi, lo;
+        split_bf16(src[i], hi, lo);
+        const int64_t o = (r * wp + x + left) * C + c;
+        dst[o] = hi;
+        dst[plane + o] = lo;
+    }
+}
+
+int launch_split_padded(const float* src, __nv_bfloat16* dst, int64_t rows, int W, int C, int wp, int left, cudaStream_t st) {
+    EVK_REQUIRE(src && dst && rows > 0 && wp >= W + left, EVK_ERR_ARG, "split_padded: bad argument");
+    split_padded_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(rows * W * C, 256), 2368), 256, 0, st>>>(src, dst, rows, W, C, wp, left);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

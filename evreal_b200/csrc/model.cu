@@ -77,6 +77,10 @@ struct evk_model {
     std::map<const float*, size_t> buf_elems;          // element count of every activation / state buffer
     std::vector<TcPlan*> plans;
     int tc_convs = 0;
+    // window mode (FireNet, 16-channel tensors at full resolution; conv.cuh ConvParams::win_c): every split companion is
+    // row-padded [2][N][H][W + 2][C] (pixel x at column x + 1)
+    int win_wp = 0;
+    std::map<const float*, size_t> split_bytes;        // allocation size of every split companion
 
     float* dalloc(size_t nfloat) {
         void* p = nullptr;
@@ -197,6 +201,33 @@ struct Builder {
         p.w_tc = (const __nv_bfloat16*)d;
     }
 
+    // Window form of a stride-1 3x3 layer whose input tensors have 16 channels (conv.cuh, ConvParams::win_c): 4 pixels of
+    // 16 channels are one 128-byte K row, 2 output pixels share a window (N = 2 * cout).  `pk` holds the packed weights /
+    // bias of the plain layer ([kh*kw*(c1+c2)][cout]); the outputs are the same memory seen as [N, H, W/2, 2*cout].
+    bool window_ok(const ConvParams& p, const Packed& pk) const {
+        return m->win_wp > 0 && m->cfg.precision == 0 && p.stride == 1 && pk.kh == 3 && pk.kw == 3 && p.c1 == 16 && (p.c2 == 0 || p.c2 == 16) &&
+               p.Wout % 2 == 0 && p.Win == p.Wout && pk.cout % 8 == 0 && 2 * pk.cout <= 128 && !p.kw_packed;
+    }
+    int apply_window(ConvParams& p, const Packed& pk) {
+        const int G = 2;
+        std::vector<float> ww, bw((size_t)G * pk.cout);
+        pack_weights_window(pk.w.data(), pk.kh, pk.kw, pk.cin, 16, pk.cout, G, ww);
+        for (int g = 0; g < G; ++g) std::copy(pk.b.begin(), pk.b.end(), bw.begin() + (size_t)g * pk.cout);
+        const int T = pk.cin / 16;
+        p.kw_packed = pk.kw; p.kw_group = G; p.win_c = 16; p.win_wp = m->win_wp;
+        p.kh = pk.kh; p.kw = 1; p.c1 = 64; p.c2 = T > 1 ? 64 : 0;
+        p.Win = p.Wout = p.Wout / G;
+        p.cout = G * pk.cout; p.cout_pad = (G * pk.cout + 15) / 16 * 16;
+        p.bias = m->upload(bw); p.w = nullptr;                     // (tensor-core only)
+        std::vector<__nv_bfloat16> wt;
+        pack_weights_tc(ww.data(), pk.kh * 64 * T, G * pk.cout, p.cout_pad, wt);
+        void* d = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
+        EVK_REQUIRE(d != nullptr && p.bias != nullptr, EVK_ERR_CUDA, "out of device memory for the window weights");
+        cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+        p.w_tc = (const __nv_bfloat16*)d;
+        return EVK_OK;
+    }
+
     int conv_packed(const Packed& pk, const float* x, int cin, int Hin, int Win, int stride, int pad, int act,
                     const float* res, float* y, int* cout_out) {
         Op op; op.kind = OP_CONV;
@@ -207,8 +238,13 @@ struct Builder {
         p.Wout = (Win + 2 * pad - pk.kw) / stride + 1;
         p.w = m->upload(pk.w); p.bias = m->upload(pk.b); p.cout = pk.cout;
         p.epi = EPI_LINEAR; p.act = act; p.res = res; p.y = y;
-        attach_tc_weights(p, pk);
         op.flops = conv_flops(p, pk.cout);
+        if (window_ok(p, pk)) {
+            int r = apply_window(p, pk);
+            if (r != EVK_OK) return r;
+        } else {
+            attach_tc_weights(p, pk);
+        }
         m->ops[0].push_back(op); m->ops[1].push_back(op);
         if (cout_out) *cout_out = pk.cout;
         return EVK_OK;
@@ -286,11 +322,16 @@ static int add_gru(Builder& B, const std::string& pfx, const float* x, int C, in
         p.kh = p.kw = k; p.stride = 1; p.pad = k / 2;
         p.w = m->upload(w); p.bias = m->upload(b); p.cout = 2 * C; p.epi = EPI_GRU_UR;
         p.h_prev = h; p.u_out = u_buf; p.hr_out = hr_buf;
+        op.flops = conv_flops(p, 2 * C);
         {
             Packed pk2; pk2.w = w; pk2.b = b; pk2.cout = 2 * C; pk2.cin = cin; pk2.kh = k; pk2.kw = k;
-            B.attach_tc_weights(p, pk2);
+            if (B.window_ok(p, pk2)) {
+                int r = B.apply_window(p, pk2);
+                if (r != EVK_OK) return r;
+            } else {
+                B.attach_tc_weights(p, pk2);
+            }
         }
-        op.flops = conv_flops(p, 2 * C);
         m->ops[0].push_back(op); m->ops[1].push_back(op);
     }
     {
@@ -303,8 +344,13 @@ static int add_gru(Builder& B, const std::string& pfx, const float* x, int C, in
         p.kh = p.kw = k; p.stride = 1; p.pad = k / 2;
         p.w = m->upload(pk.w); p.bias = m->upload(pk.b); p.cout = C; p.epi = EPI_GRU_OUT;
         p.h_prev = h; p.u_in = u_buf; p.h_new = h;
-        B.attach_tc_weights(p, pk);
         op.flops = conv_flops(p, C);
+        if (B.window_ok(p, pk)) {
+            r = B.apply_window(p, pk);
+            if (r != EVK_OK) return r;
+        } else {
+            B.attach_tc_weights(p, pk);
+        }
         m->ops[0].push_back(op); m->ops[1].push_back(op);
     }
     return EVK_OK;
@@ -635,6 +681,7 @@ static int build_firenet(evk_model* m, bool legacy) {
     const char* n_r1 = legacy ? "resblocks.0.conv" : "R1";
     const char* n_g2 = legacy ? "resblocks.0.recurrent_block" : "G2";
     const char* n_r2 = legacy ? "resblocks.1" : "R2";
+    if (c.precision == 0 && C == 16 && W % 2 == 0 && c.kernel_size == 3 && getenv("EVK_NO_WINDOW") == nullptr) m->win_wp = W + 2;
     float* xh = B.act(H, W, C);
     int r = add_head(B, n_head, "", xh, C);
     if (r != EVK_OK) return r;
@@ -667,8 +714,11 @@ static int wire_tc(evk_model* m) {
         if (it != m->split_of.end()) return it->second;
         auto sz = m->buf_elems.find(ptr);
         if (sz == m->buf_elems.end()) return nullptr;
-        __nv_bfloat16* d = (__nv_bfloat16*)m->dalloc_bytes(sz->second * 2 * sizeof(__nv_bfloat16));
+        // (window mode: rows padded from W to win_wp pixels, pads stay zero)
+        const size_t elems = m->win_wp > 0 ? sz->second / m->cfg.width * m->win_wp : sz->second;
+        __nv_bfloat16* d = (__nv_bfloat16*)m->dalloc_bytes(elems * 2 * sizeof(__nv_bfloat16));
         m->split_of[ptr] = d;
+        m->split_bytes[ptr] = elems * 2 * sizeof(__nv_bfloat16);
         return d;
     };
     for (int par = 0; par < 2; ++par)
@@ -685,7 +735,7 @@ static int wire_tc(evk_model* m) {
             for (size_t i = 0; i + 1 < m->ops[par].size(); ++i) {
                 Op& cv = m->ops[par][i];
                 Op& pr = m->ops[par][i + 1];
-                if (cv.kind != OP_CONV || cv.cp.x1s == nullptr || cv.cp.epi != EPI_LINEAR || cv.cp.cout > 32 || cv.cp.cout % 16 != 0) continue;
+                if (cv.kind != OP_CONV || cv.cp.x1s == nullptr || cv.cp.epi != EPI_LINEAR || cv.cp.cout > 32 || cv.cp.cout % 16 != 0 || cv.cp.win_c > 0) continue;
                 if (pr.kind != OP_PRED || pr.in != cv.cp.y || pr.cin != cv.cp.cout) continue;
                 cv.cp.pred_w = pr.w; cv.cp.pred_skip = pr.skip; cv.cp.pred_out = pr.out;
                 cv.cp.pred_bias = pr.bias0; cv.cp.pred_sigmoid = pr.sigmoid;
@@ -713,6 +763,9 @@ static int wire_tc(evk_model* m) {
                     break;
                 case OP_HYPER_APPLY: op.hp.inter_s = lookup(op.hp.inter); break;
                 default: break;
+            }
+            if (op.kind == OP_CONV && m->win_wp > 0 && (op.cp.ys || op.cp.hs_new || op.cp.hrs_out)) {
+                op.cp.s_wp = m->win_wp; op.cp.s_c = m->cfg.base_channels; op.cp.s_left = 1;     // row-padded split outputs
             }
         }
     // the fused prediction layer reads its skip operand (the head output) from the split planes when they exist: the
@@ -802,7 +855,10 @@ static std::string op_desc(const Op& op) {
         case OP_CONV: {
             const ConvParams& p = op.cp;
             const char* e = p.epi == EPI_LSTM ? "lstm" : p.epi == EPI_GRU_UR ? "gru_ur" : p.epi == EPI_GRU_OUT ? "gru_out" : (p.res ? "linear+res" : "linear");
-            if (p.kw_packed)
+            if (p.win_c > 0)
+                snprintf(b, sizeof b, "conv%dx%d s1 %d+%d->%d %s @%dx%d, window K rows (4 px x 16 ch), %d pixels per GEMM row (N=%d) [tcgen05 bf16x3]", p.kh, p.kw_packed,
+                         p.win_c, p.c2 ? p.win_c : 0, p.cout / p.kw_group, e, p.Hout, p.Wout * p.kw_group, p.kw_group, p.cout);
+            else if (p.kw_packed)
                 snprintf(b, sizeof b, "conv%dx%d s1 %d+0->%d head row-window%s @%dx%d, %d pixels per GEMM row (N=%d) [tcgen05 bf16x3]", p.kh, p.kw_packed,
                          op.cin, p.cout / (p.kw_group > 1 ? p.kw_group : 1), p.pred_out ? "+pred" : "", p.Hout, p.Wout * (p.kw_group > 1 ? p.kw_group : 1),
                          p.kw_group > 1 ? p.kw_group : 1, p.cout);
@@ -897,7 +953,7 @@ int evk_model_reset_states(evk_model* m, void* stream) {
         if (s.pingpong) EVK_CHECK_CUDA(cudaMemsetAsync(s.buf[1], 0, bytes, st));
         for (int k = 0; k < 2; ++k) {
             auto it = m->split_of.find(s.buf[k]);
-            if (it != m->split_of.end()) EVK_CHECK_CUDA(cudaMemsetAsync(it->second, 0, bytes, st));   // 2 bf16 planes == bytes
+            if (it != m->split_of.end()) EVK_CHECK_CUDA(cudaMemsetAsync(it->second, 0, m->split_bytes[s.buf[k]], st));
         }
     }
     EVK_CHECK_CUDA(cudaMemsetAsync(m->prev_rec, 0, sizeof(float) * (size_t)m->cfg.batch * m->cfg.height * m->cfg.width, st));
@@ -1052,7 +1108,10 @@ int evk_model_set_state(evk_model* m, int index, const float* in_nchw, void* str
     nchw_to_nhwc_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 1184), 256, 0, (cudaStream_t)stream>>>(in_nchw, cur, m->cfg.batch, s.C, s.H * s.W);
     EVK_CHECK_CUDA(cudaGetLastError());
     auto it = m->split_of.find(cur);
-    if (it != m->split_of.end()) return launch_split(cur, it->second, total, (cudaStream_t)stream);
+    if (it != m->split_of.end()) {
+        if (m->win_wp > 0) return launch_split_padded(cur, it->second, (int64_t)m->cfg.batch * s.H, s.W, s.C, m->win_wp, 1, (cudaStream_t)stream);
+        return launch_split(cur, it->second, total, (cudaStream_t)stream);
+    }
     return EVK_OK;
 }
 
