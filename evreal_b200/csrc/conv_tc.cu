@@ -47,6 +47,7 @@ struct TcArgs {
     int s_pitch, s_grp, s_off;  // split OUTPUT tensors with padded rows (window-mode consumers, ConvParams::s_wp): elements per padded
                                 // row, per GEMM row and of the left padding; 0 = dense [N,H,W,C]
     int fastps;                 // phase-stacked last decoder (cout 32, ReLU, fused prediction layer, no tensor output): straight-line epilogue
+    int fastgru;                // ConvGRU epilogues, channel counts multiples of 16: straight-line variants (window-mode FireNet)
     int fastlin;                // EPI_LINEAR, wide, 32-column chunks, no row-pair / phase / prediction: straight-line epilogue
     float act_floor;            // fastlin: lower clamp of the activation (0 for ReLU, -inf for none)
     int wide;                   // EPI_LINEAR: 256-bit stores (real and packed channel counts are multiples of 16)
@@ -544,6 +545,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         st_global_v8(a.ys + a.ys_plane + sd + o, lw);
                         st_global_v8(a.ys + a.ys_plane + sd + o + 16, lw + 8);
                     }
+                } else if (a.epi == EPI_LINEAR && a.fastlin && cw == 16) {
+                    // 16-column variant of the straight-line linear epilogue (32-column tiles split between the two warp halves)
+                    const size_t o = pix * a.creal + nb;
+                    float4 b4[4], r4[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) b4[g] = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
+                    if (a.res != nullptr) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) r4[g] = __ldg(reinterpret_cast<const float4*>(a.res + o + g * 4));
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) r4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    const float fl = a.act_floor;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        v[g * 4 + 0] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 0]) + b4[g].x + r4[g].x, fl));
+                        v[g * 4 + 1] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 1]) + b4[g].y + r4[g].y, fl));
+                        v[g * 4 + 2] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 2]) + b4[g].z + r4[g].z, fl));
+                        v[g * 4 + 3] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 3]) + b4[g].w + r4[g].w, fl));
+                    }
+                    if (a.y != nullptr) { st_global_v8(a.y + o, &v[0]); st_global_v8(a.y + o + 8, &v[8]); }
+                    if (a.ys != nullptr) {
+                        uint32_t hi8[8], lo8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(__uint_as_float(v[2 * i]), h0, l0);
+                            split_bf16(__uint_as_float(v[2 * i + 1]), h1, l1);
+                            hi8[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo8[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        st_global_v8(a.ys + sd + o, hi8);
+                        st_global_v8(a.ys + a.ys_plane + sd + o, lo8);
+                    }
                 } else if (a.epi == EPI_LINEAR && a.fastps) {
                     // Straight-line form of the last decoder's epilogue (four stacked phases of 32 channels, one phase per chunk;
                     // ReLU, then the fused 1x1 prediction layer; nothing but the image is stored): all loads up front, same
@@ -717,6 +753,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     if (a.pred_out != nullptr) {
                         pacc += a.pred_bias;
                         a.pred_out[pixl] = a.pred_sigmoid ? sigmoidf_(pacc) : pacc;
+                    }
+                } else if (a.epi == EPI_GRU_UR && a.fastgru && cw == 32) {
+                    // straight-line form (window-mode FireNet): 16 channels x {update, reset} per chunk, loads up front, SFU gates
+                    const size_t o = pix * (size_t)(a.cout >> 1) + (nb >> 1);
+                    float4 b4[8], hp[4];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) b4[g] = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) hp[g] = *reinterpret_cast<const float4*>(a.h_prev + o + g * 4);
+                    uint32_t uw[16], hw_[16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float hh[4] = {hp[g].x, hp[g].y, hp[g].z, hp[g].w};
+                        const float bb[8] = {b4[2 * g].x, b4[2 * g].y, b4[2 * g].z, b4[2 * g].w, b4[2 * g + 1].x, b4[2 * g + 1].y, b4[2 * g + 1].z, b4[2 * g + 1].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float u = fast_sigmoid(__uint_as_float(v[g * 8 + 2 * i]) + bb[2 * i]);
+                            const float r = fast_sigmoid(__uint_as_float(v[g * 8 + 2 * i + 1]) + bb[2 * i + 1]);
+                            uw[g * 4 + i] = __float_as_uint(u);
+                            hw_[g * 4 + i] = __float_as_uint(hh[i] * r);
+                        }
+                    }
+                    st_global_v8(a.u_out + o, uw); st_global_v8(a.u_out + o + 8, uw + 8);
+                    st_global_v8(a.hr_out + o, hw_); st_global_v8(a.hr_out + o + 8, hw_ + 8);
+                    if (a.hrs_out != nullptr) {
+                        uint32_t hi8[8], lo8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(__uint_as_float(hw_[2 * i]), h0, l0);
+                            split_bf16(__uint_as_float(hw_[2 * i + 1]), h1, l1);
+                            hi8[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo8[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        st_global_v8(a.hrs_out + sd + o, hi8);
+                        st_global_v8(a.hrs_out + a.hs_plane + sd + o, lo8);
+                    }
+                } else if (a.epi == EPI_GRU_OUT && a.fastgru && cw == 16) {
+                    // straight-line form: 16 channels per chunk; h' = h (1 - u) + tanh(.) u in the reference's operation order
+                    const size_t o = pix * (size_t)a.cout + nb;
+                    float4 b4[4], u4[4], h4[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        b4[g] = __ldg(reinterpret_cast<const float4*>(a.bias + nb + g * 4));
+                        u4[g] = *reinterpret_cast<const float4*>(a.u_in + o + g * 4);
+                        h4[g] = *reinterpret_cast<const float4*>(a.h_prev + o + g * 4);
+                    }
+                    uint32_t nw[16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float bb[4] = {b4[g].x, b4[g].y, b4[g].z, b4[g].w}, uu[4] = {u4[g].x, u4[g].y, u4[g].z, u4[g].w};
+                        const float hh[4] = {h4[g].x, h4[g].y, h4[g].z, h4[g].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float cand = fast_tanh(__uint_as_float(v[g * 4 + i]) + bb[i]);
+                            nw[g * 4 + i] = __float_as_uint(__fadd_rn(__fmul_rn(hh[i], __fsub_rn(1.0f, uu[i])), __fmul_rn(cand, uu[i])));
+                        }
+                    }
+                    st_global_v8(a.h_new + o, nw); st_global_v8(a.h_new + o + 8, nw + 8);
+                    if (a.hs_new != nullptr) {
+                        uint32_t hi8[8], lo8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(__uint_as_float(nw[2 * i]), h0, l0);
+                            split_bf16(__uint_as_float(nw[2 * i + 1]), h1, l1);
+                            hi8[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo8[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        st_global_v8(a.hs_new + sd + o, hi8);
+                        st_global_v8(a.hs_new + a.hs_plane + sd + o, lo8);
                     }
                 } else if (a.epi == EPI_GRU_UR) {   // packed column = channel*2 + {update, reset} (model/submodules.py:281-282)
                     const int C = a.cout >> 1;
@@ -1005,6 +1112,8 @@ int tc_plan_create(ConvParams& p) {
     a.fastlin = (a.wide && !rp && !ps && p.pred_out == nullptr && p.cout % 32 == 0 && bn % 32 == 0 && (p.act == ACT_RELU || p.act == ACT_NONE) &&
                  env_int("EVK_TC_FASTLIN", 1)) ? 1 : 0;
     a.act_floor = p.act == ACT_RELU ? 0.0f : -INFINITY;
+    a.fastgru = (((p.epi == EPI_GRU_UR && p.cout % 32 == 0 && bn % 32 == 0) || (p.epi == EPI_GRU_OUT && p.cout % 16 == 0 && bn % 16 == 0)) &&
+                 p.win_c > 0 && env_int("EVK_TC_FASTGRU", 1)) ? 1 : 0;
     a.fastps = (p.phase4 == 1 && p.cout == 32 && bn == 128 && p.pred_out != nullptr && p.y == nullptr && p.ys == nullptr && p.act == ACT_RELU &&
                 env_int("EVK_TC_FASTPS", 1)) ? 1 : 0;
     a.ux = ux;
