@@ -65,6 +65,11 @@ struct ConvParams {
     // pixels make one 128-byte K row (a 32-byte K row -- BK = 16, 32-byte swizzle -- costs ~3x per MMA), and kw_group
     // output pixels share a window (kw_group + kw_packed - 1 <= 64 / win_c).  c1 (and c2) = 64; weights from pack_weights_window.
     int win_c = 0, win_wp = 0;
+    // horizontal stride / padding when they differ from the vertical ones (stride, pad).  Used by the "pixel pair" form of
+    // a stride-2 layer with 32 input channels (first encoder): [N,H,W,32] is the same memory as [N,H,W/2,64], and output x
+    // of a 5-tap stride-2 row reads exactly the pixel pairs x-1, x, x+1 -- a kh x 3 convolution with 64 channels, horizontal
+    // stride 1 and padding 1 (weights from pack_weights_pixel_pair), whose K rows are 128 bytes instead of 64.
+    int stride_x = 0, pad_x = -1;
     // split OUTPUTS (ys / hs_new / hrs_out) written row-padded for window-mode consumers: padded width, channels per pixel, left pad
     int s_wp = 0, s_c = 0, s_left = 0;
     // "row pair" form of a stride-1 layer with cout == 32 (the last decoder): the GEMM computes output rows 2y and 2y+1
@@ -102,6 +107,8 @@ int launch_split(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s
 // host: fp32 [K][cout] (K-major rows of the SIMT layout) -> bf16 [2][cout_pad][K]
 void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out);
 
+// host: fp32 [kh*kw*cin][cout] (kw = 5, stride 2) -> pixel-pair weights [kh*3*(2*cin)][cout] (see ConvParams::stride_x)
+void pack_weights_pixel_pair(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out);
 // host: fp32 [kh*kw*cin][cout] -> row-pair weights [ (kh+1)*kw*cin ][2*cout] (see ConvParams::row_pair)
 void pack_weights_row_pair(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out);
 

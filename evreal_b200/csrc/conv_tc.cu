@@ -1053,7 +1053,8 @@ int tc_plan_create(ConvParams& p) {
     EVK_REQUIRE(!rp || (p.epi == EPI_LINEAR && p.stride == 1 && p.cout == 32 && cout_pad == 64 && p.Hout % 2 == 0 && p.res == nullptr &&
                         !p.kw_packed), EVK_ERR_ARG, "conv_tc: row-pair mode needs a stride-1 linear layer with cout 32 and an even height");
     const int e_kh = rp ? p.kh + 1 : p.kh, e_hout = rp ? p.Hout / 2 : p.Hout, e_cout = rp ? 2 * p.cout : ps ? 4 * p.cout : p.cout;
-    const int s_y = rp ? 2 : p.stride, s_x = p.stride;
+    const int s_y = rp ? 2 : p.stride, s_x = p.stride_x ? p.stride_x : p.stride;
+    const int pad_x = p.pad_x >= 0 ? p.pad_x : p.pad;
     EVK_REQUIRE(cout_pad >= e_cout && cout_pad % 16 == 0, EVK_ERR_ARG, "conv_tc: cout_pad=%d must be a multiple of 16 >= cout", cout_pad);
     static bool attr_set = false;
     if (!attr_set) {
@@ -1099,7 +1100,7 @@ int tc_plan_create(ConvParams& p) {
     TcPlan* pl = new TcPlan();
     pl->bk = bk;
     TcArgs& a = pl->a;
-    a.N = p.N; a.Hout = e_hout; a.Wout = p.Wout; a.pad_u = p.kw_packed ? 0 : p.pad; a.pad_v = p.pad; a.kh = e_kh; a.kw = p.kw;
+    a.N = p.N; a.Hout = e_hout; a.Wout = p.Wout; a.pad_u = p.kw_packed ? 0 : (ux ? pad_x : p.pad); a.pad_v = ux ? p.pad : pad_x; a.kh = e_kh; a.kw = p.kw;
     a.su = ux ? s_x : s_y; a.sv = ux ? s_y : s_x;
     a.rp = rp ? 1 : 0; a.creal = p.cout; a.hreal = ps ? 2 * p.Hout : p.Hout;
     a.ps = p.phase4; a.wreal = ps ? 2 * p.Wout : p.Wout;
@@ -1351,6 +1352,16 @@ void pack_weights_row_pair(const float* w_kc, int kh, int kw, int cin, int cout,
                     if (r < kh) out[dst + n] = w_kc[((size_t)(r * kw + q) * cin + c) * cout + n];                  // row 2y: tap r
                     if (r >= 1) out[dst + cout + n] = w_kc[((size_t)((r - 1) * kw + q) * cin + c) * cout + n];     // row 2y+1: tap r-1
                 }
+}
+
+void pack_weights_pixel_pair(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out) {
+    const int kw2 = (kw + 1) / 2;            // pixel pairs per kernel row (5 taps -> 3 pairs, the last slot of the last pair unused)
+    out.assign((size_t)kh * kw2 * 2 * cin * cout, 0.f);
+    for (int r = 0; r < kh; ++r)
+        for (int q = 0; q < kw; ++q)         // tap q = pair q/2, slot q%2
+            for (int c = 0; c < cin; ++c)
+                for (int n = 0; n < cout; ++n)
+                    out[((size_t)(r * kw2 + q / 2) * (2 * cin) + (q % 2) * cin + c) * cout + n] = w_kc[((size_t)(r * kw + q) * cin + c) * cout + n];
 }
 
 void pack_weights_window(const float* w_kc, int kh, int kw, int cin, int c_tensor, int cout, int group, std::vector<float>& out) {

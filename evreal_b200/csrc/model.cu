@@ -242,6 +242,19 @@ struct Builder {
         if (window_ok(p, pk)) {
             int r = apply_window(p, pk);
             if (r != EVK_OK) return r;
+        } else if (m->cfg.precision == 0 && stride == 2 && pad == 2 && pk.kh == 5 && pk.kw == 5 && cin == 32 && Win % 2 == 0 && res == nullptr &&
+                   tc_eligible(p) && getenv("EVK_NO_PIXEL_PAIR") == nullptr) {
+            // first encoder: pixel pairs as 64-channel K rows (conv.cuh, ConvParams::stride_x)
+            std::vector<float> w2;
+            pack_weights_pixel_pair(pk.w.data(), pk.kh, pk.kw, pk.cin, pk.cout, w2);
+            p.c1 = 2 * cin; p.Win = Win / 2; p.kw = 3; p.stride_x = 1; p.pad_x = 1; p.w = nullptr;        // (tensor-core only)
+            std::vector<__nv_bfloat16> wt;
+            p.cout_pad = (pk.cout + 15) / 16 * 16;
+            pack_weights_tc(w2.data(), pk.kh * 3 * 2 * cin, pk.cout, p.cout_pad, wt);
+            void* d = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
+            EVK_REQUIRE(d != nullptr, EVK_ERR_CUDA, "out of device memory for the pixel-pair weights");
+            cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+            p.w_tc = (const __nv_bfloat16*)d;
         } else {
             attach_tc_weights(p, pk);
         }
@@ -855,7 +868,10 @@ static std::string op_desc(const Op& op) {
         case OP_CONV: {
             const ConvParams& p = op.cp;
             const char* e = p.epi == EPI_LSTM ? "lstm" : p.epi == EPI_GRU_UR ? "gru_ur" : p.epi == EPI_GRU_OUT ? "gru_out" : (p.res ? "linear+res" : "linear");
-            if (p.win_c > 0)
+            if (p.stride_x)
+                snprintf(b, sizeof b, "conv%dx5 s%d %d+0->%d %s @%dx%d as %dx3 over pixel pairs (%d-channel K rows) [tcgen05 bf16x3]", p.kh, p.stride, p.c1 / 2, p.cout, e,
+                         p.Hout, p.Wout, p.kh, p.c1);
+            else if (p.win_c > 0)
                 snprintf(b, sizeof b, "conv%dx%d s1 %d+%d->%d %s @%dx%d, window K rows (4 px x 16 ch), %d pixels per GEMM row (N=%d) [tcgen05 bf16x3]", p.kh, p.kw_packed,
                          p.win_c, p.c2 ? p.win_c : 0, p.cout / p.kw_group, e, p.Hout, p.Wout * p.kw_group, p.kw_group, p.cout);
             else if (p.kw_packed)
