@@ -4,6 +4,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -E "^FAILED|^ERROR|passed|failed" | tee gpurun_out/r01_gpu_tests.log
 timeout 900 python bench.py > gpurun_out/r01_bench.json 2> gpurun_out/r01_bench.err; tail -2 gpurun_out/r01_bench.err
 timeout 600 python bench.py --impl reference --steps 100 --warmup 3 > gpurun_out/r01_bench_reference.json 2> gpurun_out/r01_bench_reference.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/r01_smoke.log
 timeout 600 python tools/bench_models.py --batch 36 > gpurun_out/r01_models.jsonl 2> gpurun_out/r01_models.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 # E2VID forward = 20 conv_tc launches: the fifth forward is launches 80..99
