@@ -245,6 +245,11 @@ def reduce_metric_sums(local, metric_names, group=None):
     return out
 
 
+# wall-clock seconds of the last evaluate() call on this rank, by phase (model construction, sequence open + upload,
+# per-frame loop); diagnostic only
+last_timings = {}
+
+
 def evaluate(method_names, eval_config_names=None, dataset_names=None, metrics=None, config_root="config",
              output_root="outputs", write_files=True, rank=0, world_size=1):
     """eval.py:413-444.  Returns {eval_config: {method: {dataset: MetricTracker}}} (identical on every rank)."""
@@ -252,13 +257,19 @@ def evaluate(method_names, eval_config_names=None, dataset_names=None, metrics=N
         eval_config_names = ['std']
     if metrics is None:
         metrics = ['mse', 'ssim']
+    import time
     results = OrderedDict()
+    tm = {'model_s': 0.0, 'open_s': 0.0, 'loop_s': 0.0, 'reduce_s': 0.0}
+    last_timings.clear()
+    last_timings.update(tm)
     for eval_config in get_eval_configs(eval_config_names, config_root):
         per_method = OrderedDict()
         dataset_configs = get_dataset_configs(dataset_names, config_root)
         for method_name in method_names:
             method_config = get_method_config(method_name, config_root)
+            t0 = time.perf_counter()
             model = get_model_from_checkpoint_path(method_config['model_name'], method_config['model_path'])
+            last_timings['model_s'] += time.perf_counter() - t0
             per_dataset = OrderedDict()
             for dataset_config in dataset_configs:
                 sequences = get_sequences(dataset_config, eval_config.get('dataset_kwargs', {}))
@@ -267,14 +278,20 @@ def evaluate(method_names, eval_config_names=None, dataset_names=None, metrics=N
                 local = MetricTracker()
                 for i in mine:
                     seq = sequences[i]
+                    t0 = time.perf_counter()
                     open_sequence(seq)
+                    t1 = time.perf_counter()
                     n_eval, mean_scores, _, _ = eval_method_on_sequence(
                         dataset_config['name'], eval_config, method_name, model, method_config, seq, metrics,
                         output_root, write_files)
+                    last_timings['open_s'] += t1 - t0
+                    last_timings['loop_s'] += time.perf_counter() - t1
                     for metric_name, score in mean_scores.items():
                         local.update(metric_name, score, n_eval)
                     seq.pop('dataset', None)
+                t0 = time.perf_counter()
                 per_dataset[dataset_config['name']] = reduce_metric_sums(local, metrics)
+                last_timings['reduce_s'] += time.perf_counter() - t0
             per_method[method_name] = per_dataset
         results[eval_config['name']] = per_method
     return results
