@@ -239,6 +239,31 @@ def test_reset_states_and_state_roundtrip():
     assert m.prev_recs is not None and tuple(m.prev_recs.shape) == (2, 1, 32, 48)
 
 
+def test_firenet_state_roundtrip_in_window_mode():
+    """FireNet's ConvGRU states through the `states` property while the 16-channel layers run in window mode (row-padded
+    split companions: evk_model_set_state re-splits into the padded layout): snapshot after 2 frames, run frame 3,
+    restore, run frame 3 again -> bit-identical; reset_states() in between -> identical sequences."""
+    from evreal_b200 import FireNet_legacy
+    g = golden('networks')
+    full, _ = weights_of(g, 'firenet_ckpt', 'net.')
+    m = _load(FireNet_legacy({'num_bins': 5, 'base_num_channels': 16, 'kernel_size': 3, 'recurrent_block_type': 'convgru',
+                              'num_residual_blocks': 2, 'recurrent_blocks': {'resblock': [0]}}), full)
+    vox = g['firenet_ckpt.voxels']
+    a = _frames(m, vox)
+    assert np.array_equal(a, _frames(m, vox))
+    assert any('window K rows' in d for d in m.op_descriptions())
+    m.reset_states()
+    for v in vox[:2]:
+        m(torch.from_numpy(np.ascontiguousarray(v)).cuda())
+    snap = [s.clone() for s in m.states]
+    assert len(snap) == 2 and tuple(snap[0].shape) == (1, 16, 48, 64)
+    y1 = m(torch.from_numpy(np.ascontiguousarray(vox[2])).cuda())['image'].clone()
+    m.states = snap
+    y2 = m(torch.from_numpy(np.ascontiguousarray(vox[2])).cuda())['image']
+    assert torch.equal(y1, y2)
+    assert np.array_equal(y1.cpu().numpy(), a[2])
+
+
 def test_batching_is_parity_safe():
     """two streams as one batch == the same streams run separately."""
     from evreal_b200 import E2VIDRecurrent
