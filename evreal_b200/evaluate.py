@@ -14,6 +14,7 @@ MSE/SSIM are kernels of libevreal_b200.so; scores come back to the host once per
 sequence.
 """
 import glob
+import math
 import os
 from collections import OrderedDict
 
@@ -180,6 +181,58 @@ def eval_method_on_sequence(dataset_name, eval_config, method_name, model, metho
     return tracker.get_num_quan_evaluations(), tracker.get_mean_scores(), frames, events
 
 
+def lockstep_supported(eval_config, metrics, datasets):
+    """The lock-step form covers what SequenceBatch computes on the device: 'between_frames' windows (voxel timestamp ==
+    frame timestamp), reference frames present, one sensor resolution, MSE / SSIM, no files, no colour."""
+    if eval_config.get('color', False) or not set(metrics) <= {'mse', 'ssim'} or not datasets:
+        return False
+    res0 = tuple(int(v) for v in datasets[0].sensor_resolution[:2])
+    return all(ds.has_images and ds.voxel_method['method'] == 'between_frames' and
+               tuple(int(v) for v in ds.sensor_resolution[:2]) == res0 for ds in datasets)
+
+
+def eval_method_on_sequences_lockstep(eval_config, model, method_config, sequences, metrics):
+    """eval_method_on_sequence for several sequences at once: frame k of every sequence in ONE batched voxelizer / network /
+    metric launch (pipeline.SequenceBatch).  Per-sequence semantics are the reference's (eval.py:203-246): reconstruction
+    starts at the first item within 10 s of start_time_s and stops after end_time_s, scores count inside
+    [start_time_s, end_time_s], the mean is sum(scores) / n over finite scores.  Returns [(num_evaluated, mean_scores)]."""
+    from .pipeline import SequenceBatch
+    datasets = [s.get('dataset') or open_sequence(s) for s in sequences]
+    infer_all = eval_config.get('eval_infer_all', False)
+    offsets, counts, gates = [], [], []
+    for seq, ds in zip(sequences, datasets):
+        ts = [float(ds.frame_ts[ds.window(i)[2]]) for i in range(len(ds))]        # between_frames: voxel timestamp = frame timestamp
+        first, last = 0, len(ts) - 1
+        if not infer_all:
+            first = next((i for i, t in enumerate(ts) if not t < seq['start_time_s'] - 10), len(ts))
+            last = next((i - 1 for i, t in enumerate(ts) if i >= first and t > seq['end_time_s']), len(ts) - 1)
+        offsets.append(first)
+        counts.append(max(last - first + 1, 0))
+        gates.append([seq['start_time_s'] <= t <= seq['end_time_s'] for t in ts[first:last + 1]])
+    steps = max(counts) if counts else 0
+    out = []
+    if steps > 0:
+        batch = SequenceBatch(model, datasets, method_config.get('event_tensor_normalization', False),
+                              method_config.get('post_process_norm', 'none'), resident=True, offsets=offsets, counts=counts)
+        batch.reset()
+        all_scores = torch.empty((steps, len(datasets), 2), dtype=torch.float64, device=batch.dev)
+        for k in range(steps):
+            scores, _, _ = batch.step(k)
+            all_scores[k].copy_(scores)
+        batch.check_bounds()
+        sc = all_scores.cpu().numpy()
+    col = {'mse': 0, 'ssim': 1}
+    for b in range(len(datasets)):
+        n_eval = sum(gates[b])
+        means = {}
+        for name in metrics:
+            vals = [float(sc[k, b, col[name]]) for k in range(counts[b]) if gates[b][k]]
+            vals = [v for v in vals if math.isfinite(v)]
+            means[name] = sum(vals) / len(vals) if vals else -1
+        out.append((n_eval, means))
+    return out
+
+
 class MetricTracker:
     """Count-weighted running means per metric (eval.py:249-276)."""
 
@@ -251,8 +304,10 @@ last_timings = {}
 
 
 def evaluate(method_names, eval_config_names=None, dataset_names=None, metrics=None, config_root="config",
-             output_root="outputs", write_files=True, rank=0, world_size=1):
-    """eval.py:413-444.  Returns {eval_config: {method: {dataset: MetricTracker}}} (identical on every rank)."""
+             output_root="outputs", write_files=True, rank=0, world_size=1, lockstep=0):
+    """eval.py:413-444.  Returns {eval_config: {method: {dataset: MetricTracker}}} (identical on every rank).
+    ``lockstep`` = B > 1: this rank's sequences run B at a time in lock-step (eval_method_on_sequences_lockstep) where that
+    form applies (lockstep_supported, write_files False); everything else runs one sequence at a time like the reference."""
     if eval_config_names is None:
         eval_config_names = ['std']
     if metrics is None:
@@ -276,6 +331,22 @@ def evaluate(method_names, eval_config_names=None, dataset_names=None, metrics=N
                 weights = [os.path.getsize(os.path.join(s['sequence_path'], 'events_ts.npy')) for s in sequences]
                 mine = shard_sequences(sequences, weights, world_size)[rank]
                 local = MetricTracker()
+                if lockstep > 1 and not write_files and mine:
+                    t0 = time.perf_counter()
+                    for i in mine:
+                        open_sequence(sequences[i])
+                    last_timings['open_s'] += time.perf_counter() - t0
+                    if lockstep_supported(eval_config, metrics, [sequences[i]['dataset'] for i in mine]):
+                        t0 = time.perf_counter()
+                        for c0 in range(0, len(mine), lockstep):
+                            chunk = [sequences[i] for i in mine[c0:c0 + lockstep]]
+                            for n_eval, mean_scores in eval_method_on_sequences_lockstep(eval_config, model, method_config, chunk, metrics):
+                                for metric_name, score in mean_scores.items():
+                                    local.update(metric_name, score, n_eval)
+                        last_timings['loop_s'] += time.perf_counter() - t0
+                        for i in mine:
+                            sequences[i].pop('dataset', None)
+                        mine = []
                 for i in mine:
                     seq = sequences[i]
                     t0 = time.perf_counter()

@@ -29,7 +29,10 @@ class SequenceBatch:
     RING = 4          # result slots (device + pinned host) in flight
 
     def __init__(self, model, datasets, event_tensor_normalization=False, post_process_norm='none', resident=True,
-                 device=None, compute_metrics=True):
+                 device=None, compute_metrics=True, offsets=None, counts=None):
+        """``offsets`` / ``counts`` (per sequence): step k processes item offsets[b] + k of sequence b for k < counts[b] and an
+        empty window afterwards (states are per sample, so a finished sequence does not disturb the others); the batch then
+        has max(counts) steps.  Default: item k of every sequence, min(len) steps."""
         _lib.require_cuda()
         self.lib = _lib.load()
         self.model = model
@@ -70,12 +73,14 @@ class SequenceBatch:
         self.d2h_bytes = 0
         self._nstep = 0
         # window tables (start, end, frame index) of every item, once: dataset.py:104-130 via MemMapDataset.window
+        self._offsets = [0] * B if offsets is None else [int(o) for o in offsets]
+        self._counts = None if counts is None else [int(c) for c in counts]
         n_items = len(self)
         self._win = np.zeros((B, n_items, 3), dtype=np.int64)
         max_win = 1
         for b, ds in enumerate(self.datasets):
-            for i in range(n_items):
-                i0, i1, fi = ds.window(i)
+            for i in range(n_items if self._counts is None else min(n_items, self._counts[b])):
+                i0, i1, fi = ds.window(self._offsets[b] + i)
                 self._win[b, i] = (int(i0), max(int(i1), int(i0)), int(fi) if fi is not None else 0)
             max_win = max(max_win, int((self._win[b, :, 1] - self._win[b, :, 0]).max()))
         self.max_win = max_win
@@ -114,7 +119,9 @@ class SequenceBatch:
         torch.cuda.synchronize(dev)
 
     def __len__(self):
-        return min(len(ds) for ds in self.datasets)
+        if self._counts is not None:
+            return max(self._counts) if self._counts else 0
+        return min(len(ds) - o for ds, o in zip(self.datasets, self._offsets))
 
     def reset(self):
         self.model.reset_states()

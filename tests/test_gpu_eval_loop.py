@@ -130,3 +130,27 @@ def test_plugin_surface_and_sharded_means(tmp_path):
         count = sum(p.data_dict[k]['count'] for p in parts if k in p.data_dict)
         assert count == tr.get_count(k)
         assert abs(total / count - tr.get_average(k)) <= 1e-6 * abs(tr.get_average(k))     # voxelizer atomics: order-dependent ulps
+
+
+def test_lockstep_evaluate_matches_sequential(tmp_path):
+    """evaluate(lockstep=B): this rank's sequences run B at a time through SequenceBatch (per-sequence item ranges and
+    score gates of eval.py:203-246, shorter sequences padded with empty windows) -- counts identical, dataset means equal
+    to the one-sequence-at-a-time loop (voxelizer atomics: order-dependent ulps)."""
+    from evreal_b200 import evaluate as ev
+    g = golden('eval_loop')
+    _write_plugin_tree(tmp_path, g, 5)
+    cfg_root = str(tmp_path / 'config')
+    seq = ev.evaluate(['FireNet'], ['std'], ['SYN'], ['mse', 'ssim'], config_root=cfg_root, write_files=False)['std']['FireNet']['SYN']
+    for B in (2, 4, 8):
+        ls = ev.evaluate(['FireNet'], ['std'], ['SYN'], ['mse', 'ssim'], config_root=cfg_root, write_files=False, lockstep=B)['std']['FireNet']['SYN']
+        for k in ('mse', 'ssim'):
+            assert ls.get_count(k) == seq.get_count(k) and seq.get_count(k) > 0
+            assert abs(ls.get_average(k) - seq.get_average(k)) <= 1e-6 * abs(seq.get_average(k)), (B, k)
+    # sharded + lock-step: two 'ranks' back to back
+    parts = [ev.evaluate(['FireNet'], ['std'], ['SYN'], ['mse', 'ssim'], config_root=cfg_root, write_files=False, rank=r, world_size=2,
+                         lockstep=2)['std']['FireNet']['SYN'] for r in range(2)]
+    for k in ('mse', 'ssim'):
+        total = sum(p.data_dict[k]['total'] for p in parts if k in p.data_dict)
+        count = sum(p.data_dict[k]['count'] for p in parts if k in p.data_dict)
+        assert count == seq.get_count(k)
+        assert abs(total / count - seq.get_average(k)) <= 1e-6 * abs(seq.get_average(k))

@@ -43,6 +43,7 @@ def main():
     ap.add_argument('--root', default='/tmp/evk_cfg3')
     ap.add_argument('--sequences', type=int, default=16)
     ap.add_argument('--duration', type=float, default=5.0)
+    ap.add_argument('--lockstep', type=int, default=0, help='sequences per lock-step batch on every rank (0: one at a time, like the reference)')
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -59,12 +60,12 @@ def main():
         dist.barrier()
     from evreal_b200 import evaluate as ev
     cfg_root = os.path.join(args.root, 'config')
-    ev.evaluate(['FireNet'], ['std'], ['HQF16'], ['mse', 'ssim'], config_root=cfg_root, write_files=False, rank=rank, world_size=world)  # warm-up (page cache, plans)
+    ev.evaluate(['FireNet'], ['std'], ['HQF16'], ['mse', 'ssim'], config_root=cfg_root, write_files=False, rank=rank, world_size=world, lockstep=args.lockstep)  # warm-up (page cache, plans)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    res = ev.evaluate(['FireNet'], ['std'], ['HQF16'], ['mse', 'ssim'], config_root=cfg_root, write_files=False, rank=rank, world_size=world)
+    res = ev.evaluate(['FireNet'], ['std'], ['HQF16'], ['mse', 'ssim'], config_root=cfg_root, write_files=False, rank=rank, world_size=world, lockstep=args.lockstep)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -82,7 +83,7 @@ def main():
         os.dup2(saved, 1)
         n = tr.get_count('mse')
         print(json.dumps({'config': 'cfg3: FireNet, %d HQF-shape sequences (240x180, %.0f s, U(0.5,2) Mev/s, 25 Hz), between_frames, MSE+SSIM' % (args.sequences, args.duration),
-                          'n_gpus': world, 'frames_evaluated': n, 'seconds': dt, 'frames_per_s': n / dt,
+                          'n_gpus': world, 'lockstep': args.lockstep, 'frames_evaluated': n, 'seconds': dt, 'frames_per_s': n / dt,
                           'phase_seconds_max_over_ranks': phases, 'loop_frames_per_s': n / max(phases['loop_s'], 1e-9),
                           'mse_mean': repr(tr.get_average('mse')), 'ssim_mean': repr(tr.get_average('ssim')),
                           'api': 'evreal_b200.evaluate.evaluate (config/*.json + checkpoint, batch 1 per sequence, one all-reduce of [sum(score*n), sum(n)])'}))
