@@ -191,6 +191,19 @@ def lockstep_supported(eval_config, metrics, datasets):
                tuple(int(v) for v in ds.sensor_resolution[:2]) == res0 for ds in datasets)
 
 
+def lockstep_item_range(ts, start_time_s, end_time_s, infer_all=False):
+    """(first item, number of items, score gate per item) of one sequence from its item timestamps: reconstruction starts
+    at the first item within 10 s of start_time_s and stops before the first item after end_time_s (eval.py:210-216); an
+    item's scores count when start_time_s <= t <= end_time_s (utils/eval_metrics.py:256-262; with 'between_frames'
+    windows the voxel and frame timestamps coincide, so the ts_tol_ms test always passes)."""
+    first, last = 0, len(ts) - 1
+    if not infer_all:
+        first = next((i for i, t in enumerate(ts) if not t < start_time_s - 10), len(ts))
+        last = next((i - 1 for i, t in enumerate(ts) if i >= first and t > end_time_s), len(ts) - 1)
+    count = max(last - first + 1, 0)
+    return first, count, [start_time_s <= t <= end_time_s for t in ts[first:first + count]]
+
+
 def eval_method_on_sequences_lockstep(eval_config, model, method_config, sequences, metrics):
     """eval_method_on_sequence for several sequences at once: frame k of every sequence in ONE batched voxelizer / network /
     metric launch (pipeline.SequenceBatch).  Per-sequence semantics are the reference's (eval.py:203-246): reconstruction
@@ -202,13 +215,10 @@ def eval_method_on_sequences_lockstep(eval_config, model, method_config, sequenc
     offsets, counts, gates = [], [], []
     for seq, ds in zip(sequences, datasets):
         ts = [float(ds.frame_ts[ds.window(i)[2]]) for i in range(len(ds))]        # between_frames: voxel timestamp = frame timestamp
-        first, last = 0, len(ts) - 1
-        if not infer_all:
-            first = next((i for i, t in enumerate(ts) if not t < seq['start_time_s'] - 10), len(ts))
-            last = next((i - 1 for i, t in enumerate(ts) if i >= first and t > seq['end_time_s']), len(ts) - 1)
+        first, count, gate = lockstep_item_range(ts, seq['start_time_s'], seq['end_time_s'], infer_all)
         offsets.append(first)
-        counts.append(max(last - first + 1, 0))
-        gates.append([seq['start_time_s'] <= t <= seq['end_time_s'] for t in ts[first:last + 1]])
+        counts.append(count)
+        gates.append(gate)
     steps = max(counts) if counts else 0
     out = []
     if steps > 0:

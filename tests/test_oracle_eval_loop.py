@@ -34,3 +34,25 @@ def test_e2vid_topology_sequence_with_robust_norm():
 
 def test_weighted_means():
     assert eval_loop.weighted_means([(2, {'mse': 1.0}), (0, {'mse': -1}), (6, {'mse': 3.0})]) == {'mse': 2.5}
+
+
+def test_lockstep_item_ranges_match_the_reference_loop():
+    """evaluate.lockstep_item_range (the per-sequence item range and score gate of the lock-step form) against the item
+    indices the REAL eval.eval_method_on_sequence evaluated (golden), plus the 10-second lead-in and eval_infer_all."""
+    from evreal_b200.dataset import MemMapDataset
+    from evreal_b200.evaluate import lockstep_item_range
+    g = golden('eval_loop')
+    ds = MemMapDataset(_arrays(g), num_bins=5, voxel_method={'method': 'between_frames'}, resident=False)
+    ts = [float(ds.frame_ts[ds.window(i)[2]]) for i in range(len(ds))]
+    for tag in ('firenet', 'e2vid_small'):
+        _, _, _, start, end = g[tag + '.summary']
+        first, count, gate = lockstep_item_range(ts, float(start), float(end))
+        assert [first + k for k in range(count) if gate[k]] == list(g[tag + '.indices'])
+        assert first == 0 and count == next((i for i, t in enumerate(ts) if t > end), len(ts))   # every item before the cut is reconstructed
+    # lead-in: items more than 10 s before start_time_s are not reconstructed at all
+    ts2 = [0.5 * i for i in range(60)]
+    first, count, gate = lockstep_item_range(ts2, 20.0, 25.0)
+    assert first == 20 and first + count - 1 == 50 and [first + k for k in range(count) if gate[k]] == list(range(40, 51))
+    first, count, gate = lockstep_item_range(ts2, 20.0, 25.0, infer_all=True)
+    assert (first, count) == (0, 60) and sum(gate) == 11
+    assert lockstep_item_range([], 0.0, 1.0) == (0, 0, [])
