@@ -72,7 +72,8 @@ struct ConvParams {
     int stride_x = 0, pad_x = -1;
     // split OUTPUTS (ys / hs_new / hrs_out) written row-padded for window-mode consumers: padded width, channels per pixel, left pad
     int s_wp = 0, s_c = 0, s_left = 0;
-    // "row pair" form of a stride-1 layer with cout == 32 (the last decoder): the GEMM computes output rows 2y and 2y+1
+    // "row pair" form of a stride-1 layer with cout == 32 (any such layer that is not a phase-stacked decoder, e.g. the last
+    // decoder with EVK_NO_POLY=1 or a TransposedConvLayer decoder): the GEMM computes output rows 2y and 2y+1
     // together as N = 64 columns of a (kh+1) x kw convolution with vertical stride 2 (weights of row 2y+1 shifted one tap
     // down) -- an MMA with N <= 64 costs the same ~50 cycles as one with N = 32, so this halves the MMA count per
     // output pixel at 6/5 of the taps.  w_tc then holds the stacked weights [2][64][(kh+1)*kw*cin] (pack_weights_row_pair).

@@ -24,7 +24,8 @@
 //    N tile; each loads 1/cs of the weight tile and multicasts it into every CTA's shared memory.
 //
 // With the loads out of the way the kernel is bound by tcgen05.mma ISSUE (see the MMA issuer section below): two
-// issuer warps, and shapes that keep every MMA at N >= 64 where possible (row-pair mode for cout = 32).
+// issuer warps, and shapes that keep every MMA wide and every K row 128 bytes: several output pixels per GEMM row (head,
+// FireNet window mode), output phases stacked along N (upsample-conv decoders, poly.cu), row pairs for other cout = 32 layers.
 //
 // Warp roles (384 threads, 1 CTA/SM, persistent over tiles): warp 0 = A producer, warp 3 = B producer,
 // warps 1-2 = MMA issuers (K blocks dealt alternately; warp 2 also allocates TMEM), warps 4-11 = epilogue
