@@ -104,17 +104,11 @@ class MemMapDataset(torch.utils.data.Dataset):
                 'event_count': event_count}
 
     def compute_timeblock_indices(self):
-        """'t_seconds' windows, chained (dataset.py:104-117); float64 expression order kept."""
-        timeblock_indices = []
-        start_idx = 0
+        """'t_seconds' windows (dataset.py:104-117): window i ends at the first event at or after ((t - sw) * i + t0) + t --
+        the reference's float64 expression order, evaluated for all i at once -- and starts where window i-1 ended."""
         t, sw = self.voxel_method['t'], self.voxel_method['sliding_window_t']
-        for i in range(len(self)):
-            start_time = ((t - sw) * i) + self.t0
-            end_time = start_time + t
-            end_idx = self.find_ts_index(end_time)
-            timeblock_indices.append([start_idx, end_idx])
-            start_idx = end_idx
-        return timeblock_indices
+        end_times = ((t - sw) * np.arange(len(self), dtype=np.float64) + self.t0) + t
+        return self._chained(np.searchsorted(self.filehandle["t"], end_times, side='left'))
 
     def compute_k_indices(self):
         """'k_events' windows (dataset.py:119-130)."""
@@ -122,24 +116,27 @@ class MemMapDataset(torch.utils.data.Dataset):
         return [[(k - w) * i, (k - w) * i + k] for i in range(len(self))]
 
     def compute_frame_indices(self):
-        """'between_frames' table from image_event_indices (dataset.py:287-294)."""
-        frame_indices = []
-        start_idx = 0
-        for event_idx in self.filehandle["image_event_indices"]:
-            end_idx = event_idx[0]
-            frame_indices.append([start_idx, end_idx])
-            start_idx = end_idx
-        return frame_indices
+        """'between_frames' table (dataset.py:287-294): frame j closes the window that frame j-1 opened."""
+        return self._chained(np.asarray(self.filehandle["image_event_indices"])[:, 0])
+
+    @staticmethod
+    def _chained(ends):
+        """[[0, e0], [e0, e1], ...] for window end indices e0, e1, ..."""
+        ends = [int(e) for e in ends]
+        return [[a, b] for a, b in zip([0] + ends[:-1], ends)]
 
     def choose_frames_to_use(self):
-        self.frames_to_use = list(range(0, self.num_frames))
-        if self.keep_ratio != 1:
-            assert self.voxel_method['method'] == 'between_frames', \
-                "keep_ratio can only specified for between_frames voxel method"
-            assert self.keep_ratio < 1, "keep_ratio cannot be greater than 1"
-            num_frames_to_use = int(self.num_frames * self.keep_ratio)
-            self.frames_to_use = sorted(np.random.choice(self.frames_to_use, size=num_frames_to_use, replace=False))
-            self.length = num_frames_to_use - 1
+        """keep_ratio < 1 evaluates a random subset of the frames (dataset.py:168-176; the draw is numpy's global
+        generator, as in the reference, so a seeded run picks the same frames)."""
+        every = list(range(self.num_frames))
+        self.frames_to_use = every
+        if self.keep_ratio == 1:
+            return
+        assert self.voxel_method['method'] == 'between_frames', "keep_ratio can only specified for between_frames voxel method"
+        assert self.keep_ratio < 1, "keep_ratio cannot be greater than 1"
+        kept = int(self.num_frames * self.keep_ratio)
+        self.frames_to_use = sorted(np.random.choice(every, size=kept, replace=False))
+        self.length = kept - 1
 
     def get_min_max_t(self):
         if self.has_images:
@@ -156,21 +153,23 @@ class MemMapDataset(torch.utils.data.Dataset):
         return pos if after - ts < ts - before else pos - 1
 
     def set_voxel_method(self):
-        method = self.voxel_method['method']
-        if method == 'k_events':
-            self.length = max(int(self.num_events / (self.voxel_method['k'] - self.voxel_method['sliding_window_w'])), 0)
-            self.event_indices = self.compute_k_indices()
-        elif method == 't_seconds':
-            duration = self.tk - self.t0
-            self.length = max(int(duration / (self.voxel_method['t'] - self.voxel_method['sliding_window_t'])), 0)
-            self.event_indices = self.compute_timeblock_indices()
-        elif method == 'between_frames':
+        """Dataset length and event-index table of the configured windowing (dataset.py:178-186)."""
+        vm = self.voxel_method
+        kind = vm['method']
+        if kind == 'between_frames':
             assert self.has_images, "Cannot use between_frames voxel method without images"
             self.length = self.num_frames - 1
             self.event_indices = self.compute_frame_indices()
             self.choose_frames_to_use()
+            return
+        if kind == 'k_events':
+            span, total, table = vm['k'] - vm['sliding_window_w'], self.num_events, self.compute_k_indices
+        elif kind == 't_seconds':
+            span, total, table = vm['t'] - vm['sliding_window_t'], self.tk - self.t0, self.compute_timeblock_indices
         else:
-            raise ValueError("Invalid voxel forming method chosen ({})".format(self.voxel_method))
+            raise ValueError("Invalid voxel forming method chosen ({})".format(vm))
+        self.length = max(int(total / span), 0)
+        self.event_indices = table()
 
     def __len__(self):
         return self.length

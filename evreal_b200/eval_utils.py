@@ -65,39 +65,36 @@ def post_process_normalization(img, norm):
 
 
 def torch2cv2(image):
-    """utils/eval_utils.py:38-43 (device -> host)."""
-    image = torch.squeeze(image)
-    image = image.cpu().numpy()
-    if len(image.shape) == 3:
-        image = np.transpose(image, (1, 2, 0))
-    return image
+    """utils/eval_utils.py:38-43: tensor -> numpy on the host, channels last when there is a channel axis."""
+    arr = image.squeeze().cpu().numpy()
+    return arr.transpose(1, 2, 0) if arr.ndim == 3 else arr
 
 
 def cv2torch(image, num_ch=1):
-    """utils/eval_utils.py:46-54."""
-    img_tensor = torch.as_tensor(image)
-    if len(img_tensor.shape) == 2:
-        img_tensor = torch.unsqueeze(img_tensor, 0)
+    """utils/eval_utils.py:46-54: [H,W] -> [1,num_ch,H,W] (the plane repeated), [C,H,W] -> [1,C,H,W]."""
+    t = torch.as_tensor(image)
+    if t.dim() == 2:
+        t = t[None]
         if num_ch > 1:
-            img_tensor = img_tensor.repeat(num_ch, 1, 1)
-    if len(img_tensor.shape) == 3:
-        img_tensor = torch.unsqueeze(img_tensor, 0)
-    return img_tensor
+            t = t.expand(num_ch, -1, -1).contiguous()
+    return t[None] if t.dim() == 3 else t
+
+
+def _append(path, rows, fmt):
+    with open(path, 'a', encoding="utf-8") as f:
+        f.writelines(fmt.format(k, v) for k, v in rows)
 
 
 def append_timestamp(path, description, timestamp):
-    with open(path, 'a', encoding="utf-8") as f:
-        f.write('{} {:.15f}\n'.format(description, timestamp))
+    """'<index> <timestamp with 15 decimals>' (utils/eval_utils.py:57-59)."""
+    _append(path, [(description, timestamp)], '{} {:.15f}\n')
 
 
 def append_result(path, description, result, is_int=False):
-    format_str = '{} {}\n' if is_int else '{} {:.5f}\n'
-    with open(path, 'a', encoding="utf-8") as f:
-        if isinstance(result, list):
-            for idx, elem in zip(description, result):
-                f.write(format_str.format(idx, elem))
-        else:
-            f.write(format_str.format(description, result))
+    """'<index> <score>' lines, 5 decimals unless is_int; a list of results pairs up with a list of indices
+    (utils/eval_utils.py:62-77)."""
+    rows = list(zip(description, result)) if isinstance(result, list) else [(description, result)]
+    _append(path, rows, '{} {}\n' if is_int else '{} {:.5f}\n')
 
 
 def save_inferred_image(folder, image, idx):
