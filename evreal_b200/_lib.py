@@ -54,6 +54,7 @@ SIGNATURES = {
     "evk_model_profile": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _c.POINTER(_i)]),
     "evk_model_op_desc": (_i, [_vp, _i, _c.c_char_p, _i]),
     "evk_conv2d_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "evk_pack_layer_weights": (_i, [_i, _vp, _i, _i, _i, _i, _i, _vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "evk_percentile_normalize": (_i, [_vp, _vp, _i, _i, _d, _d, _i, _vp]),
     "evk_crop": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "evk_mse_ssim": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -1,5 +1,6 @@
 // C ABI entry points (include/evreal_b200.h) for the stateless stages, error
 // reporting, and the conv dispatcher.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <vector>
@@ -110,6 +111,43 @@ int evk_percentile_normalize(const float* img, float* out, int n_images, int num
                              int apply_exp, void* stream) {
     EVK_REQUIRE(img && out, EVK_ERR_ARG, "evk_percentile_normalize: null pointer");
     return evk::percentile_normalize(img, out, n_images, numel, q_min, q_max, apply_exp, (cudaStream_t)stream);
+}
+
+int evk_pack_layer_weights(int kind, const float* w_oihw_host, int Cout, int Cin, int kh, int kw, int group, float* out_host,
+                           int64_t out_cap, int64_t* out_len) {
+    using namespace evk;
+    EVK_REQUIRE(w_oihw_host && out_host && out_len && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, EVK_ERR_ARG, "evk_pack_layer_weights: bad argument");
+    // torch [Cout][Cin][kh][kw] -> the GEMM layout of every packer's input: [(r*kw + s)*Cin + c][Cout]
+    std::vector<float> w_kc((size_t)kh * kw * Cin * Cout), out;
+    for (int n = 0; n < Cout; ++n)
+        for (int c = 0; c < Cin; ++c)
+            for (int r = 0; r < kh; ++r)
+                for (int q = 0; q < kw; ++q)
+                    w_kc[((size_t)(r * kw + q) * Cin + c) * Cout + n] = w_oihw_host[(((size_t)n * Cin + c) * kh + r) * kw + q];
+    switch (kind) {
+        case 0:
+            EVK_REQUIRE(kh == 5 && kw == 5, EVK_ERR_ARG, "evk_pack_layer_weights: phase stacking is built for 5x5 kernels");
+            pack_weights_phase4(w_kc.data(), Cin, Cout, out);
+            break;
+        case 1:
+            EVK_REQUIRE(kh == 5 && kw == 5, EVK_ERR_ARG, "evk_pack_layer_weights: border lines are built for 5x5 kernels");
+            pack_weights_ring(w_kc.data(), Cin, Cout, out);
+            break;
+        case 2:
+            EVK_REQUIRE(kw == 5, EVK_ERR_ARG, "evk_pack_layer_weights: pixel pairs are built for 5-tap rows");
+            pack_weights_pixel_pair(w_kc.data(), kh, kw, Cin, Cout, out);
+            break;
+        case 3:
+            EVK_REQUIRE(Cin % 16 == 0 && group >= 1 && group + kw - 1 <= 4, EVK_ERR_ARG, "evk_pack_layer_weights: window mode needs 16-channel tensors and group + kw - 1 <= 4");
+            pack_weights_window(w_kc.data(), kh, kw, Cin, 16, Cout, group, out);
+            break;
+        default:
+            EVK_REQUIRE(false, EVK_ERR_ARG, "evk_pack_layer_weights: unknown kind %d", kind);
+    }
+    *out_len = (int64_t)out.size();
+    EVK_REQUIRE((int64_t)out.size() <= out_cap, EVK_ERR_ARG, "evk_pack_layer_weights: output needs %lld elements", (long long)out.size());
+    std::copy(out.begin(), out.end(), out_host);
+    return EVK_OK;
 }
 
 int evk_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, const float* w_oihw_host, const float* bias_host, int Cout,

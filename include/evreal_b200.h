@@ -154,6 +154,18 @@ int evk_model_op_desc(evk_model* m, int index, char* buf, int cap);
 int evk_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, const float* w_oihw_host, const float* bias_host, int Cout,
                     int k, int stride, int pad, int act, const float* res, int precision, float* y, void* stream);
 
+/* Host-only weight re-packers of the re-shaped layers, exposed so that their index maps can be checked without a GPU
+ * (tests/test_weight_packers.py compares them with torch's own operators).  w: HOST torch layout [Cout,Cin,kh,kw].
+ *  kind 0: UpsampleConvLayer (model/submodules.py:69-97), four stacked output phases  -> [25*Cin][4*Cout]
+ *  kind 1: its border corrections, two 1x5 line convolutions, negated                 -> [2][5*Cin][4*Cout]
+ *  kind 2: stride-2 5x5 ConvLayer over pixel pairs (first encoder)                    -> [kh*3*2*Cin][Cout]
+ *  kind 3: 3x3 ConvLayer over 4-pixel windows of 16-channel tensors, `group` output pixels per row (FireNet;
+ *          Cin = 16 or 32 = cat(x, h))                                                -> [kh*(Cin/16)*64][group*Cout]
+ * Row index k = position in the GEMM's K dimension, column = packed output channel; *out_len = elements written
+ * (EVK_ERR_ARG if out_cap is too small).  No CUDA call is made. */
+int evk_pack_layer_weights(int kind, const float* w_oihw_host, int Cout, int Cin, int kh, int kw, int group, float* out_host,
+                           int64_t out_cap, int64_t* out_len);
+
 /* ------------------------------------------------------------ post-process --
  * post_process_normalization / normalize   reference: eval.py:380-395,
  * utils/eval_utils.py:15-35.  out = (v - P_qmin) / (P_qmax - P_qmin) with
