@@ -1057,7 +1057,10 @@ int tc_plan_create(ConvParams& p) {
     const int s_y = rp ? 2 : p.stride, s_x = p.stride_x ? p.stride_x : p.stride;
     const int pad_x = p.pad_x >= 0 ? p.pad_x : p.pad;
     EVK_REQUIRE(cout_pad >= e_cout && cout_pad % 16 == 0, EVK_ERR_ARG, "conv_tc: cout_pad=%d must be a multiple of 16 >= cout", cout_pad);
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};          // function attributes are per device
+    int dev_id = 0;
+    EVK_CHECK_CUDA(cudaGetDevice(&dev_id));
+    const bool attr_set = dev_id >= 0 && dev_id < 64 && attr_set_dev[dev_id];
     if (!attr_set) {
         const void* kerns[6] = {(const void*)conv_tc_kernel<64, false>, (const void*)conv_tc_kernel<32, false>,
                                 (const void*)conv_tc_kernel<64, true>, (const void*)conv_tc_kernel<32, true>,
@@ -1066,7 +1069,7 @@ int tc_plan_create(ConvParams& p) {
             EVK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             EVK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         }
-        attr_set = true;
+        if (dev_id >= 0 && dev_id < 64) attr_set_dev[dev_id] = true;
     }
     const int chunks = (p.c1 + p.c2) / bk;
     const int granule = p.epi == EPI_LSTM ? 32 : 16;

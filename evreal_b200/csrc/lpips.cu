@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(256) lpips_prep_kernel(const float* __restrict
         const int b = (int)(im % batch);
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b < n) {
-            const float v = (im < batch ? img : ref)[(int64_t)b * pixels + pix];
+            // (clamped to [0,1]: the clip of EvalMetricsTracker.update, utils/eval_metrics.py:253-255 -- a no-op for in-range frames)
+            const float v = fminf(fmaxf((im < batch ? img : ref)[(int64_t)b * pixels + pix], 0.0f), 1.0f);
             const float s = 2.0f * v - 1.0f;
             o.x = (s - (-0.030f)) / 0.458f;
             o.y = (s - (-0.088f)) / 0.448f;
@@ -80,15 +81,19 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
     }
 }
 
-// one CTA per (pair, tap): sum over pixels of sum_c lin[c] * (f0/(|f0|+eps) - f1/(|f1|+eps))^2, deterministic tree
+// kTapChunks CTAs per (pair, tap), each over a contiguous range of pixels: sum over pixels of
+// sum_c lin[c] * (f0/(|f0|+eps) - f1/(|f1|+eps))^2; fixed summation tree (partials are added in index order by lpips_sum_kernel)
+constexpr int kTapChunks = 16;
 __global__ void __launch_bounds__(256) lpips_tap_kernel(const float* __restrict__ feat, const float* __restrict__ lin, int batch, int pixels,
-                                                        int C, double* __restrict__ part /*[batch]*/) {
+                                                        int C, double* __restrict__ part /*[batch][kTapChunks]*/) {
     const int p = blockIdx.x;
     const float* f0 = feat + (size_t)p * pixels * C;
     const float* f1 = feat + (size_t)(batch + p) * pixels * C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (pixels + kTapChunks - 1) / kTapChunks;
+    const int px0 = blockIdx.y * per, px1 = min(pixels, px0 + per);
     double acc = 0.0;
-    for (int px = warp; px < pixels; px += 8) {          // a warp per pixel, lanes over channels
+    for (int px = px0 + warp; px < px1; px += 8) {       // a warp per pixel, lanes over channels
         const float* a = f0 + (size_t)px * C;
         const float* b = f1 + (size_t)px * C;
         float sa = 0.f, sb = 0.f;
@@ -111,15 +116,20 @@ __global__ void __launch_bounds__(256) lpips_tap_kernel(const float* __restrict_
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < 8; ++w) s += sm[w];
-        part[p] = s / (double)pixels;                     // spatial average
+        part[(size_t)p * kTapChunks + blockIdx.y] = s;
     }
 }
 
-__global__ void lpips_sum_kernel(const double* __restrict__ part, int taps, int batch, int n, double* __restrict__ scores) {
+struct LpPixels { int n[5]; };
+__global__ void lpips_sum_kernel(const double* __restrict__ part, int taps, int batch, int n, LpPixels pixels, double* __restrict__ scores) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     double s = 0.0;
-    for (int t = 0; t < taps; ++t) s += part[(size_t)t * batch + p];
+    for (int t = 0; t < taps; ++t) {
+        double a = 0.0;
+        for (int c = 0; c < kTapChunks; ++c) a += part[((size_t)t * batch + p) * kTapChunks + c];
+        s += a / (double)pixels.n[t];                     // spatial average of the tap
+    }
     scores[p] = s;
 }
 
@@ -254,7 +264,7 @@ static int lpips_build(evk_lpips* l) {
             l->taps[s.tap] = LpTap{y, C, H, W, dl};
         }
     }
-    l->part = (double*)l->dalloc(sizeof(double) * 5 * l->batch);
+    l->part = (double*)l->dalloc(sizeof(double) * 5 * l->batch * kTapChunks);
     EVK_REQUIRE(l->part != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
     return EVK_OK;
 }
@@ -315,12 +325,15 @@ int evk_lpips_forward(evk_lpips* l, const float* img, const float* ref, int n, d
             EVK_CHECK_CUDA(cudaGetLastError());
         }
     }
+    LpPixels px;
     for (int t = 0; t < 5; ++t) {
         const LpTap& tp = l->taps[t];
-        lpips_tap_kernel<<<n, 256, 0, st>>>(tp.feat, tp.lin, l->batch, tp.H * tp.W, tp.C, l->part + (size_t)t * l->batch);
+        px.n[t] = tp.H * tp.W;
+        lpips_tap_kernel<<<dim3((unsigned)n, kTapChunks), 256, 0, st>>>(tp.feat, tp.lin, l->batch, tp.H * tp.W, tp.C,
+                                                                        l->part + (size_t)t * l->batch * kTapChunks);
         EVK_CHECK_CUDA(cudaGetLastError());
     }
-    lpips_sum_kernel<<<ceil_div(n, 64), 64, 0, st>>>(l->part, 5, l->batch, n, scores);
+    lpips_sum_kernel<<<ceil_div(n, 64), 64, 0, st>>>(l->part, 5, l->batch, n, px, scores);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

@@ -19,23 +19,21 @@ constexpr int kTaps = 2 * kTapR + 1;
 constexpr int kTH = 16, kTW = 32;        // owned pixels per CTA
 constexpr int kIH = kTH + 2 * kTapR, kIW = kTW + 2 * kTapR;
 
-__constant__ double c_taps[kTaps];
-static bool g_taps_ready = false;
+// The taps travel as a kernel argument (a __constant__ symbol is per device and would need per-device uploads).
+struct GaussTaps { double w[kTaps]; };
 
-static int upload_taps() {
-    if (g_taps_ready) return EVK_OK;
-    double w[kTaps], s = 0.0;
+static GaussTaps make_taps() {
+    GaussTaps t;
+    double s = 0.0;
     const double sigma = 1.5;
-    for (int i = -kTapR; i <= kTapR; ++i) { w[i + kTapR] = exp(-0.5 / (sigma * sigma) * (double)(i * i)); s += w[i + kTapR]; }
-    for (int i = 0; i < kTaps; ++i) w[i] /= s;
-    EVK_CHECK_CUDA(cudaMemcpyToSymbol(c_taps, w, sizeof(w)));
-    g_taps_ready = true;
-    return EVK_OK;
+    for (int i = -kTapR; i <= kTapR; ++i) { t.w[i + kTapR] = exp(-0.5 / (sigma * sigma) * (double)(i * i)); s += t.w[i + kTapR]; }
+    for (int i = 0; i < kTaps; ++i) t.w[i] /= s;
+    return t;
 }
 
 // scipy correlate1d, symmetric branch: centre tap first, then pairs from the
 // outside in, float64 accumulate, float32 store.
-__device__ __forceinline__ float sym_filter(const float* v, int stride) {
+__device__ __forceinline__ float sym_filter(const float* v, int stride, const double* c_taps) {
     double acc = (double)v[0] * c_taps[kTapR];
 #pragma unroll
     for (int j = kTapR; j >= 1; --j) acc += ((double)v[-j * stride] + (double)v[j * stride]) * c_taps[kTapR - j];
@@ -44,7 +42,8 @@ __device__ __forceinline__ float sym_filter(const float* v, int stride) {
 
 __global__ void __launch_bounds__(256)
 mse_ssim_kernel(const float* __restrict__ img, const float* __restrict__ ref, int H, int W, int clip,
-                double* __restrict__ sums /* [n][2] */) {
+                double* __restrict__ sums /* [n][2] */, const __grid_constant__ GaussTaps taps) {
+    const double* c_taps = taps.w;
     __shared__ float sx[kIH][kIW], sy[kIH][kIW];          // x = ref, y = img (skimage argument order)
     __shared__ float vert[5][kTH][kIW];
     __shared__ double red[2][8];
@@ -92,7 +91,7 @@ mse_ssim_kernel(const float* __restrict__ img, const float* __restrict__ ref, in
             col[4][k] = __fmul_rn(a, b);
         }
 #pragma unroll
-        for (int m = 0; m < 5; ++m) vert[m][r][c] = sym_filter(&col[m][kTapR], 1);
+        for (int m = 0; m < 5; ++m) vert[m][r][c] = sym_filter(&col[m][kTapR], 1, c_taps);
     }
     __syncthreads();
 
@@ -103,11 +102,11 @@ mse_ssim_kernel(const float* __restrict__ img, const float* __restrict__ ref, in
         const int r = i / kTW, c = i % kTW;
         const int gy = y0 + r, gx = x0 + c;
         if (gy >= kTapR && gy < H - kTapR && gx >= kTapR && gx < W - kTapR) {
-            const float ux = sym_filter(&vert[0][r][c + kTapR], 1);
-            const float uy = sym_filter(&vert[1][r][c + kTapR], 1);
-            const float uxx = sym_filter(&vert[2][r][c + kTapR], 1);
-            const float uyy = sym_filter(&vert[3][r][c + kTapR], 1);
-            const float uxy = sym_filter(&vert[4][r][c + kTapR], 1);
+            const float ux = sym_filter(&vert[0][r][c + kTapR], 1, c_taps);
+            const float uy = sym_filter(&vert[1][r][c + kTapR], 1, c_taps);
+            const float uxx = sym_filter(&vert[2][r][c + kTapR], 1, c_taps);
+            const float uyy = sym_filter(&vert[3][r][c + kTapR], 1, c_taps);
+            const float uxy = sym_filter(&vert[4][r][c + kTapR], 1, c_taps);
             const float vx = __fsub_rn(uxx, __fmul_rn(ux, ux));
             const float vy = __fsub_rn(uyy, __fmul_rn(uy, uy));
             const float vxy = __fsub_rn(uxy, __fmul_rn(ux, uy));
@@ -143,11 +142,10 @@ __global__ void mse_ssim_finalize_kernel(double* sums, int n, double inv_all, do
 int mse_ssim(const float* img, const float* ref, int n, int H, int W, int clip, double* scores, cudaStream_t st) {
     EVK_REQUIRE(n > 0 && H >= kTaps && W >= kTaps, EVK_ERR_ARG,
                 "evk_mse_ssim: images must be at least %dx%d (got n=%d %dx%d)", kTaps, kTaps, n, H, W);
-    int rc = upload_taps();
-    if (rc != EVK_OK) return rc;
+    static const GaussTaps taps = make_taps();
     EVK_CHECK_CUDA(cudaMemsetAsync(scores, 0, sizeof(double) * 2 * n, st));
     dim3 grid(ceil_div(W, kTW), ceil_div(H, kTH), n);
-    mse_ssim_kernel<<<grid, 256, 0, st>>>(img, ref, H, W, clip, scores);
+    mse_ssim_kernel<<<grid, 256, 0, st>>>(img, ref, H, W, clip, scores, taps);
     EVK_CHECK_CUDA(cudaGetLastError());
     const double inv_all = 1.0 / ((double)H * W);
     const double inv_int = 1.0 / ((double)(H - 2 * kTapR) * (W - 2 * kTapR));
@@ -308,12 +306,90 @@ int percentile_normalize(const float* img, float* out, int n, int numel, double 
     EVK_REQUIRE(n > 0 && numel > 0, EVK_ERR_ARG, "evk_percentile_normalize: empty input");
     EVK_REQUIRE(q_lo >= 0 && q_hi <= 100 && q_lo <= q_hi, EVK_ERR_ARG, "evk_percentile_normalize: bad percentiles");
     const size_t smem = sizeof(unsigned int) * 2 * kSelWarps * 256;   // 64 KB
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};          // the attribute is per device
+    int dev = 0;
+    EVK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         EVK_CHECK_CUDA(cudaFuncSetAttribute(percentile_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     percentile_normalize_kernel<<<n, kSelThreads, smem, st>>>(img, out, numel, q_lo, q_hi, apply_exp);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+// ------------------------------------------------------- histogram equalisation
+// EvalMetricsTracker.histogram_equalization, hist_eq == 'global' (utils/eval_metrics.py:326-331):
+// skimage.exposure.equalize_hist(img) -> img_as_float32.  scikit-image is a third-party dependency absent from the
+// reference tree (parity unpinned); its published algorithm: hist = np.histogram(img, 256 bins over [min, max]),
+// cdf = cumsum(hist) / numel, out = np.interp(img, bin_centers, cdf).  One CTA per image.
+constexpr int kEqBins = 256;
+
+__global__ void __launch_bounds__(1024)
+equalize_hist_kernel(const float* __restrict__ img, float* __restrict__ out, int numel, int clip) {
+    __shared__ float s_min[32], s_max[32];
+    __shared__ unsigned int s_hist[kEqBins];
+    __shared__ double s_cdf[kEqBins];
+    __shared__ double s_lo, s_hi;
+    const float* v = img + (size_t)blockIdx.x * numel;
+    float* o = out + (size_t)blockIdx.x * numel;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto load = [&](int i) { const float a = v[i]; return clip ? fminf(fmaxf(a, 0.0f), 1.0f) : a; };
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = tid; i < numel; i += 1024) { const float a = load(i); mn = fminf(mn, a); mx = fmaxf(mx, a); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if (lane == 0) { s_min[warp] = mn; s_max[warp] = mx; }
+    if (tid < kEqBins) s_hist[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 32; ++w) { mn = fminf(mn, s_min[w]); mx = fmaxf(mx, s_max[w]); }
+        double lo = (double)mn, hi = (double)mx;
+        if (lo == hi) { lo -= 0.5; hi += 0.5; }          // np.histogram widens an empty range
+        s_lo = lo; s_hi = hi;
+    }
+    __syncthreads();
+    const double lo = s_lo, hi = s_hi, width = (hi - lo) / kEqBins, norm = (double)kEqBins / (hi - lo);
+    auto edge = [&](int i) { return i == kEqBins ? hi : lo + (double)i * width; };          // np.linspace(lo, hi, 257)
+    for (int i = tid; i < numel; i += 1024) {
+        const double a = (double)load(i);
+        int b = (int)((a - lo) * norm);
+        b = min(max(b, 0), kEqBins - 1);
+        if (a < edge(b)) --b;                                                        // numpy's edge corrections
+        else if (b != kEqBins - 1 && a >= edge(b + 1)) ++b;
+        atomicAdd(&s_hist[min(max(b, 0), kEqBins - 1)], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long c = 0;
+        for (int b = 0; b < kEqBins; ++b) { c += s_hist[b]; s_cdf[b] = (double)c / (double)numel; }
+    }
+    __syncthreads();
+    auto centre = [&](int j) { return (edge(j) + edge(j + 1)) * 0.5; };
+    const double c0 = centre(0), c_last = centre(kEqBins - 1);
+    for (int i = tid; i < numel; i += 1024) {
+        const double a = (double)load(i);
+        double r;
+        // np.interp over the bin centres: clamped outside, linear inside
+        if (a <= c0) r = s_cdf[0];
+        else if (a >= c_last) r = s_cdf[kEqBins - 1];
+        else {
+            int j = min(max((int)floor((a - c0) / width), 0), kEqBins - 2);
+            if (a < centre(j) && j > 0) --j;
+            else if (a >= centre(j + 1) && j < kEqBins - 2) ++j;
+            const double xj = centre(j), xj1 = centre(j + 1);
+            r = (s_cdf[j + 1] - s_cdf[j]) / (xj1 - xj) * (a - xj) + s_cdf[j];
+        }
+        o[i] = (float)r;
+    }
+}
+
+int equalize_hist(const float* img, float* out, int n, int numel, int clip, cudaStream_t st) {
+    EVK_REQUIRE(n > 0 && numel > 0, EVK_ERR_ARG, "evk_equalize_hist: empty input");
+    equalize_hist_kernel<<<n, 1024, 0, st>>>(img, out, numel, clip);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

@@ -64,9 +64,15 @@ struct evk_model {
     std::vector<void*> allocs;
     std::vector<Op> ops[2];          // per hidden-state parity
     std::vector<StateBuf> states;
-    float* in_buf = nullptr;         // [N,bins,H,W]
-    float* out_buf = nullptr;        // [N,1,H,W]
-    float* prev_rec = nullptr;       // HyperE2VID: previous padded reconstruction
+    // Network input [N,bins,H,W] and output [N,1,H,W], DOUBLE-BUFFERED by forward parity: forward k reads in_bufs[k & 1] and
+    // writes out_bufs[k & 1], so a caller may fill the next input and consume the previous output on other streams while a
+    // forward runs (pipeline.py), and HyperE2VID's "previous padded reconstruction" (model/model.py:139-143) is simply the
+    // other output buffer -- no copy.  The builders wire parity 0 (in_buf / out_buf / prev_rec); parity 1 is patched after.
+    float* in_bufs[2] = {nullptr, nullptr};
+    float* out_bufs[2] = {nullptr, nullptr};
+    float* in_buf = nullptr;         // = in_bufs[0]
+    float* out_buf = nullptr;        // = out_bufs[0]
+    float* prev_rec = nullptr;       // = out_bufs[1]
     int parity = 0;
     int last_launches = 0;
     double flops = 0.0;
@@ -696,7 +702,7 @@ static int build_firenet(evk_model* m, bool legacy) {
     const char* n_r2 = legacy ? "resblocks.1" : "R2";
     if (c.precision == 0 && C == 16 && W % 2 == 0 && c.kernel_size == 3 && getenv("EVK_NO_WINDOW") == nullptr) m->win_wp = W + 2;
     float* xh = B.act(H, W, C);
-    int r = add_head(B, n_head, "", xh, C);
+    int r = add_head(B, n_head, legacy ? "head.conv.norm_layer" : "head.norm_layer", xh, C);   // (folded when the checkpoint has one: norm = 'BN')
     if (r != EVK_OK) return r;
     float* u = B.act(H, W, C);
     float* hr = B.act(H, W, C);
@@ -797,7 +803,7 @@ static int wire_tc(evk_model* m) {
     {
         std::map<const float*, int> fp32_read;
         for (const StateBuf& sb : m->states) { fp32_read[sb.buf[0]] = 1; fp32_read[sb.buf[1]] = 1; }
-        fp32_read[m->out_buf] = 1; fp32_read[m->in_buf] = 1; fp32_read[m->prev_rec] = 1;
+        for (int k = 0; k < 2; ++k) { fp32_read[m->out_bufs[k]] = 1; fp32_read[m->in_bufs[k]] = 1; }
         for (int par = 0; par < 2; ++par)
             for (const Op& op : m->ops[par]) {
                 auto rd = [&](const float* q) { if (q) fp32_read[q] = 1; };
@@ -941,12 +947,25 @@ int evk_model_finalize(evk_model* m, void* stream) {
     EVK_REQUIRE(m, EVK_ERR_ARG, "evk_model_finalize: null model");
     EVK_REQUIRE(!m->finalized, EVK_ERR_STATE, "evk_model_finalize: already finalized");
     const evk_model_config& c = m->cfg;
-    m->in_buf = m->dalloc((size_t)c.batch * c.num_bins * c.height * c.width);
-    m->out_buf = m->dalloc((size_t)c.batch * c.height * c.width);
-    m->prev_rec = m->dalloc((size_t)c.batch * c.height * c.width);
-    EVK_REQUIRE(m->in_buf && m->out_buf && m->prev_rec, EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
+    for (int k = 0; k < 2; ++k) {
+        m->in_bufs[k] = m->dalloc((size_t)c.batch * c.num_bins * c.height * c.width);
+        m->out_bufs[k] = m->dalloc((size_t)c.batch * c.height * c.width);
+        EVK_REQUIRE(m->in_bufs[k] && m->out_bufs[k], EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
+    }
+    m->in_buf = m->in_bufs[0]; m->out_buf = m->out_bufs[0]; m->prev_rec = m->out_bufs[1];
     int r = (c.arch == EVK_ARCH_UNET_RECURRENT) ? build_unet(m) : build_firenet(m, c.arch == EVK_ARCH_FIRENET_LEGACY);
     if (r != EVK_OK) return r;
+    // parity 1 reads / writes the other input / output buffer (and its "previous reconstruction" is parity 0's output)
+    for (Op& op : m->ops[1]) {
+        auto swap_io = [&](const float*& q) {
+            if (q == m->in_bufs[0]) q = m->in_bufs[1];
+            else if (q == m->out_bufs[0]) q = m->out_bufs[1];
+            else if (q == m->out_bufs[1]) q = m->out_bufs[0];
+        };
+        auto swap_out = [&](float*& q) { if (q == m->out_bufs[0]) q = m->out_bufs[1]; };
+        swap_io(op.in); swap_out(op.out);
+        swap_io(op.hp.ev_nchw); swap_io(op.hp.prev);
+    }
     r = wire_tc(m);
     if (r != EVK_OK) return r;
     for (void* p : m->allocs) EVK_REQUIRE(p != nullptr, EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
@@ -972,7 +991,8 @@ int evk_model_reset_states(evk_model* m, void* stream) {
             if (it != m->split_of.end()) EVK_CHECK_CUDA(cudaMemsetAsync(it->second, 0, m->split_bytes[s.buf[k]], st));
         }
     }
-    EVK_CHECK_CUDA(cudaMemsetAsync(m->prev_rec, 0, sizeof(float) * (size_t)m->cfg.batch * m->cfg.height * m->cfg.width, st));
+    for (int k = 0; k < 2; ++k)      // (HyperE2VID reads the other output buffer as the previous reconstruction: zeros after a reset)
+        EVK_CHECK_CUDA(cudaMemsetAsync(m->out_bufs[k], 0, sizeof(float) * (size_t)m->cfg.batch * m->cfg.height * m->cfg.width, st));
     m->parity = 0;
     return EVK_OK;
 }
@@ -984,8 +1004,8 @@ int evk_model_forward(evk_model* m, const float* voxel, float* image, void* stre
     const evk_model_config& c = m->cfg;
     const size_t in_bytes = sizeof(float) * (size_t)c.batch * c.num_bins * c.height * c.width;
     const size_t out_bytes = sizeof(float) * (size_t)c.batch * c.height * c.width;
-    if (voxel != m->in_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(m->in_buf, voxel, in_bytes, cudaMemcpyDeviceToDevice, st));
     const int par = m->parity;
+    if (voxel != m->in_bufs[par]) EVK_CHECK_CUDA(cudaMemcpyAsync(m->in_bufs[par], voxel, in_bytes, cudaMemcpyDeviceToDevice, st));
     if (m->use_graph) {
         if (!m->graph[par]) {
             cudaGraph_t g = nullptr;
@@ -1004,8 +1024,7 @@ int evk_model_forward(evk_model* m, const float* voxel, float* image, void* stre
     }
     m->last_launches = 0;
     for (const Op& op : m->ops[par]) m->last_launches += op.kind != OP_NOP;
-    if (c.dynamic_decoder) EVK_CHECK_CUDA(cudaMemcpyAsync(m->prev_rec, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
-    if (image != m->out_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(image, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
+    if (image != m->out_bufs[par]) EVK_CHECK_CUDA(cudaMemcpyAsync(image, m->out_bufs[par], out_bytes, cudaMemcpyDeviceToDevice, st));
     m->parity ^= 1;
     return EVK_OK;
 }
@@ -1018,12 +1037,11 @@ int evk_model_profile(evk_model* m, const float* voxel, float* image, void* stre
     const evk_model_config& c = m->cfg;
     const size_t in_bytes = sizeof(float) * (size_t)c.batch * c.num_bins * c.height * c.width;
     const size_t out_bytes = sizeof(float) * (size_t)c.batch * c.height * c.width;
-    if (voxel != m->in_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(m->in_buf, voxel, in_bytes, cudaMemcpyDeviceToDevice, st));
     const int par = m->parity;
+    if (voxel != m->in_bufs[par]) EVK_CHECK_CUDA(cudaMemcpyAsync(m->in_bufs[par], voxel, in_bytes, cudaMemcpyDeviceToDevice, st));
     std::vector<cudaEvent_t> ev;
     int r = run_ops(m, par, st, &ev);
-    if (c.dynamic_decoder) EVK_CHECK_CUDA(cudaMemcpyAsync(m->prev_rec, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
-    if (image != m->out_buf) EVK_CHECK_CUDA(cudaMemcpyAsync(image, m->out_buf, out_bytes, cudaMemcpyDeviceToDevice, st));
+    if (image != m->out_bufs[par]) EVK_CHECK_CUDA(cudaMemcpyAsync(image, m->out_bufs[par], out_bytes, cudaMemcpyDeviceToDevice, st));
     cudaError_t se = cudaStreamSynchronize(st);
     const int n = (int)m->ops[par].size();
     *n_ops = n;
@@ -1051,8 +1069,8 @@ int evk_model_op_desc(evk_model* m, int index, char* buf, int cap) {
 
 int evk_model_io_buffers(evk_model* m, float** in, float** out) {
     EVK_REQUIRE(m && m->finalized, EVK_ERR_STATE, "evk_model_io_buffers: model not finalized");
-    if (in) *in = m->in_buf;
-    if (out) *out = m->out_buf;
+    if (in) *in = m->in_bufs[m->parity];
+    if (out) *out = m->out_bufs[m->parity];
     return EVK_OK;
 }
 

@@ -440,6 +440,20 @@ int u8_to_f32_batch(const uint8_t* const* frames, int n_frames, int64_t numel, f
     return EVK_OK;
 }
 
+// save_inferred_image's quantisation (utils/eval_utils.py:80-84) after the tracker's clip (utils/eval_metrics.py:253-255):
+// uint8(np.round(clip(v, 0, 1) * 255)); np.round rounds half to even = rintf
+__global__ void __launch_bounds__(256) quantize_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (uint8_t)rintf(__fmul_rn(fminf(fmaxf(in[i], 0.0f), 1.0f), 255.0f));
+}
+
+int quantize_u8(const float* in, uint8_t* out, int64_t n, cudaStream_t st) {
+    EVK_REQUIRE(n > 0, EVK_ERR_ARG, "evk_quantize_u8: empty input");
+    quantize_u8_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 1184), 256, 0, st>>>(in, out, n);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
 int u8_to_f32(const uint8_t* in, float* out, int64_t n, cudaStream_t st) {
     EVK_REQUIRE(n > 0, EVK_ERR_ARG, "evk_u8_to_f32: empty input");
     u8_to_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 1184), 256, 0, st>>>(in, out, n);

@@ -56,50 +56,42 @@ class MemMapDataset(torch.utils.data.Dataset):
         idx0, idx1 = self.get_event_indices(index)
         return idx0, idx1, index
 
-    def __getitem__(self, index):
+    def item_meta(self, index):
+        """Everything ``__getitem__`` returns except the tensors (dataset.py:33-102): (idx0, idx1, frame_index, voxel_timestamp,
+        frame_timestamp, dt, event_count).  Host integer / float64 arithmetic only: the lock-step pipeline gates and pairs
+        frames from these without voxelizing anything."""
         idx0, idx1, index = self.window(index)
         idx0, idx1 = int(idx0), int(idx1)
         event_count = max(idx1 - idx0, 0)
         t = self.filehandle["t"]
+        method = self.voxel_method['method']
         if event_count > 0:
             ts_0, ts_k = t[idx0], t[idx1 - 1]
-            voxel = self.get_voxel_grid_window(idx0, idx1)
+        elif idx0 > 0:
+            # empty window: timestamps patched like dataset.py:59-71
+            ts_0 = t[idx0 - 1:idx1][-1]
+            ts_k = ts_0 + self.voxel_method['t'] if method == 't_seconds' else self.frame_ts[index]
         else:
-            # empty window: zeros grid, timestamps patched like dataset.py:59-71
-            if idx0 > 0:
-                ts_0 = t[idx0 - 1:idx1][-1]
-                if self.voxel_method['method'] == 't_seconds':
-                    ts_k = ts_0 + self.voxel_method['t']
-                else:
-                    ts_k = self.frame_ts[index]
-            else:
-                ts_0, ts_k = 0, 0
-            voxel = self.get_empty_voxel_grid()
-
-        dt = ts_k - ts_0
-        if self.voxel_method['method'] == 't_seconds':
-            dt = self.voxel_method['t']
-
-        if self.has_images and self.voxel_method['method'] != 'between_frames':
+            ts_0, ts_k = 0, 0
+        dt = self.voxel_method['t'] if method == 't_seconds' else ts_k - ts_0
+        if self.has_images and method != 'between_frames':
             index = self.get_closest_frame_index(ts_k)
+        frame_timestamp = float(self.frame_ts[index]) if self.has_images else 0.0
+        voxel_timestamp = frame_timestamp if method == 'between_frames' else float(ts_k)
+        return idx0, idx1, index, voxel_timestamp, frame_timestamp, float(dt), event_count
 
+    def __getitem__(self, index):
+        idx0, idx1, index, voxel_timestamp, frame_timestamp, dt, event_count = self.item_meta(index)
+        voxel = self.get_voxel_grid_window(idx0, idx1) if event_count > 0 else self.get_empty_voxel_grid()
         if self.has_images:
             frame = self.get_frame_tensor(index)
-            frame_timestamp = torch.tensor(self.frame_ts[index], dtype=torch.float64)
         else:
             frame = torch.zeros((1, self.sensor_resolution[0], self.sensor_resolution[1]),
                                 dtype=torch.float32, device=voxel.device)
-            frame_timestamp = torch.tensor(0.0, dtype=torch.float64)
-
-        if self.voxel_method['method'] == 'between_frames':
-            voxel_timestamp = frame_timestamp
-        else:
-            voxel_timestamp = torch.tensor(ts_k, dtype=torch.float64)
-
         return {'frame': frame,
                 'events': voxel,
-                'frame_timestamp': frame_timestamp,
-                'voxel_timestamp': voxel_timestamp,
+                'frame_timestamp': torch.tensor(frame_timestamp, dtype=torch.float64),
+                'voxel_timestamp': torch.tensor(voxel_timestamp, dtype=torch.float64),
                 'dt': torch.tensor(dt, dtype=torch.float64),
                 'event_count': event_count}
 

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .eval_utils import append_timestamp, append_result, ensure_dir, save_inferred_image
+from .eval_utils import append_timestamp, append_result, ensure_dir, save_inferred_image, truncate_file
 
 
 def _cuda_img(img):
@@ -153,7 +153,9 @@ class EvalMetricsTracker:
 
     ``defer=True`` keeps every score on the GPU until ``finalize`` (one device->host copy per
     sequence instead of one per frame); files and score lists are identical afterwards.
-    Histogram-equalised variants (hist_eq != 'none') are outside the hot path and not built.
+    Histogram equalisation (utils/eval_metrics.py:326-350): 'global' runs on the GPU (evk_equalize_hist, skimage's
+    published algorithm -- parity unpinned, scikit-image is not installable offline), 'clahe' is the reference's own
+    cv2.createCLAHE call on the host, 'local' (skimage rank filter over a disk of radius 55) is not built.
     """
 
     def __init__(self, save_images=False, save_processed_images=False, output_dir=None, hist_eq='none',
@@ -162,11 +164,15 @@ class EvalMetricsTracker:
                  write_files=True):
         if quan_eval_metric_names is None:
             quan_eval_metric_names = ['mse', 'ssim', 'lpips']
-        if hist_eq != 'none':
-            raise ValueError(f"histogram equalisation '{hist_eq}' is outside the accelerated hot path "
-                             "(all shipped eval configs use histeq: none)")
+        if hist_eq not in ('none', 'global', 'clahe', 'local'):
+            raise ValueError(f"Unrecognized histogram equalization argument: {hist_eq}")
+        if hist_eq == 'local':
+            raise NotImplementedError("hist_eq 'local' (skimage.filters.rank.equalize over disk(55)) is not built")
         self.save_images = save_images
-        self.save_processed_images = False
+        self.save_processed_images = save_processed_images
+        if hist_eq == 'none' and self.save_processed_images:
+            print("Can not save processed images when hist_eq is none")
+            self.save_processed_images = False
         self.output_dir = output_dir
         self.hist_eq = hist_eq
         self.quan_eval_start_time = quan_eval_start_time
@@ -212,15 +218,18 @@ class EvalMetricsTracker:
             return
         host = torch.cat(self._pending).cpu().numpy()      # one D2H for the whole sequence
         self._pending = []
+        indices = self.quan_eval_indices[-len(host):]
         for metric in self.metrics:
             col = getattr(metric, 'column', None)
             if col is None:
                 continue
             metric.updated = 0
-            metric.push([float(v) for v in host[:, col]])
+            vals = [float(v) for v in host[:, col]]
+            metric.push(vals)
             if self.write_files and metric.get_num_updated() > 0:
-                append_result(self.get_metric_file_path(metric), self.quan_eval_indices[-len(host):],
-                              metric.get_last_scores(metric.get_num_updated()))
+                # BaseMetric.push drops non-finite scores: the index column drops the same rows
+                kept = [i for i, v in zip(indices, vals) if math.isfinite(v)]
+                append_result(self.get_metric_file_path(metric), kept, metric.get_last_scores(metric.get_num_updated()))
 
     def finalize(self, idx):
         self._flush_deferred()
@@ -270,7 +279,13 @@ class EvalMetricsTracker:
             ref = np.clip(ref, 0.0, 1.0) if isinstance(ref, np.ndarray) else ref.clamp(0.0, 1.0)
 
         if self.save_images and self.output_dir is not None:
-            save_inferred_image(self.output_dir, img if isinstance(img, np.ndarray) else img.squeeze().cpu().numpy(), idx)
+            save_inferred_image(self.output_dir, img if isinstance(img, np.ndarray) or img.dim() != 2 else img, idx)
+
+        img = self.histogram_equalization(img)
+        if self.has_reference_frames:
+            ref = self.histogram_equalization(ref)
+        if self.save_processed_images and self.output_dir is not None:
+            save_inferred_image(self.processed_output_dir, img, idx)
 
         inside_eval_cut = self.quan_eval_start_time <= img_ts <= self.quan_eval_end_time
         img_ref_time_diff_ms = abs(ref_ts - img_ts) * 1000
@@ -285,7 +300,7 @@ class EvalMetricsTracker:
             return
         metric_file_path = join(self.output_dir, metric_name + '.txt')
         if idx == 0:
-            open(metric_file_path, 'w', encoding="utf-8").close()
+            truncate_file(metric_file_path)
         append_result(metric_file_path, idx, metric_value, is_int)
 
     def get_num_quan_evaluations(self):
@@ -302,9 +317,37 @@ class EvalMetricsTracker:
 
     def setup_output_folders_and_files(self):
         ensure_dir(self.output_dir)
-        open(self.get_timestamps_file_path(), 'w', encoding="utf-8").close()
+        if self.save_processed_images:
+            self.processed_output_dir = self.output_dir + "_processed"
+            ensure_dir(self.processed_output_dir)
+        truncate_file(self.get_timestamps_file_path())
         for metric in self.metrics:
-            open(self.get_metric_file_path(metric), 'w', encoding="utf-8").close()
+            truncate_file(self.get_metric_file_path(metric))
+
+    def histogram_equalization(self, img):
+        """utils/eval_metrics.py:326-350 on a clipped [H, W] frame (numpy or CUDA tensor; same type out)."""
+        if self.hist_eq == 'none':
+            return img
+        if self.hist_eq == 'global':
+            was_numpy = isinstance(img, np.ndarray)
+            x = _cuda_img(img)
+            out = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().evk_equalize_hist(_lib.ptr(x), _lib.ptr(out), 1, x.numel(), 0, _lib.stream_ptr(x.device)))
+            return out.cpu().numpy() if was_numpy else out
+        if self.hist_eq == 'clahe':
+            import cv2
+            was_numpy = isinstance(img, np.ndarray)
+            a = img if was_numpy else img.cpu().numpy()
+            # img_as_ubyte of a float image in [0, 1]: round(v * 255); img_as_float32 of uint8: v / 255
+            a8 = np.round(np.clip(a, 0.0, 1.0) * 255).astype(np.uint8)
+            a8 = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(a8)
+            out = a8.astype(np.float32) / np.float32(255)
+            return out if was_numpy else torch.from_numpy(out).to(img.device)
+        raise ValueError(f"Unrecognized histogram equalization argument: {self.hist_eq}")
 
     def create_video(self):
         print("create_video is outside the accelerated hot path (create_video:false in all shipped eval configs)")
+
+    def create_processed_video(self):
+        print("create_processed_video is outside the accelerated hot path")

@@ -16,6 +16,7 @@ sequence.
 import glob
 import math
 import os
+import traceback
 from collections import OrderedDict
 
 import torch
@@ -24,7 +25,8 @@ from . import model as model_arch
 from . import parse_config
 from .dataset import MemMapDataset
 from .eval_metrics import EvalMetricsTracker
-from .eval_utils import post_process_normalization
+from . import eval_utils
+from .eval_utils import post_process_normalization, torch2cv2
 from .util import CropParameters, read_json, normalize_pad
 
 
@@ -129,7 +131,9 @@ def eval_method_on_sequence(dataset_name, eval_config, method_name, model, metho
     dataset = sequence.get('dataset') or open_sequence(sequence)
     has_reference_frames = dataset.has_images
     output_dir = os.path.join(output_root, eval_config['name'], dataset_name, sequence['name'], method_name)
-    tracker = EvalMetricsTracker(save_images=eval_config.get('save_images', True) and write_files,
+    save_images = eval_config.get('save_images', True) and write_files
+    tracker = EvalMetricsTracker(save_images=save_images,
+                                 save_processed_images=save_images and eval_config['histeq'] != 'none',
                                  output_dir=output_dir, hist_eq=eval_config['histeq'],
                                  quan_eval_metric_names=metrics,
                                  quan_eval_start_time=sequence['start_time_s'],
@@ -137,8 +141,7 @@ def eval_method_on_sequence(dataset_name, eval_config, method_name, model, metho
                                  quan_eval_ts_tol_ms=eval_config['ts_tol_ms'],
                                  has_reference_frames=has_reference_frames,
                                  color=eval_config.get('color', False), defer=True, write_files=write_files)
-    if eval_config.get('color', False):
-        raise NotImplementedError("ColorNet / CED colour evaluation is outside the accelerated hot path")
+    color = eval_config.get('color', False)
     height, width = int(dataset.sensor_resolution[0]), int(dataset.sensor_resolution[1])
     cropper = CropParameters(width, height, model.num_encoders)
     model.reset_states()
@@ -164,6 +167,18 @@ def eval_method_on_sequence(dataset_name, eval_config, method_name, model, metho
         else:
             event_rate = item['event_count'] / item['dt'].item()
         voxel = item['events'].unsqueeze(0)
+        if color:
+            # ColorNet pads its Bayer sites itself and returns the merged [3, H, W] frame (eval.py:225-232)
+            if event_tensor_normalization:
+                voxel = normalize_pad(voxel, height, width, True)
+            image = post_process_normalization(torch2cv2(model(voxel)['image']), post_process_norm)
+            if collect_images is not None:
+                collect_images.append(image.copy())
+            tracker.update(idx, image, torch2cv2(ref_frame) if has_reference_frames else None, pred_frame_ts, ref_frame_ts)
+            tracker.save_custom_metric(idx, "event_rate", event_rate)
+            frames += 1
+            events += item['event_count']
+            continue
         # normalize_event_tensor + cropper.pad in one kernel (eval.py:222-226)
         voxel = normalize_pad(voxel, cropper.height_crop_size, cropper.width_crop_size, event_tensor_normalization)
         output = model(voxel)
@@ -181,57 +196,77 @@ def eval_method_on_sequence(dataset_name, eval_config, method_name, model, metho
     return tracker.get_num_quan_evaluations(), tracker.get_mean_scores(), frames, events
 
 
+LOCKSTEP_METRICS = ('mse', 'ssim', 'lpips', 'lpips-vgg')
+
+
 def lockstep_supported(eval_config, metrics, datasets):
-    """The lock-step form covers what SequenceBatch computes on the device: 'between_frames' windows (voxel timestamp ==
-    frame timestamp), reference frames present, one sensor resolution, MSE / SSIM, no files, no colour."""
-    if eval_config.get('color', False) or not set(metrics) <= {'mse', 'ssim'} or not datasets:
+    """The lock-step form covers what SequenceBatch computes on the device: reference frames present, one sensor resolution
+    and bin count, MSE / SSIM / LPIPS, no histogram equalisation, no files, no colour.  All three windowing modes qualify
+    (frame pairing and score gates come from MemMapDataset.item_meta)."""
+    if eval_config.get('color', False) or not set(metrics) <= set(LOCKSTEP_METRICS) or not datasets:
+        return False
+    if eval_config.get('histeq', 'none') != 'none':
         return False
     res0 = tuple(int(v) for v in datasets[0].sensor_resolution[:2])
-    return all(ds.has_images and ds.voxel_method['method'] == 'between_frames' and
+    return all(ds.has_images and ds.num_bins == datasets[0].num_bins and
                tuple(int(v) for v in ds.sensor_resolution[:2]) == res0 for ds in datasets)
 
 
-def lockstep_item_range(ts, start_time_s, end_time_s, infer_all=False):
-    """(first item, number of items, score gate per item) of one sequence from its item timestamps: reconstruction starts
-    at the first item within 10 s of start_time_s and stops before the first item after end_time_s (eval.py:210-216); an
-    item's scores count when start_time_s <= t <= end_time_s (utils/eval_metrics.py:256-262; with 'between_frames'
-    windows the voxel and frame timestamps coincide, so the ts_tol_ms test always passes)."""
+def lockstep_item_range(ts, start_time_s, end_time_s, infer_all=False, frame_ts=None, ts_tol_ms=float('inf')):
+    """(first item, number of items, score gate per item) of one sequence from its item (voxel) timestamps: reconstruction
+    starts at the first item within 10 s of start_time_s and stops before the first item after end_time_s (eval.py:210-216);
+    an item's scores count when start_time_s <= t <= end_time_s and its reference frame is within ts_tol_ms of it
+    (utils/eval_metrics.py:256-262; with 'between_frames' windows the two timestamps coincide)."""
     first, last = 0, len(ts) - 1
     if not infer_all:
         first = next((i for i, t in enumerate(ts) if not t < start_time_s - 10), len(ts))
         last = next((i - 1 for i, t in enumerate(ts) if i >= first and t > end_time_s), len(ts) - 1)
     count = max(last - first + 1, 0)
-    return first, count, [start_time_s <= t <= end_time_s for t in ts[first:first + count]]
+    gates = []
+    for i in range(first, first + count):
+        ok = start_time_s <= ts[i] <= end_time_s
+        if ok and frame_ts is not None:
+            ok = abs(frame_ts[i] - ts[i]) * 1000 <= ts_tol_ms
+        gates.append(ok)
+    return first, count, gates
 
 
-def eval_method_on_sequences_lockstep(eval_config, model, method_config, sequences, metrics):
+def eval_method_on_sequences_lockstep(eval_config, model, method_config, sequences, metrics, lpips_weights=None):
     """eval_method_on_sequence for several sequences at once: frame k of every sequence in ONE batched voxelizer / network /
     metric launch (pipeline.SequenceBatch).  Per-sequence semantics are the reference's (eval.py:203-246): reconstruction
     starts at the first item within 10 s of start_time_s and stops after end_time_s, scores count inside
-    [start_time_s, end_time_s], the mean is sum(scores) / n over finite scores.  Returns [(num_evaluated, mean_scores)]."""
+    [start_time_s, end_time_s] and within ts_tol_ms of the reference frame, the mean is sum(scores) / n over finite scores.
+    Returns [(num_evaluated, mean_scores)]."""
     from .pipeline import SequenceBatch
     datasets = [s.get('dataset') or open_sequence(s) for s in sequences]
     infer_all = eval_config.get('eval_infer_all', False)
     offsets, counts, gates = [], [], []
     for seq, ds in zip(sequences, datasets):
-        ts = [float(ds.frame_ts[ds.window(i)[2]]) for i in range(len(ds))]        # between_frames: voxel timestamp = frame timestamp
-        first, count, gate = lockstep_item_range(ts, seq['start_time_s'], seq['end_time_s'], infer_all)
+        meta = [ds.item_meta(i) for i in range(len(ds))]
+        first, count, gate = lockstep_item_range([m[3] for m in meta], seq['start_time_s'], seq['end_time_s'], infer_all,
+                                                 [m[4] for m in meta], eval_config.get('ts_tol_ms', float('inf')))
         offsets.append(first)
         counts.append(count)
         gates.append(gate)
     steps = max(counts) if counts else 0
-    out = []
+    lp_name = next((m for m in metrics if m in ('lpips', 'lpips-vgg')), None)
+    lpips = None
+    if lp_name is not None:
+        from .lpips import LpipsMetric
+        lpips = (lp_name, lpips_weights if lpips_weights is not None else LpipsMetric(lp_name)._weights())
+    sc = None
     if steps > 0:
         batch = SequenceBatch(model, datasets, method_config.get('event_tensor_normalization', False),
-                              method_config.get('post_process_norm', 'none'), resident=True, offsets=offsets, counts=counts)
+                              method_config.get('post_process_norm', 'none'), resident=True, offsets=offsets, counts=counts,
+                              lpips=lpips, log_scores=True)
         batch.reset()
-        all_scores = torch.empty((steps, len(datasets), 2), dtype=torch.float64, device=batch.dev)
         for k in range(steps):
-            scores, _, _ = batch.step(k)
-            all_scores[k].copy_(scores)
+            batch.step(k)
+        batch.finish()
         batch.check_bounds()
-        sc = all_scores.cpu().numpy()
-    col = {'mse': 0, 'ssim': 1}
+        sc = batch.scores_log.cpu().numpy()
+    col = {'mse': 0, 'ssim': 1, 'lpips': 2, 'lpips-vgg': 2}
+    out = []
     for b in range(len(datasets)):
         n_eval = sum(gates[b])
         means = {}
@@ -313,66 +348,121 @@ def reduce_metric_sums(local, metric_names, group=None):
 last_timings = {}
 
 
+def _log_exception(what, e):
+    print(what)
+    print(e)
+    print(traceback.format_exc())
+
+
 def evaluate(method_names, eval_config_names=None, dataset_names=None, metrics=None, config_root="config",
-             output_root="outputs", write_files=True, rank=0, world_size=1, lockstep=0):
+             output_root="outputs", write_files=True, rank=0, world_size=1, lockstep=0, lpips_weights=None,
+             async_writer=True):
     """eval.py:413-444.  Returns {eval_config: {method: {dataset: MetricTracker}}} (identical on every rank).
     ``lockstep`` = B > 1: this rank's sequences run B at a time in lock-step (eval_method_on_sequences_lockstep) where that
-    form applies (lockstep_supported, write_files False); everything else runs one sequence at a time like the reference."""
+    form applies (lockstep_supported, write_files False); everything else runs one sequence at a time like the reference.
+
+    Failures are caught where the reference catches them (eval.py:344-352 per method, :357-375 per dataset): a method whose
+    model cannot be built is reported and skipped, a dataset that raises keeps the sequences it finished, and the run goes
+    on.  With several ranks every rank still takes part in every per-dataset all-reduce (a failed rank contributes what it
+    has, possibly nothing), so a failure on one rank never leaves the others waiting in a collective.
+    ``async_writer``: per-frame text / PNG output goes through one writer thread (eval_utils.AsyncWriter), flushed per
+    sequence -- same files, off the critical path."""
     if eval_config_names is None:
         eval_config_names = ['std']
     if metrics is None:
         metrics = ['mse', 'ssim']
     import time
     results = OrderedDict()
-    tm = {'model_s': 0.0, 'open_s': 0.0, 'loop_s': 0.0, 'reduce_s': 0.0}
+    tm = {'model_s': 0.0, 'open_s': 0.0, 'loop_s': 0.0, 'reduce_s': 0.0, 'failures': 0}
     last_timings.clear()
     last_timings.update(tm)
-    for eval_config in get_eval_configs(eval_config_names, config_root):
-        per_method = OrderedDict()
-        dataset_configs = get_dataset_configs(dataset_names, config_root)
-        for method_name in method_names:
-            method_config = get_method_config(method_name, config_root)
+    writer = eval_utils.AsyncWriter() if (write_files and async_writer) else None
+    if lpips_weights is not None:
+        from . import lpips as lpips_mod
+        lpips_mod.set_default_weights(lpips_weights)
+    old_writer = eval_utils.set_writer(writer)
+    try:
+        for eval_config in get_eval_configs(eval_config_names, config_root):
+            per_method = OrderedDict()
+            dataset_configs = get_dataset_configs(dataset_names, config_root)
+            for method_name in method_names:
+                model = method_config = None
+                try:
+                    method_config = get_method_config(method_name, config_root)
+                    t0 = time.perf_counter()
+                    model = get_model_from_checkpoint_path(method_config['model_name'], method_config['model_path'])
+                    if eval_config.get('color', False):
+                        model = model_arch.ColorNet(model)
+                    last_timings['model_s'] += time.perf_counter() - t0
+                except Exception as e:
+                    last_timings['failures'] += 1
+                    _log_exception(f"Exception while getting method {method_name}", e)
+                    model = None
+                per_dataset = OrderedDict()
+                for dataset_config in dataset_configs:
+                    local = MetricTracker()
+                    if model is not None:
+                        try:
+                            _eval_dataset(eval_config, method_name, model, method_config, dataset_config, metrics, output_root,
+                                          write_files, rank, world_size, lockstep, lpips_weights, local, writer)
+                        except Exception as e:
+                            last_timings['failures'] += 1
+                            _log_exception(f"Exception while evaluating method {method_name} on {dataset_config['name']} dataset:", e)
+                    # every rank, always: the collective count stays matched whatever happened above
+                    t0 = time.perf_counter()
+                    per_dataset[dataset_config['name']] = reduce_metric_sums(local, metrics)
+                    last_timings['reduce_s'] += time.perf_counter() - t0
+                per_method[method_name] = per_dataset
+            results[eval_config['name']] = per_method
+    finally:
+        eval_utils.set_writer(old_writer)
+        if writer is not None:
+            try:
+                writer.flush()
+            finally:
+                writer.close()
+    return results
+
+
+def _eval_dataset(eval_config, method_name, model, method_config, dataset_config, metrics, output_root, write_files, rank,
+                  world_size, lockstep, lpips_weights, local, writer):
+    """This rank's sequences of one dataset (the body of eval.py:357-368); updates ``local`` sequence by sequence, so what
+    was finished before an exception is kept (eval.py:373-375)."""
+    import time
+    sequences = get_sequences(dataset_config, eval_config.get('dataset_kwargs', {}))
+    weights = [os.path.getsize(os.path.join(s['sequence_path'], 'events_ts.npy')) for s in sequences]
+    mine = shard_sequences(sequences, weights, world_size)[rank]
+    if lockstep > 1 and not write_files and mine:
+        t0 = time.perf_counter()
+        for i in mine:
+            open_sequence(sequences[i])
+        last_timings['open_s'] += time.perf_counter() - t0
+        if lockstep_supported(eval_config, metrics, [sequences[i]['dataset'] for i in mine]):
             t0 = time.perf_counter()
-            model = get_model_from_checkpoint_path(method_config['model_name'], method_config['model_path'])
-            last_timings['model_s'] += time.perf_counter() - t0
-            per_dataset = OrderedDict()
-            for dataset_config in dataset_configs:
-                sequences = get_sequences(dataset_config, eval_config.get('dataset_kwargs', {}))
-                weights = [os.path.getsize(os.path.join(s['sequence_path'], 'events_ts.npy')) for s in sequences]
-                mine = shard_sequences(sequences, weights, world_size)[rank]
-                local = MetricTracker()
-                if lockstep > 1 and not write_files and mine:
-                    t0 = time.perf_counter()
-                    for i in mine:
-                        open_sequence(sequences[i])
-                    last_timings['open_s'] += time.perf_counter() - t0
-                    if lockstep_supported(eval_config, metrics, [sequences[i]['dataset'] for i in mine]):
-                        t0 = time.perf_counter()
-                        for c0 in range(0, len(mine), lockstep):
-                            chunk = [sequences[i] for i in mine[c0:c0 + lockstep]]
-                            for n_eval, mean_scores in eval_method_on_sequences_lockstep(eval_config, model, method_config, chunk, metrics):
-                                for metric_name, score in mean_scores.items():
-                                    local.update(metric_name, score, n_eval)
-                        last_timings['loop_s'] += time.perf_counter() - t0
-                        for i in mine:
-                            sequences[i].pop('dataset', None)
-                        mine = []
-                for i in mine:
-                    seq = sequences[i]
-                    t0 = time.perf_counter()
-                    open_sequence(seq)
-                    t1 = time.perf_counter()
-                    n_eval, mean_scores, _, _ = eval_method_on_sequence(
-                        dataset_config['name'], eval_config, method_name, model, method_config, seq, metrics,
-                        output_root, write_files)
-                    last_timings['open_s'] += t1 - t0
-                    last_timings['loop_s'] += time.perf_counter() - t1
+            for c0 in range(0, len(mine), lockstep):
+                chunk = [sequences[i] for i in mine[c0:c0 + lockstep]]
+                for n_eval, mean_scores in eval_method_on_sequences_lockstep(eval_config, model, method_config, chunk, metrics,
+                                                                             lpips_weights):
                     for metric_name, score in mean_scores.items():
                         local.update(metric_name, score, n_eval)
-                    seq.pop('dataset', None)
-                t0 = time.perf_counter()
-                per_dataset[dataset_config['name']] = reduce_metric_sums(local, metrics)
-                last_timings['reduce_s'] += time.perf_counter() - t0
-            per_method[method_name] = per_dataset
-        results[eval_config['name']] = per_method
-    return results
+            last_timings['loop_s'] += time.perf_counter() - t0
+            for i in mine:
+                sequences[i].pop('dataset', None)
+            mine = []
+    for i in mine:
+        seq = sequences[i]
+        t0 = time.perf_counter()
+        open_sequence(seq)
+        t1 = time.perf_counter()
+        try:
+            n_eval, mean_scores, _, _ = eval_method_on_sequence(
+                dataset_config['name'], eval_config, method_name, model, method_config, seq, metrics,
+                output_root, write_files)
+        finally:
+            if writer is not None:
+                writer.flush()                # the sequence's files are complete before the next one starts
+        last_timings['open_s'] += t1 - t0
+        last_timings['loop_s'] += time.perf_counter() - t1
+        for metric_name, score in mean_scores.items():
+            local.update(metric_name, score, n_eval)
+        seq.pop('dataset', None)

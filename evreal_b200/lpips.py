@@ -40,6 +40,15 @@ def state_dict_from_conv_list(w, backbone):
     return out
 
 
+_default_weights = None
+
+
+def set_default_weights(state_dict):
+    """Weights used by LpipsMetric instances created without any (the tracker builds its metrics by name only)."""
+    global _default_weights
+    _default_weights = state_dict
+
+
 class LpipsNet:
     """evk_lpips handle: ``forward(img, ref)`` -> float64 scores [n] for n <= batch pairs of [H, W] frames in [0, 1]."""
 
@@ -56,6 +65,8 @@ class LpipsNet:
             shape = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
             _lib.check(self.lib.evk_lpips_load_tensor(self.handle, name.encode(), a.ctypes.data_as(ctypes.c_void_p), shape, a.ndim))
         _lib.check(self.lib.evk_lpips_finalize(self.handle))
+        # kernels per forward: input scaling, 5 (AlexNet) / 13 (VGG16) convolutions, 3 / 4 max-poolings, 5 tap reductions, sum
+        self.launches_per_forward = 1 + (5 + 3 if self.backbone == 0 else 13 + 4) + 5 + 1
 
     @property
     def num_tensor_core_layers(self):
@@ -102,6 +113,8 @@ class LpipsMetric(BaseMetric):
     def _weights(self):
         if self._sd is not None:
             return self._sd
+        if _default_weights is not None:
+            return _default_weights
         if self._path and os.path.exists(self._path):
             sd = torch.load(self._path, map_location='cpu', weights_only=False)
             return sd.get('params', sd.get('state_dict', sd)) if isinstance(sd, dict) else sd

@@ -25,6 +25,7 @@ class _NativeModel:
         self._sd = None
         self._handle = None
         self._key = None
+        self._cache = {}          # key -> handle: one device program per (batch, H, W, device, precision) seen so far
         self._device = None
         self.precision = 0        # 0: tensor-core split-bf16 where applicable, 1: fp32 SIMT everywhere
 
@@ -68,11 +69,21 @@ class _NativeModel:
     def _config(self, batch, height, width):
         raise NotImplementedError
 
+    def clone(self):
+        """A second model of the same weights with its own device programs and recurrent state (ColorNet)."""
+        import copy
+        c = copy.copy(self)
+        c._cache, c._handle, c._key = {}, None, None
+        return c
+
+    MAX_HANDLES = 4             # device programs kept per model (ColorNet alternates between two shapes every frame)
+
     def _release(self):
-        if self._handle is not None:
-            _lib.load().evk_model_destroy(self._handle)
-            self._handle = None
-            self._key = None
+        for h in self._cache.values():
+            _lib.load().evk_model_destroy(h)
+        self._cache = {}
+        self._handle = None
+        self._key = None
 
     def __del__(self):
         try:
@@ -84,10 +95,15 @@ class _NativeModel:
         key = (batch, height, width, device, self.precision)
         if self._handle is not None and self._key == key:
             return
+        if key in self._cache:          # a shape seen before: its program and its recurrent state are still there
+            self._handle, self._key = self._cache[key], key
+            return
         if self._sd is None:
             raise _lib.EvkError("load_state_dict() must be called before the first forward")
-        self._release()
         lib = _lib.load()
+        while len(self._cache) >= self.MAX_HANDLES:
+            old = next(iter(self._cache))
+            lib.evk_model_destroy(self._cache.pop(old))
         cfg = self._config(batch, height, width)
         handle = ctypes.c_void_p()
         with torch.cuda.device(device):
@@ -101,14 +117,15 @@ class _NativeModel:
             except Exception:
                 lib.evk_model_destroy(handle)
                 raise
+        self._cache[key] = handle
         self._handle, self._key = handle, key
 
     # ---- reference API
     def reset_states(self):
-        if self._handle is not None:
-            dev = self._key[3]
+        for key, handle in self._cache.items():
+            dev = key[3]
             with torch.cuda.device(dev):
-                _lib.check(_lib.load().evk_model_reset_states(self._handle, _lib.stream_ptr(dev)))
+                _lib.check(_lib.load().evk_model_reset_states(handle, _lib.stream_ptr(dev)))
 
     def forward(self, event_tensor):
         _lib.require_cuda()
@@ -139,6 +156,19 @@ class _NativeModel:
         if hasattr(self, 'prev_recs'):
             self.prev_recs = out
         return out
+
+    def io_buffers(self):
+        """(input, output) device addresses of the handle-owned buffers the NEXT forward uses (double-buffered by parity)."""
+        i, o = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(_lib.load().evk_model_io_buffers(self._handle, ctypes.byref(i), ctypes.byref(o)))
+        return i.value, o.value
+
+    def forward_raw(self, in_ptr, out_ptr):
+        """evk_model_forward on raw device addresses (the streaming pipeline: handle-owned buffers, no copies), on the
+        current stream of the handle's device."""
+        dev = self._key[3]
+        _lib.check(_lib.load().evk_model_forward(self._handle, ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr),
+                                                 _lib.stream_ptr(dev)))
 
     # ---- introspection used by bench / tests
     def flops_per_forward(self):
@@ -217,7 +247,16 @@ class _UNetFamily(_NativeModel):
         self._num_res = kw.get('num_residual_blocks', 2)
         self._k = kw.get('kernel_size', 5)
         self._num_out = kw.get('num_output_channels', 1)
-        self._sigmoid = kw.get('final_activation', 'none') == 'sigmoid'
+        fa = kw.get('final_activation', None)
+        if fa not in (None, '', 'none', 'sigmoid') and hasattr(torch, str(fa)):
+            # the reference applies getattr(torch, name, None) (model/unet.py:95-96,137-138: unknown names mean "no
+            # activation"); only the activations of shipped checkpoints are built, and a real torch function must not
+            # silently run as the identity
+            raise _lib.EvkError("final_activation=%r is not built (supported: none, sigmoid)" % (fa,))
+        self._sigmoid = fa == 'sigmoid'
+        if kw.get('norm', None) not in (None, 'none', 'BN'):
+            raise _lib.EvkError("norm=%r is not built (eval-mode BatchNorm is folded into the convolutions; InstanceNorm "
+                                "has no running statistics to fold)" % (kw.get('norm'),))
         self._dynamic = bool(kw.get('use_dynamic_decoder', False))
         if kw.get('skip_type', 'sum') != 'sum':
             raise NameError("name 'skip_%s' is not defined" % kw.get('skip_type'))     # model/unet.py:31
@@ -318,6 +357,8 @@ class FireNet_legacy(_FireNetBase):
         self._k = int(config.get('kernel_size', 5))
         if str(config.get('recurrent_block_type', 'convgru')) != 'convgru':
             raise _lib.EvkError("FireNet_legacy with convlstm is not built")
+        if config.get('norm', None) not in (None, 'none', 'None', 'BN'):
+            raise _lib.EvkError("FireNet_legacy with norm=%r is not built" % (config.get('norm'),))
         if int(config.get('num_residual_blocks', 2)) != 2 or config.get('recurrent_blocks', {'resblock': [0]}) != {'resblock': [0]}:
             raise _lib.EvkError("only the shipped FireNet topology (2 residual blocks, recurrent resblock 0) is built")
         self.num_recurrent_units = 2
@@ -340,3 +381,88 @@ class FireNet(_FireNetBase):
 
     def _config(self, batch, height, width):
         return self._fire_config(ARCH_FIRENET, batch, height, width)
+
+
+# ---------------------------------------------------------------------------------------------- colour (CED)
+_BAYER = (('R', 0, 0), ('G', 0, 1), ('B', 1, 1), ('W', 1, 0))       # channel -> (row offset, column offset) of its 2x2 site
+
+
+def _shift_replicate(img, dx, dy):
+    """Move an image by (dx, dy) >= 0 pixels, filling the vacated border from the first valid line (utils/color_utils.py:5-17)."""
+    import numpy as np
+    out = np.roll(np.roll(img, dy, axis=0), dx, axis=1)
+    if dy > 0:
+        out[:dy, :] = out[dy, :][None, :]
+    if dx > 0:
+        out[:, :dx] = out[:, dx][:, None]
+    return out
+
+
+def merge_channels_into_color_image(channels):
+    """Half-resolution R/G/B/W reconstructions + the full-resolution grey one -> full-resolution BGR uint8 image: every
+    colour plane is doubled bilinearly and aligned to the R site, green is the mean of G and W, and the LAB lightness of
+    the result is replaced by the grey reconstruction (utils/color_utils.py:52-88).  Output tooling on the host (cv2), not
+    part of the measured path."""
+    import cv2
+    import numpy as np
+    up = {k: cv2.resize(channels[k], dsize=None, fx=2, fy=2, interpolation=cv2.INTER_LINEAR) for k in ('R', 'G', 'B', 'W')}
+    blue = _shift_replicate(up['B'], 1, 1)
+    green = cv2.addWeighted(src1=_shift_replicate(up['G'], 1, 0), alpha=0.5, src2=_shift_replicate(up['W'], 0, 1), beta=0.5,
+                            gamma=0.0, dtype=cv2.CV_8U)
+    lab = cv2.cvtColor(src=np.dstack([blue, green, up['R']]), code=cv2.COLOR_BGR2LAB)
+    lab[:, :, 0] = channels['grayscale']
+    return cv2.cvtColor(src=lab, code=cv2.COLOR_LAB2BGR)
+
+
+class ColorNet:
+    """model/model.py:46-105: the events of a Bayer-pattern sensor (CED) split into R/G/B/W sites, each reconstructed by
+    the wrapped recurrent model with its own state, plus a full-resolution grey reconstruction; the five images are merged
+    into one colour frame.
+
+    The reference runs five batch-1 forwards per frame and swaps ``model.states`` / ``model.prev_recs`` in and out around
+    each.  Recurrent state here is per SAMPLE of a device program, so the four half-resolution sites are ONE batch-4
+    forward of a second program of the same weights and the grey image a batch-1 forward of the wrapped model: no state
+    swapping, two launches of the network per frame instead of five."""
+
+    def __init__(self, model):
+        self.model = model
+        self.half = model.clone()
+        self.reset_states()
+
+    def reset_states(self):
+        self.model.reset_states()
+        self.half.reset_states()
+
+    @property
+    def num_encoders(self):
+        return self.model.num_encoders
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        self.model.to(device)
+        self.half.to(device)
+        return self
+
+    def forward(self, event_tensor):
+        from .util import CropParameters
+        x = event_tensor
+        assert x.dim() == 4 and x.shape[0] == 1, "ColorNet expects one 1 x num_bins x H x W event tensor"
+        if not x.is_cuda:
+            x = x.to(self.model._device or torch.device('cuda', torch.cuda.current_device()), non_blocking=True)
+        height, width = int(x.shape[-2]), int(x.shape[-1])
+        assert height % 2 == 0 and width % 2 == 0, "Bayer split needs even sensor dimensions"
+        crop_half = CropParameters(width // 2, height // 2, self.model.num_encoders)
+        crop_full = CropParameters(width, height, self.model.num_encoders)
+        sites = torch.cat([x[:, :, r::2, c::2] for _, r, c in _BAYER], dim=0)          # [4, bins, H/2, W/2]
+        half = crop_half.crop(self.half(crop_half.pad(sites))['image'])               # [4, 1, H/2, W/2]
+        full = crop_full.crop(self.model(crop_full.pad(x))['image'])                  # [1, 1, H, W]
+        q = lambda t: (t * 255).clamp(0, 255).to(torch.uint8).cpu().numpy()           # np.clip(img * 255, 0, 255).astype(uint8)
+        half8, full8 = q(half), q(full)
+        channels = {name: half8[i, 0] for i, (name, _, _) in enumerate(_BAYER)}
+        channels['grayscale'] = full8[0, 0]
+        bgr = merge_channels_into_color_image(channels)                               # H x W x 3 uint8
+        return {'image': torch.from_numpy(bgr).permute(2, 0, 1).float().div(255)}     # transforms.functional.to_tensor
+
+    __call__ = forward

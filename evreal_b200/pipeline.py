@@ -4,8 +4,14 @@ The reference evaluates one sequence at a time with batch 1 (eval.py:189-246, Da
 eval.py:72).  Sequences are independent (state reset per sequence, eval.py:197) and frames inside one are
 strictly serial, so the B200 form of the loop runs frame ``i`` of B sequences together: ONE voxelizer launch for
 the B windows, then ONE batched normalise+pad, network forward, crop, percentile normalisation and fused MSE/SSIM
-launch for all B.  Per-sample arithmetic is unchanged (normalize_event_tensor statistics are per sample), so
+(and LPIPS) launch for all B.  Per-sample arithmetic is unchanged (normalize_event_tensor statistics are per sample), so
 every sequence gets the frames and scores it would get alone (tests/test_gpu_pipeline.py).
+
+Stages 1 and 3 are frame-independent: with ``overlap=True`` the voxelizer / normaliser of step i+1 runs on a
+"pre" stream and crop / percentile / metrics of step i-1 on a "post" stream while the network of step i owns the main
+stream.  The network's input and output buffers are double-buffered inside the model handle for exactly this
+(``evk_model_io_buffers``); the convolution kernels are persistent and fill every SM, so the side kernels run in the
+tails between them instead of extending the critical path.
 
 Two input modes:
   * ``resident=True``  -- raw event arrays (int16 xy, float64 t, uint8 p) and reference frames are uploaded once
@@ -29,10 +35,13 @@ class SequenceBatch:
     RING = 4          # result slots (device + pinned host) in flight
 
     def __init__(self, model, datasets, event_tensor_normalization=False, post_process_norm='none', resident=True,
-                 device=None, compute_metrics=True, offsets=None, counts=None):
+                 device=None, compute_metrics=True, offsets=None, counts=None, lpips=None, overlap=True, log_scores=False):
         """``offsets`` / ``counts`` (per sequence): step k processes item offsets[b] + k of sequence b for k < counts[b] and an
         empty window afterwards (states are per sample, so a finished sequence does not disturb the others); the batch then
-        has max(counts) steps.  Default: item k of every sequence, min(len) steps."""
+        has max(counts) steps.  Default: item k of every sequence, min(len) steps.
+        ``lpips``: None, or (variant name 'lpips' | 'lpips-vgg', state_dict) -- LPIPS of every (frame, reference) pair of a
+        step in one batched call (the reference's queue of 4, utils/eval_metrics.py:141-148, is a per-pair function).
+        ``log_scores``: keep every step's scores on the device in ``scores_log [steps, B, 3]`` (mse, ssim, lpips)."""
         _lib.require_cuda()
         self.lib = _lib.load()
         self.model = model
@@ -44,6 +53,7 @@ class SequenceBatch:
             raise ValueError(f"Unrecognized normalization argument: {self.post}")
         self.resident = resident
         self.compute_metrics = compute_metrics
+        self.overlap = bool(overlap)
         self.dev = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         ds0 = self.datasets[0]
         self.H, self.W = int(ds0.sensor_resolution[0]), int(ds0.sensor_resolution[1])
@@ -51,38 +61,47 @@ class SequenceBatch:
         for ds in self.datasets:
             assert (int(ds.sensor_resolution[0]), int(ds.sensor_resolution[1])) == (self.H, self.W), \
                 "sequences batched together must share the sensor resolution"
+            assert ds.num_bins == self.bins, "sequences batched together must share num_bins"
             assert ds.has_images or not compute_metrics
         self.crop = CropParameters(self.W, self.H, model.num_encoders)
         self.Hp, self.Wp = self.crop.height_crop_size, self.crop.width_crop_size
         B, H, W, dev = self.B, self.H, self.W, self.dev
         f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            model.to(dev)
+            model._ensure(B, self.Hp, self.Wp, dev)            # device program + double-buffered input / output
         self.voxel = torch.zeros((B, self.bins, H, W), **f32)
-        self.padded = torch.empty((B, self.bins, self.Hp, self.Wp), **f32)
-        self.recon_p = torch.empty((B, 1, self.Hp, self.Wp), **f32)
         self.recon = torch.empty((B, 1, H, W), **f32)
-        self.ref = torch.zeros((B, H, W), **f32)
+        self.ref2 = torch.zeros((2, B, H, W), **f32)            # reference frames of two consecutive steps
+        self.ref = self.ref2[0]
         # results rotate through RING device slots so that the device->host copy of step i (own stream) never races
         # the kernels of step i+1
         self.image_ring = torch.empty((self.RING, B, 1, H, W), **f32)
         self.scores_ring = torch.zeros((self.RING, B, 2), dtype=torch.float64, device=dev)
+        self.lpips_ring = torch.zeros((self.RING, B), dtype=torch.float64, device=dev)
         self.scores = self.scores_ring[0]
+        self.lpips_scores = self.lpips_ring[0]
         self.image = self.image_ring[0]
         self.oob_total = torch.zeros(1, dtype=torch.int32, device=dev)
         self.launches = 0            # kernels launched by the last step (bench.py gpu_launches)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._nstep = 0
-        # window tables (start, end, frame index) of every item, once: dataset.py:104-130 via MemMapDataset.window
+        # per item of every sequence, once (dataset.py:33-102 via MemMapDataset.item_meta): event range, reference frame,
+        # voxel / frame timestamps (the score gates of utils/eval_metrics.py:256-262 are evaluated from these on the host)
         self._offsets = [0] * B if offsets is None else [int(o) for o in offsets]
         self._counts = None if counts is None else [int(c) for c in counts]
         n_items = len(self)
         self._win = np.zeros((B, n_items, 3), dtype=np.int64)
+        self.voxel_ts = np.zeros((B, n_items), dtype=np.float64)
+        self.frame_ts = np.zeros((B, n_items), dtype=np.float64)
         max_win = 1
         for b, ds in enumerate(self.datasets):
             for i in range(n_items if self._counts is None else min(n_items, self._counts[b])):
-                i0, i1, fi = ds.window(self._offsets[b] + i)
-                self._win[b, i] = (int(i0), max(int(i1), int(i0)), int(fi) if fi is not None else 0)
-            max_win = max(max_win, int((self._win[b, :, 1] - self._win[b, :, 0]).max()))
+                i0, i1, fi, vts, fts, _, _ = ds.item_meta(self._offsets[b] + i)
+                self._win[b, i] = (i0, max(i1, i0), fi)
+                self.voxel_ts[b, i], self.frame_ts[b, i] = vts, fts
+            max_win = max(max_win, int((self._win[b, :, 1] - self._win[b, :, 0]).max()) if n_items else 1)
         self.max_win = max_win
         self._src = []
         self._base = np.zeros((B, 4), dtype=np.int64)      # raw base addresses (xy, t, p, images) of every sequence
@@ -99,6 +118,29 @@ class SequenceBatch:
             self._base[b] = (xy.data_ptr(), t.data_ptr(), p.data_ptr(), im.data_ptr() if im is not None else 0)
         self._windows = (_lib.EventWindow * B)()
         self._frames = (ctypes.c_void_p * B)()
+        self.lpips_net = None
+        if lpips is not None and compute_metrics:
+            from .lpips import LpipsNet
+            name, sd = lpips
+            with torch.cuda.device(dev):
+                self.lpips_net = LpipsNet(name, sd, H, W, batch=B)
+        self.scores_log = None
+        if log_scores:
+            self.scores_log = torch.zeros((max(n_items, 1), B, 3), dtype=torch.float64, device=dev)
+        # streams and the events that order the three stages of neighbouring steps
+        if self.overlap:
+            self.pre_stream = torch.cuda.Stream(dev)
+            self.post_stream = torch.cuda.Stream(dev)
+        else:
+            self.pre_stream = self.post_stream = None
+        self._pre_issued = None          # item whose voxel tensor is (being) written into the model's next input buffer
+        self._pre_in_ptr = None
+        self._pre_done = torch.cuda.Event()
+        self._fwd_done = [torch.cuda.Event(), torch.cuda.Event()]      # by step parity
+        self._post_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self._fwd_recorded = [False, False]
+        self._post_recorded = [False, False]
+        self.result_event = None
         if not resident:
             # double-buffered device staging: slot s is filled by the copy stream while slot s^1 is being voxelized
             self.st_xy = torch.empty((2, B, max_win, 2), dtype=torch.int16, device=dev)
@@ -106,11 +148,12 @@ class SequenceBatch:
             self.st_p = torch.empty((2, B, max_win), dtype=torch.uint8, device=dev)
             self.st_im = torch.empty((2, B, H, W), dtype=torch.uint8, device=dev)
             self.host_scores = torch.empty((self.RING, B, 2), dtype=torch.float64).pin_memory()
+            self.host_lpips = torch.empty((self.RING, B), dtype=torch.float64).pin_memory()
             self.host_image = torch.empty((self.RING, B, 1, H, W), dtype=torch.float32).pin_memory()
             self.copy_stream = torch.cuda.Stream(dev)
             self.d2h_stream = torch.cuda.Stream(dev)
             self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
-            self._consumed = [None, None]                 # recorded on the compute stream after a slot was voxelized
+            self._consumed = [None, None]                 # recorded on the pre stream after a slot was voxelized
             self._d2h_done = [None] * self.RING
             self._staged = [None, None]                   # item index held (or in flight) in each staging slot
             self._last_slot = 1
@@ -124,8 +167,13 @@ class SequenceBatch:
         return min(len(ds) - o for ds, o in zip(self.datasets, self._offsets))
 
     def reset(self):
-        self.model.reset_states()
+        self.finish()
+        self.model.reset_states()            # (also rewinds the parity of the model's input / output buffers)
         self.oob_total.zero_()
+        self._pre_issued = None
+        self._nstep = 0
+        self._fwd_recorded = [False, False]
+        self._post_recorded = [False, False]
 
     # ------------------------------------------------------------------ host-mode staging
     def _stage(self, idx, slot):
@@ -153,106 +201,187 @@ class SequenceBatch:
         self._h2d_done[slot].record(self.copy_stream)
         self._staged[slot] = idx
 
-    def step(self, idx, next_idx=None):
-        """Frame ``idx`` of every sequence.  Returns (scores [B,2] float64 (mse, ssim), image [B,1,H,W], n_events).
-        In host mode the returned tensors are pinned host tensors, valid after ``self.result_event`` (or a device
-        synchronize); ``next_idx`` (default idx + 1) is the item whose windows are staged while this one computes."""
-        lib, dev, B = self.lib, self.dev, self.B
-        main = torch.cuda.current_stream(dev)
-        st = ctypes.c_void_p(main.cuda_stream)
-        launches = 0
-        h2d = d2h = 0
+    # ------------------------------------------------------------------ stage 1 of item idx -> the model's next input buffer
+    def _issue_pre(self, idx, main, par):
+        """Voxelize + normalise + pad item ``idx`` of every sequence into the input buffer of the model's next forward, and
+        convert its reference frames into ref2[par]; on the pre stream when overlapping.  Returns kernel launches issued."""
+        lib, B = self.lib, self.B
+        pre = self.pre_stream if self.overlap else main
+        st = ctypes.c_void_p(pre.cuda_stream)
         win = self._win[:, idx]
         n_events = int((win[:, 1] - win[:, 0]).sum())
+        ws, fr = self._windows, self._frames
+        launches = 0
+        if self.overlap:
+            # the buffers written below were last read by the forward / the metrics of the step before the previous one
+            if self._fwd_recorded[par]:
+                pre.wait_event(self._fwd_done[par])
+            if self._post_recorded[par]:
+                pre.wait_event(self._post_done[par])
+        if self.resident:
+            for b in range(B):
+                i0, i1 = int(win[b, 0]), int(win[b, 1])
+                w = ws[b]
+                w.xy = int(self._base[b, 0]) + i0 * 4
+                w.t = int(self._base[b, 1]) + i0 * 8
+                w.pol = int(self._base[b, 2]) + i0
+                w.n = i1 - i0
+                fr[b] = int(self._base[b, 3]) + int(win[b, 2]) * self.H * self.W
+        else:
+            slot = 0 if self._staged[0] == idx else (1 if self._staged[1] == idx else None)
+            if slot is None:                      # first step / non-sequential access: stage now
+                slot = self._last_slot ^ 1
+                self._stage(idx, slot)
+            self._last_slot = slot
+            pre.wait_event(self._h2d_done[slot])
+            xy0, t0, p0, im0 = (self.st_xy[slot].data_ptr(), self.st_t[slot].data_ptr(), self.st_p[slot].data_ptr(),
+                                self.st_im[slot].data_ptr())
+            for b in range(B):
+                w = ws[b]
+                w.xy = xy0 + b * self.max_win * 4
+                w.t = t0 + b * self.max_win * 8
+                w.pol = p0 + b * self.max_win
+                w.n = int(win[b, 1] - win[b, 0])
+                fr[b] = im0 + b * self.H * self.W
+            self._h2d_step = n_events * 13 + (B * self.H * self.W if self.compute_metrics else 0)
+        in_ptr, _ = self.model.io_buffers()
+        # empty windows -> zeros grid (dataset.py:59-71) is part of the batched call
+        _lib.check(lib.evk_voxelize_raw_batch(ws, B, self.bins, self.H, self.W, _lib.ptr(self.voxel),
+                                              _lib.ptr(self.oob_total), st))
+        launches += 3 if n_events > 0 else 2                # scratch clear, scatter, gather
+        if self.compute_metrics:
+            _lib.check(lib.evk_u8_to_f32_batch(fr, B, self.H * self.W, _lib.ptr(self.ref2[par]), st))
+            launches += 1
+        if not self.resident:
+            if self._consumed[slot] is None:
+                self._consumed[slot] = torch.cuda.Event()
+            self._consumed[slot].record(pre)
+        _lib.check(lib.evk_normalize_pad(_lib.ptr(self.voxel), ctypes.c_void_p(in_ptr), B, self.bins, self.H, self.W,
+                                         self.Hp, self.Wp, int(self.normalize), st))
+        launches += 2 if self.normalize else 1
+        self._pre_done.record(pre)
+        self._pre_issued, self._pre_in_ptr, self._pre_events = idx, in_ptr, n_events
+        return launches
+
+    def step(self, idx, next_idx=None):
+        """Frame ``idx`` of every sequence.  Returns (scores [B,2] float64 (mse, ssim), image [B,1,H,W], n_events).
+        The returned tensors are written by the post stream (host mode: pinned host tensors written by the copy stream): they
+        are valid after ``self.result_event`` -- ``wait_results()`` makes the current stream wait for it, ``finish()`` the host.
+        ``next_idx`` (default idx + 1) is the item whose windows are staged / voxelized while this one runs the network."""
+        lib, dev, B = self.lib, self.dev, self.B
+        main = torch.cuda.current_stream(dev)
+        launches = 0
+        h2d = d2h = 0
         ring = self._nstep % self.RING
+        par = self._nstep & 1
         self._nstep += 1
         with torch.cuda.device(dev):
-            ws, fr = self._windows, self._frames
-            if self.resident:
-                for b in range(B):
-                    i0, i1 = int(win[b, 0]), int(win[b, 1])
-                    w = ws[b]
-                    w.xy = int(self._base[b, 0]) + i0 * 4
-                    w.t = int(self._base[b, 1]) + i0 * 8
-                    w.pol = int(self._base[b, 2]) + i0
-                    w.n = i1 - i0
-                    fr[b] = int(self._base[b, 3]) + int(win[b, 2]) * self.H * self.W
-            else:
-                slot = 0 if self._staged[0] == idx else (1 if self._staged[1] == idx else None)
-                if slot is None:                      # first step / non-sequential access: stage now
-                    slot = self._last_slot ^ 1
-                    self._stage(idx, slot)
-                self._last_slot = slot
-                main.wait_event(self._h2d_done[slot])
-                xy0, t0, p0, im0 = (self.st_xy[slot].data_ptr(), self.st_t[slot].data_ptr(), self.st_p[slot].data_ptr(),
-                                    self.st_im[slot].data_ptr())
-                for b in range(B):
-                    w = ws[b]
-                    w.xy = xy0 + b * self.max_win * 4
-                    w.t = t0 + b * self.max_win * 8
-                    w.pol = p0 + b * self.max_win
-                    w.n = int(win[b, 1] - win[b, 0])
-                    fr[b] = im0 + b * self.H * self.W
-                h2d += n_events * 13 + (B * self.H * self.W if self.compute_metrics else 0)
-            # empty windows -> zeros grid (dataset.py:59-71) is part of the batched call
-            _lib.check(lib.evk_voxelize_raw_batch(ws, B, self.bins, self.H, self.W, _lib.ptr(self.voxel),
-                                                  _lib.ptr(self.oob_total), st))
-            launches += 1 if n_events > 0 else 0
-            if self.compute_metrics:
-                _lib.check(lib.evk_u8_to_f32_batch(fr, B, self.H * self.W, _lib.ptr(self.ref), st))
-                launches += 1
+            self.model._ensure(B, self.Hp, self.Wp, dev)
+            # ---- stage 1 (normally already issued by the previous step)
+            if self._pre_issued != idx:
+                launches += self._issue_pre(idx, main, par)
+            n_events = self._pre_events
             if not self.resident:
-                if self._consumed[slot] is None:
-                    self._consumed[slot] = torch.cuda.Event()
-                self._consumed[slot].record(main)
-                nxt = idx + 1 if next_idx is None else next_idx
-                if 0 <= nxt < self._win.shape[1] and self._staged[slot ^ 1] != nxt:
-                    self._stage(nxt, slot ^ 1)        # overlaps everything below
-            _lib.check(lib.evk_normalize_pad(_lib.ptr(self.voxel), _lib.ptr(self.padded), B, self.bins, self.H, self.W,
-                                             self.Hp, self.Wp, int(self.normalize), st))
-            launches += 2 if self.normalize else 1
-            out = self.model.forward_into(self.padded, self.recon_p)
+                h2d += self._h2d_step
+            in_ptr, out_ptr = self.model.io_buffers()
+            assert in_ptr == self._pre_in_ptr, "model parity changed under the pipeline (call reset() after model.reset_states())"
+            # ---- stage 2: the network, on the caller's stream
+            if self.overlap:
+                main.wait_event(self._pre_done)
+                if self._post_recorded[par]:
+                    main.wait_event(self._post_done[par])        # the output buffer of this parity has been consumed
+            self.model.forward_raw(in_ptr, out_ptr)
             launches += self.model.last_launch_count()
-            _lib.check(lib.evk_crop(_lib.ptr(out), _lib.ptr(self.recon), B, 1, self.Hp, self.Wp, self.H, self.W, st))
-            launches += 1
+            self._fwd_done[par].record(main)
+            self._fwd_recorded[par] = True
+            # ---- stage 1 of the next item, behind the network just enqueued
+            nxt = idx + 1 if next_idx is None else next_idx
+            if 0 <= nxt < self._win.shape[1] and nxt != idx:
+                if not self.resident and self._staged[0] != nxt and self._staged[1] != nxt:
+                    self._stage(nxt, self._last_slot ^ 1)
+                launches_next = self._issue_pre(nxt, main, par ^ 1)
+            else:
+                launches_next = 0
+                self._pre_issued = None
+            # ---- stage 3 on the post stream
+            post = self.post_stream if self.overlap else main
+            st = ctypes.c_void_p(post.cuda_stream)
+            if self.overlap:
+                post.wait_event(self._fwd_done[par])
             if not self.resident and self._d2h_done[ring] is not None:
-                main.wait_event(self._d2h_done[ring])             # slot's previous results have left the device
+                post.wait_event(self._d2h_done[ring])             # slot's previous results have left the device
             image = self.image_ring[ring]
+            row = self.scores_log[idx] if self.scores_log is not None and idx < self.scores_log.shape[0] else None
             scores = self.scores_ring[ring]
+            lp = self.lpips_ring[ring]
+            # the ring slot is what travels to the host: without a percentile pass the crop writes it directly (a shared
+            # crop buffer would be overwritten by the next step while the device->host copy of this one is still reading)
+            cropped = self.recon if self.post != 'none' else image
+            _lib.check(lib.evk_crop(ctypes.c_void_p(out_ptr), _lib.ptr(cropped), B, 1, self.Hp, self.Wp, self.H, self.W, st))
+            launches += 1
             if self.post != 'none':
                 q = (0.0, 100.0) if self.post == 'standard' else (1.0, 99.0)
                 _lib.check(lib.evk_percentile_normalize(_lib.ptr(self.recon), _lib.ptr(image), B, self.H * self.W,
                                                         q[0], q[1], int(self.post == 'exprobust'), st))
                 launches += 1
-            else:
-                image = self.recon
             if self.compute_metrics:
-                # clip of EvalMetricsTracker.update (utils/eval_metrics.py:253-255) fused into the metric kernel
-                _lib.check(lib.evk_mse_ssim(_lib.ptr(image), _lib.ptr(self.ref), B, self.H, self.W, 1,
-                                            _lib.ptr(scores), st))
+                ref = self.ref2[par]
+                # clip of EvalMetricsTracker.update (utils/eval_metrics.py:253-255) fused into the metric kernels
+                _lib.check(lib.evk_mse_ssim(_lib.ptr(image), _lib.ptr(ref), B, self.H, self.W, 1, _lib.ptr(scores), st))
                 launches += 2
-            self.scores, self.image = scores, image
+                if self.lpips_net is not None:
+                    _lib.check(lib.evk_lpips_forward(self.lpips_net.handle, _lib.ptr(image), _lib.ptr(ref), B, _lib.ptr(lp), st))
+                    launches += self.lpips_net.launches_per_forward
+                if row is not None:
+                    with torch.cuda.stream(post):
+                        row[:, :2].copy_(scores, non_blocking=True)
+                        if self.lpips_net is not None:
+                            row[:, 2].copy_(lp, non_blocking=True)
+                self.ref = ref
+            self._post_done[par].record(post)
+            self._post_recorded[par] = True
+            self.result_event = self._post_done[par]
+            self.scores, self.image, self.lpips_scores = scores, image, lp
             if not self.resident:
-                done = torch.cuda.Event()
-                done.record(main)
-                self.d2h_stream.wait_event(done)
+                self.d2h_stream.wait_event(self._post_done[par])
                 with torch.cuda.stream(self.d2h_stream):
                     self.host_scores[ring].copy_(scores, non_blocking=True)
                     self.host_image[ring].copy_(image, non_blocking=True)
+                    if self.lpips_net is not None:
+                        self.host_lpips[ring].copy_(lp, non_blocking=True)
                 if self._d2h_done[ring] is None:
                     self._d2h_done[ring] = torch.cuda.Event()
                 self._d2h_done[ring].record(self.d2h_stream)
                 self.result_event = self._d2h_done[ring]
-                d2h += scores.numel() * 8 + image.numel() * 4
+                d2h += scores.numel() * 8 + image.numel() * 4 + (lp.numel() * 8 if self.lpips_net is not None else 0)
                 scores, image = self.host_scores[ring], self.host_image[ring]
-        self.launches, self.h2d_bytes, self.d2h_bytes = launches, h2d, d2h
+                self.host_lpips_scores = self.host_lpips[ring]
+        self.launches, self.h2d_bytes, self.d2h_bytes = launches + launches_next, h2d, d2h
         return scores, image, n_events
 
+    def wait_results(self):
+        """Make the current stream wait for the results of the last step (device-side; does not block the host)."""
+        if self.result_event is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self.result_event)
+
     def finish(self):
-        """Wait for every copy in flight (host mode)."""
+        """Wait (on the host) for every stage and copy in flight."""
+        if self.overlap:
+            self.pre_stream.synchronize()
+            self.post_stream.synchronize()
         if not self.resident:
             self.copy_stream.synchronize()
             self.d2h_stream.synchronize()
+
+    def join(self, stream=None):
+        """Make ``stream`` (default: the current stream) wait for all side-stream work issued so far -- used to bracket a
+        timed region with events recorded on one stream."""
+        s = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        for side in (self.pre_stream, self.post_stream, getattr(self, 'copy_stream', None), getattr(self, 'd2h_stream', None)):
+            if side is not None:
+                e = torch.cuda.Event()
+                e.record(side)
+                s.wait_event(e)
 
     def check_bounds(self):
         n = int(self.oob_total.item())

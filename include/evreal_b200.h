@@ -127,8 +127,11 @@ int evk_model_state_shape(evk_model* m, int index, int64_t shape_nchw[4]);
 int evk_model_get_state(evk_model* m, int index, float* out_nchw, void* stream);
 int evk_model_set_state(evk_model* m, int index, const float* in_nchw, void* stream);
 int evk_model_destroy(evk_model* m);
-/* Handle-owned staging buffers: in [batch,num_bins,height,width], out [batch,1,height,width].
- * Passing these to evk_model_forward skips the device-to-device staging copies. */
+/* Handle-owned input / output buffers of the NEXT evk_model_forward call: in [batch,num_bins,height,width], out
+ * [batch,1,height,width].  They are double-buffered by forward parity (call k uses pair k & 1), so a caller may fill the
+ * input of call k+1 and read the output of call k-1 on other streams while call k runs; passing the returned pointers to
+ * evk_model_forward skips the device-to-device staging copies.  (HyperE2VID's previous reconstruction, model/model.py:139-143,
+ * is the other output buffer: the caller must not overwrite `out` of call k before call k+1 has finished.) */
 int evk_model_io_buffers(evk_model* m, float** in, float** out);
 /* kernels launched by the last forward (for bench.py's gpu_launches) */
 int evk_model_last_launch_count(evk_model* m);
@@ -206,6 +209,15 @@ int evk_lpips_destroy(evk_lpips* l);
 int evk_u8_to_f32(const uint8_t* in, float* out, int64_t numel, void* stream);
 /* n_frames frames of numel bytes each (HOST array of device pointers) -> out [n_frames, numel] float32, one launch */
 int evk_u8_to_f32_batch(const uint8_t* const* frames, int n_frames, int64_t numel, float* out, void* stream);
+
+/* EvalMetricsTracker.histogram_equalization with hist_eq == 'global' (utils/eval_metrics.py:326-331):
+ * skimage.exposure.equalize_hist (256 bins over [min, max], cdf, np.interp over the bin centres) -> float32.
+ * img/out: [n_images, numel] float32 (may alias); clip != 0 first clamps to [0,1]. */
+int evk_equalize_hist(const float* img, float* out, int n_images, int numel, int clip, void* stream);
+
+/* float32 frame -> uint8 for the PNG writer: uint8(round_half_even(clip(v, 0, 1) * 255))
+ * (save_inferred_image, utils/eval_utils.py:80-84, after the clip of EvalMetricsTracker.update, utils/eval_metrics.py:253-255) */
+int evk_quantize_u8(const float* in, uint8_t* out, int64_t numel, void* stream);
 
 #ifdef __cplusplus
 }
