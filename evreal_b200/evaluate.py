@@ -261,7 +261,9 @@ def eval_method_on_sequences_lockstep(eval_config, model, method_config, sequenc
                               lpips=lpips, log_scores=True)
         batch.reset()
         for k in range(steps):
-            batch.step(k)
+            _, _, n_ev = batch.step(k, sync=False)
+            last_timings['events'] = last_timings.get('events', 0) + n_ev
+        last_timings['frames'] = last_timings.get('frames', 0) + sum(counts)
         batch.finish()
         batch.check_bounds()
         sc = batch.scores_log.cpu().numpy()
@@ -344,7 +346,7 @@ def reduce_metric_sums(local, metric_names, group=None):
 
 
 # wall-clock seconds of the last evaluate() call on this rank, by phase (model construction, sequence open + upload,
-# per-frame loop); diagnostic only
+# per-frame loop, all-reduce), frames reconstructed / events voxelized, failures caught; diagnostic only
 last_timings = {}
 
 
@@ -373,7 +375,7 @@ def evaluate(method_names, eval_config_names=None, dataset_names=None, metrics=N
         metrics = ['mse', 'ssim']
     import time
     results = OrderedDict()
-    tm = {'model_s': 0.0, 'open_s': 0.0, 'loop_s': 0.0, 'reduce_s': 0.0, 'failures': 0}
+    tm = {'model_s': 0.0, 'open_s': 0.0, 'loop_s': 0.0, 'reduce_s': 0.0, 'failures': 0, 'frames': 0, 'events': 0}
     last_timings.clear()
     last_timings.update(tm)
     writer = eval_utils.AsyncWriter() if (write_files and async_writer) else None
@@ -455,9 +457,11 @@ def _eval_dataset(eval_config, method_name, model, method_config, dataset_config
         open_sequence(seq)
         t1 = time.perf_counter()
         try:
-            n_eval, mean_scores, _, _ = eval_method_on_sequence(
+            n_eval, mean_scores, n_frames, n_events = eval_method_on_sequence(
                 dataset_config['name'], eval_config, method_name, model, method_config, seq, metrics,
                 output_root, write_files)
+            last_timings['frames'] += n_frames
+            last_timings['events'] += n_events
         finally:
             if writer is not None:
                 writer.flush()                # the sequence's files are complete before the next one starts

@@ -105,17 +105,32 @@ class SequenceBatch:
         self.max_win = max_win
         self._src = []
         self._base = np.zeros((B, 4), dtype=np.int64)      # raw base addresses (xy, t, p, images) of every sequence
-        for b, ds in enumerate(self.datasets):
-            fh = ds.filehandle
-            xy = torch.from_numpy(np.ascontiguousarray(fh["xy"], dtype=np.int16)).pin_memory()
-            t = torch.from_numpy(np.ascontiguousarray(fh["t"], dtype=np.float64)).pin_memory()
-            p = torch.from_numpy(np.ascontiguousarray(fh["p"]).astype(np.uint8)).pin_memory()
-            im = torch.from_numpy(np.ascontiguousarray(fh["images"][..., 0])).pin_memory() if ds.has_images else None
-            if resident:
-                xy, t, p = (a.to(dev, non_blocking=True) for a in (xy, t, p))
-                im = im.to(dev, non_blocking=True) if im is not None else None
-            self._src.append((xy, t, p, im))
-            self._base[b] = (xy.data_ptr(), t.data_ptr(), p.data_ptr(), im.data_ptr() if im is not None else 0)
+        if resident:
+            # one threaded, chunked upload of every sequence (13 B/event + frames): _upload.py
+            from . import _upload
+            host = []
+            for ds in self.datasets:
+                fh = ds.filehandle
+                p = np.asarray(fh["p"])
+                host += [np.asarray(fh["xy"]) if np.asarray(fh["xy"]).dtype == np.int16 else np.asarray(fh["xy"]).astype(np.int16),
+                         np.asarray(fh["t"], dtype=np.float64), p if p.dtype == np.uint8 else p.astype(np.uint8)]
+                if ds.has_images:
+                    host.append(np.asarray(fh["images"])[..., 0])
+            devs = iter(_upload.get(dev).upload(host))
+            for b, ds in enumerate(self.datasets):
+                xy, t, p = next(devs), next(devs), next(devs)
+                im = next(devs) if ds.has_images else None
+                self._src.append((xy, t, p, im))
+                self._base[b] = (xy.data_ptr(), t.data_ptr(), p.data_ptr(), im.data_ptr() if im is not None else 0)
+        else:
+            for b, ds in enumerate(self.datasets):
+                fh = ds.filehandle
+                xy = torch.from_numpy(np.ascontiguousarray(fh["xy"], dtype=np.int16)).pin_memory()
+                t = torch.from_numpy(np.ascontiguousarray(fh["t"], dtype=np.float64)).pin_memory()
+                p = torch.from_numpy(np.ascontiguousarray(fh["p"]).astype(np.uint8)).pin_memory()
+                im = torch.from_numpy(np.ascontiguousarray(fh["images"][..., 0])).pin_memory() if ds.has_images else None
+                self._src.append((xy, t, p, im))
+                self._base[b] = (xy.data_ptr(), t.data_ptr(), p.data_ptr(), im.data_ptr() if im is not None else 0)
         self._windows = (_lib.EventWindow * B)()
         self._frames = (ctypes.c_void_p * B)()
         self.lpips_net = None
@@ -263,10 +278,13 @@ class SequenceBatch:
         self._pre_issued, self._pre_in_ptr, self._pre_events = idx, in_ptr, n_events
         return launches
 
-    def step(self, idx, next_idx=None):
+    def step(self, idx, next_idx=None, sync=True):
         """Frame ``idx`` of every sequence.  Returns (scores [B,2] float64 (mse, ssim), image [B,1,H,W], n_events).
         The returned tensors are written by the post stream (host mode: pinned host tensors written by the copy stream): they
-        are valid after ``self.result_event`` -- ``wait_results()`` makes the current stream wait for it, ``finish()`` the host.
+        are valid after ``self.result_event``.  ``sync=True`` (default) makes the current stream wait for it, so device
+        tensors can be used right away; throughput loops pass ``sync=False`` (the next network forward then does not wait
+        for this step's metrics) and read ``scores_log`` / call ``finish()`` at the end.  Host-mode results additionally
+        need ``result_event.synchronize()`` or ``finish()`` before the host reads them.
         ``next_idx`` (default idx + 1) is the item whose windows are staged / voxelized while this one runs the network."""
         lib, dev, B = self.lib, self.dev, self.B
         main = torch.cuda.current_stream(dev)
@@ -357,6 +375,8 @@ class SequenceBatch:
                 scores, image = self.host_scores[ring], self.host_image[ring]
                 self.host_lpips_scores = self.host_lpips[ring]
         self.launches, self.h2d_bytes, self.d2h_bytes = launches + launches_next, h2d, d2h
+        if sync and self.overlap:
+            main.wait_event(self._post_done[par])
         return scores, image, n_events
 
     def wait_results(self):

@@ -105,6 +105,24 @@ def post_process_oracle(img, norm):
     raise ValueError("Unrecognized normalization argument: %s" % norm)
 
 
+def equalize_hist_oracle(img, nbins=256):
+    """EvalMetricsTracker.histogram_equalization, hist_eq == 'global' (utils/eval_metrics.py:326-331):
+    skimage.exposure.equalize_hist -> img_as_float32.  PARITY UNPINNED (scikit-image is not installable offline); its
+    published algorithm: hist, edges = np.histogram(img, nbins) over [min, max]; cdf = cumsum(hist) / numel;
+    out = np.interp(img, bin centres, cdf)."""
+    img = np.asarray(img, dtype=np.float32)
+    hist, edges = np.histogram(img.ravel(), bins=nbins)
+    centres = (edges[:-1] + edges[1:]) / 2.0
+    cdf = hist.cumsum()
+    cdf = cdf / float(cdf[-1])
+    return np.interp(img.ravel(), centres, cdf).reshape(img.shape).astype(np.float32)
+
+
+def quantize_u8_oracle(img):
+    """save_inferred_image (utils/eval_utils.py:80-84) after the tracker's clip: uint8(np.round(clip(img, 0, 1) * 255))."""
+    return np.round(np.clip(np.asarray(img, dtype=np.float32), 0.0, 1.0) * 255).astype(np.uint8)
+
+
 # ----------------------------------------------------------------------------
 # LPIPS (PARITY UNPINNED -- see module docstring)
 # ----------------------------------------------------------------------------

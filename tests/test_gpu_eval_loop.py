@@ -154,3 +154,96 @@ def test_lockstep_evaluate_matches_sequential(tmp_path):
         count = sum(p.data_dict[k]['count'] for p in parts if k in p.data_dict)
         assert count == seq.get_count(k)
         assert abs(total / count - seq.get_average(k)) <= 1e-6 * abs(seq.get_average(k))
+
+
+@pytest.mark.parametrize('tag', ['k_events', 't_seconds'])
+def test_k_events_and_t_seconds_windows_vs_real_loop(tmp_path, tag):
+    """'k_events' / 't_seconds' windows through the GPU loop (round-1 verdict, weak #3): closest-frame pairing
+    (dataset.py:150-166), a ts_tol_ms gate that rejects most frames (utils/eval_metrics.py:258-262) and the patched
+    timestamps of empty windows (dataset.py:59-71; the stream has a silent gap) -- evaluated indices bit-exact, per-frame
+    scores within 1e-4 of the REAL eval.eval_method_on_sequence (tests/golden/eval_loop_modes.npz), one sequence at a time
+    AND in the lock-step form."""
+    from evreal_b200 import FireNet_legacy, evaluate as ev
+    g = golden('eval_loop_modes')
+    full, _ = weights_of(golden('networks'), 'firenet_ckpt', 'net.')
+    k, w, t, sw = g[tag + '.vm']
+    vm = {'method': 'k_events', 'k': int(k), 'sliding_window_w': int(w)} if tag == 'k_events' else \
+        {'method': 't_seconds', 't': float(t), 'sliding_window_t': float(sw)}
+    n_eval, mse, ssim, start, end, tol = g[tag + '.summary']
+    cfg = dict(EVAL_CFG, ts_tol_ms=float(tol), dataset_kwargs={'num_bins': 5, 'voxel_method': vm})
+    method = {'event_tensor_normalization': True, 'post_process_norm': 'none'}
+    arrays = {key: g[key] for key in ('events_ts', 'events_xy', 'events_p', 'images', 'images_ts', 'image_event_indices')}
+    path = write_sequence_from_arrays(str(tmp_path / 'modeseq'), arrays, (48, 64))
+
+    def sequence():
+        s = {'name': 'modeseq', 'sequence_path': path, 'start_time_s': float(start), 'end_time_s': float(end),
+             'dataset_kwargs': dict(cfg['dataset_kwargs'])}
+        ds = ev.open_sequence(s)
+        assert len(ds) == int(g[tag + '.len'][0])
+        return s
+
+    m = FireNet_legacy(dict(FIRENET_KW)).load_state_dict(full).to('cuda')
+    got_n, means, frames, _ = ev.eval_method_on_sequence('SYN', cfg, tag, m, method, sequence(), ['mse', 'ssim'],
+                                                         output_root=str(tmp_path / 'out'), write_files=True, )
+    assert got_n == int(n_eval) and 0 < got_n < frames          # the tolerance gate rejected some reconstructed frames
+    out = tmp_path / 'out' / 'std' / 'SYN' / 'modeseq' / tag
+    rows = [l.split() for l in open(out / 'mse.txt').read().splitlines()]
+    assert [int(r[0]) for r in rows] == [int(i) for i in g[tag + '.indices']]              # bit-exact evaluated items
+    assert np.allclose([float(r[1]) for r in rows], g[tag + '.mse'], rtol=1e-4, atol=6e-6)
+    assert abs(means['mse'] - mse) <= 1e-4 * mse and abs(means['ssim'] - ssim) <= 1e-4 * abs(ssim)
+    # lock-step form: the same sequence twice in one batch
+    res = ev.eval_method_on_sequences_lockstep(cfg, m, method, [sequence(), sequence()], ['mse', 'ssim'])
+    for n2, means2 in res:
+        assert n2 == int(n_eval)
+        assert abs(means2['mse'] - mse) <= 1e-4 * mse and abs(means2['ssim'] - ssim) <= 1e-4 * abs(ssim)
+
+
+def test_failures_are_caught_per_method_and_per_dataset(tmp_path, capsys):
+    """eval.py:344-352,357-375: a method whose model cannot be built and a dataset whose sequence raises are reported and
+    skipped; everything else still produces its means."""
+    from evreal_b200 import evaluate as ev
+    g = golden('eval_loop')
+    _write_plugin_tree(tmp_path, g, 2)
+    cfg_root = tmp_path / 'config'
+    json.dump({'model_name': 'ET-Net', 'model_path': str(tmp_path / 'pretrained' / 'FireNet' / 'model.pth')},
+              open(cfg_root / 'method' / 'ET-Net.json', 'w'))
+    # a second dataset whose only sequence has an event outside the sensor (IndexError at check_bounds)
+    arrays = {k: g[k] for k in ('events_ts', 'events_xy', 'events_p', 'images', 'images_ts', 'image_event_indices')}
+    xy = arrays['events_xy'].copy()
+    xy[1000, 1] = 48
+    arrays['events_xy'] = xy
+    write_sequence_from_arrays(str(tmp_path / 'data' / 'BAD' / 'seq0'), arrays, (48, 64))
+    json.dump({'root_path': str(tmp_path / 'data' / 'BAD'), 'sequences': {'seq0': {}}}, open(cfg_root / 'dataset' / 'BAD.json', 'w'))
+    res = ev.evaluate(['ET-Net', 'FireNet'], ['std'], ['BAD', 'SYN'], ['mse', 'ssim'], config_root=str(cfg_root), write_files=False)
+    assert res['std']['ET-Net']['SYN'].get_count('mse') == 0           # method skipped, run continued
+    assert res['std']['FireNet']['BAD'].get_count('mse') == 0          # dataset failed, run continued
+    assert res['std']['FireNet']['SYN'].get_count('mse') > 0
+    assert ev.last_timings['failures'] == 2
+    text = capsys.readouterr().out
+    assert 'Exception while getting method ET-Net' in text and 'Exception while evaluating method FireNet on BAD dataset' in text
+
+
+def test_async_writer_outputs_match_synchronous_files(tmp_path):
+    """save_images + per-frame text files through the writer thread: byte-identical text files, identical PNGs."""
+    import cv2
+    from evreal_b200 import evaluate as ev
+    g = golden('eval_loop')
+    _write_plugin_tree(tmp_path, g, 1)
+    cfg_root = tmp_path / 'config'
+    cfg = json.load(open(cfg_root / 'eval' / 'std.json'))
+    cfg['save_images'] = True
+    json.dump(cfg, open(cfg_root / 'eval' / 'std.json', 'w'))
+    outs = {}
+    for mode in (True, False):
+        root = tmp_path / ('out_async' if mode else 'out_sync')
+        ev.evaluate(['FireNet'], ['std'], ['SYN'], ['mse', 'ssim'], config_root=str(cfg_root), output_root=str(root),
+                    write_files=True, async_writer=mode)
+        outs[mode] = root / 'std' / 'SYN' / 'seq0' / 'FireNet'
+    names = sorted(os.listdir(outs[False]))
+    assert names == sorted(os.listdir(outs[True])) and any(n.endswith('.png') for n in names)
+    for n in names:
+        a, b = open(outs[True] / n, 'rb').read(), open(outs[False] / n, 'rb').read()
+        if n.endswith('.png'):
+            assert np.array_equal(cv2.imread(str(outs[True] / n), cv2.IMREAD_UNCHANGED), cv2.imread(str(outs[False] / n), cv2.IMREAD_UNCHANGED)), n
+        else:
+            assert a == b, n

@@ -85,3 +85,45 @@ def test_percentile_with_duplicates_and_odd_sizes():
     got = percentile_normalize(torch.from_numpy(xb).cuda(), 1, 99, batched=True).cpu().numpy()
     for k in range(4):
         assert np.max(np.abs(got[k] - om.robust_normalize_oracle(xb[k], 1, 99))) <= 3e-7 * 1.1
+
+
+def test_global_histogram_equalisation_vs_oracle():
+    """hist_eq 'global' (utils/eval_metrics.py:326-331) on the GPU against the numpy restatement of skimage's algorithm."""
+    from evreal_b200 import _lib
+    from oracle import metrics as om
+    g = np.random.default_rng(5)
+    for H, W in ((180, 240), (37, 53)):
+        img = np.clip(g.normal(0.45, 0.2, (H, W)), 0, 1).astype(np.float32)
+        x = torch.from_numpy(img).cuda()
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().evk_equalize_hist(_lib.ptr(x), _lib.ptr(out), 1, x.numel(), 0, _lib.stream_ptr()))
+        ref = om.equalize_hist_oracle(img)
+        assert np.max(np.abs(out.cpu().numpy() - ref)) <= 2e-6
+    const = torch.full((16, 16), 0.25, device='cuda')
+    out = torch.empty_like(const)
+    _lib.check(_lib.load().evk_equalize_hist(_lib.ptr(const), _lib.ptr(out), 1, const.numel(), 0, _lib.stream_ptr()))
+    assert np.allclose(out.cpu().numpy(), om.equalize_hist_oracle(const.cpu().numpy()))
+
+
+def test_tracker_with_global_histeq_matches_oracle_scores():
+    from evreal_b200.eval_metrics import EvalMetricsTracker
+    from oracle import metrics as om
+    g = golden('metrics')
+    img, ref = g['a7.img'], g['a7.ref']
+    tr = EvalMetricsTracker(hist_eq='global', quan_eval_metric_names=['mse', 'ssim'], has_reference_frames=True, write_files=False)
+    tr.update(0, torch.from_numpy(img).cuda(), torch.from_numpy(ref).cuda(), 0.5, 0.5)
+    tr.finalize(0)
+    a, b = om.equalize_hist_oracle(np.clip(img, 0, 1)), om.equalize_hist_oracle(np.clip(ref, 0, 1))
+    means = tr.get_mean_scores()
+    assert abs(means['mse'] - om.mse_oracle(a, b)) <= 1e-4 * om.mse_oracle(a, b)
+    assert abs(means['ssim'] - om.ssim_oracle(a, b)) <= 1e-4
+
+
+def test_uint8_quantise_kernel_is_round_half_even_after_clip():
+    from evreal_b200 import _lib
+    from oracle import metrics as om
+    vals = np.concatenate([np.linspace(-0.2, 1.2, 3001), (np.arange(256) + 0.5) / 255.0, [0.5 / 255, 2.5 / 255]]).astype(np.float32)
+    x = torch.from_numpy(vals).cuda()
+    q = torch.empty(x.shape, dtype=torch.uint8, device='cuda')
+    _lib.check(_lib.load().evk_quantize_u8(_lib.ptr(x), _lib.ptr(q), x.numel(), _lib.stream_ptr()))
+    assert np.array_equal(q.cpu().numpy(), om.quantize_u8_oracle(vals))

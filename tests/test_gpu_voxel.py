@@ -131,6 +131,29 @@ def test_voxelizer_large_window_vs_oracle():
     assert np.max(np.abs(grid - ref)) <= _tol(ref)
 
 
+def test_voxelizer_cfg5_top_point_vs_oracle():
+    """BASELINE cfg 5 top point (640x480, 4 M events in one 40 ms window) against the CPU oracle (round-1 verdict, weak #4:
+    the largest oracle comparison was 111 k events), in both input formats (f32 SoA and raw int16/f64/u8)."""
+    from evreal_b200 import _lib, events_to_voxel_torch
+    from oracle import event_voxel as ov
+    H, W, n = 480, 640, 4_000_000
+    g = np.random.default_rng(31)
+    xy = np.stack([g.integers(0, W, n), g.integers(0, H, n)], axis=1).astype(np.int16)
+    t = 7.25 + np.sort(g.uniform(0, 0.04, n))                     # absolute float64 seconds, like events_ts.npy
+    p = g.integers(0, 2, n).astype(np.uint8)
+    xs, ys, ts, ps = ov.raw_window_to_f32(xy, t, p)
+    ref = ov.events_to_voxel_oracle(*[torch.from_numpy(a) for a in (xs, ys, ts, ps)], 5, (H, W)).numpy()
+    grid = events_to_voxel_torch(*[torch.from_numpy(a) for a in (xs, ys, ts, ps)], 5, sensor_size=(H, W)).cpu().numpy()
+    assert np.max(np.abs(grid - ref)) <= _tol(ref)
+    raw = torch.empty((5, H, W), dtype=torch.float32, device='cuda')
+    oob = torch.zeros(1, dtype=torch.int32, device='cuda')
+    dxy, dt, dp = torch.from_numpy(xy).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(p).cuda()
+    _lib.check(_lib.load().evk_voxelize_raw(_lib.ptr(dxy), _lib.ptr(dt), _lib.ptr(dp), n, 5, H, W, _lib.ptr(raw), _lib.ptr(oob),
+                                            _lib.stream_ptr()))
+    assert int(oob.item()) == 0
+    assert np.max(np.abs(raw.cpu().numpy() - ref)) <= _tol(ref)
+
+
 def test_normalize_pad_crop_match_reference_golden():
     from evreal_b200 import CropParameters, normalize_event_tensor
     from evreal_b200.util import normalize_pad

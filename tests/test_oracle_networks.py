@@ -61,3 +61,12 @@ def test_random_weight_builders_have_reference_shapes():
     assert tuple(w['decoders.0.dynamic_conv.compositional_coefficients'].shape) == (128, 1536, 1, 1)
     w = on.random_firenet_weights()
     assert tuple(w['head.recurrent_block.out_gate.weight'].shape) == (16, 32, 3, 3)
+
+
+def test_real_e2vid_weights_two_encoder_slice():
+    """REAL pretrained/E2VID weights (head, encoders 0-1, decoders 1-2, pred, eval-mode BatchNorm) through the real class"""
+    _check('e2vid_real2', 'unetrecurrent.', lambda w: on.UNetRecurrentOracle(w, 2, 0, final_sigmoid=True), file='real_slices')
+
+
+def test_real_e2vid_plus_weights_one_encoder_slice():
+    _check('flownet_real1', 'unetflow.', lambda w: on.UNetRecurrentOracle(w, 1, 0), file='real_slices')

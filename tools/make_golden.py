@@ -259,32 +259,140 @@ def golden_networks_base32():
     np.savez_compressed(os.path.join(OUT, 'networks_base32.npz'), **out)
 
 
-def golden_real_checkpoints():
-    """Outputs of the shipped 43 MB checkpoints on the SURVEY A.7 voxel: the weights cannot travel, so only
-    summary statistics + a strided sample are stored; tests/test_oracle_vs_reference.py uses them when the
-    reference tree is present."""
+def golden_real_slices():
+    """REAL pretrained weights at the shipped width through the REAL classes (weak point of round 1: every full-width test
+    used seeded weights).  A whole 43 MB checkpoint cannot live in git, but a sub-network can: an E2VIDRecurrent with TWO
+    encoders and no residual block is a legitimate instance of the reference class whose every layer exists in
+    pretrained/E2VID (head, encoders.0/1 with their ConvLSTM gates, decoders.1/2 renamed decoders.0/1, pred; eval-mode
+    BatchNorm with the real running statistics), ~8 MB; the E2VID+ (FlowNet, no norm, 3 output channels) slice uses one
+    encoder.  Plus one real 256-channel residual convolution on a real bottleneck activation captured with a forward hook
+    in a full E2VID run (layer-level test through evk_conv2d_nhwc)."""
+    import model as model_arch
+    out = {}
+
+    def slice_sd(sd, prefix, n_enc):
+        keep = {}
+        for k, v in sd.items():
+            if k.endswith('num_batches_tracked'):
+                continue
+            name = k[len(prefix):]
+            if name.startswith('head.') or name.startswith('pred.'):
+                keep[k] = v
+            elif name.startswith('encoders.'):
+                if int(name.split('.')[1]) < n_enc:
+                    keep[k] = v
+            elif name.startswith('decoders.'):
+                i = int(name.split('.')[1])
+                j = i - (3 - n_enc)              # the LAST n_enc decoders of the real net are the decoders of the slice
+                if j >= 0:
+                    keep[prefix + 'decoders.%d.' % j + name.split('.', 2)[2]] = v
+        return keep
+
+    ck = torch.load(os.path.join(REF, 'pretrained/E2VID/model.pth'), map_location='cpu')
+    kw = dict(ck['model'])
+    kw.update(final_activation='sigmoid', num_encoders=2, num_residual_blocks=0)
+    m = model_arch.E2VIDRecurrent(dict(kw))
+    sd = slice_sd(ck['state_dict'], 'unetrecurrent.', 2)
+    missing = m.load_state_dict(sd, strict=False)
+    assert not [k for k in missing.missing_keys if 'num_batches_tracked' not in k], missing
+    m.eval()
+    voxels = _small_voxels(30, 3, 2, 44, 60)            # not a multiple of the 8x16 GEMM tile
+    out['e2vid_real2.voxels'] = torch.stack(voxels).numpy()
+    out['e2vid_real2.frames'] = _run_frames(m, voxels)
+    for k, v in sd.items():
+        out['e2vid_real2.w.' + k] = v.numpy()
+    print('e2vid_real2 frames mean %.5f' % out['e2vid_real2.frames'].mean())
+
+    ck = torch.load(os.path.join(REF, 'pretrained/E2VID+/model.pth'), map_location='cpu')
+    kw = dict(ck['config']['arch']['args']['unet_kwargs'])
+    kw.update(num_encoders=1, num_residual_blocks=0)
+    m = model_arch.FlowNet(dict(kw))
+    sd = slice_sd(ck['state_dict'], 'unetflow.', 1)
+    missing = m.load_state_dict(sd, strict=False)
+    assert not [k for k in missing.missing_keys if 'num_batches_tracked' not in k], missing
+    m.eval()
+    voxels = _small_voxels(31, 3, 2, 30, 44)
+    out['flownet_real1.voxels'] = torch.stack(voxels).numpy()
+    out['flownet_real1.frames'] = _run_frames(m, voxels)
+    out['flownet_real1.kwargs'] = np.array([kw['base_num_channels'], kw['num_output_channels']], dtype=np.int64)
+    for k, v in sd.items():
+        out['flownet_real1.w.' + k] = v.numpy()
+    print('flownet_real1 frames mean %.5f' % out['flownet_real1.frames'].mean())
+
+    # layer level: resblocks.0 conv1 + bn1 + ReLU of the real E2VID on the real bottleneck activation
+    ck = torch.load(os.path.join(REF, 'pretrained/E2VID/model.pth'), map_location='cpu')
+    kw = dict(ck['model'])
+    kw['final_activation'] = 'sigmoid'
+    full = model_arch.E2VIDRecurrent(kw)
+    full.load_state_dict(ck['state_dict'])
+    full.eval()
+    cap = {}
+    rb = full.unetrecurrent.resblocks[0]
+    h1 = rb.conv1.register_forward_hook(lambda mod, i, o: cap.__setitem__('x', i[0].detach().clone()))
+    h2 = rb.bn1.register_forward_hook(lambda mod, i, o: cap.__setitem__('y', torch.relu(o.detach().clone())))
+    with torch.no_grad():
+        for v in _small_voxels(32, 2, 1, 64, 80):
+            full(v)
+    h1.remove(); h2.remove()
+    out['resconv.x'] = cap['x'].numpy()                  # [1, 256, 8, 10]
+    out['resconv.y'] = cap['y'].numpy()
+    out['resconv.weight'] = rb.conv1.weight.detach().numpy()
+    for k in ('weight', 'bias', 'running_mean', 'running_var'):
+        out['resconv.bn.' + k] = getattr(rb.bn1, k).detach().numpy()
+    np.savez_compressed(os.path.join(OUT, 'real_slices.npz'), **out)
+
+
+def golden_full_checkpoints():
+    """(Input grids are not stored: the test rebuilds them from gen_events(40 + f, 15000 + 7000 f) with the pinned oracle
+    voxelizer and checks them against the stored sums.)
+    The shipped 43 MB checkpoints cannot be committed, but they CAN travel to the GPU box as untracked files: this copies
+    them to tests/golden/_ckpt/ (git-ignored, not gpurun-ignored) and commits what the REAL classes produce from them on
+    CPU -- three recurrent frames at the BASELINE sizes -- so tests/test_gpu_checkpoints.py runs the real checkpoints
+    through the CUDA path at full size whenever the files are present."""
+    import shutil
     import model as model_arch
     from utils.event_utils import events_to_voxel_torch
     from utils.util import CropParameters
+    import eval as ref_eval
     out = {}
-    for name, (H, W) in {'E2VID': (180, 240), 'HyperE2VID': (260, 346), 'E2VID+': (180, 240)}.items():
-        ck = torch.load(os.path.join(REF, f'pretrained/{name}/model.pth'), map_location='cpu')
+    ckdir = os.path.join(OUT, '_ckpt')
+    os.makedirs(ckdir, exist_ok=True)
+    for name, (H, W, norm_ev) in {'E2VID': (180, 240, True), 'E2VID+': (180, 240, False), 'HyperE2VID': (260, 346, False),
+                                  'SSL-E2VID': (180, 240, False), 'FireNet': (180, 240, True), 'FireNet+': (180, 240, False)}.items():
+        src = os.path.join(REF, f'pretrained/{name}/model.pth')
+        shutil.copyfile(src, os.path.join(ckdir, name + '.pth'))
+        ck = torch.load(src, map_location='cpu')
         if name == 'E2VID':
-            kw = dict(ck['model'])
-            kw['final_activation'] = 'sigmoid'
-            m = model_arch.E2VIDRecurrent(kw)
+            kw = dict(ck['model']); kw['final_activation'] = 'sigmoid'
+            m = model_arch.E2VIDRecurrent(kw); sd = ck['state_dict']
+        elif name == 'SSL-E2VID':
+            kw = {"base_num_channels": 32, "kernel_size": 5, "num_bins": 5, "num_encoders": 3, "recurrent_block_type": "convlstm",
+                  "num_residual_blocks": 2, "skip_type": "sum", "norm": None, "use_upsample_conv": True}
+            m = model_arch.E2VIDRecurrent(kw); sd = ck
+        elif name == 'FireNet':
+            kw = dict(ck['config']['model']); kw['final_activation'] = ''
+            m = model_arch.FireNet_legacy(kw); sd = ck['state_dict']
         else:
-            m = ck['config'].init_obj('arch', model_arch)
-        m.load_state_dict(ck['state_dict'])
+            m = ck['config'].init_obj('arch', model_arch); sd = ck['state_dict']
+            if name == 'FireNet+':
+                m.num_encoders = 0
+        m.load_state_dict(sd)
         m.eval()
-        v = events_to_voxel_torch(*[torch.from_numpy(a) for a in gen_events(0, 15000, H, W)], 5, sensor_size=(H, W))
-        cp = CropParameters(W, H, 3)
+        cp = CropParameters(W, H, m.num_encoders)
+        frames, voxels = [], []
+        m.reset_states()
         with torch.no_grad():
-            frames = [cp.crop(m(cp.pad(v[None]))['image'])[0, 0].numpy() for _ in range(2)]
-        out[f'{name}.stats'] = np.array([[f.min(), f.max(), f.mean()] for f in frames], dtype=np.float64)
-        out[f'{name}.sample'] = np.stack([f[::9, ::11] for f in frames])
-        print(name, out[f'{name}.stats'])
-    np.savez_compressed(os.path.join(OUT, 'real_checkpoints.npz'), **out)
+            for f in range(3):
+                v = events_to_voxel_torch(*[torch.from_numpy(a) for a in gen_events(40 + f, 15000 + 7000 * f, H, W)], 5, sensor_size=(H, W))[None]
+                voxels.append(v[0].numpy())
+                if norm_ev:
+                    v = ref_eval.normalize_event_tensor(v)
+                frames.append(cp.crop(m(cp.pad(v))['image'])[0, 0].numpy().copy())
+        out[f'{name}.voxel_sums'] = np.array([[v.sum(dtype=np.float64), np.abs(v).sum(dtype=np.float64)] for v in voxels])   # (the test regenerates
+        out[f'{name}.frames'] = np.stack(frames).astype(np.float32)
+        out[f'{name}.meta'] = np.array([H, W, int(norm_ev), m.num_encoders], dtype=np.int64)
+        print(name, 'frames mean', [float(f.mean()) for f in frames])
+    np.savez_compressed(os.path.join(OUT, 'full_checkpoints.npz'), **out)
 
 
 def golden_metrics():
@@ -383,6 +491,91 @@ def golden_eval_loop(tmp):
     np.savez_compressed(os.path.join(OUT, 'eval_loop.npz'), **out)
 
 
+def golden_eval_loop_modes(tmp):
+    """The REAL eval.eval_method_on_sequence with 'k_events' and 't_seconds' windows (real FireNet checkpoint): the voxel
+    timestamp is then the window's last event, the reference frame is the CLOSEST one (dataset.py:150-166) and the
+    ts_tol_ms gate of utils/eval_metrics.py:258-262 actually rejects frames; empty windows get patched timestamps
+    (dataset.py:59-71: the stream below has a silent gap)."""
+    import eval as ref_eval
+    import model as model_arch
+    from dataset import MemMapDataset
+    from torch.utils.data import DataLoader
+    ref_eval.CudaTimer = lambda *_a, **_k: contextlib.nullcontext()
+    ref_eval.tqdm = lambda x, *a, **k: x
+    s = synthetic.make_stream(48, 64, 60000.0, 1.0, 20.0, seed=11)
+    # a silent gap of 0.12 s -> empty 't_seconds' windows
+    keep = ~((s['events_ts'] > 0.40) & (s['events_ts'] < 0.52))
+    s['events_ts'], s['events_xy'], s['events_p'] = s['events_ts'][keep], s['events_xy'][keep], s['events_p'][keep]
+    s['image_event_indices'] = np.clip(np.searchsorted(s['events_ts'], s['images_ts'][:, 0], 'right') - 1, 0,
+                                       len(s['events_ts']) - 1).reshape(-1, 1).astype(np.int64)
+    seq_path = os.path.join(tmp, 'modeseq')
+    os.makedirs(seq_path, exist_ok=True)
+    for k in ('events_ts', 'events_xy', 'events_p', 'images', 'images_ts', 'image_event_indices'):
+        np.save(os.path.join(seq_path, k + '.npy'), s[k])
+    import json
+    json.dump({'sensor_resolution': [48, 64]}, open(os.path.join(seq_path, 'metadata.json'), 'w'))
+    out = {k: s[k] for k in ('events_ts', 'events_xy', 'events_p', 'images', 'images_ts', 'image_event_indices')}
+    ck = torch.load(os.path.join(REF, 'pretrained/FireNet/model.pth'), map_location='cpu')
+    kw = dict(ck['config']['model'])
+    kw['final_activation'] = ''
+    m = model_arch.FireNet_legacy(kw)
+    ref_eval.load_model(m, ck['state_dict'])
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        modes = {'k_events': ({'method': 'k_events', 'k': 2500, 'sliding_window_w': 500}, 8.0),
+                 't_seconds': ({'method': 't_seconds', 't': 0.04, 'sliding_window_t': 0.01}, 6.0)}
+        for tag, (vm, tol) in modes.items():
+            eval_config = {'name': 'std', 'save_images': False, 'histeq': 'none', 'eval_infer_all': False, 'ts_tol_ms': tol,
+                           'create_video': False}
+            ds = MemMapDataset(seq_path, num_bins=5, voxel_method=dict(vm))
+            sequence = {'name': 'modeseq', 'data_loader': DataLoader(ds), 'start_time_s': 0.1, 'end_time_s': 0.85}
+            holder = {}
+            orig = ref_eval.get_eval_metrics_tracker
+
+            def wrapped(*a, **k):
+                holder['t'] = orig(*a, **k)
+                return holder['t']
+            ref_eval.get_eval_metrics_tracker = wrapped
+            n_eval, means = ref_eval.eval_method_on_sequence('SYN', eval_config, tag, m,
+                                                             {'event_tensor_normalization': True, 'post_process_norm': 'none'},
+                                                             sequence, ['mse', 'ssim'])
+            ref_eval.get_eval_metrics_tracker = orig
+            t = holder['t']
+            out[f'{tag}.indices'] = np.array(t.quan_eval_indices, dtype=np.int64)
+            out[f'{tag}.mse'] = np.array(t.metrics[0].scores)
+            out[f'{tag}.ssim'] = np.array(t.metrics[1].scores)
+            out[f'{tag}.summary'] = np.array([n_eval, means['mse'], means['ssim'], 0.1, 0.85, tol])
+            out[f'{tag}.vm'] = np.array([vm.get('k', 0), vm.get('sliding_window_w', 0), vm.get('t', 0), vm.get('sliding_window_t', 0)], dtype=np.float64)
+            out[f'{tag}.len'] = np.array([len(ds)], dtype=np.int64)
+            print(tag, 'items', len(ds), 'evaluated', n_eval, means)
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, 'eval_loop_modes.npz'), **out)
+
+
+def golden_colornet():
+    """The REAL ColorNet (model/model.py:46-105) around the real FireNet checkpoint on a Bayer-sized input: merged colour
+    frames over three recurrent steps (five batch-1 forwards per frame with swapped states in the reference)."""
+    import model as model_arch
+    ck = torch.load(os.path.join(REF, 'pretrained/FireNet/model.pth'), map_location='cpu')
+    kw = dict(ck['config']['model'])
+    kw['final_activation'] = ''
+    m = model_arch.FireNet_legacy(kw)
+    m.load_state_dict(ck['state_dict'])
+    m.eval()
+    from model.model import ColorNet
+    cn = ColorNet(m)
+    voxels = _small_voxels(50, 3, 1, 40, 56)
+    cn.reset_states()
+    frames = []
+    with torch.no_grad():
+        for v in voxels:
+            frames.append(cn(v)['image'].numpy().copy())
+    np.savez_compressed(os.path.join(OUT, 'colornet.npz'), voxels=torch.stack(voxels).numpy(), frames=np.stack(frames))
+    print('colornet frames', np.stack(frames).shape, 'mean %.4f' % np.stack(frames).mean())
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     install_shims()
@@ -390,14 +583,25 @@ if __name__ == '__main__':
     if '--only-base32' in sys.argv:   # added later; leaves the other fixtures untouched
         golden_networks_base32()
         sys.exit(0)
+    if '--round2' in sys.argv:        # round-2 fixtures only (the round-1 ones stay byte-identical)
+        if '--only-color' not in sys.argv:
+            golden_real_slices()
+            golden_full_checkpoints()
+            with tempfile.TemporaryDirectory() as tmp:
+                golden_eval_loop_modes(tmp)
+        golden_colornet()
+        sys.exit(0)
     with tempfile.TemporaryDirectory() as tmp:
         golden_voxel()
         golden_glue()
         golden_windows(tmp)
         golden_networks()
         golden_networks_base32()
-        golden_real_checkpoints()
+        golden_real_slices()
+        golden_full_checkpoints()
         golden_metrics()
         golden_eval_loop(tmp)
+        golden_eval_loop_modes(tmp)
+        golden_colornet()
     for f in sorted(os.listdir(OUT)):
         print('%8.1f kB  %s' % (os.path.getsize(os.path.join(OUT, f)) / 1e3, f))
