@@ -340,9 +340,10 @@ def parity_check(torch, model_factory, arrays, ds):
     w = {k[len('unetrecurrent.'):]: v for k, v in e2vid_weights().items()}
     a = dict(arrays)
     ts = np.asarray(a['images_ts'], dtype=np.float64).copy()
+    ts = ts.reshape(-1)
     start = float(ts[1])
     ts[0] = ts[1] - 15.0                       # item 0 (always empty) is skipped by the 10-second rule: both sides start at item 1
-    a['images_ts'] = ts
+    a['images_ts'] = ts.reshape(-1, 1)
     ref = eval_loop.run_sequence(a, (H, W), on.UNetRecurrentOracle(w, final_sigmoid=True), 3, True, 'robust', start_time_s=start, max_items=3)
     batch = SequenceBatch(model_factory(), [ds], True, 'robust', resident=True, log_scores=True)
     batch.reset()

@@ -123,6 +123,88 @@ __global__ void __launch_bounds__(256) hyper_apply_kernel(const HyperParams p) {
     }
 }
 
+// (3) dynamic convolution applied to U = conv1x1(xu) (see hyper.cuh).  A warp owns a strip of kSX x kSY pixels and all CO = 128
+// output channels (4 per lane): every U value it loads (one 512-byte row of the warp per pixel and atom) feeds up to
+// 5 x 4 = 20 of its pixels from registers, so U is read ~3x from L2 instead of 25x, and the atoms of the strip -- generated
+// on the fly from the 72 basis coefficients -- are warp-uniform shared-memory broadcasts.
+constexpr int kSX = 8, kSY = 4, kSWarps = 8;
+
+template <int A, int KS, int K>
+__global__ void __launch_bounds__(kSWarps * 32, 1) hyper_apply_u_kernel(const HyperParams p, int strips_x, int strips_y, int n_strips) {
+    constexpr int L = KS * KS, R = KS / 2, LP = KS * 8;           // atoms of one (pixel, a): KS rows of 8 slots (KS used)
+    __shared__ float s_bases[K * L];
+    __shared__ __align__(16) float s_at[kSWarps][kSX * kSY][LP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < K * L; i += blockDim.x) s_bases[i] = p.bases[i];
+    __syncthreads();
+    const int CO = p.CO, CU = A * CO;
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(p.out_bias) + lane);
+    for (int s = blockIdx.x * kSWarps + warp; s < n_strips; s += gridDim.x * kSWarps) {
+        const int sx = s % strips_x, sy = (s / strips_x) % strips_y, n = s / (strips_x * strips_y);
+        const int x0 = sx * kSX, y0 = sy * kSY;
+        float4 acc[kSY * kSX];
+#pragma unroll
+        for (int i = 0; i < kSY * kSX; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int a = 0; a < A; ++a) {
+            __syncwarp();
+            // atoms of this strip for atom index a: (pixel, l) pairs dealt over the lanes
+            for (int i = lane; i < kSX * kSY * L; i += 32) {
+                const int pix = i / L, l = i - pix * L;
+                const int gy = min(y0 + pix / kSX, p.h - 1), gx = min(x0 + pix % kSX, p.w - 1);
+                const float* c = p.coef + (((size_t)n * p.h + gy) * p.w + gx) * (A * K) + a * K;
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) v = fmaf(__ldg(c + k), s_bases[k * L + l], v);
+                s_at[warp][pix][(l / KS) * 8 + (l % KS)] = v;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int ry = 0; ry < kSY + 2 * R; ++ry) {
+                const int gy = y0 - R + ry;
+                float4 u[kSX + 2 * R];
+                const bool row_ok = (unsigned)gy < (unsigned)p.h;
+#pragma unroll
+                for (int j = 0; j < kSX + 2 * R; ++j) {
+                    const int gx = x0 - R + j;
+                    u[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row_ok && (unsigned)gx < (unsigned)p.w)
+                        u[j] = __ldg(reinterpret_cast<const float4*>(p.u + (((size_t)n * p.h + gy) * p.w + gx) * CU + (size_t)a * CO) + lane);
+                }
+#pragma unroll
+                for (int py = 0; py < kSY; ++py) {
+                    const int dy = ry - py;
+                    if (dy < 0 || dy >= KS) continue;
+#pragma unroll
+                    for (int px = 0; px < kSX; ++px) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(&s_at[warp][py * kSX + px][dy * 8]);
+                        const float w4 = s_at[warp][py * kSX + px][dy * 8 + 4];
+                        const float wv[5] = {w0.x, w0.y, w0.z, w0.w, w4};
+                        float4& o = acc[py * kSX + px];
+#pragma unroll
+                        for (int dx = 0; dx < KS; ++dx) {
+                            o.x = fmaf(wv[dx], u[px + dx].x, o.x);
+                            o.y = fmaf(wv[dx], u[px + dx].y, o.y);
+                            o.z = fmaf(wv[dx], u[px + dx].z, o.z);
+                            o.w = fmaf(wv[dx], u[px + dx].w, o.w);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int py = 0; py < kSY; ++py)
+#pragma unroll
+            for (int px = 0; px < kSX; ++px) {
+                const int gy = y0 + py, gx = x0 + px;
+                if (gy >= p.h || gx >= p.w) continue;
+                const float4 o = acc[py * kSX + px];
+                const float4 r = make_float4(fmaxf(o.x + bias.x, 0.f), fmaxf(o.y + bias.y, 0.f), fmaxf(o.z + bias.z, 0.f), fmaxf(o.w + bias.w, 0.f));
+                reinterpret_cast<float4*>(p.y + (((size_t)n * p.h + gy) * p.w + gx) * CO)[lane] = r;
+            }
+    }
+}
+
 int launch_hyper(int which, const HyperParams& p, cudaStream_t st) {
     if (which == 0) {
         EVK_REQUIRE(p.H % 4 == 0 && p.W % 4 == 0 && p.bins + 1 <= 8, EVK_ERR_ARG, "hyper context: H, W must be multiples of 4 and bins <= 7");
@@ -131,6 +213,13 @@ int launch_hyper(int which, const HyperParams& p, cudaStream_t st) {
     } else if (which == 1) {
         const int64_t total = (int64_t)p.N * p.h * p.w * p.A * p.L;
         hyper_atoms_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, sizeof(float) * p.K * p.L, st>>>(p);
+    } else if (which == 3) {
+        EVK_REQUIRE(p.A == 6 && p.ks == 5 && p.K == 12 && p.CO == 128, EVK_ERR_ARG,
+                    "hyper apply (re-associated): only num_atoms=6, kernel_size=5, 12 bases, 128 output channels is built (got A=%d ks=%d K=%d CO=%d)",
+                    p.A, p.ks, p.K, p.CO);
+        const int strips_x = ceil_div(p.w, kSX), strips_y = ceil_div(p.h, kSY), n_strips = strips_x * strips_y * p.N;
+        const int blocks = std::min(ceil_div(n_strips, kSWarps), kNumSMs);
+        hyper_apply_u_kernel<6, 5, 12><<<blocks, kSWarps * 32, 0, st>>>(p, strips_x, strips_y, n_strips);
     } else {
         EVK_REQUIRE(p.A == 6 && p.ks == 5 && p.C % kACH == 0, EVK_ERR_ARG,
                     "hyper apply: only num_atoms=6, kernel_size=5, C%%32==0 is built (got A=%d ks=%d C=%d)", p.A, p.ks, p.C);

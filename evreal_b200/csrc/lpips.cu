@@ -52,6 +52,71 @@ __global__ void __launch_bounds__(256) lpips_prep_kernel(const float* __restrict
     }
 }
 
+__device__ __forceinline__ float3 lpips_scale(float v) {
+    const float s = 2.0f * fminf(fmaxf(v, 0.0f), 1.0f) - 1.0f;
+    return make_float3((s - (-0.030f)) / 0.458f, (s - (-0.088f)) / 0.448f, (s - (-0.188f)) / 0.450f);
+}
+
+// Tensor-core form of the AlexNet stem (11x11, stride 4, padding 2, 3 -> 64): space-to-depth.  Block (by, bx) of the
+// output holds input rows 4*by - 2 .. 4*by + 1 and columns 4*bx - 2 .. 4*bx + 1 (zero outside the image) as 4*4*3 = 48
+// "channels" (padded to 64: one 128-byte K row); output pixel (y, x) of the stem then reads exactly blocks y .. y+2 by
+// x .. x+2 -- an ordinary unpadded stride-1 3x3 convolution with 64 input channels (taps beyond row / column 10 get zero
+// weights).  Written directly as split-bf16 planes [2][N][Hb][Wb][64].
+__global__ void __launch_bounds__(256) lpips_prep_s2d_kernel(const float* __restrict__ img, const float* __restrict__ ref, int n, int batch,
+                                                             int H, int W, int Hb, int Wb, __nv_bfloat16* __restrict__ out) {
+    const int64_t total = (int64_t)2 * batch * Hb * Wb * 16;           // one thread per (block, sub-pixel)
+    const int64_t plane = (int64_t)2 * batch * Hb * Wb * 64;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int sp = (int)(i % 16);
+        const int bx = (int)((i / 16) % Wb);
+        const int by = (int)((i / ((int64_t)16 * Wb)) % Hb);
+        const int im = (int)(i / ((int64_t)16 * Wb * Hb));
+        const int b = im % batch;
+        const int y = 4 * by - 2 + sp / 4, x = 4 * bx - 2 + sp % 4;
+        float3 v = make_float3(0.f, 0.f, 0.f);
+        if (b < n && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W)
+            v = lpips_scale((im < batch ? img : ref)[((int64_t)b * H + y) * W + x]);
+        const int64_t o = (((int64_t)im * Hb + by) * Wb + bx) * 64 + sp * 3;
+        const float f[3] = {v.x, v.y, v.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(f[c], hi, lo);
+            out[o + c] = hi;
+            out[plane + o + c] = lo;
+        }
+        if (sp == 15) {                       // channels 48..63 stay zero
+#pragma unroll
+            for (int c = 48; c < 64; ++c) { out[o - 45 + c] = __float2bfloat16(0.f); out[plane + o - 45 + c] = __float2bfloat16(0.f); }
+        }
+    }
+}
+
+// Tensor-core form of the VGG16 stem (3x3, 3 -> 64): the row-window layout of the reconstruction networks' head
+// convolution (conv.cuh, ConvParams::kw_packed): [2][N][H][W + 8][8], pixel x at column x + 1, channels 3..7 and the pad
+// columns zero.
+__global__ void __launch_bounds__(256) lpips_prep_rowwin_kernel(const float* __restrict__ img, const float* __restrict__ ref, int n, int batch,
+                                                                int H, int W, __nv_bfloat16* __restrict__ out) {
+    const int Wp = W + 8;
+    const int64_t total = (int64_t)2 * batch * H * Wp;
+    const int64_t plane = total * 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xp = (int)(i % Wp);
+        const int y = (int)((i / Wp) % H);
+        const int im = (int)(i / ((int64_t)Wp * H));
+        const int b = im % batch, x = xp - 1;
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { hi[c] = __float2bfloat16(0.f); lo[c] = __float2bfloat16(0.f); }
+        if (b < n && (unsigned)x < (unsigned)W) {
+            const float3 v = lpips_scale((im < batch ? img : ref)[((int64_t)b * H + y) * W + x]);
+            split_bf16(v.x, hi[0], lo[0]); split_bf16(v.y, hi[1], lo[1]); split_bf16(v.z, hi[2], lo[2]);
+        }
+        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(out + plane + i * 8) = *reinterpret_cast<const uint4*>(lo);
+    }
+}
+
 // NHWC max pooling (no padding, floor mode): torch.nn.MaxPool2d(k, stride); writes fp32 and the split-bf16 copy
 __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ ys,
                                                       int N, int H, int W, int C4, int k, int s, int Ho, int Wo) {
@@ -69,7 +134,7 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
                 const float4 v = __ldg(reinterpret_cast<const float4*>(x) + (((int64_t)n * H + iy) * W + ix) * C4 + c);
                 m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
             }
-        reinterpret_cast<float4*>(y)[i] = m;
+        if (y != nullptr) reinterpret_cast<float4*>(y)[i] = m;
         if (ys != nullptr) {
             const float f[4] = {m.x, m.y, m.z, m.w};
             __nv_bfloat16 hi[4], lo[4];
@@ -147,6 +212,8 @@ struct evk_lpips {
     std::vector<LpTap> taps;
     std::vector<TcPlan*> plans;
     float* input = nullptr;
+    __nv_bfloat16* input_s = nullptr;     // tensor-core stems: space-to-depth (AlexNet) / row-window (VGG16) split-bf16 input
+    int stem_hb = 0, stem_wb = 0;         // AlexNet: blocks of the space-to-depth input
     double* part = nullptr;
     double flops = 0.0;
 
@@ -189,22 +256,31 @@ static int lpips_build(evk_lpips* l) {
     const int n_specs = l->backbone == 0 ? 5 : 13;
     const int N = 2 * l->batch;
     int H = l->H, W = l->W, C = 4;
-    l->input = (float*)l->dalloc(sizeof(float) * (size_t)N * H * W * 4);
-    EVK_REQUIRE(l->input != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
-    const float* x = l->input;
+    const bool tc = l->precision == 0;
+    // tensor-core stems: AlexNet always (space-to-depth), VGG16 when two output pixels can share a GEMM row (even width)
+    const bool stem_tc = tc && (l->backbone == 0 || W % 2 == 0) && getenv("EVK_LPIPS_SIMT_STEM") == nullptr;
+    const float* x = nullptr;
     __nv_bfloat16* xs = nullptr;
+    if (!stem_tc) {
+        l->input = (float*)l->dalloc(sizeof(float) * (size_t)N * H * W * 4);
+        EVK_REQUIRE(l->input != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
+        x = l->input;
+    }
     l->taps.assign(5, LpTap());
     for (int i = 0; i < n_specs; ++i) {
         const LpSpec& s = specs[i];
+        const bool next_tc = tc;                                   // every non-stem convolution qualifies for the tensor-core kernel
         if (s.pool_k) {
             LpLayer pl; pl.kind = 1;
             pl.C = C; pl.H = H; pl.W = W; pl.k = s.pool_k; pl.stride = s.pool_s;
             pl.Ho = (H - s.pool_k) / s.pool_s + 1; pl.Wo = (W - s.pool_k) / s.pool_s + 1;
             EVK_REQUIRE(pl.Ho > 0 && pl.Wo > 0, EVK_ERR_ARG, "evk_lpips: image %dx%d is too small for the backbone", l->H, l->W);
             const size_t n_out = (size_t)N * pl.Ho * pl.Wo * C;
-            pl.in = x; pl.out = (float*)l->dalloc(sizeof(float) * n_out);
-            pl.out_s = (__nv_bfloat16*)l->dalloc(sizeof(__nv_bfloat16) * 2 * n_out);
-            EVK_REQUIRE(pl.out && pl.out_s, EVK_ERR_CUDA, "evk_lpips: out of device memory");
+            pl.in = x;
+            // the pooled map is read by the next convolution only: split planes for the tensor-core kernel, fp32 otherwise
+            pl.out = next_tc ? nullptr : (float*)l->dalloc(sizeof(float) * n_out);
+            pl.out_s = next_tc ? (__nv_bfloat16*)l->dalloc(sizeof(__nv_bfloat16) * 2 * n_out) : nullptr;
+            EVK_REQUIRE(pl.out || pl.out_s, EVK_ERR_CUDA, "evk_lpips: out of device memory");
             l->layers.push_back(pl);
             x = pl.out; xs = pl.out_s; H = pl.Ho; W = pl.Wo;
         }
@@ -215,45 +291,99 @@ static int lpips_build(evk_lpips* l) {
         EVK_REQUIRE(w && b, EVK_ERR_KEY, "missing LPIPS backbone tensor '%s.weight' / '.bias'", sl.c_str());
         EVK_REQUIRE((int64_t)w->size() == (int64_t)s.cout * s.cin * s.k * s.k && (int)b->size() == s.cout, EVK_ERR_KEY,
                     "'%s': expected [%d,%d,%d,%d]", sl.c_str(), s.cout, s.cin, s.k, s.k);
-        const int cin_p = s.cin == 3 ? 4 : s.cin;          // the stem reads the NHWC4 input (4th channel zero)
-        const int K = s.k * s.k * cin_p;
-        std::vector<float> wk((size_t)K * s.cout, 0.f);
-        for (int n = 0; n < s.cout; ++n)
-            for (int c = 0; c < s.cin; ++c)
-                for (int r = 0; r < s.k; ++r)
-                    for (int q = 0; q < s.k; ++q)
-                        wk[((size_t)(r * s.k + q) * cin_p + c) * s.cout + n] = (*w)[(((size_t)n * s.cin + c) * s.k + r) * s.k + q];
+        auto wat = [&](int n, int c, int r, int q) { return (*w)[(((size_t)n * s.cin + c) * s.k + r) * s.k + q]; };
         LpLayer cl; cl.kind = 0;
         ConvParams& p = cl.cp;
-        p.x1 = x; p.c1 = cin_p; p.N = N; p.Hin = H; p.Win = W; p.kh = p.kw = s.k; p.stride = s.stride; p.pad = s.pad;
-        p.Hout = (H + 2 * s.pad - s.k) / s.stride + 1; p.Wout = (W + 2 * s.pad - s.k) / s.stride + 1;
-        EVK_REQUIRE(p.Hout > 0 && p.Wout > 0, EVK_ERR_ARG, "evk_lpips: image %dx%d is too small for the backbone", l->H, l->W);
-        float* dw = (float*)l->dalloc(sizeof(float) * wk.size());
-        float* db = (float*)l->dalloc(sizeof(float) * s.cout);
-        const size_t n_out = (size_t)N * p.Hout * p.Wout * s.cout;
-        float* y = (float*)l->dalloc(sizeof(float) * n_out);
-        __nv_bfloat16* ys = (__nv_bfloat16*)l->dalloc(sizeof(__nv_bfloat16) * 2 * n_out);
-        EVK_REQUIRE(dw && db && y && ys, EVK_ERR_CUDA, "evk_lpips: out of device memory");
-        cudaMemcpy(dw, wk.data(), sizeof(float) * wk.size(), cudaMemcpyHostToDevice);
-        cudaMemcpy(db, b->data(), sizeof(float) * s.cout, cudaMemcpyHostToDevice);
-        p.w = dw; p.bias = db; p.cout = s.cout; p.epi = EPI_LINEAR; p.act = ACT_RELU; p.y = y; p.ys = ys;
-        if (l->precision == 0 && xs != nullptr && tc_eligible(p)) {
-            std::vector<__nv_bfloat16> wt;
-            p.cout_pad = (s.cout + 15) / 16 * 16;
-            pack_weights_tc(wk.data(), K, s.cout, p.cout_pad, wt);
+        p.N = N; p.epi = EPI_LINEAR; p.act = ACT_RELU;
+        const int Ho = (H + 2 * s.pad - s.k) / s.stride + 1, Wo = (W + 2 * s.pad - s.k) / s.stride + 1;
+        EVK_REQUIRE(Ho > 0 && Wo > 0, EVK_ERR_ARG, "evk_lpips: image %dx%d is too small for the backbone", l->H, l->W);
+        const size_t n_out = (size_t)N * Ho * Wo * s.cout;
+        // who reads this layer's output: a tap and a following max-pooling read fp32, a following tensor-core convolution
+        // reads the split planes -- nothing else is written
+        const bool last = i + 1 == n_specs;
+        const bool next_pool = !last && specs[i + 1].pool_k != 0;
+        const bool want_f32 = s.tap >= 0 || next_pool || (!last && !next_tc);
+        const bool want_split = !last && !next_pool && next_tc;
+        float* y = want_f32 ? (float*)l->dalloc(sizeof(float) * n_out) : nullptr;
+        __nv_bfloat16* ys = want_split ? (__nv_bfloat16*)l->dalloc(sizeof(__nv_bfloat16) * 2 * n_out) : nullptr;
+        EVK_REQUIRE((y || !want_f32) && (ys || !want_split), EVK_ERR_CUDA, "evk_lpips: out of device memory");
+        std::vector<float> wk, bias(b->begin(), b->end());
+        std::vector<__nv_bfloat16> wt;
+        if (i == 0 && stem_tc && l->backbone == 0) {
+            // space-to-depth stem (lpips_prep_s2d_kernel): 3x3 over 64 channels, channel (rr*4 + ss)*3 + c of block tap (r, q)
+            // is input tap (4r + rr, 4q + ss)
+            l->stem_hb = Ho + 2; l->stem_wb = Wo + 2;
+            l->input_s = (__nv_bfloat16*)l->dalloc(sizeof(__nv_bfloat16) * 2 * (size_t)N * l->stem_hb * l->stem_wb * 64);
+            EVK_REQUIRE(l->input_s != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
+            wk.assign((size_t)9 * 64 * s.cout, 0.f);
+            for (int n = 0; n < s.cout; ++n)
+                for (int c = 0; c < 3; ++c)
+                    for (int R = 0; R < s.k; ++R)
+                        for (int Q = 0; Q < s.k; ++Q)
+                            wk[((size_t)((R / 4) * 3 + Q / 4) * 64 + ((R % 4) * 4 + Q % 4) * 3 + c) * s.cout + n] = wat(n, c, R, Q);
+            p.x1 = nullptr; p.x1s = l->input_s; p.c1 = 64; p.Hin = l->stem_hb; p.Win = l->stem_wb; p.kh = p.kw = 3; p.stride = 1; p.pad = 0;
+            p.Hout = Ho; p.Wout = Wo; p.cout = s.cout; p.cout_pad = (s.cout + 15) / 16 * 16;
+            pack_weights_tc(wk.data(), 9 * 64, s.cout, p.cout_pad, wt);
+        } else if (i == 0 && stem_tc) {
+            // row-window stem (lpips_prep_rowwin_kernel): two output pixels per GEMM row, like the networks' head convolution
+            const int G = 2;
+            l->input_s = (__nv_bfloat16*)l->dalloc(sizeof(__nv_bfloat16) * 2 * (size_t)N * H * (W + 8) * 8);
+            EVK_REQUIRE(l->input_s != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
+            std::vector<float> w3((size_t)s.k * s.k * 3 * s.cout), wr;
+            for (int n = 0; n < s.cout; ++n)
+                for (int c = 0; c < 3; ++c)
+                    for (int r = 0; r < s.k; ++r)
+                        for (int q = 0; q < s.k; ++q) w3[((size_t)(r * s.k + q) * 3 + c) * s.cout + n] = wat(n, c, r, q);
+            pack_head_weights_rowwin(w3.data(), s.k, s.k, 3, s.cout, G, wr);
+            bias.resize((size_t)G * s.cout);
+            for (int g = 1; g < G; ++g) std::copy(b->begin(), b->end(), bias.begin() + (size_t)g * s.cout);
+            p.x1 = nullptr; p.x1s = l->input_s; p.c1 = 64; p.kw_packed = s.k; p.kw_group = G;
+            p.Hin = p.Hout = H; p.Win = p.Wout = W / G; p.kh = s.k; p.kw = 1; p.stride = 1; p.pad = s.k / 2;
+            p.cout = G * s.cout; p.cout_pad = G * s.cout;
+            pack_weights_tc(wr.data(), s.k * 64, G * s.cout, p.cout_pad, wt);
+        } else {
+            const int cin_p = s.cin == 3 ? 4 : s.cin;          // the fp32 stem reads the NHWC4 input (4th channel zero)
+            const int K = s.k * s.k * cin_p;
+            wk.assign((size_t)K * s.cout, 0.f);
+            for (int n = 0; n < s.cout; ++n)
+                for (int c = 0; c < s.cin; ++c)
+                    for (int r = 0; r < s.k; ++r)
+                        for (int q = 0; q < s.k; ++q) wk[((size_t)(r * s.k + q) * cin_p + c) * s.cout + n] = wat(n, c, r, q);
+            p.x1 = x; p.c1 = cin_p; p.Hin = H; p.Win = W; p.kh = p.kw = s.k; p.stride = s.stride; p.pad = s.pad;
+            p.Hout = Ho; p.Wout = Wo; p.cout = s.cout;
+            if (tc && xs != nullptr && tc_eligible(p)) {
+                p.x1s = xs;
+                p.cout_pad = (s.cout + 15) / 16 * 16;
+                pack_weights_tc(wk.data(), K, s.cout, p.cout_pad, wt);
+            } else {
+                EVK_REQUIRE(x != nullptr, EVK_ERR_STATE, "evk_lpips: layer %d has no fp32 input for the CUDA-core kernel", i);
+                float* dw = (float*)l->dalloc(sizeof(float) * wk.size());
+                EVK_REQUIRE(dw != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
+                cudaMemcpy(dw, wk.data(), sizeof(float) * wk.size(), cudaMemcpyHostToDevice);
+                p.w = dw;
+                if (y == nullptr) {                              // the CUDA-core kernel writes fp32 only
+                    y = (float*)l->dalloc(sizeof(float) * n_out);
+                    EVK_REQUIRE(y != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
+                }
+            }
+        }
+        float* db = (float*)l->dalloc(sizeof(float) * bias.size());
+        EVK_REQUIRE(db != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
+        cudaMemcpy(db, bias.data(), sizeof(float) * bias.size(), cudaMemcpyHostToDevice);
+        p.bias = db; p.y = y; p.ys = ys;
+        if (!wt.empty()) {
             void* d = l->dalloc(wt.size() * sizeof(__nv_bfloat16));
             EVK_REQUIRE(d != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
             cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
             p.w_tc = (const __nv_bfloat16*)d;
-            p.x1s = xs;
             int r = tc_plan_create(p);
             if (r != EVK_OK) return r;
             l->plans.push_back(p.tc);
         }
-        cl.flops = 2.0 * s.cout * s.cin * s.k * s.k * (double)N * p.Hout * p.Wout;
+        cl.flops = 2.0 * s.cout * s.cin * s.k * s.k * (double)N * Ho * Wo;
         l->flops += cl.flops;
         l->layers.push_back(cl);
-        x = y; xs = ys; H = p.Hout; W = p.Wout; C = s.cout;
+        x = y; xs = ys; H = Ho; W = Wo; C = s.cout;
         if (s.tap >= 0) {
             const std::string t = std::to_string(s.tap);
             const std::vector<float>* lin = l->find({"lin" + t + ".model.1.weight", "lins." + t + ".model.1.weight"});
@@ -312,7 +442,16 @@ int evk_lpips_forward(evk_lpips* l, const float* img, const float* ref, int n, d
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t pixels = (int64_t)l->H * l->W;
     const int N = 2 * l->batch;
-    lpips_prep_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(N * pixels, 256), 2368), 256, 0, st>>>(img, ref, n, l->batch, pixels, l->input);
+    if (l->input != nullptr) {
+        lpips_prep_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(N * pixels, 256), 2368), 256, 0, st>>>(img, ref, n, l->batch, pixels, l->input);
+    } else if (l->backbone == 0) {
+        const int64_t total = (int64_t)N * l->stem_hb * l->stem_wb * 16;
+        lpips_prep_s2d_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, 0, st>>>(img, ref, n, l->batch, l->H, l->W, l->stem_hb,
+                                                                                                 l->stem_wb, l->input_s);
+    } else {
+        const int64_t total = (int64_t)N * l->H * (l->W + 8);
+        lpips_prep_rowwin_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, 0, st>>>(img, ref, n, l->batch, l->H, l->W, l->input_s);
+    }
     EVK_CHECK_CUDA(cudaGetLastError());
     for (const LpLayer& ly : l->layers) {
         if (ly.kind == 0) {

@@ -28,7 +28,7 @@ struct HostTensor {
     std::vector<int64_t> shape;
 };
 
-enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HEAD_PACK, OP_NOP, OP_ZERO_INSERT_ADD, OP_ADD_PAD, OP_RING_LINES };
+enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HYPER_APPLY_U, OP_HEAD_PACK, OP_NOP, OP_ZERO_INSERT_ADD, OP_ADD_PAD, OP_RING_LINES };
 
 struct Op {
     OpKind kind;
@@ -77,6 +77,8 @@ struct evk_model {
     int last_launches = 0;
     double flops = 0.0;
     cudaStream_t cap_stream = nullptr;
+    cudaStream_t cap_stream2 = nullptr;      // second branch of the captured graph (the two border-line convolutions of a decoder run side by side)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     bool use_graph = true;
     std::map<const float*, __nv_bfloat16*> split_of;   // fp32 activation buffer -> its split-bf16 companion
@@ -572,6 +574,38 @@ static int add_hyper_decoder(Builder& B, const std::string& pfx, const float* xu
     if (r != EVK_OK) return r;
     EVK_REQUIRE(c3 % K == 0, EVK_ERR_KEY, "basis coefficient channels (%d) not a multiple of the %d bases", c3, K);
     const int A = c3 / K;
+    const HostTensor* cc = m->find(pfx + ".dynamic_conv.compositional_coefficients");
+    const HostTensor* cb = m->find(pfx + ".dynamic_conv.bias");
+    EVK_REQUIRE(cc && cc->shape.size() == 4 && (int)cc->shape[1] == C * A && cc->shape[2] == 1 && cc->shape[3] == 1, EVK_ERR_KEY,
+                "'%s.dynamic_conv.compositional_coefficients': expected [Cout, %d, 1, 1]", pfx.c_str(), C * A);
+    const int Co = (int)cc->shape[0];
+    // Re-associated form (hyper.cuh (3)): the static 1x1 convolution first, on the tensor cores, with the weights regrouped
+    // per atom -- U[a*Co + o] = sum_c W[o][c*A + a] * xu[c] -- then the per-pixel 5x5 atoms applied to U.  Taken when the
+    // shapes are the shipped ones and the tensor-core path is on; the literal order (atoms -> dynamic conv -> 1x1) otherwise.
+    if (c.precision == 0 && A == 6 && K == 12 && ks == 5 && Co == 128 && C % 64 == 0 && getenv("EVK_HYPER_LITERAL") == nullptr) {
+        Packed pu;
+        pu.cout = A * Co; pu.cin = C; pu.kh = pu.kw = 1;
+        pu.w.assign((size_t)C * A * Co, 0.f);
+        pu.b.assign((size_t)A * Co, 0.f);
+        for (int o = 0; o < Co; ++o)
+            for (int ci = 0; ci < C; ++ci)
+                for (int a = 0; a < A; ++a)
+                    pu.w[(size_t)ci * (A * Co) + (size_t)a * Co + o] = cc->data[(size_t)o * (C * A) + (size_t)ci * A + a];
+        float* u = B.act(h, w, A * Co);
+        int cu = 0;
+        r = B.conv_packed(pu, xu, C, h, w, 1, 0, ACT_NONE, nullptr, u, &cu);
+        if (r != EVK_OK) return r;
+        m->ops[0].back().flops = 2.0 * Co * (double)(C * A) * (double)B.N * h * w;      // the reference's 1x1 (1536 -> 128): same multiply-adds
+        m->ops[1].back().flops = m->ops[0].back().flops;
+        std::vector<float> bias(Co, 0.f);
+        if (cb) bias = cb->data;
+        Op op; op.kind = OP_HYPER_APPLY_U;
+        op.hp.N = B.N; op.hp.coef = f3; op.hp.bases = m->upload(bases->data); op.hp.u = u; op.hp.out_bias = m->upload(bias); op.hp.y = y;
+        op.hp.h = h; op.hp.w = w; op.hp.A = A; op.hp.K = K; op.hp.L = L; op.hp.ks = ks; op.hp.C = C; op.hp.CO = Co;
+        op.flops = 2.0 * A * K * L * (double)B.N * h * w + 2.0 * A * L * C * (double)B.N * h * w;   // atoms + the reference's atom application
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+        return EVK_OK;
+    }
     float* atoms = B.act(h, w, A * L);
     float* inter = B.act(h, w, C * A);
     {
@@ -813,8 +847,8 @@ static int wire_tc(evk_model* m) {
                         rd(op.cp.res); rd(op.cp.c_prev); rd(op.cp.h_prev); rd(op.cp.u_in); rd(op.cp.pred_skip);
                         break;
                     case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_PRED: case OP_ADD_PAD: rd(op.in); rd(op.skip); break;
-                    case OP_HYPER_CONTEXT: case OP_HYPER_ATOMS: case OP_HYPER_APPLY:
-                        rd(op.hp.ev_nchw); rd(op.hp.prev); rd(op.hp.coef); rd(op.hp.atoms); rd(op.hp.xu);   // (ctx / inter are outputs here)
+                    case OP_HYPER_CONTEXT: case OP_HYPER_ATOMS: case OP_HYPER_APPLY: case OP_HYPER_APPLY_U:
+                        rd(op.hp.ev_nchw); rd(op.hp.prev); rd(op.hp.coef); rd(op.hp.atoms); rd(op.hp.xu); rd(op.hp.u);   // (ctx / inter / y are outputs here)
                         break;
                     default: break;
                 }
@@ -841,11 +875,28 @@ static int wire_tc(evk_model* m) {
     return EVK_OK;
 }
 
-static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent_t>* ev = nullptr) {
+// `side` != nullptr (graph capture only): the horizontal border-line convolution of every phase-stacked decoder is issued
+// on `side` (forked after the border-line kernel, joined before the decoder's main convolution), so the two small
+// correction launches -- ~one tile per SM each, latency bound -- overlap instead of running back to back.
+static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent_t>* ev = nullptr, cudaStream_t side = nullptr) {
+    bool forked = false;
     for (const Op& op : m->ops[par]) {
         int r = EVK_OK;
         if (ev) {
             cudaEvent_t e; EVK_CHECK_CUDA(cudaEventCreate(&e)); EVK_CHECK_CUDA(cudaEventRecord(e, st)); ev->push_back(e);
+        }
+        if (side != nullptr && op.kind == OP_CONV && op.ring_line == 1) {
+            EVK_CHECK_CUDA(cudaEventRecord(m->ev_fork, st));
+            EVK_CHECK_CUDA(cudaStreamWaitEvent(side, m->ev_fork, 0));
+            r = launch_conv(op.cp, m->cfg.precision, side);
+            if (r != EVK_OK) return r;
+            EVK_CHECK_CUDA(cudaEventRecord(m->ev_join, side));
+            forked = true;
+            continue;
+        }
+        if (forked && op.kind == OP_CONV && op.ring_line == 0) {          // the decoder's main convolution reads both corrections
+            EVK_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
+            forked = false;
         }
         switch (op.kind) {
             case OP_HEAD: r = launch_head_conv(op.in, op.w, op.b, op.out, op.out_s, op.N, op.cin, op.H, op.W, op.k, op.cout, st); break;
@@ -904,6 +955,7 @@ static std::string op_desc(const Op& op) {
         case OP_HEAD_PACK: snprintf(b, sizeof b, "head pack NCHW -> row-window split bf16 @%dx%d", op.H, op.W); break;
         case OP_HYPER_CONTEXT: snprintf(b, sizeof b, "hyper context x0.25"); break;
         case OP_HYPER_ATOMS: snprintf(b, sizeof b, "hyper atoms A=%d K=%d L=%d @%dx%d", op.hp.A, op.hp.K, op.hp.L, op.hp.h, op.hp.w); break;
+        case OP_HYPER_APPLY_U: snprintf(b, sizeof b, "hyper atoms + dynamic conv applied to U = conv1x1(x) (re-associated) C=%d A=%d Cout=%d @%dx%d", op.hp.C, op.hp.A, op.hp.CO, op.hp.h, op.hp.w); break;
         default: snprintf(b, sizeof b, "hyper dynamic conv C=%d A=%d @%dx%d", op.hp.C, op.hp.A, op.hp.h, op.hp.w); break;
     }
     return b;
@@ -972,6 +1024,9 @@ int evk_model_finalize(evk_model* m, void* stream) {
     m->flops = 0.0;
     for (const Op& op : m->ops[0]) m->flops += op.flops;
     EVK_CHECK_CUDA(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+    EVK_CHECK_CUDA(cudaStreamCreateWithFlags(&m->cap_stream2, cudaStreamNonBlocking));
+    EVK_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    EVK_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     EVK_CHECK_CUDA(cudaDeviceSynchronize());
     m->sd.clear();
     m->finalized = true;
@@ -1010,7 +1065,8 @@ int evk_model_forward(evk_model* m, const float* voxel, float* image, void* stre
         if (!m->graph[par]) {
             cudaGraph_t g = nullptr;
             EVK_CHECK_CUDA(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-            int r = run_ops(m, par, m->cap_stream);
+            static const bool fork_ok = getenv("EVK_NO_GRAPH_FORK") == nullptr;
+            int r = run_ops(m, par, m->cap_stream, nullptr, fork_ok ? m->cap_stream2 : nullptr);
             cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
             if (r != EVK_OK) { if (g) cudaGraphDestroy(g); return r; }
             EVK_CHECK_CUDA(e);
@@ -1091,6 +1147,9 @@ int evk_model_destroy(evk_model* m) {
     for (int i = 0; i < 2; ++i)
         if (m->graph[i]) cudaGraphExecDestroy(m->graph[i]);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+    if (m->cap_stream2) cudaStreamDestroy(m->cap_stream2);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     for (TcPlan* pl : m->plans) tc_plan_destroy(pl);
     for (void* p : m->allocs)
         if (p) cudaFree(p);

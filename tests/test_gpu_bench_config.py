@@ -21,9 +21,9 @@ def _streams(B, H, W, rate, fps, rows):
         # frame 0 moved 15 s into the past: the reference's "skip items more than 10 s before the evaluation window" rule
         # (eval.py:212-213) then skips exactly item 0 (the always-empty window), and the oracle starts at item 1 from zero
         # state like the batch below
-        ts = np.asarray(a['images_ts'], dtype=np.float64).copy()
+        ts = np.asarray(a['images_ts'], dtype=np.float64).reshape(-1).copy()
         ts[0] = ts[1] - 15.0
-        a['images_ts'] = ts
+        a['images_ts'] = ts.reshape(-1, 1)
     dss = [MemMapDataset(a, num_bins=5, voxel_method={'method': 'between_frames'}, resident=False) for a in arrs]
     return arrs, dss
 

@@ -210,7 +210,7 @@ def test_failures_are_caught_per_method_and_per_dataset(tmp_path, capsys):
     # a second dataset whose only sequence has an event outside the sensor (IndexError at check_bounds)
     arrays = {k: g[k] for k in ('events_ts', 'events_xy', 'events_p', 'images', 'images_ts', 'image_event_indices')}
     xy = arrays['events_xy'].copy()
-    xy[1000, 1] = 48
+    xy[20000, 1] = 48                      # y == H, in a window the loop voxelizes (events before frame 0 never are)
     arrays['events_xy'] = xy
     write_sequence_from_arrays(str(tmp_path / 'data' / 'BAD' / 'seq0'), arrays, (48, 64))
     json.dump({'root_path': str(tmp_path / 'data' / 'BAD'), 'sequences': {'seq0': {}}}, open(cfg_root / 'dataset' / 'BAD.json', 'w'))

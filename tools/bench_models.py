@@ -37,18 +37,22 @@ def main():
         n_items = len(batch)
         idx = 1
         for _ in range(5):
-            batch.step(idx); idx = idx % (n_items - 1) + 1
+            batch.step(idx, idx % (n_items - 1) + 1, sync=False); idx = idx % (n_items - 1) + 1
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
         ev = 0
         for _ in range(args.steps):
-            _, _, n = batch.step(idx); ev += n; idx = idx % (n_items - 1) + 1
+            _, _, n = batch.step(idx, idx % (n_items - 1) + 1, sync=False); ev += n; idx = idx % (n_items - 1) + 1
+        batch.join()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        rows = model.profile_forward(batch.padded)
-        rows = model.profile_forward(batch.padded)
+        batch.finish()
+        from evreal_b200.util import normalize_pad
+        padded = normalize_pad(batch.voxel, batch.Hp, batch.Wp, norm)
+        rows = model.profile_forward(padded)
+        rows = model.profile_forward(padded)
         fwd = sum(r[1] for r in rows)
         print(json.dumps({"model": name, "H": H, "W": W, "batch_streams": args.batch, "steps": args.steps,
                           "frames_per_s": args.batch * args.steps / (ms * 1e-3), "events_per_s": ev / (ms * 1e-3),
