@@ -538,6 +538,7 @@ def run_ours(args):
 
     def timed(batch, k_steps, warm, all_ranks=True):
         batch.reset()
+        batch.wait_uploaded()                     # `value`: every input byte is resident in HBM before anything is timed
         idx = 1                                   # item 0 of 'between_frames' is always the empty window
         nn = len(batch)
         for _ in range(warm):

@@ -18,7 +18,11 @@ _lock = threading.Lock()
 
 
 class Uploader:
-    def __init__(self, device, workers=4, chunk_bytes=16 << 20):
+    def __init__(self, device, workers=None, chunk_bytes=8 << 20):
+        import os
+        if workers is None:
+            world = max(int(os.environ.get("WORLD_SIZE", "1")), 1)
+            workers = max(2, min(8, (os.cpu_count() or 4) // world))
         self.dev = torch.device(device)
         self.workers, self.chunk = workers, chunk_bytes
         self.pool = ThreadPoolExecutor(max_workers=workers)
@@ -26,10 +30,15 @@ class Uploader:
         self.views = [[b.numpy() for b in pair] for pair in self.pinned]
         self.streams = [torch.cuda.Stream(self.dev) for _ in range(workers)]
         self.events = [[None, None] for _ in range(workers)]
+        self.locks = [threading.Lock() for _ in range(workers)]      # a worker slot (pinned pair + stream) serves one upload at a time
 
     def _work(self, j, jobs):
         """jobs: [(src uint8 numpy view, dst uint8 device tensor view)] of at most chunk bytes each."""
         stream = self.streams[j]
+        with self.locks[j]:
+            self._copy_jobs(j, stream, jobs)
+
+    def _copy_jobs(self, j, stream, jobs):
         for k, (src, dst) in enumerate(jobs):
             slot = k & 1
             ev = self.events[j][slot]
@@ -43,18 +52,27 @@ class Uploader:
                     ev = self.events[j][slot] = torch.cuda.Event()
                 ev.record(stream)
 
+    def alloc_like(self, a):
+        return torch.empty(a.shape, dtype=torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype, device=self.dev)
+
+    def jobs(self, a, t, lo=0, hi=None):
+        """Copy jobs (chunks) for rows [lo, hi) of the C-contiguous host array ``a`` into the same rows of device tensor ``t``."""
+        hi = a.shape[0] if hi is None else hi
+        if hi <= lo:
+            return []
+        src = a[lo:hi].reshape(-1).view(np.uint8)
+        dst = t[lo:hi].reshape(-1).view(torch.uint8)
+        return [(src[off:off + self.chunk], dst[off:off + self.chunk]) for off in range(0, src.shape[0], self.chunk)]
+
     def upload(self, arrays):
         """[numpy array, ...] (C-contiguous) -> [device tensor, ...] of the same dtypes / shapes; returns after all copies
         have completed."""
         outs, jobs = [], []
         for a in arrays:
             a = np.ascontiguousarray(a)
-            t = torch.empty(a.shape, dtype=torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype, device=self.dev)
+            t = self.alloc_like(a)
             outs.append(t)
-            src = a.reshape(-1).view(np.uint8)
-            dst = t.reshape(-1).view(torch.uint8)
-            for off in range(0, src.shape[0], self.chunk):
-                jobs.append((src[off:off + self.chunk], dst[off:off + self.chunk]))
+            jobs += self.jobs(a, t)
         if not jobs:
             return outs
         with torch.cuda.device(self.dev):
@@ -64,6 +82,72 @@ class Uploader:
             for s in self.streams:
                 s.synchronize()
         return outs
+
+
+class StreamedUpload:
+    """Handle of an upload running in the background, slice by slice (a slice = the events / frames of a range of steps of
+    every sequence of a lock-step batch): ``wait(j, stream)`` blocks the HOST until slice j's copies have been issued and
+    makes ``stream`` wait (on the device) until they have completed, so the first steps run while later slices are still
+    crossing PCIe."""
+
+    def __init__(self, uploader, slices):
+        self.up = uploader
+        self.n = len(slices)
+        W = uploader.workers
+        self.issued = [threading.Event() for _ in range(self.n)]
+        self.pending = [W] * self.n
+        self.lock = threading.Lock()
+        self.events = [[torch.cuda.Event() for _ in range(W)] for _ in range(self.n)]
+        self.waited = -1
+        self.error = None
+        self.futs = [uploader.pool.submit(self._work, j, [sl[j::W] for sl in slices]) for j in range(W)]
+
+    def _work(self, j, per_slice):
+        up = self.up
+        try:
+            with up.locks[j], torch.cuda.device(up.dev):
+                k = 0
+                for si, jobs in enumerate(per_slice):
+                    for src, dst in jobs:
+                        slot = k & 1
+                        k += 1
+                        ev = up.events[j][slot]
+                        if ev is not None:
+                            ev.synchronize()
+                        n = src.shape[0]
+                        np.copyto(up.views[j][slot][:n], src)
+                        with torch.cuda.stream(up.streams[j]):
+                            dst.copy_(up.pinned[j][slot][:n], non_blocking=True)
+                            if ev is None:
+                                ev = up.events[j][slot] = torch.cuda.Event()
+                            ev.record(up.streams[j])
+                    self.events[si][j].record(up.streams[j])
+                    with self.lock:
+                        self.pending[si] -= 1
+                        if self.pending[si] == 0:
+                            self.issued[si].set()
+        except Exception as e:                  # never leave the consumer waiting
+            self.error = e
+            for ev in self.issued:
+                ev.set()
+
+    def wait(self, j, stream):
+        j = min(j, self.n - 1)
+        while self.waited < j:
+            self.waited += 1
+            self.issued[self.waited].wait()
+            if self.error is not None:
+                raise self.error
+            for ev in self.events[self.waited]:
+                stream.wait_event(ev)
+
+    def finish(self):
+        for f in self.futs:
+            f.result()
+        if self.error is not None:
+            raise self.error
+        for s in self.up.streams:
+            s.synchronize()
 
 
 def get(device):

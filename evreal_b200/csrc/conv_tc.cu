@@ -81,6 +81,8 @@ struct TcArgs {
     const float* h_prev; const float* u_in; float* u_out; float* hr_out; __nv_bfloat16* hrs_out;   // ConvGRU epilogues
     const float* pred_w; const float* pred_skip; float* pred_out; float pred_bias; int pred_sigmoid;
     const __nv_bfloat16* pred_skip_s; long long pred_skip_plane;
+    int hiprio;                 // 1: producer / MMA-issuer roles on the four HIGHEST warp ids (the scheduler favours high warp ids: the
+                                //    issuers must not queue behind eight busy epilogue warps when tiles are short)
     int exp;                    // DBG kernels only (EVK_TC_EXP bit mask): 1 skip weight loads, 2 skip activation loads, 4 skip epilogue stores
     unsigned long long* dbg;    // EVK_TC_TIMING: per-CTA clock64 phase counters [grid][8], else nullptr
 };
@@ -165,7 +167,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
     const uint32_t bar_tempty = bar_tfull + 16u;              // [2] accumulator drained by the epilogue
     const uint32_t slot = bar_tempty + 16u;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // logical warp (role) <- physical warp: by default physical warps 8..11 take the producer / issuer roles 0..3 and physical
+    // warps 0..7 the epilogue roles 4..11 (an epilogue warp's tensor-memory lane quadrant is its PHYSICAL warp id % 4; role - 4
+    // == physical id there, so the quadrant arithmetic below is unchanged)
+    const int lane = threadIdx.x & 31;
+    const int warp = a.hiprio ? (int)(((threadIdx.x >> 5) + 4) % 12) : (int)(threadIdx.x >> 5);
     const int cs = a.cs;
     const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
     const int cid = blockIdx.x / cs, ncl = gridDim.x / cs;
@@ -444,13 +450,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             const size_t pix = ((size_t)t.img * a.Hout + oy) * a.Wout + ox;
             // split outputs in a row-padded layout: offset of this GEMM row's record relative to its dense offset pix * s_grp
             const long long sd = a.s_pitch ? (long long)((size_t)t.img * a.Hout + oy) * (a.s_pitch - a.Wout * a.s_grp) + a.s_off : 0;
+            const int cw = a.cw;
+            const int nchunks = (a.bn + cw - 1) / cw;
             const long long t0 = DBG ? clock64() : 0;
             mbar_wait(bar_tfull + 8u * as, aph);
             if (DBG) w_tf += clock64() - t0;
             tc_fence_after();
             const uint32_t t_row = tmem_base + as * (uint32_t)a.acc_stride + ((uint32_t)(wq * 32) << 16);
-            const int cw = a.cw;
-            const int nchunks = (a.bn + cw - 1) / cw;
             for (int c = half; c < nchunks; c += 2) {
                 const int j0 = c * cw;
                 uint32_t v[32];
@@ -777,7 +783,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         }
                     }
                     st_global_v8(a.u_out + o, uw); st_global_v8(a.u_out + o + 8, uw + 8);
-                    st_global_v8(a.hr_out + o, hw_); st_global_v8(a.hr_out + o + 8, hw_ + 8);
+                    if (a.hr_out != nullptr) { st_global_v8(a.hr_out + o, hw_); st_global_v8(a.hr_out + o + 8, hw_ + 8); }   // (fp32 copy only for a CUDA-core consumer)
                     if (a.hrs_out != nullptr) {
                         uint32_t hi8[8], lo8[8];
 #pragma unroll
@@ -842,7 +848,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         const float u3 = sigmoidf_(__uint_as_float(v[g * 8 + 6]) + b1.z), r3 = sigmoidf_(__uint_as_float(v[g * 8 + 7]) + b1.w);
                         *reinterpret_cast<float4*>(a.u_out + o + g * 4) = make_float4(u0, u1, u2, u3);
                         hr[g * 4 + 0] = hp.x * r0; hr[g * 4 + 1] = hp.y * r1; hr[g * 4 + 2] = hp.z * r2; hr[g * 4 + 3] = hp.w * r3;
-                        *reinterpret_cast<float4*>(a.hr_out + o + g * 4) = make_float4(hr[g * 4 + 0], hr[g * 4 + 1], hr[g * 4 + 2], hr[g * 4 + 3]);
+                        if (a.hr_out != nullptr) *reinterpret_cast<float4*>(a.hr_out + o + g * 4) = make_float4(hr[g * 4 + 0], hr[g * 4 + 1], hr[g * 4 + 2], hr[g * 4 + 3]);
                         if (a.hrs_out != nullptr) {
                             __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
@@ -1157,6 +1163,7 @@ int tc_plan_create(ConvParams& p) {
         a.ys_plane = a.hs_plane = (long long)p.N * p.Hout * a.s_pitch;
     }
     a.dbg = nullptr;
+    a.hiprio = env_int("EVK_TC_HIPRIO", 1) ? 1 : 0;
     a.exp = env_int("EVK_TC_EXP", 0);
     const uint32_t row_bytes = bk * 2;
     const size_t a_stage = 2 * (size_t)a.ar * 8 * row_bytes;

@@ -132,8 +132,11 @@ constexpr int kSX = 8, kSY = 4, kSWarps = 8;
 template <int A, int KS, int K>
 __global__ void __launch_bounds__(kSWarps * 32, 1) hyper_apply_u_kernel(const HyperParams p, int strips_x, int strips_y, int n_strips) {
     constexpr int L = KS * KS, R = KS / 2, LP = KS * 8;           // atoms of one (pixel, a): KS rows of 8 slots (KS used)
-    __shared__ float s_bases[K * L];
-    __shared__ __align__(16) float s_at[kSWarps][kSX * kSY][LP];
+    constexpr int NC = A * K;                                      // basis coefficients per pixel
+    extern __shared__ __align__(16) float s_dyn[];
+    float* s_bases = s_dyn;                                         // [K][L]
+    float (*s_at)[kSX * kSY][LP] = reinterpret_cast<float (*)[kSX * kSY][LP]>(s_dyn + ((K * L + 3) & ~3));
+    float (*s_coef)[kSX * kSY][NC] = reinterpret_cast<float (*)[kSX * kSY][NC]>(&s_at[kSWarps][0][0]);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < K * L; i += blockDim.x) s_bases[i] = p.bases[i];
     __syncthreads();
@@ -145,17 +148,24 @@ __global__ void __launch_bounds__(kSWarps * 32, 1) hyper_apply_u_kernel(const Hy
         float4 acc[kSY * kSX];
 #pragma unroll
         for (int i = 0; i < kSY * kSX; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // the strip's basis coefficients, once, coalesced: a strip row is kSX * NC contiguous floats
+        __syncwarp();
+        for (int py = 0; py < kSY; ++py) {
+            const int gy = min(y0 + py, p.h - 1);
+            const int valid = min(kSX, p.w - x0) * NC;
+            const float* src = p.coef + (((size_t)n * p.h + gy) * p.w + x0) * NC;
+            for (int i = lane; i < kSX * NC; i += 32) s_coef[warp][py * kSX][i] = i < valid ? __ldg(src + i) : 0.f;
+        }
 #pragma unroll 1
         for (int a = 0; a < A; ++a) {
             __syncwarp();
             // atoms of this strip for atom index a: (pixel, l) pairs dealt over the lanes
             for (int i = lane; i < kSX * kSY * L; i += 32) {
                 const int pix = i / L, l = i - pix * L;
-                const int gy = min(y0 + pix / kSX, p.h - 1), gx = min(x0 + pix % kSX, p.w - 1);
-                const float* c = p.coef + (((size_t)n * p.h + gy) * p.w + gx) * (A * K) + a * K;
+                const float* c = &s_coef[warp][pix][a * K];
                 float v = 0.f;
 #pragma unroll
-                for (int k = 0; k < K; ++k) v = fmaf(__ldg(c + k), s_bases[k * L + l], v);
+                for (int k = 0; k < K; ++k) v = fmaf(c[k], s_bases[k * L + l], v);
                 s_at[warp][pix][(l / KS) * 8 + (l % KS)] = v;
             }
             __syncwarp();
@@ -219,7 +229,15 @@ int launch_hyper(int which, const HyperParams& p, cudaStream_t st) {
                     p.A, p.ks, p.K, p.CO);
         const int strips_x = ceil_div(p.w, kSX), strips_y = ceil_div(p.h, kSY), n_strips = strips_x * strips_y * p.N;
         const int blocks = std::min(ceil_div(n_strips, kSWarps), kNumSMs);
-        hyper_apply_u_kernel<6, 5, 12><<<blocks, kSWarps * 32, 0, st>>>(p, strips_x, strips_y, n_strips);
+        const size_t smem = sizeof(float) * (((12 * 25 + 3) & ~3) + (size_t)kSWarps * kSX * kSY * (5 * 8 + 6 * 12));
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        EVK_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            EVK_CHECK_CUDA(cudaFuncSetAttribute(hyper_apply_u_kernel<6, 5, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        hyper_apply_u_kernel<6, 5, 12><<<blocks, kSWarps * 32, smem, st>>>(p, strips_x, strips_y, n_strips);
     } else {
         EVK_REQUIRE(p.A == 6 && p.ks == 5 && p.C % kACH == 0, EVK_ERR_ARG,
                     "hyper apply: only num_atoms=6, kernel_size=5, C%%32==0 is built (got A=%d ks=%d C=%d)", p.A, p.ks, p.C);

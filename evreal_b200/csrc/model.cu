@@ -860,6 +860,9 @@ static int wire_tc(evk_model* m) {
                         !fp32_read.count(op.cp.y) && (op.cp.ys != nullptr || op.cp.pred_out != nullptr)) {
                         op.cp.y = nullptr;
                     }
+                    // ConvGRU: h * reset is consumed by the candidate convolution only -- through its split planes on the tensor-core path
+                    if (op.kind == OP_CONV && op.cp.x1s != nullptr && op.cp.epi == EPI_GRU_UR && op.cp.hrs_out != nullptr && op.cp.hr_out != nullptr &&
+                        !fp32_read.count(op.cp.hr_out)) op.cp.hr_out = nullptr;
                     if ((op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD) && op.out_s != nullptr && !fp32_read.count(op.out)) op.out = nullptr;
                     if (op.kind == OP_HYPER_APPLY && op.hp.inter_s != nullptr && !fp32_read.count(op.hp.inter)) op.hp.inter = nullptr;
                 }

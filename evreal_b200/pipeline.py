@@ -105,23 +105,39 @@ class SequenceBatch:
         self.max_win = max_win
         self._src = []
         self._base = np.zeros((B, 4), dtype=np.int64)      # raw base addresses (xy, t, p, images) of every sequence
+        self._stream_up = None
         if resident:
-            # one threaded, chunked upload of every sequence (13 B/event + frames): _upload.py
+            # threaded, chunked upload of every sequence (13 B/event + frames, _upload.py), issued in TIME SLICES: the events /
+            # frames of the first steps of every sequence first, so the loop starts while later slices are still in flight
             from . import _upload
-            host = []
-            for ds in self.datasets:
-                fh = ds.filehandle
-                p = np.asarray(fh["p"])
-                host += [np.asarray(fh["xy"]) if np.asarray(fh["xy"]).dtype == np.int16 else np.asarray(fh["xy"]).astype(np.int16),
-                         np.asarray(fh["t"], dtype=np.float64), p if p.dtype == np.uint8 else p.astype(np.uint8)]
-                if ds.has_images:
-                    host.append(np.asarray(fh["images"])[..., 0])
-            devs = iter(_upload.get(dev).upload(host))
+            up = _upload.get(dev)
+            n_slices = max(1, min(8, n_items // 16))
+            self._slice_of = [min(i * n_slices // max(n_items, 1), n_slices - 1) for i in range(max(n_items, 1))]
+            slices = [[] for _ in range(n_slices)]
             for b, ds in enumerate(self.datasets):
-                xy, t, p = next(devs), next(devs), next(devs)
-                im = next(devs) if ds.has_images else None
+                fh = ds.filehandle
+                xy_h = np.ascontiguousarray(np.asarray(fh["xy"]) if np.asarray(fh["xy"]).dtype == np.int16 else np.asarray(fh["xy"]).astype(np.int16))
+                t_h = np.ascontiguousarray(np.asarray(fh["t"], dtype=np.float64))
+                p_h = np.asarray(fh["p"])
+                p_h = np.ascontiguousarray(p_h if p_h.dtype == np.uint8 else p_h.astype(np.uint8))
+                im_h = np.ascontiguousarray(np.asarray(fh["images"])[..., 0]) if ds.has_images else None
+                xy, t, p = up.alloc_like(xy_h), up.alloc_like(t_h), up.alloc_like(p_h)
+                im = up.alloc_like(im_h) if im_h is not None else None
                 self._src.append((xy, t, p, im))
                 self._base[b] = (xy.data_ptr(), t.data_ptr(), p.data_ptr(), im.data_ptr() if im is not None else 0)
+                # slice j needs every event below the largest window end and every frame up to the largest frame index of its items
+                e_lo = f_lo = 0
+                for j in range(n_slices):
+                    items = [i for i in range(n_items) if self._slice_of[i] == j]
+                    last = j == n_slices - 1
+                    e_hi = len(t_h) if last else max([int(self._win[b, i, 1]) for i in items] + [e_lo])
+                    f_hi = (len(im_h) if im_h is not None else 0) if last else max([int(self._win[b, i, 2]) + 1 for i in items] + [f_lo])
+                    e_hi, f_hi = max(e_hi, e_lo), max(f_hi, f_lo)
+                    slices[j] += up.jobs(xy_h, xy, e_lo, e_hi) + up.jobs(t_h, t, e_lo, e_hi) + up.jobs(p_h, p, e_lo, e_hi)
+                    if im_h is not None:
+                        slices[j] += up.jobs(im_h, im, f_lo, f_hi)
+                    e_lo, f_lo = e_hi, f_hi
+            self._stream_up = _upload.StreamedUpload(up, slices)
         else:
             for b, ds in enumerate(self.datasets):
                 fh = ds.filehandle
@@ -174,7 +190,8 @@ class SequenceBatch:
             self._last_slot = 1
             self._host_windows = (_lib.EventWindow * B)()
             self._host_frames = (ctypes.c_void_p * B)()
-        torch.cuda.synchronize(dev)
+        if self._stream_up is None:
+            torch.cuda.synchronize(dev)
 
     def __len__(self):
         if self._counts is not None:
@@ -182,7 +199,7 @@ class SequenceBatch:
         return min(len(ds) - o for ds, o in zip(self.datasets, self._offsets))
 
     def reset(self):
-        self.finish()
+        self._sync_streams()                 # (not the background upload: the first steps run while later slices arrive)
         self.model.reset_states()            # (also rewinds the parity of the model's input / output buffers)
         self.oob_total.zero_()
         self._pre_issued = None
@@ -234,6 +251,8 @@ class SequenceBatch:
             if self._post_recorded[par]:
                 pre.wait_event(self._post_done[par])
         if self.resident:
+            if self._stream_up is not None:
+                self._stream_up.wait(self._slice_of[min(idx, len(self._slice_of) - 1)], pre)
             for b in range(B):
                 i0, i1 = int(win[b, 0]), int(win[b, 1])
                 w = ws[b]
@@ -385,7 +404,18 @@ class SequenceBatch:
             torch.cuda.current_stream(self.dev).wait_event(self.result_event)
 
     def finish(self):
-        """Wait (on the host) for every stage and copy in flight."""
+        """Wait (on the host) for every stage and copy in flight, the background upload included."""
+        if self._stream_up is not None:
+            self._stream_up.finish()
+        self._sync_streams()
+
+    def wait_uploaded(self):
+        """Block until every sequence is completely resident in HBM (benchmarks: nothing may still be crossing PCIe when a
+        timed region that claims resident inputs starts)."""
+        if self._stream_up is not None:
+            self._stream_up.finish()
+
+    def _sync_streams(self):
         if self.overlap:
             self.pre_stream.synchronize()
             self.post_stream.synchronize()

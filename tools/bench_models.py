@@ -34,6 +34,7 @@ def main():
         model.to('cuda')
         batch = SequenceBatch(model, dss, norm, post, resident=True)
         batch.reset()
+        batch.wait_uploaded()
         n_items = len(batch)
         idx = 1
         for _ in range(5):
