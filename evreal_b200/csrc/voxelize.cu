@@ -12,6 +12,10 @@
 // reduction units are request-rate bound (~83 requests/clk measured, tools/microbench/red_bench.cu) and a v4
 // request costs the same as a scalar one, so this halves the scatter time of the two-scalar-reds form.  A gather
 // pass then writes the reference's planar [bins,H,W] layout (bin 3g = slot 0 of group g + slot 3 of group g-1).
+// Small windows skip the scratch grid: below ~S/8 events (S = scratch bytes; 170k events at 240x180, 1.2M at 640x480; measured
+// crossover at 640x480 between 0.8M and 2M) clearing and gathering the 1.6x larger interleaved grid plus two extra launches
+// cost more than the second reduction per event, so each event issues TWO
+// scalar RED.ADD.F32 straight into the (cleared) planar grid -- one launch, no gather pass.
 // Algorithmic bytes per window: 16*N (f32 SoA) or 13*N (raw int16/f64/u8) + 4*bins*H*W for the grid.
 #include <algorithm>
 
@@ -30,6 +34,7 @@ static inline int vox_groups(int bins) { return (bins - 1) / 3 + 1; }
 // One event's contribution.  tn is the normalised time in [0, bins-1]; only
 // floor(tn) and floor(tn)+1 can have weight max(0, 1-|tn-b|) > 0, so the
 // reference's five passes collapse to two adds with identical float values.
+template <bool kDirect = false>
 __device__ __forceinline__ void scatter_event(float xf, float yf, float tn, float pol, const VoxGeom g,
                                               float* __restrict__ scratch, int& oob) {
     int xi = (int)xf;   // truncation toward zero == tensor.long()
@@ -48,6 +53,13 @@ __device__ __forceinline__ void scatter_event(float xf, float yf, float tn, floa
     const float w0 = 1.0f - fabsf(tn - (float)b0), w1 = 1.0f - fabsf(tn - (float)(b0 + 1));
     const float c0 = (b0 >= 0 && w0 > 0.0f) ? pol * w0 : 0.0f;
     const float c1 = (b0 + 1 < g.bins && w1 > 0.0f) ? pol * w1 : 0.0f;
+    if (kDirect) {                                    // planar grid [bins][H][W]: one scalar reduction per non-zero weight
+        float* cell = scratch + ((size_t)max(b0, 0) * g.H + yi) * g.W + xi;
+        if (b0 >= 0 && w0 > 0.0f) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cell), "f"(c0) : "memory");
+        if (b0 + 1 < g.bins && w1 > 0.0f)
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cell + (b0 >= 0 ? (size_t)g.H * g.W : 0)), "f"(c1) : "memory");
+        return;
+    }
     const int o = b0 - 3 * grp;                       // slot of bin b0 in its group: -1 (b0 == -1), 0, 1 or 2
     const float v0 = o == 0 ? c0 : (o == -1 ? c1 : 0.0f);
     const float v1 = o == 1 ? c0 : (o == 0 ? c1 : 0.0f);
@@ -94,7 +106,7 @@ struct TimeNorm {
     }
 };
 
-template <bool kVec>
+template <bool kVec, bool kDirect>
 __global__ void __launch_bounds__(kVoxThreads)
 voxelize_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ t,
                     const float* __restrict__ p, int64_t n, int64_t head, VoxGeom g,
@@ -118,24 +130,25 @@ voxelize_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, co
         for (int64_t v = tid; v < nvec; v += nthreads) {
             const float4 xv = __ldcs(x4 + v), yv = __ldcs(y4 + v), tv = __ldcs(t4 + v), pv = __ldcs(p4 + v);
             const int64_t i = head + v * 4;
-            scatter_event(xv.x, yv.x, tn(tv.x, i + 0), pv.x, g, grid, oob);
-            scatter_event(xv.y, yv.y, tn(tv.y, i + 1), pv.y, g, grid, oob);
-            scatter_event(xv.z, yv.z, tn(tv.z, i + 2), pv.z, g, grid, oob);
-            scatter_event(xv.w, yv.w, tn(tv.w, i + 3), pv.w, g, grid, oob);
+            scatter_event<kDirect>(xv.x, yv.x, tn(tv.x, i + 0), pv.x, g, grid, oob);
+            scatter_event<kDirect>(xv.y, yv.y, tn(tv.y, i + 1), pv.y, g, grid, oob);
+            scatter_event<kDirect>(xv.z, yv.z, tn(tv.z, i + 2), pv.z, g, grid, oob);
+            scatter_event<kDirect>(xv.w, yv.w, tn(tv.w, i + 3), pv.w, g, grid, oob);
         }
         const int64_t tail0 = head + nvec * 4;
         const int64_t nscalar = head + (n - tail0);
         for (int64_t s = tid; s < nscalar; s += nthreads) {
             const int64_t i = s < head ? s : tail0 + (s - head);
-            scatter_event(x[i], y[i], tn(t[i], i), p[i], g, grid, oob);
+            scatter_event<kDirect>(x[i], y[i], tn(t[i], i), p[i], g, grid, oob);
         }
     } else {
-        for (int64_t i = tid; i < n; i += nthreads) scatter_event(x[i], y[i], tn(t[i], i), p[i], g, grid, oob);
+        for (int64_t i = tid; i < n; i += nthreads) scatter_event<kDirect>(x[i], y[i], tn(t[i], i), p[i], g, grid, oob);
     }
     if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
 }
 
 // Raw on-disk layout: xy int16 pairs, t float64 absolute, pol uint8 {0,1}.
+template <bool kDirect>
 __device__ __forceinline__ void voxelize_raw_body(const int16_t* __restrict__ xy, const double* __restrict__ t,
                                                   const uint8_t* __restrict__ pol, int64_t n, VoxGeom g, float* __restrict__ grid,
                                                   int* __restrict__ oob_count, int64_t tid, int64_t nthreads) {
@@ -154,16 +167,17 @@ __device__ __forceinline__ void voxelize_raw_body(const int16_t* __restrict__ xy
         const float yf = (float)(short)(c >> 16);
         const float tf = (float)(__ldcs(t + i) - t0d);
         const float pf = (float)((double)pol[i] * 2.0 - 1.0);
-        scatter_event(xf, yf, tn(tf, i), pf, g, grid, oob);
+        scatter_event<kDirect>(xf, yf, tn(tf, i), pf, g, grid, oob);
     }
     if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
 }
 
+template <bool kDirect>
 __global__ void __launch_bounds__(kVoxThreads)
 voxelize_raw_kernel(const int16_t* __restrict__ xy, const double* __restrict__ t, const uint8_t* __restrict__ pol,
                     int64_t n, VoxGeom g, float* __restrict__ grid, int* __restrict__ oob_count) {
-    voxelize_raw_body(xy, t, pol, n, g, grid, oob_count, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
-                      (int64_t)gridDim.x * blockDim.x);
+    voxelize_raw_body<kDirect>(xy, t, pol, n, g, grid, oob_count, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                               (int64_t)gridDim.x * blockDim.x);
 }
 
 // Several windows (one per sequence of a lock-step batch) in ONE launch: blockIdx.y = window, grids contiguous.
@@ -175,13 +189,23 @@ struct VoxBatch {
     long long n[kVoxBatch];
 };
 
+template <bool kDirect>
 __global__ void __launch_bounds__(kVoxThreads)
 voxelize_raw_batch_kernel(const __grid_constant__ VoxBatch wb, VoxGeom g, float* __restrict__ grids, int* __restrict__ oob_count) {
     const int w = blockIdx.y;
     const int64_t n = wb.n[w];
     if (n <= 0) return;                      // empty window: the (pre-zeroed) grid stays zero (dataset.py:59-71)
-    voxelize_raw_body(wb.xy[w], wb.t[w], wb.pol[w], n, g, grids + (size_t)w * 4 * g.groups * g.H * g.W, oob_count,
-                      (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+    const size_t per_grid = kDirect ? (size_t)g.bins * g.H * g.W : (size_t)4 * g.groups * g.H * g.W;
+    voxelize_raw_body<kDirect>(wb.xy[w], wb.t[w], wb.pol[w], n, g, grids + (size_t)w * per_grid, oob_count,
+                               (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+// Direct (two scalar reductions per event, planar grid) below this many events per window: S / 8 with S = bytes of the
+// interleaved scratch grid (see the file header); EVK_VOX_DIRECT_MAX overrides (0 = never, <0 = always).
+static int64_t vox_direct_max(const VoxGeom& g) {
+    static const char* e = getenv("EVK_VOX_DIRECT_MAX");
+    if (e && e[0]) { const long long v = atoll(e); return v < 0 ? INT64_MAX : (int64_t)v; }
+    return (int64_t)((size_t)16 * g.groups * g.H * g.W / 8);
 }
 
 static int vox_grid_blocks(int64_t n, int per_thread) {
@@ -225,21 +249,29 @@ int voxelize_f32(const float* x, const float* y, const float* t, const float* p,
     EVK_REQUIRE(n > 0, EVK_ERR_ARG, "evk_voxelize: empty window (n=%lld); the reference indexes ts[-1]", (long long)n);
     EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize: bad geometry bins=%d H=%d W=%d", bins, H, W);
     VoxGeom g{bins, H, W, vox_groups(bins)};
+    const bool direct = n <= vox_direct_max(g);
     float* scratch = nullptr;
-    int r = vox_scratch_begin(&scratch, g, 1, st);
-    if (r != EVK_OK) return r;
+    if (direct) {
+        EVK_CHECK_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)bins * H * W, st));
+        scratch = grid;
+    } else {
+        int r = vox_scratch_begin(&scratch, g, 1, st);
+        if (r != EVK_OK) return r;
+    }
     // all four arrays must share the same 16-byte phase for the vector body
     auto phase = [](const void* q) { return (int)(((uintptr_t)q >> 2) & 3); };
     const bool same = phase(x) == phase(y) && phase(y) == phase(t) && phase(t) == phase(p) &&
                       (((uintptr_t)x | (uintptr_t)y | (uintptr_t)t | (uintptr_t)p) & 3) == 0;
     if (same && n >= 64) {
         int64_t head = (4 - phase(x)) & 3;
-        voxelize_f32_kernel<true><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, scratch, oob_count);
+        if (direct) voxelize_f32_kernel<true, true><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, scratch, oob_count);
+        else voxelize_f32_kernel<true, false><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, scratch, oob_count);
     } else {
-        voxelize_f32_kernel<false><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, scratch, oob_count);
+        if (direct) voxelize_f32_kernel<false, true><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, scratch, oob_count);
+        else voxelize_f32_kernel<false, false><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, scratch, oob_count);
     }
     EVK_CHECK_CUDA(cudaGetLastError());
-    return vox_scratch_end(scratch, grid, g, 1, st);
+    return direct ? EVK_OK : vox_scratch_end(scratch, grid, g, 1, st);
 }
 
 int voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int64_t n, int bins, int H, int W,
@@ -248,10 +280,16 @@ int voxelize_raw(const int16_t* xy, const double* t, const uint8_t* pol, int64_t
     EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize_raw: bad geometry");
     EVK_REQUIRE(((uintptr_t)xy & 3) == 0 && ((uintptr_t)t & 7) == 0, EVK_ERR_ARG, "evk_voxelize_raw: misaligned arrays");
     VoxGeom g{bins, H, W, vox_groups(bins)};
+    if (n <= vox_direct_max(g)) {
+        EVK_CHECK_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)bins * H * W, st));
+        voxelize_raw_kernel<true><<<vox_grid_blocks(n, 2), kVoxThreads, 0, st>>>(xy, t, pol, n, g, grid, oob_count);
+        EVK_CHECK_CUDA(cudaGetLastError());
+        return EVK_OK;
+    }
     float* scratch = nullptr;
     int r = vox_scratch_begin(&scratch, g, 1, st);
     if (r != EVK_OK) return r;
-    voxelize_raw_kernel<<<vox_grid_blocks(n, 2), kVoxThreads, 0, st>>>(xy, t, pol, n, g, scratch, oob_count);
+    voxelize_raw_kernel<false><<<vox_grid_blocks(n, 2), kVoxThreads, 0, st>>>(xy, t, pol, n, g, scratch, oob_count);
     EVK_CHECK_CUDA(cudaGetLastError());
     return vox_scratch_end(scratch, grid, g, 1, st);
 }
@@ -261,10 +299,18 @@ int voxelize_raw_batch(const evk_event_window* windows, int n_windows, int bins,
     EVK_REQUIRE(windows && grids && n_windows > 0, EVK_ERR_ARG, "evk_voxelize_raw_batch: bad argument");
     EVK_REQUIRE(bins > 0 && H > 0 && W > 0, EVK_ERR_ARG, "evk_voxelize_raw_batch: bad geometry");
     VoxGeom g{bins, H, W, vox_groups(bins)};
-    const size_t scratch_elems = (size_t)4 * g.groups * H * W;
+    int64_t n_largest = 0;
+    for (int i = 0; i < n_windows; ++i) n_largest = std::max<int64_t>(n_largest, windows[i].n);
+    const bool direct = n_largest <= vox_direct_max(g);
+    const size_t scratch_elems = direct ? (size_t)bins * H * W : (size_t)4 * g.groups * H * W;
     float* scratch = nullptr;
-    int r = vox_scratch_begin(&scratch, g, n_windows, st);
-    if (r != EVK_OK) return r;
+    if (direct) {
+        EVK_CHECK_CUDA(cudaMemsetAsync(grids, 0, sizeof(float) * scratch_elems * n_windows, st));
+        scratch = grids;
+    } else {
+        int r = vox_scratch_begin(&scratch, g, n_windows, st);
+        if (r != EVK_OK) return r;
+    }
     for (int w0 = 0; w0 < n_windows; w0 += kVoxBatch) {
         const int cnt = std::min(kVoxBatch, n_windows - w0);
         VoxBatch wb;
@@ -284,10 +330,11 @@ int voxelize_raw_batch(const evk_event_window* windows, int n_windows, int bins,
         int64_t bx = ceil_div64(nmax, (int64_t)kVoxThreads * 2);
         const int64_t cap = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / cnt);
         bx = std::max<int64_t>(1, std::min(bx, cap));
-        voxelize_raw_batch_kernel<<<dim3((unsigned)bx, (unsigned)cnt), kVoxThreads, 0, st>>>(wb, g, scratch + scratch_elems * w0, oob_count);
+        if (direct) voxelize_raw_batch_kernel<true><<<dim3((unsigned)bx, (unsigned)cnt), kVoxThreads, 0, st>>>(wb, g, scratch + scratch_elems * w0, oob_count);
+        else voxelize_raw_batch_kernel<false><<<dim3((unsigned)bx, (unsigned)cnt), kVoxThreads, 0, st>>>(wb, g, scratch + scratch_elems * w0, oob_count);
         EVK_CHECK_CUDA(cudaGetLastError());
     }
-    return vox_scratch_end(scratch, grids, g, n_windows, st);
+    return direct ? EVK_OK : vox_scratch_end(scratch, grids, g, n_windows, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -349,6 +396,32 @@ normalize_pad_kernel(const float* __restrict__ in, float* __restrict__ out, cons
             stddev = fmaxf(stddev, 1e-6f);
         }
     }
+    if ((Wp & 3) == 0) {
+        // four output columns per thread (one 16-byte store; the index arithmetic of the scalar form cost more than the bytes)
+        const int W4 = Wp >> 2;
+        const int64_t total4 = (int64_t)C * Hp * W4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+            const int x4 = (int)(i % W4);
+            const int64_t row = i / W4;
+            const int yo = (int)(row % Hp);
+            const int c = (int)(row / Hp);
+            const int yi = yo - top;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if ((unsigned)yi < (unsigned)H) {
+                const float* src = in + ((size_t)s * C + c) * H * W + (size_t)yi * W;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int xi = x4 * 4 + k - left;
+                    if ((unsigned)xi < (unsigned)W) {
+                        const float a = src[xi];
+                        v[k] = (active && a != 0.0f) ? __fdiv_rn(__fsub_rn(a, mean), stddev) : (active ? 0.0f : a);
+                    }
+                }
+            }
+            reinterpret_cast<float4*>(out + (size_t)s * total)[i] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int xo = (int)(i % Wp);
         const int yo = (int)((i / Wp) % Hp);
@@ -381,7 +454,8 @@ int normalize_pad(const float* in, float* out, int n_samples, int C, int H, int 
     // CropParameters: top/left get the ceil half (utils/util.py:43-46)
     const int top = (Hp - H + 1) / 2, left = (Wp - W + 1) / 2;
     const int64_t total = (int64_t)C * Hp * Wp;
-    dim3 grid((unsigned)std::min<int64_t>(ceil_div64(total, 256 * 2), 1184), n_samples);
+    const int64_t work = (Wp & 3) == 0 ? total / 4 : total;
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(work, 256), std::max(1, kNumSMs * 8 / n_samples))), n_samples);
     normalize_pad_kernel<<<grid, 256, 0, st>>>(in, out, stats, C, H, W, Hp, Wp, top, left, do_norm);
     EVK_CHECK_CUDA(cudaGetLastError());
     if (stats) EVK_CHECK_CUDA(cudaFreeAsync(stats, st));

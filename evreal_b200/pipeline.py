@@ -282,7 +282,10 @@ class SequenceBatch:
         # empty windows -> zeros grid (dataset.py:59-71) is part of the batched call
         _lib.check(lib.evk_voxelize_raw_batch(ws, B, self.bins, self.H, self.W, _lib.ptr(self.voxel),
                                               _lib.ptr(self.oob_total), st))
-        launches += 3 if n_events > 0 else 2                # scratch clear, scatter, gather
+        # grid clear + scatter (two reductions per event straight into the planar grid) for windows below ~2*groups*H*W events,
+        # else scratch clear + scatter (one vector reduction per event) + gather: voxelize.cu
+        direct = int((win[:, 1] - win[:, 0]).max()) <= 2 * ((self.bins - 1) // 3 + 1) * self.H * self.W
+        launches += (2 if direct else 3) if n_events > 0 else 1
         if self.compute_metrics:
             _lib.check(lib.evk_u8_to_f32_batch(fr, B, self.H * self.W, _lib.ptr(self.ref2[par]), st))
             launches += 1

@@ -20,6 +20,8 @@ def main():
     ap.add_argument('--batch', type=int, default=24)
     ap.add_argument('--model', default='e2vid', choices=['e2vid', 'firenet', 'hyper'])
     ap.add_argument('--voxel-only', action='store_true', help='cfg 5 voxelizer launches only (640x480, 4M events)')
+    ap.add_argument('--voxel-events', type=int, default=4_000_000)
+    ap.add_argument('--lpips', default='', help="'lpips' or 'lpips-vgg': batched LPIPS calls only (36 pairs at 240x180)")
     args = ap.parse_args()
     import torch
     import evreal_b200 as evk
@@ -28,7 +30,7 @@ def main():
     from evreal_b200.pipeline import SequenceBatch
     if args.voxel_only:
         lib = _lib.load()
-        n, Hv, Wv = 4_000_000, 480, 640
+        n, Hv, Wv = args.voxel_events, 480, 640
         g = torch.Generator(device='cuda').manual_seed(1)
         x = torch.randint(0, Wv, (n,), device='cuda', generator=g).float()
         y = torch.randint(0, Hv, (n,), device='cuda', generator=g).float()
@@ -38,6 +40,16 @@ def main():
         for _ in range(args.steps):
             _lib.check(lib.evk_voxelize(_lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), n, 5, Hv, Wv, _lib.ptr(grid), None,
                                         _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        return
+    if args.lpips:
+        sys.path.insert(0, ROOT)
+        import bench
+        from evreal_b200.lpips import LpipsNet
+        ln = LpipsNet(args.lpips, bench.seeded_lpips_weights('alex' if args.lpips == 'lpips' else 'vgg'), 180, 240, batch=36)
+        a, b = torch.rand((36, 180, 240), device='cuda'), torch.rand((36, 180, 240), device='cuda')
+        for _ in range(args.steps):
+            ln(a, b)
         torch.cuda.synchronize()
         return
     shapes = {'e2vid': (180, 240, 1e6, 24.0), 'firenet': (180, 240, 1e6, 25.0), 'hyper': (260, 346, 5e6, 45.0)}
