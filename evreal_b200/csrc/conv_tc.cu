@@ -50,6 +50,8 @@ struct TcArgs {
     int fastps;                 // phase-stacked last decoder (cout 32, ReLU, fused prediction layer, no tensor output): straight-line epilogue
     int fastgru;                // ConvGRU epilogues, channel counts multiples of 16: straight-line variants (window-mode FireNet)
     int fastlin;                // EPI_LINEAR, wide, 32-column chunks, no row-pair / phase / prediction: straight-line epilogue
+    int predw;                  // window mode (2 pixels x 16 channels per GEMM row, 16-column chunks): the 1x1 prediction layer of FireNet fused
+                                //    into the straight-line epilogue -- a chunk is one pixel, its thread holds all 16 channels
     float act_floor;            // fastlin: lower clamp of the activation (0 for ReLU, -inf for none)
     int wide;                   // EPI_LINEAR: 256-bit stores (real and packed channel counts are multiples of 16)
     int ps, wreal;              // phase-stacked mode (ConvParams::phase4): column block a*2+b -> output pixel (2oy+a, 2ox+b); output width
@@ -572,6 +574,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         v[g * 4 + 1] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 1]) + b4[g].y + r4[g].y, fl));
                         v[g * 4 + 2] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 2]) + b4[g].z + r4[g].z, fl));
                         v[g * 4 + 3] = __float_as_uint(fmaxf(__uint_as_float(v[g * 4 + 3]) + b4[g].w + r4[g].w, fl));
+                    }
+                    if (a.predw) {                  // out[pixel] = sum_c w[c] * y[pixel, c] + b  (summation order of pred_kernel)
+                        float pacc = 0.f;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.pred_w + g * 4));
+                            pacc = fmaf(__uint_as_float(v[g * 4 + 0]), w4.x, pacc);
+                            pacc = fmaf(__uint_as_float(v[g * 4 + 1]), w4.y, pacc);
+                            pacc = fmaf(__uint_as_float(v[g * 4 + 2]), w4.z, pacc);
+                            pacc = fmaf(__uint_as_float(v[g * 4 + 3]), w4.w, pacc);
+                        }
+                        pacc += a.pred_bias;
+                        a.pred_out[pix * 2 + (size_t)(nb >> 4)] = a.pred_sigmoid ? sigmoidf_(pacc) : pacc;
                     }
                     if (a.y != nullptr) { st_global_v8(a.y + o, &v[0]); st_global_v8(a.y + o + 8, &v[8]); }
                     if (a.ys != nullptr) {
@@ -1116,11 +1131,14 @@ int tc_plan_create(ConvParams& p) {
     a.ps = p.phase4; a.wreal = ps ? 2 * p.Wout : p.Wout;
     a.ring_h = p.ring_h; a.ring_v = p.ring_v;
     // 16-column chunks for 32-column tiles: both halves of the epilogue warps get a chunk (linear, ConvGRU)
-    a.cw = ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_UR || p.epi == EPI_GRU_OUT) && bn == 32 && p.pred_out == nullptr && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
+    const bool predw = p.pred_out != nullptr && p.win_c == 16 && p.kw_group == 2 && p.cout == 32 && bn == 32 && p.epi == EPI_LINEAR && p.pred_skip == nullptr &&
+                       p.pred_skip_s == nullptr && !rp && !ps;
+    a.predw = predw ? 1 : 0;
+    a.cw = ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_UR || p.epi == EPI_GRU_OUT) && bn == 32 && (p.pred_out == nullptr || predw) && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
     // ... and 8-column chunks for 16-column tiles (FireNet's 16-channel layers)
     if ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_OUT) && bn == 16 && p.pred_out == nullptr && env_int("EVK_TC_CW8", 1)) a.cw = 8;
     a.wide = (p.epi == EPI_LINEAR && p.cout % 16 == 0 && a.cw >= 16 && env_int("EVK_TC_WIDE_ST", 1)) ? 1 : 0;
-    a.fastlin = (a.wide && !rp && !ps && p.pred_out == nullptr && p.cout % 32 == 0 && bn % 32 == 0 && (p.act == ACT_RELU || p.act == ACT_NONE) &&
+    a.fastlin = (a.wide && !rp && !ps && (p.pred_out == nullptr || predw) && p.cout % 32 == 0 && bn % 32 == 0 && (p.act == ACT_RELU || p.act == ACT_NONE) &&
                  env_int("EVK_TC_FASTLIN", 1)) ? 1 : 0;
     a.act_floor = p.act == ACT_RELU ? 0.0f : -INFINITY;
     a.fastgru = (((p.epi == EPI_GRU_UR && p.cout % 32 == 0 && bn % 32 == 0) || (p.epi == EPI_GRU_OUT && p.cout % 16 == 0 && bn % 16 == 0)) &&
@@ -1146,6 +1164,10 @@ int tc_plan_create(ConvParams& p) {
     a.bias = p.bias; a.res = p.res; a.y = p.y; a.ys = p.ys;
     a.pred_skip_s = p.pred_skip_s; a.pred_skip_plane = p.pred_skip_plane;
     a.pred_w = p.pred_w; a.pred_skip = p.pred_skip; a.pred_out = p.pred_out; a.pred_bias = p.pred_bias; a.pred_sigmoid = p.pred_sigmoid;
+    if (p.pred_out != nullptr && p.win_c > 0 && !(a.predw && a.fastlin && a.cw == 16)) {
+        delete pl;
+        EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: the window-mode fused prediction layer needs the 16-column straight-line epilogue");
+    }
     if (p.pred_out != nullptr && (p.epi != EPI_LINEAR || bn < e_cout || p.cout > 32)) {
         delete pl;
         EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: the fused prediction layer needs all %d channels in one 32-column chunk (bn=%d)", p.cout, bn);

@@ -215,6 +215,124 @@ __global__ void __launch_bounds__(kSWarps * 32, 1) hyper_apply_u_kernel(const Hy
     }
 }
 
+// (3b) the same computation with the U tile staged in shared memory.  CTA = 8 rows x 16 columns of output pixels, all 128
+// output channels; a stage = (atom a, 64-channel half): the 12 x 20 pixel halo tile of that slice of U (61 kB) arrives by
+// cp.async (zero fill outside the image) into one of two buffers while the previous stage computes.  Warp w owns tile rows
+// 2w', columns 8w'' (2 x 8 pixels); a lane owns 2 channels of the half.  Per stage a warp pulls its 6 x 12 pixel strip of U
+// into registers once (72 conflict-free 8-byte loads) and then walks its 16 pixels: 7 broadcast 16-byte loads of the pixel's
+// 25 atoms, 50 multiply-adds out of registers.  U crosses L2 -> SM 1.9x (halo) instead of 3x, every load is overlapped, and
+// the multiply-add pipe sees ~3 instructions per shared-memory wavefront.
+constexpr int kTX = 16, kTY = 8, kHX = kTX + 4, kHY = kTY + 4, kHalf = 64;
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool ok) {
+    const int n = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
+template <int A, int KS, int K>
+__global__ void __launch_bounds__(256, 1) hyper_apply_u2_kernel(const HyperParams p, int tiles_x, int tiles_y, int n_tiles) {
+    constexpr int L = KS * KS, LP = 28, NC = A * K;                 // 25 atoms padded to 28 floats (7 x 16 bytes)
+    extern __shared__ __align__(16) float s_dyn[];
+    float* s_u = s_dyn;                                               // [2][kHY][kHX][kHalf]
+    float* s_at = s_u + 2 * kHY * kHX * kHalf;                        // [128 px][LP]
+    float* s_coef = s_at + kTX * kTY * LP;                            // [128 px][NC]
+    float* s_bases = s_coef + kTX * kTY * NC;                         // [K][L]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < K * L; i += 256) s_bases[i] = p.bases[i];
+    const int CO = p.CO, CU = A * CO;
+    const int wy = (warp >> 1) * 2, wx = (warp & 1) * 8;              // the warp's 2 x 8 pixels inside the tile
+    const uint32_t s_u_addr = (uint32_t)__cvta_generic_to_shared(s_u);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+        const int x0 = tx * kTX, y0 = ty * kTY;
+        __syncthreads();                                              // previous tile done with s_coef / s_at / s_u
+        // basis coefficients of the tile (coalesced: 8 rows of up to 16 * NC contiguous floats)
+        for (int i = tid; i < kTY * kTX * NC; i += 256) {
+            const int row = i / (kTX * NC), rem = i - row * (kTX * NC);
+            const int gy = min(y0 + row, p.h - 1), gx = x0 + rem / NC;
+            s_coef[i] = gx < p.w ? __ldg(p.coef + (((size_t)n * p.h + gy) * p.w + x0) * NC + rem) : 0.f;
+        }
+        auto issue = [&](int stage) {                                 // stage -> (a, half); 12 x 20 pixels x 16 chunks of 16 bytes
+            const int a = stage >> 1, hf = stage & 1;
+            const uint32_t dst0 = s_u_addr + (uint32_t)(stage & 1) * (kHY * kHX * kHalf * 4);
+            for (int i = tid; i < kHY * kHX * (kHalf / 4); i += 256) {
+                const int c4 = i % (kHalf / 4), pix = i / (kHalf / 4);
+                const int gy = y0 - 2 + pix / kHX, gx = x0 - 2 + pix % kHX;
+                const bool ok = (unsigned)gy < (unsigned)p.h && (unsigned)gx < (unsigned)p.w;
+                const float* src = p.u + (((size_t)n * p.h + (ok ? gy : 0)) * p.w + (ok ? gx : 0)) * CU + (size_t)a * CO + hf * kHalf + c4 * 4;
+                cp_async16_zfill(dst0 + (uint32_t)(pix * kHalf + c4 * 4) * 4, src, ok);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        float2 acc[2][16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { acc[0][i] = make_float2(0.f, 0.f); acc[1][i] = make_float2(0.f, 0.f); }
+        issue(0);
+#pragma unroll 1
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {                              // (unrolled: acc[hf] stays in registers)
+            const int stage = 2 * a + hf;
+            __syncthreads();                                          // everyone done with the buffer the next stage overwrites, and with s_at
+            if (stage + 1 < 2 * A) issue(stage + 1);
+            if (hf == 0) {                                            // atoms of this tile for atom index a
+                for (int i = tid; i < kTX * kTY * L; i += 256) {
+                    const int pix = i / L, l = i - pix * L;
+                    const float* c = s_coef + pix * NC + a * K;
+                    float v = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) v = fmaf(c[k], s_bases[k * L + l], v);
+                    s_at[pix * LP + l] = v;
+                }
+            }
+            if (stage + 1 < 2 * A) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            float2 u[6][12];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    // (asm volatile: the strip is loaded ONCE per stage and lives in registers; left to itself the compiler re-reads
+                    // shared memory for every tap and the kernel becomes shared-memory bound)
+                    const uint32_t addr = s_u_addr + (uint32_t)(((stage & 1) * (kHY * kHX) + (wy + r) * kHX + wx + c) * kHalf + 2 * lane) * 4u;
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(u[r][c].x), "=f"(u[r][c].y) : "r"(addr));
+                }
+#pragma unroll
+            for (int py = 0; py < 2; ++py)
+#pragma unroll
+                for (int px = 0; px < 8; ++px) {
+                    const float4* at4 = reinterpret_cast<const float4*>(s_at + ((wy + py) * kTX + wx + px) * LP);
+                    float w[LP];
+#pragma unroll
+                    for (int q = 0; q < LP / 4; ++q) { const float4 t = at4[q]; w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w; }
+                    float2 o = acc[hf][py * 8 + px];
+#pragma unroll
+                    for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < KS; ++dx) {
+                            o.x = fmaf(w[dy * KS + dx], u[py + dy][px + dx].x, o.x);
+                            o.y = fmaf(w[dy * KS + dx], u[py + dy][px + dx].y, o.y);
+                        }
+                    acc[hf][py * 8 + px] = o;
+                }
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const float2 bias = __ldg(reinterpret_cast<const float2*>(p.out_bias + hf * kHalf) + lane);
+#pragma unroll
+            for (int py = 0; py < 2; ++py)
+#pragma unroll
+                for (int px = 0; px < 8; ++px) {
+                    const int gy = y0 + wy + py, gx = x0 + wx + px;
+                    if (gy >= p.h || gx >= p.w) continue;
+                    const float2 o = acc[hf][py * 8 + px];
+                    reinterpret_cast<float2*>(p.y + (((size_t)n * p.h + gy) * p.w + gx) * CO + hf * kHalf)[lane] =
+                        make_float2(fmaxf(o.x + bias.x, 0.f), fmaxf(o.y + bias.y, 0.f));
+                }
+        }
+    }
+}
+
 int launch_hyper(int which, const HyperParams& p, cudaStream_t st) {
     if (which == 0) {
         EVK_REQUIRE(p.H % 4 == 0 && p.W % 4 == 0 && p.bins + 1 <= 8, EVK_ERR_ARG, "hyper context: H, W must be multiples of 4 and bins <= 7");
@@ -227,6 +345,21 @@ int launch_hyper(int which, const HyperParams& p, cudaStream_t st) {
         EVK_REQUIRE(p.A == 6 && p.ks == 5 && p.K == 12 && p.CO == 128, EVK_ERR_ARG,
                     "hyper apply (re-associated): only num_atoms=6, kernel_size=5, 12 bases, 128 output channels is built (got A=%d ks=%d K=%d CO=%d)",
                     p.A, p.ks, p.K, p.CO);
+        static const bool v1 = getenv("EVK_HYPER_APPLY_V1") != nullptr;
+        if (!v1) {
+            const int tiles_x = ceil_div(p.w, kTX), tiles_y = ceil_div(p.h, kTY), n_tiles = tiles_x * tiles_y * p.N;
+            const size_t smem2 = sizeof(float) * ((size_t)2 * kHY * kHX * kHalf + (size_t)kTX * kTY * 28 + (size_t)kTX * kTY * 72 + 12 * 25);
+            static bool attr2[64] = {false};
+            int dev2 = 0;
+            EVK_CHECK_CUDA(cudaGetDevice(&dev2));
+            if (dev2 < 0 || dev2 >= 64 || !attr2[dev2]) {
+                EVK_CHECK_CUDA(cudaFuncSetAttribute(hyper_apply_u2_kernel<6, 5, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                if (dev2 >= 0 && dev2 < 64) attr2[dev2] = true;
+            }
+            hyper_apply_u2_kernel<6, 5, 12><<<std::min(n_tiles, kNumSMs), 256, smem2, st>>>(p, tiles_x, tiles_y, n_tiles);
+            EVK_CHECK_CUDA(cudaGetLastError());
+            return EVK_OK;
+        }
         const int strips_x = ceil_div(p.w, kSX), strips_y = ceil_div(p.h, kSY), n_strips = strips_x * strips_y * p.N;
         const int blocks = std::min(ceil_div(n_strips, kSWarps), kNumSMs);
         const size_t smem = sizeof(float) * (((12 * 25 + 3) & ~3) + (size_t)kSWarps * kSX * kSY * (5 * 8 + 6 * 12));

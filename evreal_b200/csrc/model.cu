@@ -788,8 +788,13 @@ static int wire_tc(evk_model* m) {
             for (size_t i = 0; i + 1 < m->ops[par].size(); ++i) {
                 Op& cv = m->ops[par][i];
                 Op& pr = m->ops[par][i + 1];
-                if (cv.kind != OP_CONV || cv.cp.x1s == nullptr || cv.cp.epi != EPI_LINEAR || cv.cp.cout > 32 || cv.cp.cout % 16 != 0 || cv.cp.win_c > 0) continue;
-                if (pr.kind != OP_PRED || pr.in != cv.cp.y || pr.cin != cv.cp.cout) continue;
+                if (cv.kind != OP_CONV || cv.cp.x1s == nullptr || cv.cp.epi != EPI_LINEAR || cv.cp.cout > 32 || cv.cp.cout % 16 != 0) continue;
+                if (pr.kind != OP_PRED || pr.in != cv.cp.y) continue;
+                if (cv.cp.win_c > 0) {
+                    // window mode (FireNet): a GEMM row is two pixels of 16 channels; fused only in that exact shape, no skip operand
+                    if (!(cv.cp.win_c == 16 && cv.cp.kw_group == 2 && cv.cp.cout == 32 && pr.cin == 16 && pr.skip == nullptr) ||
+                        getenv("EVK_NO_PRED_FUSION_WIN") != nullptr) continue;
+                } else if (pr.cin != cv.cp.cout) continue;
                 cv.cp.pred_w = pr.w; cv.cp.pred_skip = pr.skip; cv.cp.pred_out = pr.out;
                 cv.cp.pred_bias = pr.bias0; cv.cp.pred_sigmoid = pr.sigmoid;
                 cv.flops += pr.flops;
