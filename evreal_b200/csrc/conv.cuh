@@ -138,7 +138,17 @@ int launch_upsample2x_add(const float* x, const float* skip, float* y, __nv_bflo
 // y[N,2H,2W,C]: (x + skip) at the even positions, zero elsewhere (ConvTranspose2d stride 2 as a stride-1 convolution)
 int launch_zero_insert2x_add(const float* x, const float* skip, float* y, __nv_bfloat16* ys, int N, int H, int W, int C, cudaStream_t st);
 // NCHW fp32 [N,cin,H,W] (cin <= 8) -> packed split-bf16 row-window tensor [2][N][H][W+8][8], pixel x at column x + left
-int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st);
+// (src_H x src_W = size of the source planes, sampled every `stride` pixels: nearest-neighbour reduction by an integer factor)
+int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st, int src_H = 0,
+                     int src_W = 0, int stride = 1, int src_planes = 0);
+
+// ---- SPADE-E2VID glue (spade.cu)
+int launch_add_split(const float* x, const float* s, float* out, __nv_bfloat16* out_s, int64_t n, cudaStream_t st);
+int launch_spade_shuffle(const float* c0, const float* gb, const float* alpha, const float* shift, float* out, __nv_bfloat16* out_s, int N,
+                         int h, int w, int C, cudaStream_t st);
+int launch_spade_pred(const float* x, const float* head, const float* w, const float* bias_host3, float* prev, float* image, int N, int64_t HW,
+                      int C, cudaStream_t st);
+int launch_spade_first_frame(float* in, float* prev, int N, int bins, int64_t HW, cudaStream_t st);
 // host: [kh*kw*cin][cout] (cin = T tensors of c_tensor channels) -> window K layout [kh*T*64][group*cout]
 // (k = r*64*T + t*64 + slot*c_tensor + c; output pixel g of a group reads tap q from window slot g + q)
 void pack_weights_window(const float* w_kc, int kh, int kw, int cin, int c_tensor, int cout, int group, std::vector<float>& out);

@@ -250,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     }
             }
         }
-        if (DBG && lane == 0) a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)w_ea;
+        if (DBG && lane == 0) a.dbg[blockIdx.x * 12 + 4] = (unsigned long long)w_ea;
     } else if (warp == 3) {
         // ===== B producer: one K block (tpb taps x BK channels of the weight tile) per stage; with a cluster every CTA loads
         // 1/cs of the rows and multicasts them to all CTAs (same smem offset, same barrier offset everywhere)
@@ -297,7 +297,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         }
                     }
         }
-        if (DBG && lane == 0) a.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_eb;
+        if (DBG && lane == 0) a.dbg[blockIdx.x * 12 + 5] = (unsigned long long)w_eb;
         // tail: every arrive the peers send to this CTA's empty barriers must land before the CTA exits
         if (cs > 1) {
             for (int i = 0; i < a.b_stages; ++i) {       // = the waits of b_stages more (virtual) uses: the previous use of
@@ -427,10 +427,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             __syncwarp();
         }
         if (DBG && lane == 0 && role == 0) {
-            a.dbg[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_begin);
-            a.dbg[blockIdx.x * 8 + 1] = (unsigned long long)w_te;
-            a.dbg[blockIdx.x * 8 + 2] = (unsigned long long)w_fa;
-            a.dbg[blockIdx.x * 8 + 3] = (unsigned long long)w_fb;
+            a.dbg[blockIdx.x * 12 + 0] = (unsigned long long)(clock64() - t_begin);
+            a.dbg[blockIdx.x * 12 + 1] = (unsigned long long)w_te;
+            a.dbg[blockIdx.x * 12 + 2] = (unsigned long long)w_fa;
+            a.dbg[blockIdx.x * 12 + 3] = (unsigned long long)w_fb;
         }
     } else if (warp >= 4) {
         // ===== epilogue: 8 warps; warp (4 + e) owns TMEM lane quadrant e % 4 (its hardware-accessible lanes) and
@@ -440,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const int row = wq * 32 + lane;
         const int lu = row & 7, lv = row >> 3;
         uint32_t it = 0;
-        long long w_tf = 0;
+        long long w_tf = 0, w_ld = 0, w_rest = 0;
         const long long e_begin = DBG ? clock64() : 0;
         for (int st = cid; st < n_super; st += ncl, ++it) {
             const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
@@ -463,6 +463,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                 const int j0 = c * cw;
                 uint32_t v[32];
                 __syncwarp();                     // tcgen05.ld is .sync.aligned: reconverge after the masked stores
+                const long long t_c0 = DBG ? clock64() : 0;
                 {
                     uint32_t u[32];
                     if (cw == 32) {
@@ -504,6 +505,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             v[i] = __float_as_uint(__uint_as_float(v[i]) + (__uint_as_float(u[i]) + __uint_as_float(w[i])));
                     }
                 }
+                const long long t_c1 = DBG ? clock64() : 0;
+                if (DBG) w_ld += t_c1 - t_c0;
+                struct RestTimer { long long& acc; long long t0; bool on; __device__ ~RestTimer() { if (on) acc += clock64() - t0; } } rest_timer{w_rest, t_c1, DBG};
                 if (c + 2 >= nchunks) {           // last TMEM read of this warp for this tile: release the stage
                     tc_fence_before();
                     __syncwarp();
@@ -934,8 +938,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             }
         }
         if (DBG && e == 0 && lane == 0) {
-            a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - e_begin);
-            a.dbg[blockIdx.x * 8 + 7] = (unsigned long long)w_tf;
+            a.dbg[blockIdx.x * 12 + 6] = (unsigned long long)(clock64() - e_begin);
+            a.dbg[blockIdx.x * 12 + 7] = (unsigned long long)w_tf;
+            a.dbg[blockIdx.x * 12 + 8] = (unsigned long long)w_ld;
+            a.dbg[blockIdx.x * 12 + 9] = (unsigned long long)w_rest;
         }
     }
     tc_fence_before();
@@ -1321,7 +1327,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
 
 static int launch_conv_tc_timed(const ConvParams& p, cudaStream_t st) {
     TcPlan& pl = *p.tc;
-    const size_t n = (size_t)pl.grid.x * 8;
+    const size_t n = (size_t)pl.grid.x * 12;
     unsigned long long* d = nullptr;
     EVK_CHECK_CUDA(cudaMalloc(&d, n * sizeof(unsigned long long)));
     EVK_CHECK_CUDA(cudaMemsetAsync(d, 0, n * sizeof(unsigned long long), st));
@@ -1333,22 +1339,22 @@ static int launch_conv_tc_timed(const ConvParams& p, cudaStream_t st) {
     std::vector<unsigned long long> h(n);
     EVK_CHECK_CUDA(cudaMemcpy(h.data(), d, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     cudaFree(d);
-    double avg[8] = {0}, mx[8] = {0};
-    for (size_t i = 0; i < n; ++i) { avg[i % 8] += (double)h[i] / pl.grid.x; mx[i % 8] = std::max(mx[i % 8], (double)h[i]); }
+    double avg[12] = {0}, mx[12] = {0};
+    for (size_t i = 0; i < n; ++i) { avg[i % 12] += (double)h[i] / pl.grid.x; mx[i % 12] = std::max(mx[i % 12], (double)h[i]); }
     const TcArgs& a = pl.a;
     const long n_super = (long)a.n_tiles * ((a.m_tiles + a.cs - 1) / a.cs);
     const double tiles_per_cta = (double)n_super * a.cs / pl.grid.x;
     const double k16 = (double)(a.chunks1 + a.chunks2) * a.kh * a.kw * (pl.bk / 16);
     fprintf(stderr, "TIMING %dx%d s%d c%d->%d @%dx%dx%d bn=%d cs=%d ux=%d grid=%u tiles/cta=%.1f k16/tile=%.0f | mma total %.0f (max %.0f) cyc = %.1f cyc/k16 | "
-            "mma waits: tempty %.0f fullA %.0f fullB %.0f | producers wait: emptyA %.0f emptyB %.0f | epi total %.0f wait tfull %.0f\n",
+            "mma waits: tempty %.0f fullA %.0f fullB %.0f | producers wait: emptyA %.0f emptyB %.0f | epi total %.0f wait tfull %.0f tmem-read %.0f rest-of-chunk %.0f\n",
             a.kh, a.kw, a.su > a.sv ? a.su : a.sv, (a.chunks1 + a.chunks2) * pl.bk, a.cout, a.N, a.Hout, a.Wout, a.bn, a.cs, a.ux, pl.grid.x, tiles_per_cta, k16,
-            avg[0], mx[0], avg[0] / (tiles_per_cta * k16), avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
+            avg[0], mx[0], avg[0] / (tiles_per_cta * k16), avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7], avg[8], avg[9]);
     return EVK_OK;
 }
 
 // ------------------------------------------------------------------ head input: NCHW fp32 -> packed row-window split bf16
 __global__ void __launch_bounds__(256) head_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int cin,
-                                                        int H, int W, int left) {
+                                                        int H, int W, int left, int src_H, int src_W, int stride, int src_planes) {
     const int64_t total = (int64_t)N * H * W;
     const int64_t plane = (int64_t)N * H * (W + 8) * 8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1358,7 +1364,7 @@ __global__ void __launch_bounds__(256) head_pack_kernel(const float* __restrict_
         __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const float v = c < cin ? __ldg(x + (((int64_t)n * cin + c) * H + yy) * W + xx) : 0.f;
+            const float v = c < cin ? __ldg(x + (((int64_t)n * src_planes + c) * src_H + (int64_t)yy * stride) * src_W + (int64_t)xx * stride) : 0.f;
             split_bf16(v, hi[c], lo[c]);
         }
         const int64_t o = (((int64_t)n * H + yy) * (W + 8) + xx + left) * 8;
@@ -1367,10 +1373,15 @@ __global__ void __launch_bounds__(256) head_pack_kernel(const float* __restrict_
     }
 }
 
-int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st) {
-    EVK_REQUIRE(x_nchw && packed && cin >= 1 && cin <= 8 && left >= 0 && left <= 7, EVK_ERR_ARG, "head_pack: bad argument");
+int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st, int src_H, int src_W,
+                     int stride, int src_planes) {
+    EVK_REQUIRE(x_nchw && packed && cin >= 1 && cin <= 8 && left >= 0 && left <= 7 && stride >= 1, EVK_ERR_ARG, "head_pack: bad argument");
+    if (src_H <= 0) src_H = H * stride;
+    if (src_W <= 0) src_W = W * stride;
+    if (src_planes <= 0) src_planes = cin;
     const int64_t total = (int64_t)N * H * W;
-    head_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, 0, st>>>(x_nchw, packed, N, cin, H, W, left);
+    head_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, 0, st>>>(x_nchw, packed, N, cin, H, W, left, src_H, src_W, stride,
+                                                                                             src_planes);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

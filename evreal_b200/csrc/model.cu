@@ -28,7 +28,7 @@ struct HostTensor {
     std::vector<int64_t> shape;
 };
 
-enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HYPER_APPLY_U, OP_HEAD_PACK, OP_NOP, OP_ZERO_INSERT_ADD, OP_ADD_PAD, OP_RING_LINES };
+enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HYPER_APPLY_U, OP_HEAD_PACK, OP_NOP, OP_ZERO_INSERT_ADD, OP_ADD_PAD, OP_RING_LINES, OP_ADD_SPLIT, OP_SPADE_SHUFFLE, OP_SPADE_PRED };
 
 struct Op {
     OpKind kind;
@@ -43,6 +43,12 @@ struct Op {
     int ring_line = 0;                // OP_CONV: 1 / 2 = horizontal / vertical border-line convolution of a phase-stacked decoder
     float bias0 = 0.f;
     int sigmoid = 0;
+    // OP_HEAD_PACK: source planes [N, src_planes, srcH, srcW] sampled every `stride` pixels (0 = the op's own H x W, stride 1)
+    int srcH = 0, srcW = 0, stride = 1, src_planes = 0;
+    // OP_SPADE_SHUFFLE: in = conv output [N,H,W,4*cout], skip = (gamma | beta) [N,2H,2W,2*cout], w = alpha, b = shift -> out / out_s
+    // OP_SPADE_PRED: in = last hidden state, skip = head, w = [cin][3], bias3 -> prev3 (NCHW, 3 planes) and out (image)
+    float bias3[3] = {0.f, 0.f, 0.f};
+    float* prev3 = nullptr;
     HyperParams hp;             // OP_HYPER_*
     double flops = 0.0;
 };
@@ -74,6 +80,8 @@ struct evk_model {
     float* out_buf = nullptr;        // = out_bufs[0]
     float* prev_rec = nullptr;       // = out_bufs[1]
     int parity = 0;
+    float* prev3 = nullptr;          // SPADE-E2VID: previous 3-channel reconstruction [N,3,H,W] (the SPADE layers' conditioning input)
+    bool spade_first = true;         // SPADE-E2VID: no previous reconstruction yet (model/spade_e2v.py:140-147)
     int last_launches = 0;
     double flops = 0.0;
     cudaStream_t cap_stream = nullptr;
@@ -383,15 +391,18 @@ static int add_resblock(Builder& B, const std::string& pfx, const float* x, floa
     return B.conv(pfx + ".conv2.weight", pfx + ".conv2.bias", pfx + ".bn2", tmp, C, H, W, 1, 1, ACT_RELU, x, y, nullptr);
 }
 
-static int add_head(Builder& B, const std::string& conv_pfx, const std::string& bn, float* y, int cout_expected) {
+// ConvLayer whose input is an NCHW tensor with <= 8 channels (the event tensor; SPADE's 3-channel conditioning image): packed
+// into the row-window layout and run as a (kh x 1) implicit GEMM on the tensor cores, or on CUDA cores for other shapes.
+// src: [N, cin, srcH, srcW] sampled every `stride` pixels -> H x W (nearest reduction by an integer factor; stride 1 for the head).
+static int add_rowwin_conv(Builder& B, const std::string& conv_pfx, const std::string& bn, const float* src, int srcH, int srcW, int stride,
+                           int H, int W, int act, float* y, int cout_expected, int cin_expected) {
     evk_model* m = B.m;
     Packed pk;
     int r = pack_conv(m, conv_pfx + ".weight", conv_pfx + ".bias", bn, nullptr, pk);
     if (r != EVK_OK) return r;
-    EVK_REQUIRE(pk.cin == m->cfg.num_bins && pk.cout == cout_expected, EVK_ERR_KEY,
+    EVK_REQUIRE(pk.cin == cin_expected && pk.cout == cout_expected, EVK_ERR_KEY,
                 "'%s': expected [%d,%d,k,k], checkpoint has [%d,%d,%d,%d]", conv_pfx.c_str(), cout_expected,
-                m->cfg.num_bins, pk.cout, pk.cin, pk.kh, pk.kw);
-    const int H = m->cfg.height, W = m->cfg.width;
+                cin_expected, pk.cout, pk.cin, pk.kh, pk.kw);
     const double flops = 2.0 * pk.cout * pk.cin * pk.kh * pk.kw * (double)B.N * H * W;
     if (m->cfg.precision == 0 && pk.cin <= 8 && pk.kw <= 8 && pk.kh == pk.kw && pk.cout % 16 == 0 && getenv("EVK_HEAD_SIMT") == nullptr) {
         // tensor-core head: pack the NCHW event tensor into the row-window layout (conv.cuh) and run the layer as a
@@ -401,7 +412,8 @@ static int add_head(Builder& B, const std::string& conv_pfx, const std::string& 
         EVK_REQUIRE(packed != nullptr, EVK_ERR_CUDA, "out of device memory for the packed head input");
         {
             Op op; op.kind = OP_HEAD_PACK;
-            op.in = m->in_buf; op.out_s = packed; op.N = B.N; op.cin = pk.cin; op.H = H; op.W = W; op.k = pk.kw;
+            op.in = src; op.out_s = packed; op.N = B.N; op.cin = pk.cin; op.H = H; op.W = W; op.k = pk.kw;
+            op.srcH = srcH; op.srcW = srcW; op.stride = stride; op.src_planes = pk.cin;
             m->ops[0].push_back(op); m->ops[1].push_back(op);
         }
         // G consecutive output pixels per GEMM row (conv.cuh, ConvParams::kw_group): N = G * cout columns per MMA
@@ -415,7 +427,7 @@ static int add_head(Builder& B, const std::string& conv_pfx, const std::string& 
         p.N = B.N; p.Hin = p.Hout = H; p.Win = p.Wout = W / G; p.kh = pk.kh; p.kw = 1; p.stride = 1; p.pad = pk.kh / 2;
         std::vector<float> bg((size_t)G * pk.cout);
         for (int g = 0; g < G; ++g) std::copy(pk.b.begin(), pk.b.end(), bg.begin() + (size_t)g * pk.cout);
-        p.bias = m->upload(bg); p.cout = G * pk.cout; p.epi = EPI_LINEAR; p.act = ACT_RELU; p.y = y;
+        p.bias = m->upload(bg); p.cout = G * pk.cout; p.epi = EPI_LINEAR; p.act = act; p.y = y;
         std::vector<float> wr;
         pack_head_weights_rowwin(pk.w.data(), pk.kh, pk.kw, pk.cin, pk.cout, G, wr);
         std::vector<__nv_bfloat16> wt;
@@ -430,12 +442,19 @@ static int add_head(Builder& B, const std::string& conv_pfx, const std::string& 
         m->ops[0].push_back(op); m->ops[1].push_back(op);
         return EVK_OK;
     }
+    EVK_REQUIRE(stride == 1 && act == ACT_RELU, EVK_ERR_ARG, "'%s': the CUDA-core head kernel covers the plain ReLU head only", conv_pfx.c_str());
     Op op; op.kind = OP_HEAD;
-    op.in = m->in_buf; op.w = m->upload(pk.w); op.b = m->upload(pk.b); op.out = y;
+    op.in = src; op.w = m->upload(pk.w); op.b = m->upload(pk.b); op.out = y;
     op.N = B.N; op.cin = pk.cin; op.H = H; op.W = W; op.k = pk.kh; op.cout = pk.cout;
     op.flops = flops;
     m->ops[0].push_back(op); m->ops[1].push_back(op);
     return EVK_OK;
+}
+
+static int add_head(Builder& B, const std::string& conv_pfx, const std::string& bn, float* y, int cout_expected) {
+    evk_model* m = B.m;
+    return add_rowwin_conv(B, conv_pfx, bn, m->in_buf, m->cfg.height, m->cfg.width, 1, m->cfg.height, m->cfg.width, ACT_RELU, y, cout_expected,
+                           m->cfg.num_bins);
 }
 
 static int add_pred(Builder& B, const std::string& pfx, const float* x, const float* skip, int cin, int H, int W) {
@@ -623,6 +642,21 @@ static int add_hyper_decoder(Builder& B, const std::string& pfx, const float* xu
                   ACT_RELU, nullptr, y, nullptr);
 }
 
+// Parity fix-up: the builders wire every consumer of a ConvLSTM's new hidden state against the parity-0 target (buf[1]); in the
+// parity-1 program the same pointers must read buf[0] (that is where parity 1 writes h_new).
+static void fix_hidden_parity(evk_model* m, const std::vector<int>& hstate) {
+    for (Op& op : m->ops[1]) {
+        for (size_t i = 0; i < hstate.size(); ++i) {
+            const StateBuf& s = m->states[hstate[i]];
+            auto fix = [&](const float*& p) { if (p == s.buf[1]) p = s.buf[0]; };
+            if (op.kind == OP_CONV && op.cp.epi == EPI_LSTM) { fix(op.cp.x1); continue; }   // x2/h_new already per parity
+            if (op.kind == OP_CONV) { fix(op.cp.x1); fix(op.cp.res); }
+            if (op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD || op.kind == OP_PRED || op.kind == OP_ADD_PAD || op.kind == OP_ADD_SPLIT ||
+                op.kind == OP_SPADE_PRED) { fix(op.in); fix(op.skip); }
+        }
+    }
+}
+
 // E2VID / E2VID+ / SSL-E2VID / HyperE2VID (model/unet.py:107-143)
 static int build_unet(evk_model* m) {
     const evk_model_config& c = m->cfg;
@@ -710,17 +744,122 @@ static int build_unet(evk_model* m) {
     }
     r = add_pred(B, "pred", x, head, C, H, W);
     if (r != EVK_OK) return r;
-    // Parity fix-up: every pointer equal to "new hidden state of parity 0" (buf[1]) in the
-    // parity-1 program must read buf[0] instead (that is where parity 1 writes h_new).
-    for (Op& op : m->ops[1]) {
-        for (int i = 0; i < E; ++i) {
-            const StateBuf& s = m->states[hstate[i]];
-            auto fix = [&](const float*& p) { if (p == s.buf[1]) p = s.buf[0]; };
-            if (op.kind == OP_CONV && op.cp.epi == EPI_LSTM) { fix(op.cp.x1); continue; }   // x2/h_new already per parity
-            if (op.kind == OP_CONV) { fix(op.cp.x1); fix(op.cp.res); }
-            if (op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD || op.kind == OP_PRED || op.kind == OP_ADD_PAD) { fix(op.in); fix(op.skip); }
+    fix_hidden_parity(m, hstate);
+    return EVK_OK;
+}
+
+// SPADE-E2VID (model/spade_e2v.py:113-179, Unet6): fixed widths 32 / 64 / 128 / 256, recurrent encoders rec0 (stride 1, full
+// resolution) / rec1 / rec2, two residual blocks, pixel-shuffle decoders up0 / up1 with SPADE normalisation conditioned on the
+// previous 3-channel reconstruction, a recurrent last decoder up2, and a 3-channel sigmoid prediction whose mean is the image.
+static int build_spade(evk_model* m) {
+    const evk_model_config& c = m->cfg;
+    Builder B{m, c.batch};
+    EVK_REQUIRE(c.num_bins == 5 && c.height % 4 == 0 && c.width % 4 == 0, EVK_ERR_ARG,
+                "SPADE-E2VID: 5 bins and an input that is a multiple of 4 (CropParameters pads to 8) are required (got %d bins, %dx%d)", c.num_bins,
+                c.height, c.width);
+    EVK_REQUIRE(c.precision == 0, EVK_ERR_ARG, "SPADE-E2VID is built on the tensor-core path only (precision 0)");
+    const int H = c.height, W = c.width;
+    m->prev3 = m->dalloc((size_t)c.batch * 3 * H * W);
+    EVK_REQUIRE(m->prev3 != nullptr, EVK_ERR_CUDA, "out of device memory");
+    float* head = B.act(H, W, 32);
+    int r = add_head(B, "fc", "", head, 32);
+    if (r != EVK_OK) return r;
+    std::vector<int> hstate;
+    // RecurrentConvLayer: conv5x5 (no bias) + BN + ReLU + ConvLSTM
+    auto rec = [&](const std::string& pfx, const float* x, int cin, int cout, int h, int w, int stride, const float** out) -> int {
+        const int ho = (h + 4 - 5) / stride + 1, wo = (w + 4 - 5) / stride + 1;
+        float* y = B.act(ho, wo, cout);
+        int rr = B.conv(pfx + ".conv0.weight", "", pfx + ".bn", x, cin, h, w, stride, 2, ACT_RELU, nullptr, y, nullptr);
+        if (rr != EVK_OK) return rr;
+        const int hs = make_state(m, cout, ho, wo, true);
+        if (hs < 0) return hs;
+        const int cs = make_state(m, cout, ho, wo, false);
+        if (cs < 0) return cs;
+        rr = add_lstm(B, pfx + ".recurrent_block", y, cout, ho, wo, hs, cs);
+        if (rr != EVK_OK) return rr;
+        hstate.push_back(hs);
+        *out = m->states[hs].buf[1];
+        return EVK_OK;
+    };
+    const float *x0 = nullptr, *x1 = nullptr, *x2 = nullptr, *x3 = nullptr;
+    if ((r = rec("rec0", head, 32, 64, H, W, 1, &x0)) != EVK_OK) return r;
+    if ((r = rec("rec1", x0, 64, 128, H, W, 2, &x1)) != EVK_OK) return r;
+    if ((r = rec("rec2", x1, 128, 256, H / 2, W / 2, 2, &x2)) != EVK_OK) return r;
+    const int H4 = H / 4, W4 = W / 4;
+    float* tmp = B.act(H4, W4, 256);
+    float* y0 = B.act(H4, W4, 256);
+    float* y1 = B.act(H4, W4, 256);
+    if ((r = add_resblock(B, "res0", x2, tmp, y0, 256, H4, W4)) != EVK_OK) return r;
+    if ((r = add_resblock(B, "res1", y0, tmp, y1, 256, H4, W4)) != EVK_OK) return r;
+    auto add_sum = [&](const float* a, const float* b, int C, int h, int w) -> float* {
+        float* o = B.act(h, w, C);
+        Op op; op.kind = OP_ADD_SPLIT;
+        op.in = a; op.skip = b; op.out = o; op.N = B.N; op.H = h; op.W = w; op.cin = C;
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+        return o;
+    };
+    // UpConvLayer3: conv3x3 C -> 4*Co (no bias), PixelShuffle(2), SPADE(Co, 3), ReLU   (h x w = input size)
+    auto up = [&](const std::string& pfx, const float* x, int C, int Co, int h, int w, float** out) -> int {
+        float* c0 = B.act(h, w, 4 * Co);
+        int rr = B.conv(pfx + ".conv0.weight", "", "", x, C, h, w, 1, 1, ACT_NONE, nullptr, c0, nullptr);
+        if (rr != EVK_OK) return rr;
+        const int ho = 2 * h, wo = 2 * w;
+        EVK_REQUIRE(H % ho == 0 && H / ho == W / wo, EVK_ERR_ARG, "SPADE-E2VID: decoder resolution %dx%d does not divide the input", ho, wo);
+        const std::string n = pfx + ".norm";
+        // segmap = nearest(prev3 -> ho x wo) -> conv3x3 3 -> 64 + ReLU (row-window tensor-core form of a <= 8-channel NCHW input)
+        float* actv = B.act(ho, wo, 64);
+        rr = add_rowwin_conv(B, n + ".mlp_shared.0", "", m->prev3, H, W, H / ho, ho, wo, ACT_RELU, actv, 64, 3);
+        if (rr != EVK_OK) return rr;
+        // gamma | beta as ONE convolution 64 -> 2*Co
+        Packed pg, pb, pk;
+        if ((rr = pack_conv(m, n + ".mlp_gamma.weight", n + ".mlp_gamma.bias", "", nullptr, pg)) != EVK_OK) return rr;
+        if ((rr = pack_conv(m, n + ".mlp_beta.weight", n + ".mlp_beta.bias", "", nullptr, pb)) != EVK_OK) return rr;
+        EVK_REQUIRE(pg.cout == Co && pb.cout == Co && pg.cin == 64 && pb.cin == 64 && pg.kh == 3 && pb.kh == 3, EVK_ERR_KEY,
+                    "'%s': unexpected SPADE gamma / beta shapes", n.c_str());
+        pk.cout = 2 * Co; pk.cin = 64; pk.kh = pk.kw = 3;
+        pk.w.resize((size_t)9 * 64 * 2 * Co);
+        pk.b.resize((size_t)2 * Co);
+        for (int k = 0; k < 9 * 64; ++k)
+            for (int o = 0; o < Co; ++o) {
+                pk.w[(size_t)k * 2 * Co + o] = pg.w[(size_t)k * Co + o];
+                pk.w[(size_t)k * 2 * Co + Co + o] = pb.w[(size_t)k * Co + o];
+            }
+        for (int o = 0; o < Co; ++o) { pk.b[o] = pg.b[o]; pk.b[Co + o] = pb.b[o]; }
+        float* gb = B.act(ho, wo, 2 * Co);
+        if ((rr = B.conv_packed(pk, actv, 64, ho, wo, 1, 1, ACT_NONE, nullptr, gb, nullptr)) != EVK_OK) return rr;
+        const HostTensor* mean = m->find(n + ".param_free_norm.running_mean");
+        const HostTensor* var = m->find(n + ".param_free_norm.running_var");
+        EVK_REQUIRE(mean && var && (int)mean->data.size() == Co && (int)var->data.size() == Co, EVK_ERR_KEY, "missing '%s.param_free_norm' statistics", n.c_str());
+        std::vector<float> alpha(Co), shift(Co);
+        for (int o = 0; o < Co; ++o) {
+            const double a = 1.0 / std::sqrt((double)var->data[o] + 1e-5);
+            alpha[o] = (float)a;
+            shift[o] = (float)(-(double)mean->data[o] * a);
         }
+        float* o = B.act(ho, wo, Co);
+        Op op; op.kind = OP_SPADE_SHUFFLE;
+        op.in = c0; op.skip = gb; op.w = m->upload(alpha); op.b = m->upload(shift); op.out = o; op.N = B.N; op.H = h; op.W = w; op.cout = Co;
+        EVK_REQUIRE(op.w && op.b, EVK_ERR_CUDA, "out of device memory");
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
+        *out = o;
+        return EVK_OK;
+    };
+    float *u0 = nullptr, *u1 = nullptr;
+    if ((r = up("up0", add_sum(y1, x2, 256, H4, W4), 256, 128, H4, W4, &u0)) != EVK_OK) return r;
+    if ((r = up("up1", add_sum(u0, x1, 128, H / 2, W / 2), 128, 64, H / 2, W / 2, &u1)) != EVK_OK) return r;
+    if ((r = rec("up2", add_sum(u1, x0, 64, H, W), 64, 32, H, W, 1, &x3)) != EVK_OK) return r;
+    {
+        Packed pk;
+        if ((r = pack_conv(m, "conv_img.weight", "conv_img.bias", "bn_img", nullptr, pk)) != EVK_OK) return r;
+        EVK_REQUIRE(pk.cin == 32 && pk.cout == 3 && pk.kh == 1, EVK_ERR_KEY, "'conv_img': expected [3,32,1,1]");
+        Op op; op.kind = OP_SPADE_PRED;
+        op.in = x3; op.skip = head; op.w = m->upload(pk.w); op.out = m->out_buf; op.prev3 = m->prev3;
+        for (int k = 0; k < 3; ++k) op.bias3[k] = pk.b[k];
+        op.N = B.N; op.cin = 32; op.H = H; op.W = W;
+        op.flops = 2.0 * 3 * 32 * (double)B.N * H * W;
+        m->ops[0].push_back(op); m->ops[1].push_back(op);
     }
+    fix_hidden_parity(m, hstate);
     return EVK_OK;
 }
 
@@ -807,7 +946,7 @@ static int wire_tc(evk_model* m) {
     for (int par = 0; par < 2; ++par)
         for (Op& op : m->ops[par]) {
             switch (op.kind) {
-                case OP_HEAD: case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: op.out_s = lookup(op.out); break;
+                case OP_HEAD: case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_ADD_SPLIT: case OP_SPADE_SHUFFLE: op.out_s = lookup(op.out); break;
                 case OP_CONV:
                     if (op.cp.epi == EPI_LINEAR) op.cp.ys = lookup(op.cp.y);
                     if (op.cp.epi == EPI_LSTM) op.cp.hs_new = lookup(op.cp.h_new);
@@ -851,7 +990,8 @@ static int wire_tc(evk_model* m) {
                         if (op.cp.x1s == nullptr) { rd(op.cp.x1); rd(op.cp.x2); }
                         rd(op.cp.res); rd(op.cp.c_prev); rd(op.cp.h_prev); rd(op.cp.u_in); rd(op.cp.pred_skip);
                         break;
-                    case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_PRED: case OP_ADD_PAD: rd(op.in); rd(op.skip); break;
+                    case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_PRED: case OP_ADD_PAD: case OP_ADD_SPLIT: case OP_SPADE_SHUFFLE:
+                    case OP_SPADE_PRED: rd(op.in); rd(op.skip); break;
                     case OP_HYPER_CONTEXT: case OP_HYPER_ATOMS: case OP_HYPER_APPLY: case OP_HYPER_APPLY_U:
                         rd(op.hp.ev_nchw); rd(op.hp.prev); rd(op.hp.coef); rd(op.hp.atoms); rd(op.hp.xu); rd(op.hp.u);   // (ctx / inter / y are outputs here)
                         break;
@@ -868,7 +1008,8 @@ static int wire_tc(evk_model* m) {
                     // ConvGRU: h * reset is consumed by the candidate convolution only -- through its split planes on the tensor-core path
                     if (op.kind == OP_CONV && op.cp.x1s != nullptr && op.cp.epi == EPI_GRU_UR && op.cp.hrs_out != nullptr && op.cp.hr_out != nullptr &&
                         !fp32_read.count(op.cp.hr_out)) op.cp.hr_out = nullptr;
-                    if ((op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD) && op.out_s != nullptr && !fp32_read.count(op.out)) op.out = nullptr;
+                    if ((op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD || op.kind == OP_ADD_SPLIT || op.kind == OP_SPADE_SHUFFLE) &&
+                        op.out_s != nullptr && !fp32_read.count(op.out)) op.out = nullptr;
                     if (op.kind == OP_HYPER_APPLY && op.hp.inter_s != nullptr && !fp32_read.count(op.hp.inter)) op.hp.inter = nullptr;
                 }
     }
@@ -914,7 +1055,10 @@ static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent
             case OP_NOP: break;
             case OP_ADD_PAD: r = launch_add_pad_split(op.in, op.skip, op.out_s, op.N, op.H, op.W, op.cin, st); break;
             case OP_RING_LINES: r = launch_ring_lines(op.out_s, op.lines_h, op.lines_v, op.N, op.H, op.W, op.cin, st); break;
-            case OP_HEAD_PACK: r = launch_head_pack(op.in, op.out_s, op.N, op.cin, op.H, op.W, op.k / 2, st); break;
+            case OP_HEAD_PACK: r = launch_head_pack(op.in, op.out_s, op.N, op.cin, op.H, op.W, op.k / 2, st, op.srcH, op.srcW, op.stride, op.src_planes); break;
+            case OP_ADD_SPLIT: r = launch_add_split(op.in, op.skip, op.out, op.out_s, (int64_t)op.N * op.H * op.W * op.cin, st); break;
+            case OP_SPADE_SHUFFLE: r = launch_spade_shuffle(op.in, op.skip, op.w, op.b, op.out, op.out_s, op.N, op.H, op.W, op.cout, st); break;
+            case OP_SPADE_PRED: r = launch_spade_pred(op.in, op.skip, op.w, op.bias3, op.prev3, op.out, op.N, (int64_t)op.H * op.W, op.cin, st); break;
             case OP_PRED: r = launch_pred(op.in, op.skip, op.w, op.bias0, op.out, (int64_t)op.N * op.H * op.W, op.cin, op.sigmoid, st); break;
             default: r = launch_hyper(op.kind - OP_HYPER_CONTEXT, op.hp, st); break;
         }
@@ -961,6 +1105,9 @@ static std::string op_desc(const Op& op) {
         case OP_ADD_PAD: snprintf(b, sizeof b, "add + replicate pad -> split bf16 C=%d @%dx%d", op.cin, op.H, op.W); break;
         case OP_RING_LINES: snprintf(b, sizeof b, "border lines of u_ext -> split bf16 C=%d @%dx%d", op.cin, 2 * op.H, 2 * op.W); break;
         case OP_HEAD_PACK: snprintf(b, sizeof b, "head pack NCHW -> row-window split bf16 @%dx%d", op.H, op.W); break;
+        case OP_ADD_SPLIT: snprintf(b, sizeof b, "skip add -> split bf16 C=%d @%dx%d", op.cin, op.H, op.W); break;
+        case OP_SPADE_SHUFFLE: snprintf(b, sizeof b, "pixel shuffle x2 + SPADE (BatchNorm, (1+gamma), beta) + ReLU C=%d @%dx%d", op.cout, 2 * op.H, 2 * op.W); break;
+        case OP_SPADE_PRED: snprintf(b, sizeof b, "SPADE-E2VID prediction: relu(x + head) -> 1x1 %d->3 + BN + sigmoid, image = mean @%dx%d", op.cin, op.H, op.W); break;
         case OP_HYPER_CONTEXT: snprintf(b, sizeof b, "hyper context x0.25"); break;
         case OP_HYPER_ATOMS: snprintf(b, sizeof b, "hyper atoms A=%d K=%d L=%d @%dx%d", op.hp.A, op.hp.K, op.hp.L, op.hp.h, op.hp.w); break;
         case OP_HYPER_APPLY_U: snprintf(b, sizeof b, "hyper atoms + dynamic conv applied to U = conv1x1(x) (re-associated) C=%d A=%d Cout=%d @%dx%d", op.hp.C, op.hp.A, op.hp.CO, op.hp.h, op.hp.w); break;
@@ -976,7 +1123,7 @@ extern "C" {
 
 int evk_model_create(const evk_model_config* cfg, evk_model** out) {
     EVK_REQUIRE(cfg && out, EVK_ERR_ARG, "evk_model_create: null argument");
-    EVK_REQUIRE(cfg->arch >= 0 && cfg->arch <= 2, EVK_ERR_ARG, "evk_model_create: unknown arch %d", cfg->arch);
+    EVK_REQUIRE(cfg->arch >= 0 && cfg->arch <= 3, EVK_ERR_ARG, "evk_model_create: unknown arch %d", cfg->arch);
     EVK_REQUIRE(cfg->batch >= 1 && cfg->height > 0 && cfg->width > 0 && cfg->num_bins > 0 && cfg->base_channels > 0 &&
                     cfg->base_channels % 4 == 0,
                 EVK_ERR_ARG, "evk_model_create: bad config (batch=%d %dx%d bins=%d base=%d)", cfg->batch, cfg->height,
@@ -1013,7 +1160,8 @@ int evk_model_finalize(evk_model* m, void* stream) {
         EVK_REQUIRE(m->in_bufs[k] && m->out_bufs[k], EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
     }
     m->in_buf = m->in_bufs[0]; m->out_buf = m->out_bufs[0]; m->prev_rec = m->out_bufs[1];
-    int r = (c.arch == EVK_ARCH_UNET_RECURRENT) ? build_unet(m) : build_firenet(m, c.arch == EVK_ARCH_FIRENET_LEGACY);
+    int r = c.arch == EVK_ARCH_UNET_RECURRENT ? build_unet(m) : c.arch == EVK_ARCH_SPADE_E2VID ? build_spade(m)
+                                                                                                  : build_firenet(m, c.arch == EVK_ARCH_FIRENET_LEGACY);
     if (r != EVK_OK) return r;
     // parity 1 reads / writes the other input / output buffer (and its "previous reconstruction" is parity 0's output)
     for (Op& op : m->ops[1]) {
@@ -1057,6 +1205,7 @@ int evk_model_reset_states(evk_model* m, void* stream) {
     for (int k = 0; k < 2; ++k)      // (HyperE2VID reads the other output buffer as the previous reconstruction: zeros after a reset)
         EVK_CHECK_CUDA(cudaMemsetAsync(m->out_bufs[k], 0, sizeof(float) * (size_t)m->cfg.batch * m->cfg.height * m->cfg.width, st));
     m->parity = 0;
+    m->spade_first = true;
     return EVK_OK;
 }
 
@@ -1069,6 +1218,12 @@ int evk_model_forward(evk_model* m, const float* voxel, float* image, void* stre
     const size_t out_bytes = sizeof(float) * (size_t)c.batch * c.height * c.width;
     const int par = m->parity;
     if (voxel != m->in_bufs[par]) EVK_CHECK_CUDA(cudaMemcpyAsync(m->in_bufs[par], voxel, in_bytes, cudaMemcpyDeviceToDevice, st));
+    if (c.arch == EVK_ARCH_SPADE_E2VID && m->spade_first) {
+        // no previous reconstruction yet: x_org = the first three bins, shifted / scaled to [0, 1] in place (spade_e2v.py:140-145)
+        int r = launch_spade_first_frame(m->in_bufs[par], m->prev3, c.batch, c.num_bins, (int64_t)c.height * c.width, st);
+        if (r != EVK_OK) return r;
+        m->spade_first = false;
+    }
     if (m->use_graph) {
         if (!m->graph[par]) {
             cudaGraph_t g = nullptr;
@@ -1103,6 +1258,11 @@ int evk_model_profile(evk_model* m, const float* voxel, float* image, void* stre
     const size_t out_bytes = sizeof(float) * (size_t)c.batch * c.height * c.width;
     const int par = m->parity;
     if (voxel != m->in_bufs[par]) EVK_CHECK_CUDA(cudaMemcpyAsync(m->in_bufs[par], voxel, in_bytes, cudaMemcpyDeviceToDevice, st));
+    if (c.arch == EVK_ARCH_SPADE_E2VID && m->spade_first) {
+        int r0 = launch_spade_first_frame(m->in_bufs[par], m->prev3, c.batch, c.num_bins, (int64_t)c.height * c.width, st);
+        if (r0 != EVK_OK) return r0;
+        m->spade_first = false;
+    }
     std::vector<cudaEvent_t> ev;
     int r = run_ops(m, par, st, &ev);
     if (image != m->out_bufs[par]) EVK_CHECK_CUDA(cudaMemcpyAsync(image, m->out_bufs[par], out_bytes, cudaMemcpyDeviceToDevice, st));

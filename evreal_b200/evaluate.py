@@ -92,8 +92,12 @@ def open_sequence(sequence, device=None):
 # ------------------------------------------------------------------ model factory
 def build_model(model_name, checkpoint):
     """Checkpoint dialects by method name (eval.py:124-158) -> (model, state_dict)."""
-    if model_name in ("SPADE-E2VID", "ET-Net"):
-        raise NotImplementedError(f"{model_name} is outside the accelerated hot path (SURVEY 2: out of scope)")
+    if model_name == "ET-Net":
+        raise NotImplementedError(f"{model_name} (transformer) is outside the accelerated hot path (SURVEY 2: out of scope)")
+    if model_name == "SPADE-E2VID":                       # eval.py:130-133: bare state_dict, num_encoders set on the instance
+        model = model_arch.SpadeE2vid()
+        model.num_encoders = 3
+        return model, checkpoint
     if model_name == "SSL-E2VID":
         unet_kwargs = {"base_num_channels": 32, "kernel_size": 5, "num_bins": 5, "num_encoders": 3,
                        "recurrent_block_type": "convlstm", "num_residual_blocks": 2, "skip_type": "sum", "norm": None,

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-ARCH_UNET, ARCH_FIRENET_LEGACY, ARCH_FIRENET = 0, 1, 2
+ARCH_UNET, ARCH_FIRENET_LEGACY, ARCH_FIRENET, ARCH_SPADE = 0, 1, 2, 3
 
 
 class _NativeModel:
@@ -381,6 +381,47 @@ class FireNet(_FireNetBase):
 
     def _config(self, batch, height, width):
         return self._fire_config(ARCH_FIRENET, batch, height, width)
+
+
+class SpadeE2vid(_NativeModel):
+    """model/spade_e2v.py:113-179 (Unet6, pretrained/SPADE-E2VID; `model.SpadeE2vid` in the reference's model/__init__.py).
+    The class has no constructor arguments; eval.py:130-133 sets ``num_encoders = 3`` on the instance.  ``states`` are the four
+    ConvLSTM (hidden, cell) pairs; the previous 3-channel reconstruction that conditions the SPADE layers lives in the device
+    program and is cleared by ``reset_states``."""
+    _prefix = ''
+    _arch = ARCH_SPADE
+
+    def __init__(self):
+        super().__init__()
+        self.num_bins = 5
+        self.num_encoders = 3
+        self.prev_recs = None
+
+    def _config(self, batch, height, width):
+        return _lib.ModelConfig(arch=ARCH_SPADE, num_bins=5, base_channels=32, num_encoders=3, num_residual_blocks=2, kernel_size=5,
+                                num_output_channels=3, final_sigmoid=1, dynamic_decoder=0, batch=batch, height=height, width=width,
+                                precision=self.precision)
+
+    def reset_states(self):
+        super().reset_states()
+        self.prev_recs = None
+
+    @property
+    def states(self):
+        s = self._get_states()
+        if s is None:
+            return None
+        return [(s[2 * i], s[2 * i + 1]) for i in range(4)]
+
+    @states.setter
+    def states(self, states):
+        if states is None or self._handle is None:
+            _NativeModel.reset_states(self)
+            return
+        flat = []
+        for h, c in states:
+            flat += [h, c]
+        self._set_states(flat)
 
 
 # ---------------------------------------------------------------------------------------------- colour (CED)

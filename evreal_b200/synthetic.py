@@ -161,6 +161,41 @@ def firenet_state_dict(seed=0, prefix='net.', base=16, bins=5):
     return w
 
 
+def spade_state_dict(seed=0):
+    """pretrained/SPADE-E2VID (model/spade_e2v.py Unet6) state_dict: the class has no width parameters."""
+    import torch
+    g = np.random.default_rng(seed)
+    w = {}
+
+    def put(pfx, d):
+        for kk, v in d.items():
+            w[pfx + '.' + kk] = v
+
+    def bn(c, affine=True):
+        d = _bn_w(g, c)
+        if not affine:
+            d = {k: v for k, v in d.items() if k.startswith('running')}
+        return d
+    put('fc', _conv_w(g, 32, 5, 5))
+    for name, cin, cout in (('rec0', 32, 64), ('rec1', 64, 128), ('rec2', 128, 256), ('up2', 64, 32)):
+        put(name + '.conv0', _conv_w(g, cout, cin, 5, bias=False, gain=1.4))
+        put(name + '.bn', bn(cout))
+        put(name + '.recurrent_block.Gates', _conv_w(g, 4 * cout, 2 * cout, 3))
+    for name in ('res0', 'res1'):
+        for c, b in (('conv1', 'bn1'), ('conv2', 'bn2')):
+            put(name + '.' + c, _conv_w(g, 256, 256, 3, bias=False))
+            put(name + '.' + b, bn(256))
+    for name, cin, cout in (('up0', 256, 128), ('up1', 128, 64)):
+        put(name + '.conv0', _conv_w(g, 4 * cout, cin, 3, bias=False, gain=1.4))
+        put(name + '.norm.param_free_norm', bn(cout, affine=False))
+        put(name + '.norm.mlp_shared.0', _conv_w(g, 64, 3, 3))
+        put(name + '.norm.mlp_gamma', _conv_w(g, cout, 64, 3, gain=0.5))
+        put(name + '.norm.mlp_beta', _conv_w(g, cout, 64, 3, gain=0.5))
+    put('conv_img', _conv_w(g, 3, 32, 1))
+    put('bn_img', bn(3))
+    return w
+
+
 E2VID_KWARGS = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
                 'base_num_channels': 32, 'num_residual_blocks': 2, 'use_upsample_conv': True, 'norm': 'BN',
                 'final_activation': 'sigmoid'}

@@ -93,6 +93,7 @@ typedef struct evk_model evk_model;
 #define EVK_ARCH_UNET_RECURRENT 0   /* E2VIDRecurrent / FlowNet: E2VID, E2VID+, SSL-E2VID, HyperE2VID */
 #define EVK_ARCH_FIRENET_LEGACY 1   /* FireNet_legacy  (pretrained/FireNet)  */
 #define EVK_ARCH_FIRENET 2          /* FireNet         (pretrained/FireNet+) */
+#define EVK_ARCH_SPADE_E2VID 3      /* Unet6           (pretrained/SPADE-E2VID; model/spade_e2v.py:113-179) */
 
 typedef struct {
     int arch;                 /* EVK_ARCH_* */

@@ -22,6 +22,8 @@ Follows, in /root/reference:
   model/model.py:147-190       FireNet (FireNet+ checkpoint)
   model/legacy.py:32-111,155+  UNetFire / FireNet_legacy (FireNet checkpoint)
   model/hyper/hyper_dynamic.py:7-92  context fusion, atom generation, dynamic conv
+  model/spade_e2v.py:7-179     SPADE-E2VID (Unet6: stride-1 recurrent encoder at full resolution, pixel-shuffle decoders with
+                               SPADE normalisation conditioned on the previous reconstruction, recurrent last decoder)
 """
 import torch
 import torch.nn.functional as F
@@ -214,6 +216,74 @@ class FireNetOracle:
         x = self.states[1] = conv_gru(w, 'G2', x, self.states[1])
         x = residual_block(w, 'R2', x)
         return conv_layer(w, 'pred', x, 1, 0, relu=False)
+
+
+class SpadeE2vidOracle:
+    """pretrained/SPADE-E2VID: model/spade_e2v.py:113-179 (Unet6).  Per SAMPLE where the reference is per tensor (the
+    first-frame min / max of x[:, :3], :140-145): the reference only ever runs batch 1, and batching independent
+    sequences must not couple them.  Note the reference's in-place quirk: x_org is a VIEW of the input, so the head
+    convolution of the first frame sees the normalised first three bins."""
+    num_encoders = 3          # eval.py:131-132
+
+    def __init__(self, weights):
+        self.w = weights
+        self.reset_states()
+
+    def reset_states(self):
+        self.states = None
+        self.prev_recs = None
+
+    def _rec(self, pfx, x, state, stride):
+        w = self.w
+        y = F.conv2d(x, w[pfx + '.conv0.weight'], None, stride, 2)
+        y = torch.relu(_bn(w, pfx + '.bn', y))
+        st = conv_lstm(w, pfx + '.recurrent_block', y, state)
+        return st[0], st
+
+    def _res(self, pfx, x):
+        w = self.w
+        y = torch.relu(_bn(w, pfx + '.bn1', F.conv2d(x, w[pfx + '.conv1.weight'], None, 1, 1)))
+        y = _bn(w, pfx + '.bn2', F.conv2d(y, w[pfx + '.conv2.weight'], None, 1, 1))
+        return torch.relu(y + x)
+
+    def _up(self, pfx, x, x_org):
+        w = self.w
+        y = F.pixel_shuffle(F.conv2d(x, w[pfx + '.conv0.weight'], None, 1, 1), 2)
+        n = pfx + '.norm'
+        normalized = F.batch_norm(y, w[n + '.param_free_norm.running_mean'], w[n + '.param_free_norm.running_var'], None, None,
+                                  False, 0.0, BN_EPS)
+        seg = F.interpolate(x_org, size=y.shape[-2:], mode='nearest')
+        actv = torch.relu(F.conv2d(seg, w[n + '.mlp_shared.0.weight'], w[n + '.mlp_shared.0.bias'], 1, 1))
+        gamma = F.conv2d(actv, w[n + '.mlp_gamma.weight'], w[n + '.mlp_gamma.bias'], 1, 1)
+        beta = F.conv2d(actv, w[n + '.mlp_beta.weight'], w[n + '.mlp_beta.bias'], 1, 1)
+        return torch.relu(normalized * (1 + gamma) + beta)
+
+    @torch.no_grad()
+    def __call__(self, x):
+        w = self.w
+        x = x.clone()
+        prev = self.states if self.states is not None else [None] * 4
+        if self.prev_recs is None:
+            x_org = x[:, :3]                                   # a view: the head below sees the change
+            for n in range(x.shape[0]):
+                x_org[n] -= x_org[n].min()
+                if x_org[n].max() > 0:
+                    x_org[n] /= x_org[n].max()
+        else:
+            x_org = self.prev_recs
+        head = torch.relu(F.conv2d(x, w['fc.weight'], w['fc.bias'], 1, 2))
+        x0, s0 = self._rec('rec0', head, prev[0], 1)
+        x1, s1 = self._rec('rec1', x0, prev[1], 2)
+        x2, s2 = self._rec('rec2', x1, prev[2], 2)
+        y = self._res('res1', self._res('res0', x2))
+        y = self._up('up0', y + x2, x_org)
+        y = self._up('up1', y + x1, x_org)
+        y, s3 = self._rec('up2', y + x0, prev[3], 1)
+        img = F.conv2d(torch.relu(y + head), w['conv_img.weight'], w['conv_img.bias'])
+        img = torch.sigmoid(_bn(w, 'bn_img', img))
+        self.states = [s0, s1, s2, s3]
+        self.prev_recs = img
+        return img.mean(1, keepdim=True)
 
 
 # ---------------------------------------------------------------------------

@@ -70,3 +70,14 @@ def test_real_e2vid_weights_two_encoder_slice():
 
 def test_real_e2vid_plus_weights_one_encoder_slice():
     _check('flownet_real1', 'unetflow.', lambda w: on.UNetRecurrentOracle(w, 1, 0), file='real_slices')
+
+
+def test_spade_e2vid_oracle_vs_real_class():
+    """SPADE-E2VID (model/spade_e2v.py) restatement against frames of the real Unet6 with seeded weights (regenerated here from
+    the seed), three recurrent frames: the first takes the normalised-event branch of x_org, the others the previous output."""
+    from evreal_b200 import synthetic
+    g = golden('spade')
+    o = on.SpadeE2vidOracle(synthetic.spade_state_dict(7))
+    got = _run(o, g['seeded.voxels'])
+    ref = g['seeded.frames']
+    assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= 2e-6

@@ -16,7 +16,7 @@ def main():
     from evreal_b200 import synthetic
     from evreal_b200.dataset import MemMapDataset
     from evreal_b200.pipeline import SequenceBatch
-    shapes = {'e2vid': (180, 240, 1e6, 24.0), 'firenet': (180, 240, 1e6, 25.0), 'hyper': (260, 346, 5e6, 45.0)}
+    shapes = {'e2vid': (180, 240, 1e6, 24.0), 'firenet': (180, 240, 1e6, 25.0), 'hyper': (260, 346, 5e6, 45.0), 'spade': (180, 240, 1e6, 24.0)}
     for name in args.models.split(','):
         H, W, rate, fps = shapes[name]
         dur = (args.steps + 12) / fps
@@ -25,6 +25,9 @@ def main():
         if name == 'e2vid':
             model = evk.E2VIDRecurrent(dict(synthetic.E2VID_KWARGS)).load_state_dict(synthetic.unet_state_dict(0, norm_bn=True))
             norm, post = True, 'robust'
+        elif name == 'spade':
+            model = evk.SpadeE2vid().load_state_dict(synthetic.spade_state_dict(0))
+            norm, post = False, 'none'
         elif name == 'hyper':
             model = evk.E2VIDRecurrent(dict(synthetic.HYPER_KWARGS)).load_state_dict(synthetic.unet_state_dict(0, dynamic_decoder=True))
             norm, post = False, 'none'

@@ -554,6 +554,47 @@ def golden_eval_loop_modes(tmp):
     np.savez_compressed(os.path.join(OUT, 'eval_loop_modes.npz'), **out)
 
 
+def golden_spade(copy_ckpt=True):
+    """SPADE-E2VID (model/spade_e2v.py Unet6) through the REAL class: (1) seeded weights from evreal_b200.synthetic (the test
+    regenerates them from the seed: 43 MB of weights are not stored), batch 1, 40x56, three recurrent frames -- the first
+    one takes the normalised-event branch of x_org, the others the previous reconstruction; (2) the shipped checkpoint at
+    180x240 (padded to 184x240 by CropParameters(num_encoders = 3), eval.py:131-132), three frames, .pth copied next to
+    the other untracked checkpoints."""
+    import shutil
+    from model.spade_e2v import Unet6
+    from utils.event_utils import events_to_voxel_torch
+    from utils.util import CropParameters
+    out = {}
+    m = Unet6()
+    m.load_state_dict(synthetic.spade_state_dict(7))
+    m.eval()
+    voxels = _small_voxels(60, 3, 1, 40, 56)
+    m.reset_states()
+    with torch.no_grad():
+        out['seeded.frames'] = np.stack([m(v.clone())['image'].numpy().copy() for v in voxels])
+    out['seeded.voxels'] = torch.stack(voxels).numpy()
+    src = os.path.join(REF, 'pretrained/SPADE-E2VID/model.pth')
+    if copy_ckpt:
+        os.makedirs(os.path.join(OUT, '_ckpt'), exist_ok=True)
+        shutil.copyfile(src, os.path.join(OUT, '_ckpt', 'SPADE-E2VID.pth'))
+    m = Unet6()
+    m.load_state_dict(torch.load(src, map_location='cpu'))
+    m.eval()
+    H, W = 180, 240
+    cp = CropParameters(W, H, 3)
+    frames, sums = [], []
+    m.reset_states()
+    with torch.no_grad():
+        for f in range(3):
+            v = events_to_voxel_torch(*[torch.from_numpy(a) for a in gen_events(40 + f, 15000 + 7000 * f, H, W)], 5, sensor_size=(H, W))[None]
+            sums.append([float(v.sum(dtype=torch.float64)), float(v.abs().sum(dtype=torch.float64))])
+            frames.append(cp.crop(m(cp.pad(v))['image'])[0, 0].numpy().copy())
+    out['ckpt.frames'] = np.stack(frames).astype(np.float32)
+    out['ckpt.voxel_sums'] = np.array(sums)
+    print('spade seeded mean %.5f  ckpt frames mean' % out['seeded.frames'].mean(), [float(f.mean()) for f in frames])
+    np.savez_compressed(os.path.join(OUT, 'spade.npz'), **out)
+
+
 def golden_colornet():
     """The REAL ColorNet (model/model.py:46-105) around the real FireNet checkpoint on a Bayer-sized input: merged colour
     frames over three recurrent steps (five batch-1 forwards per frame with swapped states in the reference)."""
@@ -583,6 +624,9 @@ if __name__ == '__main__':
     if '--only-base32' in sys.argv:   # added later; leaves the other fixtures untouched
         golden_networks_base32()
         sys.exit(0)
+    if '--only-spade' in sys.argv:
+        golden_spade()
+        sys.exit(0)
     if '--round2' in sys.argv:        # round-2 fixtures only (the round-1 ones stay byte-identical)
         if '--only-color' not in sys.argv:
             golden_real_slices()
@@ -590,6 +634,7 @@ if __name__ == '__main__':
             with tempfile.TemporaryDirectory() as tmp:
                 golden_eval_loop_modes(tmp)
         golden_colornet()
+        golden_spade()
         sys.exit(0)
     with tempfile.TemporaryDirectory() as tmp:
         golden_voxel()
@@ -603,5 +648,6 @@ if __name__ == '__main__':
         golden_eval_loop(tmp)
         golden_eval_loop_modes(tmp)
         golden_colornet()
+        golden_spade()
     for f in sorted(os.listdir(OUT)):
         print('%8.1f kB  %s' % (os.path.getsize(os.path.join(OUT, f)) / 1e3, f))
