@@ -8,7 +8,7 @@ fallback: using any op without the built library or without a CUDA device raises
 """
 from . import _lib  # noqa: F401
 from .event_utils import events_to_voxel_torch, events_to_image_torch, events_to_voxel_raw  # noqa: F401
-from .model import E2VIDRecurrent, FlowNet, FireNet, FireNet_legacy, SpadeE2vid, ColorNet  # noqa: F401
+from .model import E2VIDRecurrent, FlowNet, FireNet, FireNet_legacy, SpadeE2vid, EITR, ColorNet  # noqa: F401
 from .util import CropParameters, normalize_event_tensor  # noqa: F401
 
 __version__ = "0.1.0"

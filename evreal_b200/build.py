@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libevreal_b200.so")
-SOURCES = ["api.cu", "voxelize.cu", "metrics.cu", "conv_simt.cu", "conv_tc.cu", "poly.cu", "hyper.cu", "spade.cu", "model.cu", "lpips.cu"]
+SOURCES = ["api.cu", "voxelize.cu", "metrics.cu", "conv_simt.cu", "conv_tc.cu", "poly.cu", "hyper.cu", "spade.cu", "etnet.cu", "model.cu", "lpips.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

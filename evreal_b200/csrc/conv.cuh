@@ -142,6 +142,14 @@ int launch_zero_insert2x_add(const float* x, const float* skip, float* y, __nv_b
 int launch_head_pack(const float* x_nchw, __nv_bfloat16* packed, int N, int cin, int H, int W, int left, cudaStream_t st, int src_H = 0,
                      int src_W = 0, int stride = 1, int src_planes = 0);
 
+// ---- ET-Net token path (etnet.cu)
+int launch_layernorm256(const float* x, const float* gamma, const float* beta, float* out, __nv_bfloat16* out_s, int64_t T, cudaStream_t st);
+int launch_attention(const float* q, int q_stride, const float* k, const float* v, int kv_stride, float* out, __nv_bfloat16* out_s, int N, int Lq,
+                     int Lk, cudaStream_t st);
+int launch_add_pos(const float* x, const float* pos, float* out, int N, int64_t per_sample, cudaStream_t st);
+int launch_avg6(const float* const* six, float* out, int64_t n, cudaStream_t st);
+void sine_position_table(int n, int d, std::vector<float>& out);
+
 // ---- SPADE-E2VID glue (spade.cu)
 int launch_add_split(const float* x, const float* s, float* out, __nv_bfloat16* out_s, int64_t n, cudaStream_t st);
 int launch_spade_shuffle(const float* c0, const float* gb, const float* alpha, const float* shift, float* out, __nv_bfloat16* out_s, int N,

@@ -28,7 +28,7 @@ struct HostTensor {
     std::vector<int64_t> shape;
 };
 
-enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HYPER_APPLY_U, OP_HEAD_PACK, OP_NOP, OP_ZERO_INSERT_ADD, OP_ADD_PAD, OP_RING_LINES, OP_ADD_SPLIT, OP_SPADE_SHUFFLE, OP_SPADE_PRED };
+enum OpKind { OP_HEAD, OP_CONV, OP_UPSAMPLE_ADD, OP_PRED, OP_HYPER_CONTEXT, OP_HYPER_ATOMS, OP_HYPER_APPLY, OP_HYPER_APPLY_U, OP_HEAD_PACK, OP_NOP, OP_ZERO_INSERT_ADD, OP_ADD_PAD, OP_RING_LINES, OP_ADD_SPLIT, OP_SPADE_SHUFFLE, OP_SPADE_PRED, OP_LAYERNORM, OP_ATTENTION, OP_ADD_POS, OP_AVG6 };
 
 struct Op {
     OpKind kind;
@@ -49,6 +49,11 @@ struct Op {
     // OP_SPADE_PRED: in = last hidden state, skip = head, w = [cin][3], bias3 -> prev3 (NCHW, 3 planes) and out (image)
     float bias3[3] = {0.f, 0.f, 0.f};
     float* prev3 = nullptr;
+    // ET-Net token path.  OP_LAYERNORM: in, w = gamma, b = beta -> out / out_s over N*H*W tokens of 256 channels.
+    // OP_ATTENTION: in = q, skip = k, w = v (row-strided views of the projection outputs: q_stride / kv_stride floats per token),
+    // H*W query tokens, Lk key tokens -> out / out_s.  OP_ADD_POS: out = in + w (sine table [H*W][256]).  OP_AVG6: out = mean(six).
+    int q_stride = 0, kv_stride = 0, Lk = 0;
+    const float* six[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     HyperParams hp;             // OP_HYPER_*
     double flops = 0.0;
 };
@@ -652,7 +657,8 @@ static void fix_hidden_parity(evk_model* m, const std::vector<int>& hstate) {
             if (op.kind == OP_CONV && op.cp.epi == EPI_LSTM) { fix(op.cp.x1); continue; }   // x2/h_new already per parity
             if (op.kind == OP_CONV) { fix(op.cp.x1); fix(op.cp.res); }
             if (op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD || op.kind == OP_PRED || op.kind == OP_ADD_PAD || op.kind == OP_ADD_SPLIT ||
-                op.kind == OP_SPADE_PRED) { fix(op.in); fix(op.skip); }
+                op.kind == OP_SPADE_PRED || op.kind == OP_LAYERNORM || op.kind == OP_ADD_POS) { fix(op.in); fix(op.skip); }
+                if (op.kind == OP_AVG6) for (int k = 0; k < 6; ++k) fix(op.six[k]);
         }
     }
 }
@@ -863,6 +869,215 @@ static int build_spade(evk_model* m) {
     return EVK_OK;
 }
 
+// ET-Net (model/eitr/u_trans.py:13-123 mls_tpa): E2VID's head, three recurrent stride-2 encoders and upsample-conv decoders around a
+// multi-scale token path.  A token tensor [N, L, 256] (L = h*w tokens of the 1/8-resolution map, row-major) IS the NHWC activation
+// [N, h, w, 256], so every nn.Linear (attention in / out projections, feed-forward) is a 1x1 convolution on the tensor-core kernel
+// with the residual add in its epilogue; LayerNorm, attention, the sine table and the final average are etnet.cu.
+static int pack_linear(const evk_model* m, const std::string& wname, const std::string& bname, int row0, int rows, int cin_expected, Packed& out) {
+    const HostTensor* w = m->find(wname);
+    const HostTensor* b = m->find(bname);
+    EVK_REQUIRE(w && b && w->shape.size() == 2 && (int)w->shape[1] == cin_expected && row0 + rows <= (int)w->shape[0] &&
+                    (int)b->data.size() == (int)w->shape[0],
+                EVK_ERR_KEY, "'%s': missing or unexpected linear layer shape", wname.c_str());
+    const int ci = cin_expected;
+    out.cout = rows; out.cin = ci; out.kh = out.kw = 1;
+    out.w.resize((size_t)ci * rows);
+    out.b.resize(rows);
+    for (int n = 0; n < rows; ++n) {
+        out.b[n] = b->data[row0 + n];
+        for (int c = 0; c < ci; ++c) out.w[(size_t)c * rows + n] = w->data[(size_t)(row0 + n) * ci + c];
+    }
+    return EVK_OK;
+}
+
+static int build_etnet(evk_model* m) {
+    const evk_model_config& c = m->cfg;
+    Builder B{m, c.batch};
+    EVK_REQUIRE(c.height % 8 == 0 && c.width % 8 == 0, EVK_ERR_ARG, "ET-Net: input %dx%d must be a multiple of 8 (CropParameters.pad)", c.height, c.width);
+    EVK_REQUIRE(m->find("head.norm_layer.weight") == nullptr && m->find("head.norm_layer.running_mean") == nullptr, EVK_ERR_KEY,
+                "ET-Net with a normalisation layer is not built (the shipped checkpoint has norm = None)");
+    const int D = 256, FF = 1024;
+    int H = c.height, W = c.width, C = 32;
+    float* head = B.act(H, W, C);
+    int r = add_head(B, "head.conv2d", "", head, C);
+    if (r != EVK_OK) return r;
+    const float* x = head;
+    std::vector<int> hstate(3);
+    const float* blocks[3];
+    int bh[3], bw[3];
+    for (int i = 0; i < 3; ++i) {
+        const std::string pfx = "DownsampleConv." + std::to_string(i);
+        const int Co = 2 * C, Ho = (H + 4 - 5) / 2 + 1, Wo = (W + 4 - 5) / 2 + 1;
+        float* xe = B.act(Ho, Wo, Co);
+        r = B.conv(pfx + ".conv.conv2d.weight", pfx + ".conv.conv2d.bias", "", x, C, H, W, 2, 2, ACT_RELU, nullptr, xe, nullptr);
+        if (r != EVK_OK) return r;
+        const int hs = make_state(m, Co, Ho, Wo, true);
+        if (hs < 0) return hs;
+        const int cs = make_state(m, Co, Ho, Wo, false);
+        if (cs < 0) return cs;
+        r = add_lstm(B, pfx + ".recurrent_block", xe, Co, Ho, Wo, hs, cs);
+        if (r != EVK_OK) return r;
+        hstate[i] = hs;
+        C = Co; H = Ho; W = Wo;
+        x = m->states[hs].buf[1];
+        blocks[i] = x; bh[i] = H; bw[i] = W;
+    }
+    const int h = H, w = W, L = h * w;          // token grid = the 1/8-resolution map
+    EVK_REQUIRE(C == D && bh[1] == 2 * h && bw[1] == 2 * w && bh[0] == 4 * h && bw[0] == 4 * w, EVK_ERR_ARG, "ET-Net: unexpected encoder pyramid");
+    std::vector<float> pos_host;
+    sine_position_table(L, D, pos_host);
+    const float* pos = m->upload(pos_host);
+    EVK_REQUIRE(pos != nullptr, EVK_ERR_CUDA, "out of device memory");
+    auto push = [&](const Op& op) { m->ops[0].push_back(op); m->ops[1].push_back(op); };
+    auto tokens = [&](int ch) { return B.act(h, w, ch); };
+    auto layernorm = [&](const std::string& pfx, const float* in) -> float* {
+        const HostTensor* g = m->find(pfx + ".weight");
+        const HostTensor* b = m->find(pfx + ".bias");
+        if (!(g && b && (int)g->data.size() == D && (int)b->data.size() == D)) { set_error("'%s': missing LayerNorm(256) parameters", pfx.c_str()); return nullptr; }
+        float* o = tokens(D);
+        Op op; op.kind = OP_LAYERNORM;
+        op.in = in; op.w = m->upload(g->data); op.b = m->upload(b->data); op.out = o; op.N = B.N; op.H = h; op.W = w; op.cin = D;
+        push(op);
+        return o;
+    };
+    // y = act(x W^T + b) [+ res] over the tokens: rows [row0, row0 + rows) of an nn.Linear weight
+    auto linear = [&](const std::string& wname, const std::string& bname, int row0, int rows, const float* in, int cin, int act, const float* res,
+                      float** out) -> int {
+        Packed pk;
+        int rr = pack_linear(m, wname, bname, row0, rows, cin, pk);
+        if (rr != EVK_OK) return rr;
+        *out = tokens(rows);
+        return B.conv_packed(pk, in, cin, h, w, 1, 0, act, res, *out, nullptr);
+    };
+    auto attention = [&](const float* q, int qs, const float* k, const float* v, int kvs) -> float* {
+        float* o = tokens(D);
+        Op op; op.kind = OP_ATTENTION;
+        op.in = q; op.skip = k; op.w = v; op.q_stride = qs; op.kv_stride = kvs; op.Lk = L; op.out = o; op.N = B.N; op.H = h; op.W = w; op.cin = D;
+        op.flops = 4.0 * (double)B.N * L * L * D;
+        push(op);
+        return o;
+    };
+    // x + MultiheadAttention(q_in, kv_in, kv_in): fused q|k|v projection when the inputs coincide (self attention)
+    auto mha = [&](const std::string& pfx, const float* xres, const float* q_in, const float* kv_in, float** out) -> int {
+        const std::string wi = pfx + ".in_proj_weight", bi = pfx + ".in_proj_bias";
+        float* a = nullptr;
+        int rr;
+        if (q_in == kv_in) {
+            float* qkv = nullptr;
+            if ((rr = linear(wi, bi, 0, 3 * D, q_in, D, ACT_NONE, nullptr, &qkv)) != EVK_OK) return rr;
+            a = attention(qkv, 3 * D, qkv + D, qkv + 2 * D, 3 * D);
+        } else {
+            float *q = nullptr, *kv = nullptr;
+            if ((rr = linear(wi, bi, 0, D, q_in, D, ACT_NONE, nullptr, &q)) != EVK_OK) return rr;
+            if ((rr = linear(wi, bi, D, 2 * D, kv_in, D, ACT_NONE, nullptr, &kv)) != EVK_OK) return rr;
+            a = attention(q, D, kv, kv + D, 2 * D);
+        }
+        return linear(pfx + ".out_proj.weight", pfx + ".out_proj.bias", 0, D, a, D, ACT_NONE, xres, out);
+    };
+    auto ffn = [&](const std::string& pfx, const float* xres, const float* n, float** out) -> int {
+        float* f = nullptr;
+        int rr = linear(pfx + ".linear1.weight", pfx + ".linear1.bias", 0, FF, n, D, ACT_RELU, nullptr, &f);
+        if (rr != EVK_OK) return rr;
+        return linear(pfx + ".linear2.weight", pfx + ".linear2.bias", 0, D, f, FF, ACT_NONE, xres, out);
+    };
+    // words of the three scales: the 1/8 map itself, 2x2 patches of the 1/4 map, 4x4 patches of the 1/2 map (fp32 CUDA-core
+    // convolutions on the hidden states: stride = kernel, no padding)
+    const float* words[3] = {blocks[2], nullptr, nullptr};
+    for (int s = 1; s < 3; ++s) {
+        const std::string nm = "split" + std::to_string(s);
+        Packed pk;
+        if ((r = pack_conv(m, nm + ".weight", nm + ".bias", "", nullptr, pk)) != EVK_OK) return r;
+        const int kk = 1 << s, ci = D >> s;
+        EVK_REQUIRE(pk.cin == ci && pk.cout == D && pk.kh == kk && pk.kw == kk, EVK_ERR_KEY, "'%s': expected [256,%d,%d,%d]", nm.c_str(), ci, kk, kk);
+        float* o = tokens(D);
+        Op op; op.kind = OP_CONV;
+        ConvParams& p = op.cp;
+        p.x1 = blocks[2 - s]; p.c1 = ci; p.N = B.N; p.Hin = bh[2 - s]; p.Win = bw[2 - s]; p.Hout = h; p.Wout = w;
+        p.kh = p.kw = kk; p.stride = kk; p.pad = 0; p.w = m->upload(pk.w); p.bias = m->upload(pk.b); p.cout = D;
+        p.epi = EPI_LINEAR; p.act = ACT_NONE; p.y = o;
+        op.flops = conv_flops(p, D);
+        push(op);
+        words[s] = o;
+    }
+    const float* hs[3];
+    const float* hc[3];
+    for (int s = 0; s < 3; ++s) {              // three pre-norm encoder layers per scale; the sine table is added once
+        const std::string enc = "trans_encoder" + std::to_string(s) + ".encoder.layers.";
+        float* xs = tokens(D);
+        {
+            Op op; op.kind = OP_ADD_POS;
+            op.in = words[s]; op.w = pos; op.out = xs; op.N = B.N; op.H = h; op.W = w; op.cin = D;
+            push(op);
+        }
+        const float* xcur = xs;
+        for (int i = 0; i < 3; ++i) {
+            const std::string p = enc + std::to_string(i);
+            float* n1 = layernorm(p + ".norm1", xcur);
+            if (!n1) return EVK_ERR_KEY;
+            float* x1 = nullptr;
+            if ((r = mha(p + ".self_attn", xcur, n1, n1, &x1)) != EVK_OK) return r;
+            float* n2 = layernorm(p + ".norm2", x1);
+            if (!n2) return EVK_ERR_KEY;
+            float* x2 = nullptr;
+            if ((r = ffn(p, x1, n2, &x2)) != EVK_OK) return r;
+            xcur = x2;
+        }
+        hs[s] = xcur;
+    }
+    for (int s = 0; s < 3; ++s) {              // two decoder layers per scale, cross attention to the coarser scale's tokens
+        const std::string dec = "trans_decoder" + std::to_string(s) + ".decoder.layers.";
+        const float* memory = hs[s == 0 ? 0 : s - 1];
+        const float* xcur = hs[s];
+        for (int i = 0; i < 2; ++i) {
+            const std::string p = dec + std::to_string(i);
+            float* n1 = layernorm(p + ".norm1", xcur);
+            if (!n1) return EVK_ERR_KEY;
+            float* x1 = nullptr;
+            if ((r = mha(p + ".self_attn", xcur, n1, n1, &x1)) != EVK_OK) return r;
+            float* nq = layernorm(p + ".norm21", x1);
+            float* nm = layernorm(p + ".norm22", memory);
+            if (!nq || !nm) return EVK_ERR_KEY;
+            float* x2 = nullptr;
+            if ((r = mha(p + ".cross_attn", x1, nq, nm, &x2)) != EVK_OK) return r;
+            float* n3 = layernorm(p + ".norm3", x2);
+            if (!n3) return EVK_ERR_KEY;
+            float* x3 = nullptr;
+            if ((r = ffn(p, x2, n3, &x3)) != EVK_OK) return r;
+            xcur = x3;
+        }
+        hc[s] = xcur;
+    }
+    float* t = tokens(D);
+    {
+        Op op; op.kind = OP_AVG6;
+        for (int s = 0; s < 3; ++s) { op.six[s] = hs[s]; op.six[3 + s] = hc[s]; }
+        op.out = t; op.N = B.N; op.H = h; op.W = w; op.cin = D;
+        push(op);
+    }
+    // decoders (UpsampleConvLayer on x + skip) and the prediction layer, as in E2VID
+    x = t;
+    for (int i = 0; i < 3; ++i) {
+        const std::string pfx = "UpsampleConv." + std::to_string(i);
+        const float* skip = blocks[2 - i];
+        float* y = B.act(2 * H, 2 * W, C / 2);
+        if (c.precision == 0 && H >= 2 && W >= 2 && getenv("EVK_NO_POLY") == nullptr) {
+            r = add_poly_decoder(B, pfx, x, skip, C, H, W, y);
+        } else {
+            float* up = B.act(2 * H, 2 * W, C);
+            Op op; op.kind = OP_UPSAMPLE_ADD;
+            op.in = x; op.skip = skip; op.out = up; op.N = B.N; op.H = H; op.W = W; op.cin = C;
+            push(op);
+            r = B.conv(pfx + ".conv2d.weight", pfx + ".conv2d.bias", "", up, C, 2 * H, 2 * W, 1, 2, ACT_RELU, nullptr, y, nullptr);
+        }
+        if (r != EVK_OK) return r;
+        x = y; C /= 2; H *= 2; W *= 2;
+    }
+    r = add_pred(B, "pred", x, head, C, H, W);
+    if (r != EVK_OK) return r;
+    fix_hidden_parity(m, hstate);
+    return EVK_OK;
+}
+
 // FireNet_legacy (model/legacy.py:79-111) and FireNet (model/model.py:178-190)
 static int build_firenet(evk_model* m, bool legacy) {
     const evk_model_config& c = m->cfg;
@@ -946,7 +1161,8 @@ static int wire_tc(evk_model* m) {
     for (int par = 0; par < 2; ++par)
         for (Op& op : m->ops[par]) {
             switch (op.kind) {
-                case OP_HEAD: case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_ADD_SPLIT: case OP_SPADE_SHUFFLE: op.out_s = lookup(op.out); break;
+                case OP_HEAD: case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_ADD_SPLIT: case OP_SPADE_SHUFFLE: case OP_LAYERNORM: case OP_ATTENTION:
+                    op.out_s = lookup(op.out); break;
                 case OP_CONV:
                     if (op.cp.epi == EPI_LINEAR) op.cp.ys = lookup(op.cp.y);
                     if (op.cp.epi == EPI_LSTM) op.cp.hs_new = lookup(op.cp.h_new);
@@ -992,6 +1208,9 @@ static int wire_tc(evk_model* m) {
                         break;
                     case OP_UPSAMPLE_ADD: case OP_ZERO_INSERT_ADD: case OP_PRED: case OP_ADD_PAD: case OP_ADD_SPLIT: case OP_SPADE_SHUFFLE:
                     case OP_SPADE_PRED: rd(op.in); rd(op.skip); break;
+                    case OP_LAYERNORM: case OP_ADD_POS: rd(op.in); break;
+                    case OP_ATTENTION: rd(op.in); rd(op.skip); break;        // (v lives in the same projection output as k)
+                    case OP_AVG6: for (int k = 0; k < 6; ++k) rd(op.six[k]); break;
                     case OP_HYPER_CONTEXT: case OP_HYPER_ATOMS: case OP_HYPER_APPLY: case OP_HYPER_APPLY_U:
                         rd(op.hp.ev_nchw); rd(op.hp.prev); rd(op.hp.coef); rd(op.hp.atoms); rd(op.hp.xu); rd(op.hp.u);   // (ctx / inter / y are outputs here)
                         break;
@@ -1008,7 +1227,8 @@ static int wire_tc(evk_model* m) {
                     // ConvGRU: h * reset is consumed by the candidate convolution only -- through its split planes on the tensor-core path
                     if (op.kind == OP_CONV && op.cp.x1s != nullptr && op.cp.epi == EPI_GRU_UR && op.cp.hrs_out != nullptr && op.cp.hr_out != nullptr &&
                         !fp32_read.count(op.cp.hr_out)) op.cp.hr_out = nullptr;
-                    if ((op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD || op.kind == OP_ADD_SPLIT || op.kind == OP_SPADE_SHUFFLE) &&
+                    if ((op.kind == OP_UPSAMPLE_ADD || op.kind == OP_ZERO_INSERT_ADD || op.kind == OP_ADD_SPLIT || op.kind == OP_SPADE_SHUFFLE ||
+                         op.kind == OP_LAYERNORM || op.kind == OP_ATTENTION) &&
                         op.out_s != nullptr && !fp32_read.count(op.out)) op.out = nullptr;
                     if (op.kind == OP_HYPER_APPLY && op.hp.inter_s != nullptr && !fp32_read.count(op.hp.inter)) op.hp.inter = nullptr;
                 }
@@ -1059,6 +1279,10 @@ static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent
             case OP_ADD_SPLIT: r = launch_add_split(op.in, op.skip, op.out, op.out_s, (int64_t)op.N * op.H * op.W * op.cin, st); break;
             case OP_SPADE_SHUFFLE: r = launch_spade_shuffle(op.in, op.skip, op.w, op.b, op.out, op.out_s, op.N, op.H, op.W, op.cout, st); break;
             case OP_SPADE_PRED: r = launch_spade_pred(op.in, op.skip, op.w, op.bias3, op.prev3, op.out, op.N, (int64_t)op.H * op.W, op.cin, st); break;
+            case OP_LAYERNORM: r = launch_layernorm256(op.in, op.w, op.b, op.out, op.out_s, (int64_t)op.N * op.H * op.W, st); break;
+            case OP_ATTENTION: r = launch_attention(op.in, op.q_stride, op.skip, op.w, op.kv_stride, op.out, op.out_s, op.N, op.H * op.W, op.Lk, st); break;
+            case OP_ADD_POS: r = launch_add_pos(op.in, op.w, op.out, op.N, (int64_t)op.H * op.W * op.cin, st); break;
+            case OP_AVG6: r = launch_avg6(op.six, op.out, (int64_t)op.N * op.H * op.W * op.cin, st); break;
             case OP_PRED: r = launch_pred(op.in, op.skip, op.w, op.bias0, op.out, (int64_t)op.N * op.H * op.W, op.cin, op.sigmoid, st); break;
             default: r = launch_hyper(op.kind - OP_HYPER_CONTEXT, op.hp, st); break;
         }
@@ -1108,6 +1332,10 @@ static std::string op_desc(const Op& op) {
         case OP_ADD_SPLIT: snprintf(b, sizeof b, "skip add -> split bf16 C=%d @%dx%d", op.cin, op.H, op.W); break;
         case OP_SPADE_SHUFFLE: snprintf(b, sizeof b, "pixel shuffle x2 + SPADE (BatchNorm, (1+gamma), beta) + ReLU C=%d @%dx%d", op.cout, 2 * op.H, 2 * op.W); break;
         case OP_SPADE_PRED: snprintf(b, sizeof b, "SPADE-E2VID prediction: relu(x + head) -> 1x1 %d->3 + BN + sigmoid, image = mean @%dx%d", op.cin, op.H, op.W); break;
+        case OP_LAYERNORM: snprintf(b, sizeof b, "LayerNorm(%d) over %d tokens -> split bf16", op.cin, op.H * op.W); break;
+        case OP_ATTENTION: snprintf(b, sizeof b, "attention 8 heads x 32, %d queries x %d keys (fp32, online softmax)", op.H * op.W, op.Lk); break;
+        case OP_ADD_POS: snprintf(b, sizeof b, "tokens + sine position table, %d tokens", op.H * op.W); break;
+        case OP_AVG6: snprintf(b, sizeof b, "mean of the six token sets (3 encoder + 3 decoder outputs), %d tokens", op.H * op.W); break;
         case OP_HYPER_CONTEXT: snprintf(b, sizeof b, "hyper context x0.25"); break;
         case OP_HYPER_ATOMS: snprintf(b, sizeof b, "hyper atoms A=%d K=%d L=%d @%dx%d", op.hp.A, op.hp.K, op.hp.L, op.hp.h, op.hp.w); break;
         case OP_HYPER_APPLY_U: snprintf(b, sizeof b, "hyper atoms + dynamic conv applied to U = conv1x1(x) (re-associated) C=%d A=%d Cout=%d @%dx%d", op.hp.C, op.hp.A, op.hp.CO, op.hp.h, op.hp.w); break;
@@ -1123,7 +1351,7 @@ extern "C" {
 
 int evk_model_create(const evk_model_config* cfg, evk_model** out) {
     EVK_REQUIRE(cfg && out, EVK_ERR_ARG, "evk_model_create: null argument");
-    EVK_REQUIRE(cfg->arch >= 0 && cfg->arch <= 3, EVK_ERR_ARG, "evk_model_create: unknown arch %d", cfg->arch);
+    EVK_REQUIRE(cfg->arch >= 0 && cfg->arch <= 4, EVK_ERR_ARG, "evk_model_create: unknown arch %d", cfg->arch);
     EVK_REQUIRE(cfg->batch >= 1 && cfg->height > 0 && cfg->width > 0 && cfg->num_bins > 0 && cfg->base_channels > 0 &&
                     cfg->base_channels % 4 == 0,
                 EVK_ERR_ARG, "evk_model_create: bad config (batch=%d %dx%d bins=%d base=%d)", cfg->batch, cfg->height,
@@ -1160,7 +1388,7 @@ int evk_model_finalize(evk_model* m, void* stream) {
         EVK_REQUIRE(m->in_bufs[k] && m->out_bufs[k], EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
     }
     m->in_buf = m->in_bufs[0]; m->out_buf = m->out_bufs[0]; m->prev_rec = m->out_bufs[1];
-    int r = c.arch == EVK_ARCH_UNET_RECURRENT ? build_unet(m) : c.arch == EVK_ARCH_SPADE_E2VID ? build_spade(m)
+    int r = c.arch == EVK_ARCH_UNET_RECURRENT ? build_unet(m) : c.arch == EVK_ARCH_SPADE_E2VID ? build_spade(m) : c.arch == EVK_ARCH_ETNET ? build_etnet(m)
                                                                                                   : build_firenet(m, c.arch == EVK_ARCH_FIRENET_LEGACY);
     if (r != EVK_OK) return r;
     // parity 1 reads / writes the other input / output buffer (and its "previous reconstruction" is parity 0's output)

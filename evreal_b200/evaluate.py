@@ -92,8 +92,6 @@ def open_sequence(sequence, device=None):
 # ------------------------------------------------------------------ model factory
 def build_model(model_name, checkpoint):
     """Checkpoint dialects by method name (eval.py:124-158) -> (model, state_dict)."""
-    if model_name == "ET-Net":
-        raise NotImplementedError(f"{model_name} (transformer) is outside the accelerated hot path (SURVEY 2: out of scope)")
     if model_name == "SPADE-E2VID":                       # eval.py:130-133: bare state_dict, num_encoders set on the instance
         model = model_arch.SpadeE2vid()
         model.num_encoders = 3
@@ -113,7 +111,9 @@ def build_model(model_name, checkpoint):
         model = model_arch.FireNet_legacy(unet_kwargs)
     else:
         model = checkpoint['config'].init_obj('arch', model_arch)
-        if model_name == "FireNet+":
+        if model_name == "ET-Net":                        # eval.py:149-152
+            model.num_encoders = 3
+        elif model_name == "FireNet+":
             model.num_encoders = 0
     return model, checkpoint['state_dict']
 

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-ARCH_UNET, ARCH_FIRENET_LEGACY, ARCH_FIRENET, ARCH_SPADE = 0, 1, 2, 3
+ARCH_UNET, ARCH_FIRENET_LEGACY, ARCH_FIRENET, ARCH_SPADE, ARCH_ETNET = 0, 1, 2, 3, 4
 
 
 class _NativeModel:
@@ -416,6 +416,43 @@ class SpadeE2vid(_NativeModel):
     @states.setter
     def states(self, states):
         if states is None or self._handle is None:
+            _NativeModel.reset_states(self)
+            return
+        flat = []
+        for h, c in states:
+            flat += [h, c]
+        self._set_states(flat)
+
+
+class EITR(_NativeModel):
+    """model/eitr/eitr.py:4-16 over model/eitr/u_trans.py:13-123 (mls_tpa, pretrained/ET-Net): ``EITR(eitr_kwargs)`` with
+    ``num_bins`` and ``norm``; eval.py:149-150 sets ``num_encoders = 3`` on the instance.  ``states`` are the three ConvLSTM
+    (hidden, cell) pairs of the recurrent encoders.  Only norm = None (the shipped checkpoint) is built."""
+    _prefix = ''
+    _arch = ARCH_ETNET
+
+    def __init__(self, eitr_kwargs):
+        super().__init__()
+        self.num_bins = int(eitr_kwargs['num_bins'])
+        if eitr_kwargs.get('norm', None) not in (None, 'none', 'None'):
+            raise _lib.EvkError("ET-Net with norm=%r is not built (the shipped checkpoint has none)" % (eitr_kwargs.get('norm'),))
+        self.num_encoders = 3
+
+    def _config(self, batch, height, width):
+        return _lib.ModelConfig(arch=ARCH_ETNET, num_bins=self.num_bins, base_channels=32, num_encoders=3, num_residual_blocks=0,
+                                kernel_size=5, num_output_channels=1, final_sigmoid=1, dynamic_decoder=0, batch=batch, height=height,
+                                width=width, precision=self.precision)
+
+    @property
+    def states(self):
+        s = self._get_states()
+        if s is None:
+            return [None] * 3
+        return [(s[2 * i], s[2 * i + 1]) for i in range(3)]
+
+    @states.setter
+    def states(self, states):
+        if self._handle is None or all(s is None for s in states):
             _NativeModel.reset_states(self)
             return
         flat = []

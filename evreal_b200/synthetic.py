@@ -196,6 +196,55 @@ def spade_state_dict(seed=0):
     return w
 
 
+def etnet_state_dict(seed=0):
+    """pretrained/ET-Net (model/eitr/u_trans.py mls_tpa, norm None) state_dict: fixed widths."""
+    import torch
+    g = np.random.default_rng(seed)
+    w = {}
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+
+    def put(pfx, d):
+        for kk, v in d.items():
+            w[pfx + '.' + kk] = v
+
+    def linear(pfx, out_c, in_c, gain=1.0):
+        w[pfx + '.weight'] = f32(g.standard_normal((out_c, in_c)) * (gain / in_c ** 0.5))
+        w[pfx + '.bias'] = f32(g.standard_normal(out_c) * 0.05)
+
+    def ln(pfx):
+        w[pfx + '.weight'] = f32(1.0 + 0.1 * g.standard_normal(256))
+        w[pfx + '.bias'] = f32(0.05 * g.standard_normal(256))
+
+    def mha(pfx):
+        w[pfx + '.in_proj_weight'] = f32(g.standard_normal((768, 256)) / 16.0)
+        w[pfx + '.in_proj_bias'] = f32(g.standard_normal(768) * 0.05)
+        linear(pfx + '.out_proj', 256, 256)
+    put('head.conv2d', _conv_w(g, 32, 5, 5))
+    cin = 32
+    for i in range(3):
+        put('DownsampleConv.%d.conv.conv2d' % i, _conv_w(g, 2 * cin, cin, 5, gain=1.4))
+        put('DownsampleConv.%d.recurrent_block.Gates' % i, _conv_w(g, 8 * cin, 4 * cin, 3))
+        cin *= 2
+    put('split1', _conv_w(g, 256, 128, 2))
+    put('split2', _conv_w(g, 256, 64, 4))
+    for s_ in range(3):
+        for i in range(3):
+            p = 'trans_encoder%d.encoder.layers.%d' % (s_, i)
+            mha(p + '.self_attn'); ln(p + '.norm1'); ln(p + '.norm2')
+            linear(p + '.linear1', 1024, 256, 1.4); linear(p + '.linear2', 256, 1024)
+        for i in range(2):
+            p = 'trans_decoder%d.decoder.layers.%d' % (s_, i)
+            mha(p + '.self_attn'); mha(p + '.cross_attn')
+            for nn_ in ('norm1', 'norm21', 'norm22', 'norm3'):
+                ln(p + '.' + nn_)
+            linear(p + '.linear1', 1024, 256, 1.4); linear(p + '.linear2', 256, 1024)
+    for i in range(3):
+        put('UpsampleConv.%d.conv2d' % i, _conv_w(g, cin // 2, cin, 5, gain=1.4))
+        cin //= 2
+    put('pred.conv2d', _conv_w(g, 1, 32, 1))
+    return w
+
+
 E2VID_KWARGS = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
                 'base_num_channels': 32, 'num_residual_blocks': 2, 'use_upsample_conv': True, 'norm': 'BN',
                 'final_activation': 'sigmoid'}

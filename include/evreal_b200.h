@@ -94,6 +94,7 @@ typedef struct evk_model evk_model;
 #define EVK_ARCH_FIRENET_LEGACY 1   /* FireNet_legacy  (pretrained/FireNet)  */
 #define EVK_ARCH_FIRENET 2          /* FireNet         (pretrained/FireNet+) */
 #define EVK_ARCH_SPADE_E2VID 3      /* Unet6           (pretrained/SPADE-E2VID; model/spade_e2v.py:113-179) */
+#define EVK_ARCH_ETNET 4            /* EITR / mls_tpa  (pretrained/ET-Net; model/eitr/u_trans.py:13-123) */
 
 typedef struct {
     int arch;                 /* EVK_ARCH_* */

@@ -22,6 +22,7 @@ Follows, in /root/reference:
   model/model.py:147-190       FireNet (FireNet+ checkpoint)
   model/legacy.py:32-111,155+  UNetFire / FireNet_legacy (FireNet checkpoint)
   model/hyper/hyper_dynamic.py:7-92  context fusion, atom generation, dynamic conv
+  model/eitr/*.py              ET-Net (u_trans.py:13-123 mls_tpa, transformer_encoder.py, transformer_decoder.py, position_encoding.py)
   model/spade_e2v.py:7-179     SPADE-E2VID (Unet6: stride-1 recurrent encoder at full resolution, pixel-shuffle decoders with
                                SPADE normalisation conditioned on the previous reconstruction, recurrent last decoder)
 """
@@ -284,6 +285,105 @@ class SpadeE2vidOracle:
         self.states = [s0, s1, s2, s3]
         self.prev_recs = img
         return img.mean(1, keepdim=True)
+
+
+def sine_position_table(n, d=256):
+    """model/eitr/position_encoding.py:15-23 (float64 table, stored as float32)."""
+    import numpy as np
+    pos = np.arange(n, dtype=np.float64)[:, None]
+    j = np.arange(d)
+    ang = pos / np.power(10000, 2 * (j // 2) / d)
+    ang[:, 0::2] = np.sin(ang[:, 0::2])
+    ang[:, 1::2] = np.cos(ang[:, 1::2])
+    return torch.from_numpy(ang.astype(np.float32))
+
+
+def _mha(w, pfx, q_in, kv_in, nhead=8):
+    """nn.MultiheadAttention forward (eval, no masks): tokens [L, N, E]; in_proj split q | k | v; q scaled by head_dim^-0.5."""
+    L, N, E = q_in.shape
+    S = kv_in.shape[0]
+    Wi, bi = w[pfx + '.in_proj_weight'], w[pfx + '.in_proj_bias']
+    q = F.linear(q_in, Wi[:E], bi[:E])
+    k = F.linear(kv_in, Wi[E:2 * E], bi[E:2 * E])
+    v = F.linear(kv_in, Wi[2 * E:], bi[2 * E:])
+    hd = E // nhead
+    q = q.reshape(L, N * nhead, hd).transpose(0, 1) * (hd ** -0.5)
+    k = k.reshape(S, N * nhead, hd).transpose(0, 1)
+    v = v.reshape(S, N * nhead, hd).transpose(0, 1)
+    a = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)
+    o = torch.bmm(a, v).transpose(0, 1).reshape(L, N, E)
+    return F.linear(o, w[pfx + '.out_proj.weight'], w[pfx + '.out_proj.bias'])
+
+
+def _ln(w, pfx, x):
+    return F.layer_norm(x, (x.shape[-1],), w[pfx + '.weight'], w[pfx + '.bias'], 1e-5)
+
+
+def _ffn(w, pfx, x):
+    return F.linear(torch.relu(F.linear(x, w[pfx + '.linear1.weight'], w[pfx + '.linear1.bias'])), w[pfx + '.linear2.weight'],
+                    w[pfx + '.linear2.bias'])
+
+
+class ETNetOracle:
+    """pretrained/ET-Net (model/eitr/u_trans.py:13-123, transformer_encoder.py, transformer_decoder.py): E2VID's head, three
+    recurrent stride-2 encoders and upsample-conv decoders around a multi-scale token path -- the 1/8-resolution feature map
+    and 2x2 / 4x4 patch embeddings of the 1/4 and 1/2 maps, each through three pre-norm encoder layers (sine positions added
+    once), then two-layer decoders with cross attention to the coarser scale's tokens; the six token sets are averaged."""
+    num_encoders = 3          # eval.py:152-153
+
+    def __init__(self, weights):
+        self.w = weights
+        self.reset_states()
+
+    def reset_states(self):
+        self.states = [None] * 3
+
+    def _encoder(self, pfx, src, pos, layers=3):
+        w = self.w
+        x = src + pos
+        for i in range(layers):
+            p = '%s.encoder.layers.%d' % (pfx, i)
+            n = _ln(w, p + '.norm1', x)
+            x = x + _mha(w, p + '.self_attn', n, n)
+            x = x + _ffn(w, p, _ln(w, p + '.norm2', x))
+        return x
+
+    def _decoder(self, pfx, tgt, memory, layers=2):
+        w = self.w
+        x = tgt
+        for i in range(layers):
+            p = '%s.decoder.layers.%d' % (pfx, i)
+            n = _ln(w, p + '.norm1', x)
+            x = x + _mha(w, p + '.self_attn', n, n)
+            x = x + _mha(w, p + '.cross_attn', _ln(w, p + '.norm21', x), _ln(w, p + '.norm22', memory))
+            x = x + _ffn(w, p, _ln(w, p + '.norm3', x))
+        return x
+
+    @torch.no_grad()
+    def __call__(self, x):
+        w = self.w
+        x = conv_layer(w, 'head', x, 1, 2)
+        head = x
+        blocks = []
+        for i in range(3):
+            x = conv_layer(w, 'DownsampleConv.%d.conv' % i, x, 2, 2)
+            self.states[i] = conv_lstm(w, 'DownsampleConv.%d.recurrent_block' % i, x, self.states[i])
+            x = self.states[i][0]
+            blocks.append(x)
+        N, _, H, W = head.shape
+        tok = lambda t: t.flatten(2).permute(2, 0, 1)                     # [N, 256, h, w] -> [L, N, 256]
+        words = [tok(blocks[2]), tok(F.conv2d(blocks[1], w['split1.weight'], w['split1.bias'], 2)),
+                 tok(F.conv2d(blocks[0], w['split2.weight'], w['split2.bias'], 4))]
+        pos = sine_position_table(words[0].shape[0])[:, None, :]
+        hs = [self._encoder('trans_encoder%d' % i, words[i], pos) for i in range(3)]
+        hc = [self._decoder('trans_decoder0', hs[0], hs[0]), self._decoder('trans_decoder1', hs[1], hs[0]),
+              self._decoder('trans_decoder2', hs[2], hs[1])]
+        t = (hs[0] + hs[1] + hs[2] + hc[0] + hc[1] + hc[2]) / 6
+        y = t.permute(1, 2, 0).reshape(N, 256, H // 8, W // 8)
+        for i in range(3):
+            y = upsample_conv(w, 'UpsampleConv.%d' % i, y + blocks[2 - i], 5)
+        img = conv_layer(w, 'pred', y + head, 1, 0, relu=False)
+        return torch.sigmoid(img)
 
 
 # ---------------------------------------------------------------------------

@@ -81,3 +81,14 @@ def test_spade_e2vid_oracle_vs_real_class():
     got = _run(o, g['seeded.voxels'])
     ref = g['seeded.frames']
     assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= 2e-6
+
+
+def test_etnet_oracle_vs_real_class():
+    """ET-Net (model/eitr/*) restatement against frames of the real EITR class with seeded weights (regenerated here from the
+    seed): batch 2, 40x56 (35 tokens per scale), three recurrent frames."""
+    from evreal_b200 import synthetic
+    g = golden('etnet')
+    o = on.ETNetOracle(synthetic.etnet_state_dict(9))
+    got = _run(o, g['seeded.voxels'])
+    ref = g['seeded.frames']
+    assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= 2e-6

@@ -595,6 +595,43 @@ def golden_spade(copy_ckpt=True):
     np.savez_compressed(os.path.join(OUT, 'spade.npz'), **out)
 
 
+def golden_etnet(copy_ckpt=True):
+    """ET-Net (model/eitr) through the REAL class: seeded weights from evreal_b200.synthetic (regenerated by the test), batch 2,
+    40x56 (35 tokens), three recurrent frames; and the shipped checkpoint at 180x240 (690 tokens), three frames."""
+    import shutil
+    import model as model_arch
+    from utils.event_utils import events_to_voxel_torch
+    from utils.util import CropParameters
+    out = {}
+    m = model_arch.EITR({'num_bins': 5, 'norm': None})
+    m.load_state_dict(synthetic.etnet_state_dict(9))
+    m.eval()
+    voxels = _small_voxels(70, 3, 2, 40, 56)
+    out['seeded.frames'] = _run_frames(m, voxels)
+    out['seeded.voxels'] = torch.stack(voxels).numpy()
+    src = os.path.join(REF, 'pretrained/ET-Net/model.pth')
+    if copy_ckpt:
+        os.makedirs(os.path.join(OUT, '_ckpt'), exist_ok=True)
+        shutil.copyfile(src, os.path.join(OUT, '_ckpt', 'ET-Net.pth'))
+    ck = torch.load(src, map_location='cpu')
+    m = ck['config'].init_obj('arch', model_arch)
+    m.load_state_dict(ck['state_dict'])
+    m.eval()
+    H, W = 180, 240
+    cp = CropParameters(W, H, 3)
+    frames, sums = [], []
+    m.reset_states()
+    with torch.no_grad():
+        for f in range(3):
+            v = events_to_voxel_torch(*[torch.from_numpy(a) for a in gen_events(40 + f, 15000 + 7000 * f, H, W)], 5, sensor_size=(H, W))[None]
+            sums.append([float(v.sum(dtype=torch.float64)), float(v.abs().sum(dtype=torch.float64))])
+            frames.append(cp.crop(m(cp.pad(v))['image'])[0, 0].numpy().copy())
+    out['ckpt.frames'] = np.stack(frames).astype(np.float32)
+    out['ckpt.voxel_sums'] = np.array(sums)
+    print('etnet seeded mean %.5f  ckpt frames mean' % out['seeded.frames'].mean(), [float(f.mean()) for f in frames])
+    np.savez_compressed(os.path.join(OUT, 'etnet.npz'), **out)
+
+
 def golden_colornet():
     """The REAL ColorNet (model/model.py:46-105) around the real FireNet checkpoint on a Bayer-sized input: merged colour
     frames over three recurrent steps (five batch-1 forwards per frame with swapped states in the reference)."""
@@ -627,6 +664,9 @@ if __name__ == '__main__':
     if '--only-spade' in sys.argv:
         golden_spade()
         sys.exit(0)
+    if '--only-etnet' in sys.argv:
+        golden_etnet()
+        sys.exit(0)
     if '--round2' in sys.argv:        # round-2 fixtures only (the round-1 ones stay byte-identical)
         if '--only-color' not in sys.argv:
             golden_real_slices()
@@ -635,6 +675,7 @@ if __name__ == '__main__':
                 golden_eval_loop_modes(tmp)
         golden_colornet()
         golden_spade()
+        golden_etnet()
         sys.exit(0)
     with tempfile.TemporaryDirectory() as tmp:
         golden_voxel()
@@ -649,5 +690,6 @@ if __name__ == '__main__':
         golden_eval_loop_modes(tmp)
         golden_colornet()
         golden_spade()
+        golden_etnet()
     for f in sorted(os.listdir(OUT)):
         print('%8.1f kB  %s' % (os.path.getsize(os.path.join(OUT, f)) / 1e3, f))
