@@ -95,6 +95,15 @@ struct ConvParams {
     // skip operand of the fused prediction layer as split-bf16 planes (hi + lo = the value to 2^-17): when set it replaces
     // pred_skip, and the producer of the skip tensor (the head) need not write its fp32 copy at all
     const __nv_bfloat16* pred_skip_s = nullptr; long long pred_skip_plane = 0;
+    // "mixed" operand decomposition (conv_tc.cu, MIXED kernels): x.w ~ x16.w16 + x8.wl8 + xl8.w8 -- one fp16 product and two fp8
+    // products at twice the rate (2 tensor-pipe units instead of the 3 of bf16x3; measured 1.5-2.5e-5 end to end on the shipped
+    // E2VID weights against 5e-6, tools/mixed_numerics_probe.py).  mixed = 1: x1s / x2s are mixed-format companions (plane 0 =
+    // fp16(16 v), plane 1 = per 64-channel chunk [e5m2(v) | e5m2(4096 (v - x16))]) and the kernel reads w_mx / w_iscale.
+    // Plain layers only (c1, c2 multiples of 64; no row-window / pixel-pair / row-pair forms).
+    int mixed = 0;
+    const __nv_bfloat16* w_mx = nullptr;  // [2][cout_pad][K] 2-byte slots: plane 0 fp16(w S[n] / 16), plane 1 per 64-k chunk [e4m3(wl S[n]) | e4m3(w S[n] / 4096)]
+    const float* w_iscale = nullptr;      // [cout_pad] 1 / S[n] (S[n] a power of two)
+    int ys_mixed = 0, hs_mixed = 0;       // the split copy this layer writes (ys / hs_new) is in the mixed format
     struct TcPlan* tc = nullptr;          // tensor maps + tiling, built once per layer (tc_plan_create)
 };
 
@@ -108,6 +117,11 @@ int launch_split(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s
 // host: fp32 [K][cout] (K-major rows of the SIMT layout) -> bf16 [2][cout_pad][K]
 void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out);
 
+// host: fp32 [K][cout] -> mixed-format weights (ConvParams::w_mx, K % 64 == 0) and the inverse column scales
+void pack_weights_mixed(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out, std::vector<float>& iscale);
+bool tc_mixed_capable(const ConvParams& p);      // layer shape can run as a MIXED kernel
+// fp32 NHWC [pixels][C] (C % 64 == 0) -> mixed-format companion
+int launch_split_mixed(const float* src, __nv_bfloat16* dst, int64_t pixels, int C, cudaStream_t st);
 // host: fp32 [kh*kw*cin][cout] (kw = 5, stride 2) -> pixel-pair weights [kh*3*(2*cin)][cout] (see ConvParams::stride_x)
 void pack_weights_pixel_pair(const float* w_kc, int kh, int kw, int cin, int cout, std::vector<float>& out);
 // host: fp32 [kh*kw*cin][cout] -> row-pair weights [ (kh+1)*kw*cin ][2*cout] (see ConvParams::row_pair)
@@ -119,9 +133,9 @@ void pack_weights_phase4(const float* w_kc, int cin, int cout, std::vector<float
 // host: NEGATED pre-summed out-of-bounds tap weights of the two border-line convolutions, [2][5*cin][4*cout]
 void pack_weights_ring(const float* w_kc, int cin, int cout, std::vector<float>& out);
 // out[2][N][H+4][W+4][C] = split_bf16(x + skip), replicate padding of 2
-int launch_add_pad_split(const float* x, const float* skip, __nv_bfloat16* out, int N, int H, int W, int C, cudaStream_t st);
+int launch_add_pad_split(const float* x, const float* skip, __nv_bfloat16* out, int N, int H, int W, int C, cudaStream_t st, int mixed = 0);
 // u_ext just outside the four borders as split-bf16 line images [2][2N][2W+4][C] (horizontal) / [2][2N][2H+4][C] (vertical)
-int launch_ring_lines(const __nv_bfloat16* xp, __nv_bfloat16* lines_h, __nv_bfloat16* lines_v, int N, int H, int W, int C, cudaStream_t st);
+int launch_ring_lines(const __nv_bfloat16* xp, __nv_bfloat16* lines_h, __nv_bfloat16* lines_v, int N, int H, int W, int C, cudaStream_t st, int mixed = 0);
 
 int launch_conv_simt(const ConvParams& p, cudaStream_t st);
 // dispatcher: tensor-core split-bf16 kernel when the shape qualifies and precision == 0, else fp32 SIMT

@@ -32,6 +32,7 @@
 // (thread = accumulator row = output pixel).  Two independent shared-memory rings (A: box stages, B: one K block per
 // stage); the accumulator is double-buffered in tensor memory so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -75,6 +76,8 @@ struct TcArgs {
     int acc_stride;             // TMEM columns per accumulator stage (= acc_cols, or 2 * acc_cols with own_acc)
     uint32_t tmem_cols;
     const float* bias;
+    const float* iscale;        // MIXED kernels: 1 / S[n] per packed output column (ConvParams::w_iscale)
+    int ys_mixed, hs_mixed;     // the split copy written by this epilogue is in the mixed (fp16 | fp8 pair) format
     const float* res;
     float* y;
     __nv_bfloat16* ys; long long ys_plane;
@@ -93,6 +96,7 @@ struct TcPlan {
     CUtensorMap tm_x1, tm_x2, tm_w;
     TcArgs a;
     int bk;
+    bool mixed = false;
     dim3 grid;
     size_t smem;
 };
@@ -118,6 +122,17 @@ __device__ __forceinline__ float fast_act(float v, int act) {
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* w) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
                  "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
+// 16 channels held as fp32 bit patterns v[0..15]
+__device__ __forceinline__ void store_mixed16(__nv_bfloat16* base, long long plane, size_t o, int c0, const uint32_t* v) {
+    uint32_t h[8], x[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mixed_cvt2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]), h[i], x[i], l[i]);
+    st_global_v8(base + o, h);
+    uint8_t* b1 = reinterpret_cast<uint8_t*>(base + plane) + 2 * o - (size_t)(c0 & 63);
+    *reinterpret_cast<uint4*>(b1) = make_uint4(x[0] | (x[1] << 16), x[2] | (x[3] << 16), x[4] | (x[5] << 16), x[6] | (x[7] << 16));
+    *reinterpret_cast<uint4*>(b1 + 64) = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
 }
 
 struct TileCoord { int nt, img, ou0, ov0; bool dummy; };
@@ -150,7 +165,7 @@ __device__ __forceinline__ void tv_range(const TcArgs& a, int nt, int ntaps, int
     if (a.ps == 3) { if ((nt & 1) == 0) tv1 = ntaps - 1; else tv0 = 1; }
 }
 
-template <int BK, bool DBG>
+template <int BK, bool DBG, bool MIXED = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                const __grid_constant__ CUtensorMap tm_w, const TcArgs a) {
@@ -331,8 +346,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         // not seen complete yet (the parity test would pass on the stale phase).
         // Barriers that guard data read by both issuers' MMAs (A stage free, accumulator complete) count two commits.
         const uint32_t role = (uint32_t)(warp - 1);
-        const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * a.bn));
-        const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)a.bn);
+        // MIXED (see "mixed operands" at the top of the host section): plane 0 = fp16, plane 1 = fp8 pairs; per 32-byte K step
+        //   D[:, 0:bn] (+)= A16 * B16^T  (kind::f16, K = 16)   and   D[:, 0:bn] += [x8 | xl8] * [wl8 | w8]^T  (kind::f8f6f4, K = 32)
+        const uint32_t idesc2 = MIXED ? umma_idesc_f16(128, (uint32_t)a.bn) : umma_idesc_bf16(128, (uint32_t)(2 * a.bn));
+        const uint32_t idesc1 = MIXED ? umma_idesc_f8_e5m2_e4m3(128, (uint32_t)a.bn) : umma_idesc_bf16(128, (uint32_t)a.bn);
+        const uint32_t b2 = MIXED ? (b_plane >> 4) : 0u;      // second MMA's weight operand: plane 1 (MIXED) or B_hi again
         const uint32_t desc_hi = (uint32_t)(umma_desc_kmajor(0, ROW_BYTES) >> 32);
         auto mk = [&](uint32_t lo) -> uint64_t { return ((uint64_t)desc_hi << 32) | lo; };
         auto lo_of = [](uint32_t addr) -> uint32_t { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
@@ -394,7 +412,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                         for (int k = 0; k < BK / 16; ++k) {
                                             // +16 elements (32 B) along K inside the swizzle atom = +2 in the 16-byte address field
                                             tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, k == 0 ? acc0 : 1u);
-                                            tc_mma_bf16(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + 2 * k), idesc1, 1u);
+                                            if (MIXED) tc_mma_f8(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + b2 + 2 * k), idesc1, 1u);
+                                            else tc_mma_bf16(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + 2 * k), idesc1, 1u);
                                         }
                                     } else {
                                         uint32_t al = ah_lo, bl = bh_lo, acc = acc0;
@@ -403,7 +422,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                             for (int k = 0; k < BK / 16; ++k) {
                                                 tc_mma_bf16(d_tmem, mk(al + 2 * k), mk(bl + 2 * k), idesc2, acc);
                                                 acc = 1u;
-                                                tc_mma_bf16(d_tmem, mk(al + a_plane16 + 2 * k), mk(bl + 2 * k), idesc1, 1u);
+                                                if (MIXED) tc_mma_f8(d_tmem, mk(al + a_plane16 + 2 * k), mk(bl + b2 + 2 * k), idesc1, 1u);
+                                                else tc_mma_bf16(d_tmem, mk(al + a_plane16 + 2 * k), mk(bl + 2 * k), idesc1, 1u);
                                             }
                                         }
                                     }
@@ -465,25 +485,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                 __syncwarp();                     // tcgen05.ld is .sync.aligned: reconverge after the masked stores
                 const long long t_c0 = DBG ? clock64() : 0;
                 {
+                    // bf16x3: columns [0, bn) hold hi*hi + lo*hi, columns [bn, 2bn) hi*lo; MIXED: one accumulator of bn columns
                     uint32_t u[32];
                     if (cw == 32) {
                         tc_ld_32x32(t_row + (uint32_t)j0, v);
-                        tc_ld_32x32(t_row + (uint32_t)(a.bn + j0), u);
+                        if (!MIXED) tc_ld_32x32(t_row + (uint32_t)(a.bn + j0), u);
                     } else if (cw == 16) {
 #pragma unroll
                         for (int i = 16; i < 32; ++i) { v[i] = 0u; u[i] = 0u; }
                         tc_ld_32x16(t_row + (uint32_t)j0, v);
-                        tc_ld_32x16(t_row + (uint32_t)(a.bn + j0), u);
+                        if (!MIXED) tc_ld_32x16(t_row + (uint32_t)(a.bn + j0), u);
                     } else {
 #pragma unroll
                         for (int i = 8; i < 32; ++i) { v[i] = 0u; u[i] = 0u; }
                         tc_ld_32x8(t_row + (uint32_t)j0, v);
-                        tc_ld_32x8(t_row + (uint32_t)(a.bn + j0), u);
+                        if (!MIXED) tc_ld_32x8(t_row + (uint32_t)(a.bn + j0), u);
+                    }
+                    if (MIXED && a.own_acc) {         // second issuer's accumulator
+                        if (cw == 32) tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + j0), u);
+                        else if (cw == 16) tc_ld_32x16(t_row + (uint32_t)(a.acc_cols + j0), u);
+                        else tc_ld_32x8(t_row + (uint32_t)(a.acc_cols + j0), u);
                     }
                     tc_wait_ld();
+                    if (!MIXED || a.own_acc) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-                    if (a.own_acc) {                  // second issuer's accumulator (fixed order: deterministic bits)
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+                    }
+                    if (!MIXED && a.own_acc) {        // second issuer's accumulator (fixed order: deterministic bits)
                         uint32_t w[32];
                         if (cw == 32) {
                             tc_ld_32x32(t_row + (uint32_t)(a.acc_cols + j0), u);
@@ -515,6 +543,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                 }
                 const int nb = n0 + j0;
                 if (!valid || nb >= a.cout || (DBG && (a.exp & 4))) continue;
+                if (MIXED) {                      // the accumulator holds S[n] * (x . w): undo the per-column weight scale (a power of two)
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (g * 4 >= cw) break;
+                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.iscale + nb + g * 4));
+                        v[g * 4 + 0] = __float_as_uint(__uint_as_float(v[g * 4 + 0]) * s4.x);
+                        v[g * 4 + 1] = __float_as_uint(__uint_as_float(v[g * 4 + 1]) * s4.y);
+                        v[g * 4 + 2] = __float_as_uint(__uint_as_float(v[g * 4 + 2]) * s4.z);
+                        v[g * 4 + 3] = __float_as_uint(__uint_as_float(v[g * 4 + 3]) * s4.w);
+                    }
+                }
                 if (a.epi == EPI_LINEAR && a.fastlin && cw == 32) {
                     // Straight-line form of the common case (bias [+ residual] -> ReLU / none -> fp32 and / or split-bf16 stores,
                     // channel counts multiples of 32): no per-group branches, all loads issued up front.  The generic path below
@@ -543,7 +582,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
 #pragma unroll
                         for (int g = 0; g < 4; ++g) st_global_v8(a.y + o + g * 8, &v[g * 8]);
                     }
-                    if (a.ys != nullptr) {
+                    if (a.ys != nullptr && a.ys_mixed) {
+                        store_mixed16(a.ys, a.ys_plane, o, nb, &v[0]);
+                        store_mixed16(a.ys, a.ys_plane, o + 16, nb + 16, &v[16]);
+                    } else if (a.ys != nullptr) {
                         uint32_t hw[16], lw[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -558,7 +600,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         st_global_v8(a.ys + a.ys_plane + sd + o, lw);
                         st_global_v8(a.ys + a.ys_plane + sd + o + 16, lw + 8);
                     }
-                } else if (a.epi == EPI_LINEAR && a.fastlin && cw == 16) {
+                } else if (!MIXED && a.epi == EPI_LINEAR && a.fastlin && cw == 16) {
                     // 16-column variant of the straight-line linear epilogue (32-column tiles split between the two warp halves)
                     const size_t o = pix * a.creal + nb;
                     float4 b4[4], r4[4];
@@ -752,7 +794,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
 #pragma unroll
                             for (int i = 0; i < 4; ++i) v[g * 4 + i] = __float_as_uint(f[i]);
                             if ((g & 1) && a.y != nullptr) st_global_v8(a.y + o + (g - 1) * 4, &v[(g - 1) * 4]);
-                            if ((g & 3) == 3 && a.ys != nullptr) {
+                            if ((g & 3) == 3 && a.ys != nullptr && a.ys_mixed) {
+                                store_mixed16(a.ys, a.ys_plane, o + (g - 3) * 4, nbr + (g - 3) * 4, &v[(g - 3) * 4]);
+                            } else if ((g & 3) == 3 && a.ys != nullptr) {
                                 uint32_t hw[8], lw[8];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
@@ -780,7 +824,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         pacc += a.pred_bias;
                         a.pred_out[pixl] = a.pred_sigmoid ? sigmoidf_(pacc) : pacc;
                     }
-                } else if (a.epi == EPI_GRU_UR && a.fastgru && cw == 32) {
+                } else if (!MIXED && a.epi == EPI_GRU_UR && a.fastgru && cw == 32) {
                     // straight-line form (window-mode FireNet): 16 channels x {update, reset} per chunk, loads up front, SFU gates
                     const size_t o = pix * (size_t)(a.cout >> 1) + (nb >> 1);
                     float4 b4[8], hp[4];
@@ -816,7 +860,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         st_global_v8(a.hrs_out + sd + o, hi8);
                         st_global_v8(a.hrs_out + a.hs_plane + sd + o, lo8);
                     }
-                } else if (a.epi == EPI_GRU_OUT && a.fastgru && cw == 16) {
+                } else if (!MIXED && a.epi == EPI_GRU_OUT && a.fastgru && cw == 16) {
                     // straight-line form: 16 channels per chunk; h' = h (1 - u) + tanh(.) u in the reference's operation order
                     const size_t o = pix * (size_t)a.cout + nb;
                     float4 b4[4], u4[4], h4[4];
@@ -851,7 +895,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         st_global_v8(a.hs_new + sd + o, hi8);
                         st_global_v8(a.hs_new + a.hs_plane + sd + o, lo8);
                     }
-                } else if (a.epi == EPI_GRU_UR) {   // packed column = channel*2 + {update, reset} (model/submodules.py:281-282)
+                } else if (!MIXED && a.epi == EPI_GRU_UR) {   // packed column = channel*2 + {update, reset} (model/submodules.py:281-282)
                     const int C = a.cout >> 1;
                     const size_t o = pix * C + (nb >> 1);
                     float hr[16];
@@ -876,7 +920,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             *reinterpret_cast<uint2*>(a.hrs_out + a.hs_plane + sd + o + g * 4) = *reinterpret_cast<uint2*>(lo);
                         }
                     }
-                } else if (a.epi == EPI_GRU_OUT) {  // h' = h (1 - u) + tanh(.) u (model/submodules.py:283-285)
+                } else if (!MIXED && a.epi == EPI_GRU_OUT) {  // h' = h (1 - u) + tanh(.) u (model/submodules.py:283-285)
                     const size_t o = pix * a.cout + nb;
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
@@ -922,7 +966,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                     *reinterpret_cast<float4*>(a.c_new + o + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
                     *reinterpret_cast<float4*>(a.h_new + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                     *reinterpret_cast<float4*>(a.h_new + o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-                    if (a.hs_new != nullptr) {
+                    if (a.hs_new != nullptr && a.hs_mixed) {
+                        store_mixed8(a.hs_new, a.hs_plane, o, nb >> 2, hn);
+                    } else if (a.hs_new != nullptr) {
                         __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) split_bf16(hn[i], hi[i], lo[i]);
@@ -1048,6 +1094,39 @@ void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vect
         }
 }
 
+// Mixed operands.  With S = S[n] (a power of two per output channel, max|w[:, n]| S in (2^17.8, 2^18.8]):
+//   plane 0:  w16 = fp16(w S / 16)                       x16 side: fp16(16 x)            product = S x16 w16
+//   plane 1:  wl8 = e4m3((w - 16 w16 / S) S)             x8  = e5m2(x)                   product = S x wl
+//             w8  = e4m3(w S / 4096)                     xl8 = e5m2(4096 (x - x16))      product = S xl w
+// so the accumulator is S[n] (x . w) and the epilogue multiplies column n by 1 / S[n] (exact).  |16 w16| <= 28672, |wl S| <= 128,
+// |w8| <= 112: inside fp16 / e4m3; activations up to 4094 before fp16 saturates.
+void pack_weights_mixed(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out, std::vector<float>& iscale) {
+    out.assign((size_t)2 * cout_pad * K, __float2bfloat16(0.0f));
+    iscale.assign((size_t)cout_pad + 32, 1.0f);
+    uint16_t* p0 = reinterpret_cast<uint16_t*>(out.data());
+    uint8_t* p1 = reinterpret_cast<uint8_t*>(out.data() + (size_t)cout_pad * K);
+    for (int n = 0; n < cout; ++n) {
+        float wmax = 0.f;
+        for (int k = 0; k < K; ++k) wmax = std::max(wmax, std::fabs(w_kc[(size_t)k * cout + n]));
+        const float S = wmax > 0.f ? std::exp2(std::floor(std::log2(458752.0f / wmax))) : 1.0f;
+        iscale[n] = 1.0f / S;
+        for (int k = 0; k < K; ++k) {
+            const float w = w_kc[(size_t)k * cout + n];
+            const __half h = __float2half_rn(w * S * 0.0625f);
+            p0[(size_t)n * K + k] = *reinterpret_cast<const uint16_t*>(&h);
+            const float wl = w - __half2float(h) * 16.0f / S;
+            uint8_t* row = p1 + ((size_t)n * K + (size_t)(k / 64) * 64) * 2;
+            row[k % 64] = (uint8_t)__nv_cvt_float_to_fp8(wl * S, __NV_SATFINITE, __NV_E4M3);
+            row[64 + k % 64] = (uint8_t)__nv_cvt_float_to_fp8(w * S * (1.0f / 4096.0f), __NV_SATFINITE, __NV_E4M3);
+        }
+    }
+}
+
+bool tc_mixed_capable(const ConvParams& p) {
+    return p.c1 > 0 && p.c1 % 64 == 0 && p.c2 % 64 == 0 && !p.kw_packed && !p.win_c && !p.stride_x && !p.row_pair &&
+           (p.epi == EPI_LINEAR || p.epi == EPI_LSTM) && (p.pred_out == nullptr || p.phase4 == 1) && p.cout_pad % 32 == 0 && tc_eligible(p);
+}
+
 template <int BK>
 static int max_clusters(int cs, size_t smem) {
     auto kern = conv_tc_kernel<BK, false>;
@@ -1071,6 +1150,10 @@ static int max_clusters(int cs, size_t smem) {
 int tc_plan_create(ConvParams& p) {
     EVK_REQUIRE(tc_eligible(p), EVK_ERR_ARG, "conv_tc: shape not eligible for the tensor-core path");
     EVK_REQUIRE(p.x1s && p.w_tc && (p.c2 == 0 || p.x2s), EVK_ERR_ARG, "conv_tc: split operands missing");
+    EVK_REQUIRE(!p.mixed || (tc_mixed_capable(p) && p.w_mx && p.w_iscale), EVK_ERR_ARG, "conv_tc: layer cannot run with mixed operands");
+    EVK_REQUIRE(!(p.ys_mixed || p.hs_mixed) || ((p.epi == EPI_LSTM ? p.cout / 4 : p.cout) % 64 == 0 && !p.row_pair && p.s_wp == 0 &&
+                                                 (p.epi == EPI_LSTM || p.epi == EPI_LINEAR)),
+                EVK_ERR_ARG, "conv_tc: this epilogue cannot write a mixed-format split copy");
     const int bk = pick_bk(p);
     const int cout_pad = p.cout_pad;
     const bool rp = p.row_pair != 0;
@@ -1089,9 +1172,10 @@ int tc_plan_create(ConvParams& p) {
     EVK_CHECK_CUDA(cudaGetDevice(&dev_id));
     const bool attr_set = dev_id >= 0 && dev_id < 64 && attr_set_dev[dev_id];
     if (!attr_set) {
-        const void* kerns[6] = {(const void*)conv_tc_kernel<64, false>, (const void*)conv_tc_kernel<32, false>,
+        const void* kerns[8] = {(const void*)conv_tc_kernel<64, false>, (const void*)conv_tc_kernel<32, false>,
                                 (const void*)conv_tc_kernel<64, true>, (const void*)conv_tc_kernel<32, true>,
-                                (const void*)conv_tc_kernel<16, false>, (const void*)conv_tc_kernel<16, true>};
+                                (const void*)conv_tc_kernel<16, false>, (const void*)conv_tc_kernel<16, true>,
+                                (const void*)conv_tc_kernel<64, false, true>, (const void*)conv_tc_kernel<64, true, true>};
         for (const void* k : kerns) {
             EVK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             EVK_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1113,6 +1197,7 @@ int tc_plan_create(ConvParams& p) {
             if (ps && bn % 32 != 0) continue;             // a 32-column epilogue chunk must not straddle two phases
             if (ps2 && bn != (ps3 ? 1 : 2) * p.cout) continue;        // phase pairs: one row phase per N tile; single phases: one per tile
             if (f_bn > 0 && bn != f_bn && cout_pad % f_bn == 0 && f_bn % granule == 0) continue;
+            if ((p.mixed || p.ys_mixed || p.hs_mixed) && bn % 32 != 0) continue;      // 32-column chunks only
             for (int cs = 1; cs <= 4; cs *= 2) {
                 if ((bn / cs) % 8 != 0 || bn % cs != 0) continue;
                 if (f_cs > 0 && cs != f_cs && (bn / f_cs) % 8 == 0 && f_cs <= 4) continue;
@@ -1130,6 +1215,7 @@ int tc_plan_create(ConvParams& p) {
     int cs = best.cs;
     TcPlan* pl = new TcPlan();
     pl->bk = bk;
+    pl->mixed = p.mixed != 0;
     TcArgs& a = pl->a;
     a.N = p.N; a.Hout = e_hout; a.Wout = p.Wout; a.pad_u = p.kw_packed ? 0 : (ux ? pad_x : p.pad); a.pad_v = ux ? p.pad : pad_x; a.kh = e_kh; a.kw = p.kw;
     a.su = ux ? s_x : s_y; a.sv = ux ? s_y : s_x;
@@ -1140,7 +1226,8 @@ int tc_plan_create(ConvParams& p) {
     const bool predw = p.pred_out != nullptr && p.win_c == 16 && p.kw_group == 2 && p.cout == 32 && bn == 32 && p.epi == EPI_LINEAR && p.pred_skip == nullptr &&
                        p.pred_skip_s == nullptr && !rp && !ps;
     a.predw = predw ? 1 : 0;
-    a.cw = ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_UR || p.epi == EPI_GRU_OUT) && bn == 32 && (p.pred_out == nullptr || predw) && env_int("EVK_TC_CW16", 1)) ? 16 : 32;
+    a.cw = ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_UR || p.epi == EPI_GRU_OUT) && bn == 32 && (p.pred_out == nullptr || predw) && env_int("EVK_TC_CW16", 1) &&
+            !p.mixed && !p.ys_mixed) ? 16 : 32;
     // ... and 8-column chunks for 16-column tiles (FireNet's 16-channel layers)
     if ((p.epi == EPI_LINEAR || p.epi == EPI_GRU_OUT) && bn == 16 && p.pred_out == nullptr && env_int("EVK_TC_CW8", 1)) a.cw = 8;
     a.wide = (p.epi == EPI_LINEAR && p.cout % 16 == 0 && a.cw >= 16 && env_int("EVK_TC_WIDE_ST", 1)) ? 1 : 0;
@@ -1168,6 +1255,7 @@ int tc_plan_create(ConvParams& p) {
     }
     a.ar = 16 + a.g_ntaps[0] - 1;
     a.bias = p.bias; a.res = p.res; a.y = p.y; a.ys = p.ys;
+    a.iscale = p.w_iscale; a.ys_mixed = p.ys_mixed; a.hs_mixed = p.hs_mixed;
     a.pred_skip_s = p.pred_skip_s; a.pred_skip_plane = p.pred_skip_plane;
     a.pred_w = p.pred_w; a.pred_skip = p.pred_skip; a.pred_out = p.pred_out; a.pred_bias = p.pred_bias; a.pred_sigmoid = p.pred_sigmoid;
     if (p.pred_out != nullptr && p.win_c > 0 && !(a.predw && a.fastlin && a.cw == 16)) {
@@ -1216,7 +1304,7 @@ int tc_plan_create(ConvParams& p) {
     if (bs < 2) { delete pl; EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: tile does not fit shared memory (bn=%d)", bn); }
     a.a_stages = as; a.b_stages = bs;
     // per accumulator stage: [hi*hi + lo*hi | hi*lo] = 2*bn columns, read in 32-column windows (bn%32 tail -> pad)
-    a.acc_cols = (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;
+    a.acc_cols = p.mixed ? (bn + 31) / 32 * 32 : (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;      // (MIXED: one accumulator of bn columns)
     const int kb = ps3 ? (a.chunks1 + a.chunks2) * (a.ku - 1) * (a.kv - 1) : (a.chunks1 + a.chunks2) * (ps2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0));
     a.issuers = (kb >= 2 && env_int("EVK_TC_ISSUERS", 2) == 2) ? 2 : 1;
     a.own_acc = (a.issuers == 2 && 4 * a.acc_cols <= 512 && env_int("EVK_TC_OWN_ACC", 1)) ? 1 : 0;
@@ -1268,12 +1356,12 @@ int tc_plan_create(ConvParams& p) {
         const uint64_t str[2] = {K * 2, (uint64_t)cout_pad * K * 2};
         const uint32_t box[3] = {(uint32_t)bk, (uint32_t)(bn / cs), 1};
         const uint32_t es[3] = {1, 1, 1};
-        r = encode_tmap_bf16(&pl->tm_w, p.w_tc, 3, dims, str, box, es, (int)row_bytes);
+        r = encode_tmap_bf16(&pl->tm_w, p.mixed ? p.w_mx : p.w_tc, 3, dims, str, box, es, (int)row_bytes);
     }
     if (r != EVK_OK) { delete pl; return r; }
     if (env_int("EVK_TC_VERBOSE", 0))
-        fprintf(stderr, "conv_tc plan: %dx%d s%d %d+%d->%d @%dx%dx%d  ux=%d bn=%d cs=%d issuers=%d tpb=%d stages A%d/B%d ar=%d grid=%u smem=%zu\n", p.kh, p.kw,
-                p.stride, p.c1, p.c2, p.cout, p.N, p.Hout, p.Wout, ux, bn, cs, a.issuers, a.tpb, as, bs, a.ar, pl->grid.x, pl->smem);
+        fprintf(stderr, "conv_tc plan: %dx%d s%d %d+%d->%d @%dx%dx%d  ux=%d bn=%d cs=%d issuers=%d own_acc=%d tpb=%d stages A%d/B%d ar=%d grid=%u smem=%zu%s\n", p.kh, p.kw,
+                p.stride, p.c1, p.c2, p.cout, p.N, p.Hout, p.Wout, ux, bn, cs, a.issuers, a.own_acc, a.tpb, as, bs, a.ar, pl->grid.x, pl->smem, p.mixed ? " MIXED" : "");
     p.tc = pl;
     return EVK_OK;
 }
@@ -1312,7 +1400,10 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t st) {
     }
     cfg.attrs = at; cfg.numAttrs = (unsigned)na;
     const bool dbg = pl.a.dbg != nullptr;
-    if (pl.bk == 64) {
+    if (pl.mixed) {
+        if (dbg) EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, true, true>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
+        else EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, true>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
+    } else if (pl.bk == 64) {
         if (dbg) EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, true>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
         else EVK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false>, pl.tm_x1, pl.tm_x2, pl.tm_w, pl.a));
     } else if (pl.bk == 32) {
@@ -1447,6 +1538,25 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ sr
 int launch_split(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t st) {
     EVK_REQUIRE(src && dst && n > 0, EVK_ERR_ARG, "split: bad argument");
     split_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n, 256), 2368), 256, 0, st>>>(src, dst, n);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
+// fp32 NHWC -> mixed-format companion (evk_model_set_state), 8 channels per thread
+__global__ void __launch_bounds__(256) split_mixed_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t groups, int C,
+                                                          long long plane) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = i * 8;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(src + o)), a1 = __ldg(reinterpret_cast<const float4*>(src + o + 4));
+        const float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        store_mixed8(dst, plane, (size_t)o, (int)(o % C), f);
+    }
+}
+
+int launch_split_mixed(const float* src, __nv_bfloat16* dst, int64_t pixels, int C, cudaStream_t st) {
+    EVK_REQUIRE(src && dst && pixels > 0 && C % 64 == 0, EVK_ERR_ARG, "split_mixed: bad argument");
+    const int64_t groups = pixels * C / 8;
+    split_mixed_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(groups, 256), 2368), 256, 0, st>>>(src, dst, groups, C, (long long)pixels * C);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

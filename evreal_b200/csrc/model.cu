@@ -40,6 +40,7 @@ struct Op {
     const float* skip = nullptr;
     __nv_bfloat16* out_s = nullptr;   // OP_HEAD / OP_UPSAMPLE_ADD: split-bf16 copy of `out` for a tensor-core consumer
     __nv_bfloat16* lines_h = nullptr; __nv_bfloat16* lines_v = nullptr;   // OP_RING_LINES outputs
+    int mixed = 0;                    // OP_ADD_PAD / OP_RING_LINES: the padded split tensor is in the mixed format (conv.cuh, ConvParams::mixed)
     int ring_line = 0;                // OP_CONV: 1 / 2 = horizontal / vertical border-line convolution of a phase-stacked decoder
     float bias0 = 0.f;
     int sigmoid = 0;
@@ -102,6 +103,10 @@ struct evk_model {
     // row-padded [2][N][H][W + 2][C] (pixel x at column x + 1)
     int win_wp = 0;
     std::map<const float*, size_t> split_bytes;        // allocation size of every split companion
+    // mixed operands (conv.cuh, ConvParams::mixed): on unless EVK_MIXED=0; the fp32 buffers whose companion is in the mixed format
+    bool mixed_enabled = true;
+    std::map<const float*, int> mixed_bufs;            // fp32 buffer -> channels per pixel
+    int mixed_convs = 0;
 
     float* dalloc(size_t nfloat) {
         void* p = nullptr;
@@ -220,6 +225,15 @@ struct Builder {
         void* d = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
         if (d) cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
         p.w_tc = (const __nv_bfloat16*)d;
+        // the mixed-operand form of the same weights (conv.cuh, ConvParams::mixed); wire_tc decides which one the layer runs
+        if (m->mixed_enabled && tc_mixed_capable(p)) {
+            std::vector<float> isc;
+            pack_weights_mixed(pk.w.data(), pk.kh * pk.kw * pk.cin, pk.cout, p.cout_pad, wt, isc);
+            void* dm = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
+            if (dm) cudaMemcpy(dm, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+            p.w_mx = (const __nv_bfloat16*)dm;
+            p.w_iscale = m->upload(isc);
+        }
     }
 
     // Window form of a stride-1 3x3 layer whose input tensors have 16 channels (conv.cuh, ConvParams::win_c): 4 pixels of
@@ -308,7 +322,7 @@ static int add_lstm(Builder& B, const std::string& pfx, const float* x, int C, i
     const float* w = m->upload(pk.w);
     const float* b = m->upload(pk.b);
     ConvParams wt;   // carries the tensor-core weights shared by both parities
-    wt.c1 = C; wt.c2 = C; wt.stride = 1; wt.cout = 4 * C; wt.epi = EPI_LSTM;
+    wt.c1 = C; wt.c2 = C; wt.stride = 1; wt.cout = 4 * C; wt.epi = EPI_LSTM; wt.kh = wt.kw = 3;
     B.attach_tc_weights(wt, pk);
     for (int par = 0; par < 2; ++par) {
         Op op; op.kind = OP_CONV;
@@ -316,7 +330,7 @@ static int add_lstm(Builder& B, const std::string& pfx, const float* x, int C, i
         p.x1 = x; p.c1 = C; p.x2 = m->states[hs].buf[par]; p.c2 = C;
         p.N = B.N; p.Hin = p.Hout = H; p.Win = p.Wout = W; p.kh = p.kw = 3; p.stride = 1; p.pad = 1;
         p.w = w; p.bias = b; p.cout = 4 * C; p.epi = EPI_LSTM;
-        p.w_tc = wt.w_tc; p.cout_pad = wt.cout_pad;
+        p.w_tc = wt.w_tc; p.cout_pad = wt.cout_pad; p.w_mx = wt.w_mx; p.w_iscale = wt.w_iscale;
         p.c_prev = m->states[cs].buf[0]; p.c_new = m->states[cs].buf[0];
         p.h_new = m->states[hs].buf[par ^ 1];
         op.flops = conv_flops(p, 4 * C);
@@ -487,6 +501,8 @@ static int add_poly_decoder(Builder& B, const std::string& pfx, const float* x, 
     if (r != EVK_OK) return r;
     EVK_REQUIRE(pk.cin == C && pk.kh == 5 && pk.kw == 5, EVK_ERR_KEY, "'%s': unexpected decoder shape", pfx.c_str());
     const int Co = pk.cout, N = B.N;
+    const char* mp = getenv("EVK_MIXED_POLY");
+    const int mixed = (m->mixed_enabled && C % 64 == 0 && !(mp && mp[0] == '0')) ? 1 : 0;      // mixed operands (conv.cuh, ConvParams::mixed)
     const size_t plane = (size_t)N * (H + 4) * (W + 4) * C;
     __nv_bfloat16* xp = (__nv_bfloat16*)m->dalloc_bytes(2 * plane * sizeof(__nv_bfloat16));
     // border corrections: u_ext lines just outside the four borders -> two 1x5 tensor-core convolutions (poly.cu)
@@ -497,12 +513,12 @@ static int add_poly_decoder(Builder& B, const std::string& pfx, const float* x, 
     EVK_REQUIRE(xp && lines[0] && lines[1] && ring[0] && ring[1], EVK_ERR_CUDA, "out of device memory for the phase-stacked decoder");
     {
         Op op; op.kind = OP_ADD_PAD;
-        op.in = x; op.skip = skip; op.out_s = xp; op.N = N; op.H = H; op.W = W; op.cin = C;
+        op.in = x; op.skip = skip; op.out_s = xp; op.N = N; op.H = H; op.W = W; op.cin = C; op.mixed = mixed;
         m->ops[0].push_back(op); m->ops[1].push_back(op);
     }
     {
         Op op; op.kind = OP_RING_LINES;
-        op.out_s = xp; op.lines_h = lines[0]; op.lines_v = lines[1]; op.N = N; op.H = H; op.W = W; op.cin = C;
+        op.out_s = xp; op.lines_h = lines[0]; op.lines_v = lines[1]; op.N = N; op.H = H; op.W = W; op.cin = C; op.mixed = mixed;
         m->ops[0].push_back(op); m->ops[1].push_back(op);
     }
     {
@@ -545,6 +561,17 @@ static int add_poly_decoder(Builder& B, const std::string& pfx, const float* x, 
     cudaMemcpy(d, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
     p.w_tc = (const __nv_bfloat16*)d;
     EVK_REQUIRE(tc_eligible(p), EVK_ERR_ARG, "'%s': phase-stacked decoder is not eligible for the tensor-core path", pfx.c_str());
+    if (mixed) {
+        std::vector<float> isc;
+        pack_weights_mixed(wc.data(), 25 * C, 4 * Co, p.cout_pad, wt, isc);
+        void* dm = m->dalloc_bytes(wt.size() * sizeof(__nv_bfloat16));
+        EVK_REQUIRE(dm != nullptr, EVK_ERR_CUDA, "out of device memory for the phase-stacked weights");
+        cudaMemcpy(dm, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+        p.w_mx = (const __nv_bfloat16*)dm;
+        p.w_iscale = m->upload(isc);
+        p.mixed = 1;
+        m->mixed_convs++;
+    }
     op.flops = 2.0 * Co * C * 25.0 * (double)N * (2 * H) * (2 * W);      // the reference's arithmetic (no credit for the zeros)
     op.cin = C; op.H = 2 * H; op.W = 2 * W;
     m->ops[0].push_back(op); m->ops[1].push_back(op);
@@ -1154,6 +1181,59 @@ static int wire_tc(evk_model* m) {
                 cv.flops += pr.flops;
                 pr.kind = OP_NOP; pr.flops = 0.0;
             }
+    // Mixed operands: a layer runs MIXED when its shape allows it and every companion it reads is in the mixed format; a companion
+    // is in the mixed format when every producer of its buffer can write it (tensor-core linear / ConvLSTM epilogues, channel
+    // counts multiples of 64) and every tensor-core consumer runs MIXED.  Greatest fixed point, both parities at once.
+    if (m->mixed_enabled) {
+        std::map<const float*, int> chan;                  // buffers tensor-core convolutions read: channels per pixel
+        std::map<const float*, bool> ok;
+        auto is_tc = [&](const Op& op) { return op.kind == OP_CONV && op.cp.w_tc != nullptr && tc_eligible(op.cp); };
+        for (int par = 0; par < 2; ++par)
+            for (const Op& op : m->ops[par]) {
+                if (!is_tc(op)) continue;
+                if (op.cp.x1 != nullptr) { chan[op.cp.x1] = op.cp.c1; ok[op.cp.x1] = true; }
+                if (op.cp.c2) { chan[op.cp.x2] = op.cp.c2; ok[op.cp.x2] = true; }
+            }
+        // producers
+        std::map<const float*, int> produced;
+        for (int par = 0; par < 2; ++par)
+            for (const Op& op : m->ops[par]) {
+                auto out_of = [&](const float* q, bool capable) { if (q && ok.count(q)) { produced[q]++; if (!capable) ok[q] = false; } };
+                if (op.kind == OP_CONV) {
+                    const ConvParams& p = op.cp;
+                    const bool tc = is_tc(op) && (p.x1 == nullptr || true);
+                    if (p.epi == EPI_LINEAR) out_of(p.y, tc && p.cout % 64 == 0 && !p.row_pair && p.pred_out == nullptr && !p.kw_group && !p.win_c);
+                    else if (p.epi == EPI_LSTM) out_of(p.h_new, tc && (p.cout / 4) % 64 == 0);
+                    else { out_of(p.h_new, false); out_of(p.hr_out, false); }
+                } else {
+                    out_of(op.out, false);
+                    out_of(op.hp.inter, false);
+                }
+            }
+        for (auto& kv : ok) if (!produced.count(kv.first)) kv.second = false;       // (a buffer nobody here writes: keep the plain format)
+        bool changed = true;
+        while (changed) {
+            changed = false;
+            for (int par = 0; par < 2; ++par)
+                for (const Op& op : m->ops[par]) {
+                    if (!is_tc(op)) continue;
+                    const ConvParams& p = op.cp;
+                    const bool in_ok = p.x1 != nullptr && ok[p.x1] && (!p.c2 || ok[p.x2]);
+                    if (p.w_mx != nullptr && tc_mixed_capable(p) && in_ok) continue;      // runs MIXED
+                    if (p.x1 != nullptr && ok[p.x1]) { ok[p.x1] = false; changed = true; }
+                    if (p.c2 && ok[p.x2]) { ok[p.x2] = false; changed = true; }
+                }
+        }
+        for (auto& kv : ok) if (kv.second) m->mixed_bufs[kv.first] = chan[kv.first];
+        for (int par = 0; par < 2; ++par)
+            for (Op& op : m->ops[par]) {
+                if (op.kind != OP_CONV) continue;
+                ConvParams& p = op.cp;
+                if (is_tc(op) && p.x1 != nullptr && m->mixed_bufs.count(p.x1)) { p.mixed = 1; if (par == 0) m->mixed_convs++; }
+                if (p.epi == EPI_LINEAR && p.y && m->mixed_bufs.count(p.y)) p.ys_mixed = 1;
+                if (p.epi == EPI_LSTM && p.h_new && m->mixed_bufs.count(p.h_new)) p.hs_mixed = 1;
+            }
+    }
     auto lookup = [&](const float* ptr) -> __nv_bfloat16* {
         auto it = m->split_of.find(ptr);
         return it == m->split_of.end() ? nullptr : it->second;
@@ -1273,8 +1353,8 @@ static int run_ops(evk_model* m, int par, cudaStream_t st, std::vector<cudaEvent
             case OP_UPSAMPLE_ADD: r = launch_upsample2x_add(op.in, op.skip, op.out, op.out_s, op.N, op.H, op.W, op.cin, st); break;
             case OP_ZERO_INSERT_ADD: r = launch_zero_insert2x_add(op.in, op.skip, op.out, op.out_s, op.N, op.H, op.W, op.cin, st); break;
             case OP_NOP: break;
-            case OP_ADD_PAD: r = launch_add_pad_split(op.in, op.skip, op.out_s, op.N, op.H, op.W, op.cin, st); break;
-            case OP_RING_LINES: r = launch_ring_lines(op.out_s, op.lines_h, op.lines_v, op.N, op.H, op.W, op.cin, st); break;
+            case OP_ADD_PAD: r = launch_add_pad_split(op.in, op.skip, op.out_s, op.N, op.H, op.W, op.cin, st, op.mixed); break;
+            case OP_RING_LINES: r = launch_ring_lines(op.out_s, op.lines_h, op.lines_v, op.N, op.H, op.W, op.cin, st, op.mixed); break;
             case OP_HEAD_PACK: r = launch_head_pack(op.in, op.out_s, op.N, op.cin, op.H, op.W, op.k / 2, st, op.srcH, op.srcW, op.stride, op.src_planes); break;
             case OP_ADD_SPLIT: r = launch_add_split(op.in, op.skip, op.out, op.out_s, (int64_t)op.N * op.H * op.W * op.cin, st); break;
             case OP_SPADE_SHUFFLE: r = launch_spade_shuffle(op.in, op.skip, op.w, op.b, op.out, op.out_s, op.N, op.H, op.W, op.cout, st); break;
@@ -1315,11 +1395,12 @@ static std::string op_desc(const Op& op) {
                 snprintf(b, sizeof b, "conv1x5 %d->4x%d %s border correction of the next layer @%dx%d lines [tcgen05 bf16x3]", p.c1, p.cout / 4,
                          op.ring_line == 1 ? "horizontal" : "vertical", p.Hout, p.Wout);
             else if (p.phase4)
-                snprintf(b, sizeof b, "conv5x5 s1 %d+0->%d linear%s @%dx%d as 4 stacked phases (N=%d%s) on %dx%d [tcgen05 bf16x3]", p.c1, p.cout,
-                         p.pred_out ? "+pred" : "", 2 * p.Hout, 2 * p.Wout, 4 * p.cout, p.phase4 == 2 ? ", 4 of 5 tap rows per tile" : p.phase4 == 3 ? ", 4x4 of 5x5 taps per tile" : "", p.Hout, p.Wout);
+                snprintf(b, sizeof b, "conv5x5 s1 %d+0->%d linear%s @%dx%d as 4 stacked phases (N=%d%s) on %dx%d [tcgen05 %s]", p.c1, p.cout,
+                         p.pred_out ? "+pred" : "", 2 * p.Hout, 2 * p.Wout, 4 * p.cout, p.phase4 == 2 ? ", 4 of 5 tap rows per tile" : p.phase4 == 3 ? ", 4x4 of 5x5 taps per tile" : "", p.Hout, p.Wout,
+                         p.mixed ? "f16+2xf8" : "bf16x3");
             else
                 snprintf(b, sizeof b, "conv%dx%d s%d %d+%d->%d %s%s @%dx%d [%s]", p.kh, p.kw, p.stride, p.c1, p.c2, p.cout, e,
-                         p.pred_out ? "+pred" : "", p.Hout, p.Wout, p.tc ? "tcgen05 bf16x3" : "simt fp32");
+                         p.pred_out ? "+pred" : "", p.Hout, p.Wout, p.tc ? (p.mixed ? "tcgen05 f16+2xf8" : "tcgen05 bf16x3") : "simt fp32");
             break;
         }
         case OP_UPSAMPLE_ADD: snprintf(b, sizeof b, "upsample2x_add C=%d @%dx%d", op.cin, 2 * op.H, 2 * op.W); break;
@@ -1363,6 +1444,8 @@ int evk_model_create(const evk_model_config* cfg, evk_model** out) {
     m->cfg = *cfg;
     const char* ng = getenv("EVK_NO_GRAPH");
     m->use_graph = !(ng && ng[0] == '1');
+    const char* mx = getenv("EVK_MIXED");
+    m->mixed_enabled = cfg->precision == 0 && !(mx && mx[0] == '0');
     *out = m;
     return EVK_OK;
 }
@@ -1598,6 +1681,8 @@ int evk_model_set_state(evk_model* m, int index, const float* in_nchw, void* str
     EVK_CHECK_CUDA(cudaGetLastError());
     auto it = m->split_of.find(cur);
     if (it != m->split_of.end()) {
+        auto mx = m->mixed_bufs.find(cur);
+        if (mx != m->mixed_bufs.end()) return launch_split_mixed(cur, it->second, (int64_t)m->cfg.batch * s.H * s.W, mx->second, (cudaStream_t)stream);
         if (m->win_wp > 0) return launch_split_padded(cur, it->second, (int64_t)m->cfg.batch * s.H, s.W, s.C, m->win_wp, 1, (cudaStream_t)stream);
         return launch_split(cur, it->second, total, (cudaStream_t)stream);
     }

@@ -88,7 +88,7 @@ void pack_weights_ring(const float* w_kc, int cin, int cout, std::vector<float>&
 // ------------------------------------------------------------------ (x + skip) -> replicate-padded split-bf16 planes
 __global__ void __launch_bounds__(256)
 add_pad_split_kernel(const float* __restrict__ x, const float* __restrict__ skip, __nv_bfloat16* __restrict__ out, long long plane,
-                     int N, int H, int W, int C8) {
+                     int N, int H, int W, int C8, int mixed) {
     const int Hp = H + 4, Wp = W + 4;
     const int64_t total = (int64_t)N * Hp * Wp * C8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -107,20 +107,21 @@ add_pad_split_kernel(const float* __restrict__ x, const float* __restrict__ skip
             v1.x += s1.x; v1.y += s1.y; v1.z += s1.z; v1.w += s1.w;
         }
         const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const size_t o = i * 8;
+        if (mixed) { store_mixed8(out, plane, o, c8 * 8, f); continue; }     // mixed-operand consumer (tc.cuh)
         __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) split_bf16(f[e], hi[e], lo[e]);
-        const size_t o = i * 8;
         *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(hi);
         *reinterpret_cast<uint4*>(out + plane + o) = *reinterpret_cast<const uint4*>(lo);
     }
 }
 
-int launch_add_pad_split(const float* x, const float* skip, __nv_bfloat16* out, int N, int H, int W, int C, cudaStream_t st) {
-    EVK_REQUIRE(x && out && C % 8 == 0, EVK_ERR_ARG, "add_pad_split: bad argument (C=%d)", C);
+int launch_add_pad_split(const float* x, const float* skip, __nv_bfloat16* out, int N, int H, int W, int C, cudaStream_t st, int mixed) {
+    EVK_REQUIRE(x && out && C % 8 == 0 && (!mixed || C % 64 == 0), EVK_ERR_ARG, "add_pad_split: bad argument (C=%d)", C);
     const int64_t total = (int64_t)N * (H + 4) * (W + 4) * (C / 8);
     const long long plane = (long long)N * (H + 4) * (W + 4) * C;
-    add_pad_split_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 4736), 256, 0, st>>>(x, skip, out, plane, N, H, W, C / 8);
+    add_pad_split_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 4736), 256, 0, st>>>(x, skip, out, plane, N, H, W, C / 8, mixed);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }
@@ -134,7 +135,7 @@ int launch_add_pad_split(const float* x, const float* skip, __nv_bfloat16* out, 
 // lines are ZERO outside [0, Ho): the taps whose row is outside as well belong to the horizontal correction.
 __global__ void __launch_bounds__(256)
 ring_lines_kernel(const __nv_bfloat16* __restrict__ xp, long long xp_plane, __nv_bfloat16* __restrict__ lh, __nv_bfloat16* __restrict__ lv,
-                  int N, int H, int W, int C8) {
+                  int N, int H, int W, int C8, int mixed) {
     const int Ho = 2 * H, Wo = 2 * W, Wp = W + 4, C = C8 * 8;
     const int64_t nh = (int64_t)2 * N * (Wo + 4) * C8, nv = (int64_t)2 * N * (Ho + 4) * C8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nh + nv; i += (int64_t)gridDim.x * blockDim.x) {
@@ -158,6 +159,13 @@ ring_lines_kernel(const __nv_bfloat16* __restrict__ xp, long long xp_plane, __nv
                 for (int dx = 0; dx < 2; ++dx) {
                     const float wgt = (dy ? 1.0f - wyA : wyA) * (dx ? 1.0f - wxA : wxA);
                     const size_t o = (((size_t)n * (H + 4) + rowA + dy) * Wp + colA + dx) * (size_t)C + (size_t)c8 * 8;
+                    if (mixed) {
+                        float e8[8];
+                        load_mixed8(xp, xp_plane, o, c8 * 8, e8);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = fmaf(wgt, e8[e], v[e]);
+                        continue;
+                    }
                     const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(xp + o));
                     const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(xp + xp_plane + o));
                     const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h4);
@@ -176,11 +184,11 @@ ring_lines_kernel(const __nv_bfloat16* __restrict__ xp, long long xp_plane, __nv
     }
 }
 
-int launch_ring_lines(const __nv_bfloat16* xp, __nv_bfloat16* lines_h, __nv_bfloat16* lines_v, int N, int H, int W, int C, cudaStream_t st) {
+int launch_ring_lines(const __nv_bfloat16* xp, __nv_bfloat16* lines_h, __nv_bfloat16* lines_v, int N, int H, int W, int C, cudaStream_t st, int mixed) {
     EVK_REQUIRE(xp && lines_h && lines_v && C % 8 == 0 && H >= 2 && W >= 2, EVK_ERR_ARG, "ring_lines: bad argument (C=%d)", C);
     const int64_t total = (int64_t)2 * N * (2 * W + 4 + 2 * H + 4) * (C / 8);
     ring_lines_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, 0, st>>>(
-        xp, (long long)N * (H + 4) * (W + 4) * C, lines_h, lines_v, N, H, W, C / 8);
+        xp, (long long)N * (H + 4) * (W + 4) * C, lines_h, lines_v, N, H, W, C / 8, mixed);
     EVK_CHECK_CUDA(cudaGetLastError());
     return EVK_OK;
 }

@@ -7,6 +7,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "evk_common.cuh"
 
@@ -129,6 +131,15 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f8f6f4 (8-bit float operands, K = 32 per instruction, twice the kind::f16 rate), same accumulator
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // 32 lanes x 32 columns of fp32 accumulators: thread i of the warp receives lane (base+i), columns col..col+31
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -177,8 +188,50 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// kind::f16 with FP16 operands, and kind::f8f6f4 with A = E5M2, B = E4M3 (the "mixed" operand decomposition, conv_tc.cu)
+__device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t umma_idesc_f8_e5m2_e4m3(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// ---- "mixed" split records (consumers: MIXED kernels).  A pixel of C channels (C % 64 == 0) is 2*C bytes in either plane:
+// plane 0 = fp16(16 v) [C]; plane 1 = per 64-channel chunk 64 bytes e5m2(v) then 64 bytes e5m2(4096 (v - x16)), x16 = fp16(16 v) / 16.
+// o = element offset of the record's first channel (2-byte units, = pixel * C + c0), c0 = that channel's index in its pixel.
+__device__ __forceinline__ void mixed_cvt2(float v0, float v1, uint32_t& h2, uint32_t& x2, uint32_t& l2) {
+    const float s0 = fminf(fmaxf(v0 * 16.0f, -65504.0f), 65504.0f), s1 = fminf(fmaxf(v1 * 16.0f, -65504.0f), 65504.0f);
+    const __half2 h = __floats2half2_rn(s0, s1);
+    h2 = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 hf = __half22float2(h);
+    x2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(v0, v1), __NV_SATFINITE, __NV_E5M2);
+    l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x * 0.0625f) * 4096.0f, (v1 - hf.y * 0.0625f) * 4096.0f), __NV_SATFINITE, __NV_E5M2);
+}
+__device__ __forceinline__ void store_mixed8(__nv_bfloat16* base, long long plane, size_t o, int c0, const float* f) {
+    uint32_t h[4], x[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mixed_cvt2(f[2 * i], f[2 * i + 1], h[i], x[i], l[i]);
+    *reinterpret_cast<uint4*>(base + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    uint8_t* b1 = reinterpret_cast<uint8_t*>(base + plane) + 2 * o - (size_t)(c0 & 63);
+    *reinterpret_cast<uint2*>(b1) = make_uint2(x[0] | (x[1] << 16), x[2] | (x[3] << 16));
+    *reinterpret_cast<uint2*>(b1 + 64) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+}
+// inverse of store_mixed8 for readers outside the tensor-core kernels: v ~ x16 + xl8 (the e5m2(v) copy is not needed)
+__device__ __forceinline__ void load_mixed8(const __nv_bfloat16* base, long long plane, size_t o, int c0, float* f) {
+    const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(base + o));
+    const uint2 l2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(base + plane) + 2 * o - (size_t)(c0 & 63) + 64));
+    const __half2* hp = reinterpret_cast<const __half2*>(&h4);
+    const uint8_t* lb = reinterpret_cast<const uint8_t*>(&l2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 hf = __half22float2(hp[i]);
+        const __half_raw r0 = {(unsigned short)(lb[2 * i] << 8)}, r1 = {(unsigned short)(lb[2 * i + 1] << 8)};      // e5m2 = the high byte of an fp16
+        f[2 * i] = hf.x * 0.0625f + __half2float(__half(r0)) * (1.0f / 4096.0f);
+        f[2 * i + 1] = hf.y * 0.0625f + __half2float(__half(r1)) * (1.0f / 4096.0f);
+    }
 }
 }  // namespace evk
