@@ -86,6 +86,7 @@ struct TcArgs {
     const float* h_prev; const float* u_in; float* u_out; float* hr_out; __nv_bfloat16* hrs_out;   // ConvGRU epilogues
     const float* pred_w; const float* pred_skip; float* pred_out; float pred_bias; int pred_sigmoid;
     const __nv_bfloat16* pred_skip_s; long long pred_skip_plane;
+    int poll;                   // look-ahead poll of the issuer's next weight barrier: 0 before the issue (try_wait), 1 none, 2 after it (test_wait)
     int hiprio;                 // 1: producer / MMA-issuer roles on the four HIGHEST warp ids (the scheduler favours high warp ids: the
                                 //    issuers must not queue behind eight busy epilogue warps when tiles are short)
     int exp;                    // DBG kernels only (EVK_TC_EXP bit mask): 1 skip weight loads, 2 skip activation loads, 4 skip epilogue stores
@@ -361,7 +362,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const uint32_t kb_total = a.ps == 3 ? (uint32_t)(chunks * (a.ku - 1) * (a.kv - 1)) : (uint32_t)(chunks * (a.ps == 2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0)));
         uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0, gblk = 0;
         bool b_ready = false;
-        long long w_te = 0, w_fa = 0, w_fb = 0;
+        long long w_te = 0, w_fa = 0, w_fb = 0, w_try = 0, w_issue = 0;
         const long long t_begin = DBG ? clock64() : 0;
         for (int st = cid; st < n_super; st += ncl, ++it) {
             const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
@@ -401,17 +402,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                 // this issuer's NEXT block: poll its barrier now, the round trip hides behind the issue
                                 uint32_t s2 = sB + 1u + two, ph2 = phB;
                                 if (s2 >= nbs) { s2 -= nbs; ph2 ^= 1u; }
-                                b_ready = mbar_try_wait(bar_fb + 8u * s2, ph2);
+                                t0 = DBG ? clock64() : 0;
+                                if (a.poll == 0) b_ready = mbar_try_wait(bar_fb + 8u * s2, ph2);
+                                else b_ready = false;
+                                if (DBG) w_try += clock64() - t0;
                                 if (two && !own && blk > 0) {     // my turn: the other issuer has issued block blk - 1
                                     if (role) asm volatile("bar.sync 2, 64;" ::: "memory"); else asm volatile("bar.sync 1, 64;" ::: "memory");
                                 }
+                                t0 = DBG ? clock64() : 0;
                                 if (elect_one()) {
                                     const uint32_t acc0 = (own ? fresh : blk == 0u) ? 0u : 1u;
                                     if (a.tpb == 1) {             // (kept separate: no loop-carried state on the hot single-tap path)
 #pragma unroll
                                         for (int k = 0; k < BK / 16; ++k) {
                                             // +16 elements (32 B) along K inside the swizzle atom = +2 in the 16-byte address field
-                                            tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, k == 0 ? acc0 : 1u);
+                                            if (!DBG || !(a.exp & 8)) tc_mma_bf16(d_tmem, mk(ah_lo + 2 * k), mk(bh_lo + 2 * k), idesc2, k == 0 ? acc0 : 1u);
+                                            if (DBG && (a.exp & 16)) continue;
                                             if (MIXED) tc_mma_f8(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + b2 + 2 * k), idesc1, 1u);
                                             else tc_mma_bf16(d_tmem, mk(ah_lo + a_plane16 + 2 * k), mk(bh_lo + 2 * k), idesc1, 1u);
                                         }
@@ -431,6 +437,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                     if (cs > 1) tc_commit_mc(bar_free, cmask); else tc_commit(bar_free);
                                 }
                                 __syncwarp();
+                                if (a.poll == 2) b_ready = mbar_test_wait(bar_fb + 8u * s2, ph2);      // (after the issue: never delays it)
+                                if (DBG) w_issue += clock64() - t0;
                                 fresh = false;
                                 if (two && !own && blk + 1 < kb_total) {  // hand the turn to the other issuer
                                     if (role) asm volatile("bar.arrive 1, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory");
@@ -451,6 +459,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             a.dbg[blockIdx.x * 12 + 1] = (unsigned long long)w_te;
             a.dbg[blockIdx.x * 12 + 2] = (unsigned long long)w_fa;
             a.dbg[blockIdx.x * 12 + 3] = (unsigned long long)w_fb;
+            a.dbg[blockIdx.x * 12 + 10] = (unsigned long long)w_try;
+            a.dbg[blockIdx.x * 12 + 11] = (unsigned long long)w_issue;
         }
     } else if (warp >= 4) {
         // ===== epilogue: 8 warps; warp (4 + e) owns TMEM lane quadrant e % 4 (its hardware-accessible lanes) and
@@ -1067,13 +1077,17 @@ static double slice_cycles(int bn) {
     return 130.0 + bn * (150.0 - 130.0) / 64.0;
 }
 
-static double tile_cost(int bk, int ku, int kv, int stride, int chunks, int bn, int cs, long ctas, int* ar_out) {
+// MIXED kernels: two MMAs of N = bn per slice, bound by the operand fetch from shared memory (A 4 kB + B bn * 32 B per MMA at
+// ~85 B/clk: 190 cycles at bn = 128, 285 at bn = 256 -- per output column the wide tile is a quarter cheaper)
+static double slice_cycles_mixed(int bn) { return 2.0 * (4096.0 + 32.0 * bn) / 85.0 + (bn >= 256 ? 0.0 : 0.0); }
+
+static double tile_cost(int bk, int ku, int kv, int stride, int chunks, int bn, int cs, long ctas, int* ar_out, bool mixed = false) {
     const int ngroups = stride == 2 ? 2 : 1;
     const int max_taps = stride == 2 ? (kv + 1) / 2 : kv;
     const int ar = 16 + max_taps - 1;
     if (ar_out) *ar_out = ar;
     const double k16 = (double)chunks * ku * kv * (bk / 16);
-    const double t_mma = k16 * slice_cycles(bn);
+    const double t_mma = k16 * (mixed ? slice_cycles_mixed(bn) : slice_cycles(bn));
     const double a_bytes = (double)chunks * ku * ngroups * 2.0 * ar * 8 * bk * 2;
     const double b_bytes = (double)chunks * ku * kv * 2.0 * bn * bk * 2 / cs;
     const double active = (double)std::min<long>(ctas, kNumSMs);
@@ -1191,7 +1205,9 @@ int tc_plan_create(ConvParams& p) {
         const int hu = ux ? p.Wout : e_hout, hv = ux ? e_hout : p.Wout;
         const long m_tiles = (long)ceil_div(hu, 8) * ceil_div(hv, 16) * p.N;
         const int ku = ux ? p.kw : e_kh, kv = ux ? e_kh : p.kw;
-        for (int bn = 128; bn >= 16; bn -= 16) {
+        // (MIXED: one accumulator of bn columns per stage, so a 256-column tile fits tensor memory)
+        static const int mixed_bn_max = env_int("EVK_TC_MIXED_BN", 128);      // (256 fits tensor memory but leaves two weight stages: measured 50 % slower)
+        for (int bn = (p.mixed && !ps) ? mixed_bn_max : 128; bn >= 16; bn -= 16) {
             if (cout_pad % bn != 0 || bn % granule != 0) continue;
             if ((p.pred_out != nullptr || rp) && bn != cout_pad) continue;
             if (ps && bn % 32 != 0) continue;             // a 32-column epilogue chunk must not straddle two phases
@@ -1205,7 +1221,7 @@ int tc_plan_create(ConvParams& p) {
                 const long ctas = n_super * cs;
                 const long slots = (long)(kNumSMs / cs) * cs;
                 const long waves = (ctas + slots - 1) / slots;
-                const double cost = (double)waves * tile_cost(bk, ps2 ? ku - 1 : ku, ps3 ? kv - 1 : kv, ux ? s_y : s_x, chunks, bn, cs, ctas, nullptr);
+                const double cost = (double)waves * tile_cost(bk, ps2 ? ku - 1 : ku, ps3 ? kv - 1 : kv, ux ? s_y : s_x, chunks, bn, cs, ctas, nullptr, p.mixed != 0);
                 if (best.bn == 0 || cost < best.cost) best = {ux, bn, cs, cost};
             }
         }
@@ -1280,6 +1296,7 @@ int tc_plan_create(ConvParams& p) {
     }
     a.dbg = nullptr;
     a.hiprio = env_int("EVK_TC_HIPRIO", 1) ? 1 : 0;
+    a.poll = p.mixed ? env_int("EVK_TC_POLL", 2) : 0;
     a.exp = env_int("EVK_TC_EXP", 0);
     const uint32_t row_bytes = bk * 2;
     const size_t a_stage = 2 * (size_t)a.ar * 8 * row_bytes;
@@ -1437,9 +1454,9 @@ static int launch_conv_tc_timed(const ConvParams& p, cudaStream_t st) {
     const double tiles_per_cta = (double)n_super * a.cs / pl.grid.x;
     const double k16 = (double)(a.chunks1 + a.chunks2) * a.kh * a.kw * (pl.bk / 16);
     fprintf(stderr, "TIMING %dx%d s%d c%d->%d @%dx%dx%d bn=%d cs=%d ux=%d grid=%u tiles/cta=%.1f k16/tile=%.0f | mma total %.0f (max %.0f) cyc = %.1f cyc/k16 | "
-            "mma waits: tempty %.0f fullA %.0f fullB %.0f | producers wait: emptyA %.0f emptyB %.0f | epi total %.0f wait tfull %.0f tmem-read %.0f rest-of-chunk %.0f\n",
+            "mma waits: tempty %.0f fullA %.0f fullB %.0f try-next %.0f issue+commit %.0f | producers wait: emptyA %.0f emptyB %.0f | epi total %.0f wait tfull %.0f tmem-read %.0f rest-of-chunk %.0f\n",
             a.kh, a.kw, a.su > a.sv ? a.su : a.sv, (a.chunks1 + a.chunks2) * pl.bk, a.cout, a.N, a.Hout, a.Wout, a.bn, a.cs, a.ux, pl.grid.x, tiles_per_cta, k16,
-            avg[0], mx[0], avg[0] / (tiles_per_cta * k16), avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7], avg[8], avg[9]);
+            avg[0], mx[0], avg[0] / (tiles_per_cta * k16), avg[1], avg[2], avg[3], avg[10], avg[11], avg[4], avg[5], avg[6], avg[7], avg[8], avg[9]);
     return EVK_OK;
 }
 

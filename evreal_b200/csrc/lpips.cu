@@ -26,6 +26,7 @@ struct LpLayer {
     int kind = 0;                 // 0 conv (+ReLU), 1 max pool
     ConvParams cp;
     const float* in = nullptr; float* out = nullptr; __nv_bfloat16* out_s = nullptr;
+    int mixed = 0;              // max pooling: out_s is written in the mixed-operand format (conv.cuh, ConvParams::mixed)
     int C = 0, H = 0, W = 0, k = 0, stride = 0, Ho = 0, Wo = 0;
     double flops = 0.0;
 };
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(256) lpips_prep_rowwin_kernel(const float* __r
 
 // NHWC max pooling (no padding, floor mode): torch.nn.MaxPool2d(k, stride); writes fp32 and the split-bf16 copy
 __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ ys,
-                                                      int N, int H, int W, int C4, int k, int s, int Ho, int Wo) {
+                                                      int N, int H, int W, int C4, int k, int s, int Ho, int Wo, int mixed) {
     const int64_t total = (int64_t)N * Ho * Wo * C4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
         if (y != nullptr) reinterpret_cast<float4*>(y)[i] = m;
         if (ys != nullptr) {
             const float f[4] = {m.x, m.y, m.z, m.w};
+            if (mixed) { store_mixed4(ys, (long long)total * 4, (size_t)i * 4, c * 4, f); continue; }      // mixed-operand consumer (tc.cuh)
             __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) split_bf16(f[e], hi[e], lo[e]);
@@ -328,6 +330,11 @@ static int lpips_build(evk_lpips* l) {
         x = l->input;
     }
     l->taps.assign(5, LpTap());
+    // mixed operands (conv.cuh, ConvParams::mixed): every non-stem convolution has cin % 64 == 0 and reads a companion written by
+    // the previous convolution's epilogue or by the max pooling, so the whole chain after the stem runs MIXED (EVK_MIXED=0: bf16x3)
+    const char* mxe = getenv("EVK_MIXED");
+    const bool mixed_on = tc && !(mxe && mxe[0] == '0');
+    auto layer_mixed = [&](int i) { return mixed_on && i > 0 && i < n_specs && specs[i].cin % 64 == 0 && (specs[i].cout + 15) / 16 * 16 % 32 == 0; };
     for (int i = 0; i < n_specs; ++i) {
         const LpSpec& s = specs[i];
         const bool next_tc = tc;                                   // every non-stem convolution qualifies for the tensor-core kernel
@@ -342,6 +349,7 @@ static int lpips_build(evk_lpips* l) {
             pl.out = next_tc ? nullptr : (float*)l->dalloc(sizeof(float) * n_out);
             pl.out_s = next_tc ? (__nv_bfloat16*)l->dalloc(sizeof(__nv_bfloat16) * 2 * n_out) : nullptr;
             EVK_REQUIRE(pl.out || pl.out_s, EVK_ERR_CUDA, "evk_lpips: out of device memory");
+            pl.mixed = (pl.out_s != nullptr && layer_mixed(i)) ? 1 : 0;
             l->layers.push_back(pl);
             x = pl.out; xs = pl.out_s; H = pl.Ho; W = pl.Wo;
         }
@@ -416,6 +424,18 @@ static int lpips_build(evk_lpips* l) {
                 p.x1s = xs;
                 p.cout_pad = (s.cout + 15) / 16 * 16;
                 pack_weights_tc(wk.data(), K, s.cout, p.cout_pad, wt);
+                if (layer_mixed(i)) {
+                    EVK_REQUIRE(tc_mixed_capable(p), EVK_ERR_STATE, "evk_lpips: layer %d cannot run with mixed operands", i);
+                    std::vector<__nv_bfloat16> wm;
+                    std::vector<float> isc;
+                    pack_weights_mixed(wk.data(), K, s.cout, p.cout_pad, wm, isc);
+                    void* dm = l->dalloc(wm.size() * sizeof(__nv_bfloat16));
+                    float* di = (float*)l->dalloc(isc.size() * sizeof(float));
+                    EVK_REQUIRE(dm != nullptr && di != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
+                    cudaMemcpy(dm, wm.data(), wm.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+                    cudaMemcpy(di, isc.data(), isc.size() * sizeof(float), cudaMemcpyHostToDevice);
+                    p.w_mx = (const __nv_bfloat16*)dm; p.w_iscale = di; p.mixed = 1;
+                }
             } else {
                 EVK_REQUIRE(x != nullptr, EVK_ERR_STATE, "evk_lpips: layer %d has no fp32 input for the CUDA-core kernel", i);
                 float* dw = (float*)l->dalloc(sizeof(float) * wk.size());
@@ -432,6 +452,7 @@ static int lpips_build(evk_lpips* l) {
         EVK_REQUIRE(db != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
         cudaMemcpy(db, bias.data(), sizeof(float) * bias.size(), cudaMemcpyHostToDevice);
         p.bias = db; p.y = y; p.ys = ys;
+        p.ys_mixed = (ys != nullptr && layer_mixed(i + 1) && s.cout % 64 == 0) ? 1 : 0;
         if (!wt.empty()) {
             void* d = l->dalloc(wt.size() * sizeof(__nv_bfloat16));
             EVK_REQUIRE(d != nullptr, EVK_ERR_CUDA, "evk_lpips: out of device memory");
@@ -521,7 +542,7 @@ int evk_lpips_forward(evk_lpips* l, const float* img, const float* ref, int n, d
         } else {
             const int64_t total = (int64_t)N * ly.Ho * ly.Wo * (ly.C / 4);
             maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 2368), 256, 0, st>>>(ly.in, ly.out, ly.out_s, N, ly.H, ly.W,
-                                                                                                ly.C / 4, ly.k, ly.stride, ly.Ho, ly.Wo);
+                                                                                                ly.C / 4, ly.k, ly.stride, ly.Ho, ly.Wo, ly.mixed);
             EVK_CHECK_CUDA(cudaGetLastError());
         }
     }

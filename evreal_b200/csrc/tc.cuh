@@ -45,6 +45,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking poll (try_wait may suspend the thread for a hardware time limit when the phase is not complete yet)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded spin: a pipeline bug becomes a trapped launch ("unspecified launch failure") instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
@@ -219,6 +231,16 @@ __device__ __forceinline__ void store_mixed8(__nv_bfloat16* base, long long plan
     uint8_t* b1 = reinterpret_cast<uint8_t*>(base + plane) + 2 * o - (size_t)(c0 & 63);
     *reinterpret_cast<uint2*>(b1) = make_uint2(x[0] | (x[1] << 16), x[2] | (x[3] << 16));
     *reinterpret_cast<uint2*>(b1 + 64) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+}
+// 4 consecutive channels (c0 % 4 == 0)
+__device__ __forceinline__ void store_mixed4(__nv_bfloat16* base, long long plane, size_t o, int c0, const float* f) {
+    uint32_t h[2], x[2], l[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) mixed_cvt2(f[2 * i], f[2 * i + 1], h[i], x[i], l[i]);
+    *reinterpret_cast<uint2*>(base + o) = make_uint2(h[0], h[1]);
+    uint8_t* b1 = reinterpret_cast<uint8_t*>(base + plane) + 2 * o - (size_t)(c0 & 63);
+    *reinterpret_cast<uint32_t*>(b1) = x[0] | (x[1] << 16);
+    *reinterpret_cast<uint32_t*>(b1 + 64) = l[0] | (l[1] << 16);
 }
 // inverse of store_mixed8 for readers outside the tensor-core kernels: v ~ x16 + xl8 (the e5m2(v) copy is not needed)
 __device__ __forceinline__ void load_mixed8(const __nv_bfloat16* base, long long plane, size_t o, int c0, float* f) {

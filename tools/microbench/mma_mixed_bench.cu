@@ -1,0 +1,114 @@
+// Microbenchmark 3: tensor-pipe time of the operand decompositions of conv_tc.cu with the operands resident in shared memory
+// (no TMA, no epilogue, no barrier waits): cycles per 32-byte K step of a 128-row tile for
+//   pattern 0  bf16x3      A_hi*[B_hi;B_lo] (N = 2bn, kind::f16)  +  A_lo*B_hi (N = bn, kind::f16)
+//   pattern 1  mixed       A16*B16 (N = bn, kind::f16, K = 16)    +  A8*B8 (N = bn, kind::f8f6f4, K = 32)
+//   pattern 2  f16 only    one kind::f16 MMA of N = bn per step
+//   pattern 3  f8 only     one kind::f8f6f4 MMA of N = bn per step
+//   pattern 4  mixed, grouped: the four kind::f16 MMAs of a K block first, then its four kind::f8f6f4 MMAs
+// with one issuer, or two issuers on their own accumulators (free-running) -- is the pipe time additive over kinds, and what
+// does alternating the kind cost?
+#include <cstdio>
+#include <vector>
+#include "../../evreal_b200/csrc/tc.cuh"
+using namespace evk;
+namespace evk { void set_error(const char*, ...) {} }
+
+struct Args { int bn, pattern, issuers, blocks, b_stages, a_atoms; };
+
+__global__ void __launch_bounds__(256, 1) mixed_bench(Args a, long long* out) {
+    constexpr uint32_t ROW_BYTES = 128, ATOM = 1024;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t bars[8];
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0;
+    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1); mbar_fence_init(); }
+    if (warp == 2) tc_alloc(smem_u32(&slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = slot;
+    const uint32_t a_plane = (uint32_t)a.a_atoms * ATOM, a_stage = 2 * a_plane;
+    const uint32_t b_plane = (uint32_t)a.bn * ROW_BYTES, b_stage = 2 * b_plane;
+    const uint32_t smem_b = base + 2 * a_stage;
+    if (warp < a.issuers) {
+        const int role = warp;
+        const uint32_t bn = (uint32_t)a.bn;
+        const uint32_t id_bf2 = umma_idesc_bf16(128, 2 * bn), id_bf1 = umma_idesc_bf16(128, bn);
+        const uint32_t id_f16 = umma_idesc_f16(128, bn), id_f8 = umma_idesc_f8_e5m2_e4m3(128, bn);
+        const uint32_t desc_hi = (uint32_t)(umma_desc_kmajor(0, ROW_BYTES) >> 32);
+        auto mk = [&](uint32_t lo) -> uint64_t { return ((uint64_t)desc_hi << 32) | lo; };
+        auto lo_of = [](uint32_t addr) -> uint32_t { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+        const uint32_t a_plane16 = a_plane >> 4, b_plane16 = b_plane >> 4;
+        const uint32_t acc_cols = a.pattern == 0 ? 2 * bn : bn;
+        const uint32_t d = tmem_base + (uint32_t)role * acc_cols;
+        const uint32_t bar = smem_u32(&bars[role]);
+        uint32_t sB = 0;
+        const long long t0 = clock64();
+        for (int blk = 0; blk < a.blocks; ++blk) {
+            const uint32_t al = lo_of(base + (uint32_t)(blk & 1) * a_stage + (uint32_t)(blk % 3) * ATOM);
+            const uint32_t bl = lo_of(smem_b + sB * b_stage);
+            if (++sB == (uint32_t)a.b_stages) sB = 0;
+            if (elect_one()) {
+                if (a.pattern == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tc_mma_bf16(d, mk(al + 2 * k), mk(bl + 2 * k), id_bf2, 1u);
+                        tc_mma_bf16(d, mk(al + a_plane16 + 2 * k), mk(bl + 2 * k), id_bf1, 1u);
+                    }
+                } else if (a.pattern == 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tc_mma_bf16(d, mk(al + 2 * k), mk(bl + 2 * k), id_f16, 1u);
+                        tc_mma_f8(d, mk(al + a_plane16 + 2 * k), mk(bl + b_plane16 + 2 * k), id_f8, 1u);
+                    }
+                } else if (a.pattern == 2) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_bf16(d, mk(al + 2 * k), mk(bl + 2 * k), id_f16, 1u);
+                } else if (a.pattern == 3) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_f8(d, mk(al + a_plane16 + 2 * k), mk(bl + b_plane16 + 2 * k), id_f8, 1u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_bf16(d, mk(al + 2 * k), mk(bl + 2 * k), id_f16, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_f8(d, mk(al + a_plane16 + 2 * k), mk(bl + b_plane16 + 2 * k), id_f8, 1u);
+                }
+                tc_commit(smem_u32(&bars[4 + role]));
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tc_commit(bar);
+        __syncwarp();
+        mbar_wait(bar, 0);
+        const long long t2 = clock64();
+        if (lane == 0 && role == 0) out[blockIdx.x] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc_dealloc(tmem_base, 512);
+}
+
+int main() {
+    long long* d;
+    cudaMalloc(&d, 148 * sizeof(long long));
+    cudaFuncSetAttribute(mixed_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    const char* names[5] = {"bf16x3 (N=2bn + N=bn)", "mixed f16+f8 alternating", "f16 only", "f8 only", "mixed, four f16 then four f8"};
+    for (int bn : {128, 256})
+        for (int issuers = 1; issuers <= 2; ++issuers)
+            for (int pattern = 0; pattern < 5; ++pattern) {
+                if (bn == 256 && (pattern == 0 || issuers == 2)) continue;        // tensor memory: 512 columns
+                Args a = {bn, pattern, issuers, 2000, bn == 256 ? 2 : 4, 18};
+                mixed_bench<<<148, 256, 210 * 1024>>>(a, d);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("%s: %s\n", names[pattern], cudaGetErrorString(e)); return 1; }
+                std::vector<long long> h(148);
+                cudaMemcpy(h.data(), d, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+                double tot = 0;
+                for (int i = 0; i < 148; ++i) tot += h[i];
+                const double steps = (double)a.blocks * 4 * issuers;
+                printf("bn=%3d issuers=%d %-32s %.1f cyc per K step per CTA\n", bn, issuers, names[pattern], tot / 148 / steps);
+            }
+    return 0;
+}
