@@ -290,6 +290,10 @@ def network_roofline(model, padded, pk, frames=6):
             "frac": ach / pk["tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
             "kernel": "implicit-GEMM convolution family (all conv launches of one forward)",
             "launches_per_forward": len(conv), "algorithmic_flops_per_forward": conv_fl,
+            "mixed_operand_launches": sum("f16+2xf8" in l["op"] for l in conv),
+            "operands": "fp32 semantics from split operands: x.w = x16.w16 + x8.wl8 + xl8.w8 (one fp16 product + two fp8 products at twice "
+                        "the rate = 2 tensor-pipe units per algorithmic FLOP) in the layers marked f16+2xf8, three bf16 products (3 units) in "
+                        "the rest: the ceiling of `frac` is between 1/3 and 1/2",
             "share_of_forward_time": conv_ms / total_ms if total_ms > 0 else None,
             "forward_ms_eager": total_ms, "peak_source": pk["source"] + ", sustained bf16", "layers": layers}
 
@@ -650,7 +654,7 @@ def run_ours(args):
         return 0
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (bf16x3 split on tensor cores where enabled, fp32 accumulate)", "data": "synthetic",
+            "dtype": "f32 (split operands on the tensor cores: fp16 + 2 x fp8 products, or 3 bf16 products where a layer's shape rules that out; fp32 accumulate)", "data": "synthetic",
             "events_per_s": events / (ms * 1e-3),
             "config": {"workload": WORKLOAD, "batch_streams_per_gpu": B, "frames_per_step": B * world,
                        "l2": "inputs larger than L2: every step voxelizes a new window of %d resident streams (%.0f MB of raw events per GPU, each byte read once)" % (B, B * RATE * DURATION * 13 / 1e6),

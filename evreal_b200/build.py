@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed (see above)")
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart", "-lpthread"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -5,6 +5,9 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "conv.cuh"
 
 namespace evk {
@@ -153,6 +156,27 @@ int evk_pack_layer_weights(int kind, const float* w_oihw_host, int Cout, int Cin
             EVK_REQUIRE(Cin % 16 == 0 && group >= 1 && group + kw - 1 <= 4, EVK_ERR_ARG, "evk_pack_layer_weights: window mode needs 16-channel tensors and group + kw - 1 <= 4");
             pack_weights_window(w_kc.data(), kh, kw, Cin, 16, Cout, group, out);
             break;
+        case 4: {
+            // mixed operands (conv.cuh, ConvParams::mixed), DECODED: [3][K][Cout] = 16 w16 / S, wl8 / S, 4096 w8 / S
+            const int K = kh * kw * Cin, cp = (Cout + 31) / 32 * 32;
+            EVK_REQUIRE(K % 64 == 0, EVK_ERR_ARG, "evk_pack_layer_weights: mixed operands need kh*kw*Cin %% 64 == 0");
+            std::vector<__nv_bfloat16> packed;
+            std::vector<float> isc;
+            pack_weights_mixed(w_kc.data(), K, Cout, cp, packed, isc);
+            const uint16_t* p0 = reinterpret_cast<const uint16_t*>(packed.data());
+            const uint8_t* p1 = reinterpret_cast<const uint8_t*>(packed.data() + (size_t)cp * K);
+            out.assign((size_t)3 * K * Cout, 0.f);
+            for (int n = 0; n < Cout; ++n)
+                for (int k = 0; k < K; ++k) {
+                    __half_raw hr; hr.x = p0[(size_t)n * K + k];
+                    const uint8_t* row = p1 + ((size_t)n * K + (size_t)(k / 64) * 64) * 2;
+                    const __half_raw l = __nv_cvt_fp8_to_halfraw(row[k % 64], __NV_E4M3), w8 = __nv_cvt_fp8_to_halfraw(row[64 + k % 64], __NV_E4M3);
+                    out[((size_t)0 * K + k) * Cout + n] = __half2float(__half(hr)) * 16.0f * isc[n];
+                    out[((size_t)1 * K + k) * Cout + n] = __half2float(__half(l)) * isc[n];
+                    out[((size_t)2 * K + k) * Cout + n] = __half2float(__half(w8)) * 4096.0f * isc[n];
+                }
+            break;
+        }
         default:
             EVK_REQUIRE(false, EVK_ERR_ARG, "evk_pack_layer_weights: unknown kind %d", kind);
     }

@@ -35,6 +35,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "conv.cuh"
@@ -362,7 +363,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const uint32_t kb_total = a.ps == 3 ? (uint32_t)(chunks * (a.ku - 1) * (a.kv - 1)) : (uint32_t)(chunks * (a.ps == 2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0)));
         uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0, gblk = 0;
         bool b_ready = false;
-        long long w_te = 0, w_fa = 0, w_fb = 0, w_try = 0, w_issue = 0;
+        long long w_te = 0, w_fa = 0, w_fb = 0, w_try = 0, w_issue = 0, w_body = 0;
         const long long t_begin = DBG ? clock64() : 0;
         for (int st = cid; st < n_super; st += ncl, ++it) {
             const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
@@ -391,6 +392,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         for (int j0 = tv0; j0 < tv1; j0 += a.tpb, ++blk, ++gblk) {
                             const int ntb = min(a.tpb, tv1 - j0);               // taps in this K block
                             if (two == 0u || ((own ? gblk : blk) & 1u) == role) {
+                                const long long t_body = DBG ? clock64() : 0;
                                 const uint32_t bh_lo = lo_of(smem_b + sB * b_stage);
                                 const uint32_t bar_free = bar_eb + 8u * sB;
                                 if (!b_ready) {
@@ -398,7 +400,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                     mbar_wait(bar_fb + 8u * sB, phB);
                                     if (DBG) w_fb += clock64() - t0;
                                 }
+                                t0 = DBG ? clock64() : 0;
                                 tc_fence_after();
+                                if (DBG) w_te += clock64() - t0;        // (DBG: the "tempty" counter also carries the per-block fence)
                                 // this issuer's NEXT block: poll its barrier now, the round trip hides behind the issue
                                 uint32_t s2 = sB + 1u + two, ph2 = phB;
                                 if (s2 >= nbs) { s2 -= nbs; ph2 ^= 1u; }
@@ -443,6 +447,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                 if (two && !own && blk + 1 < kb_total) {  // hand the turn to the other issuer
                                     if (role) asm volatile("bar.arrive 1, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory");
                                 }
+                                if (DBG) w_body += clock64() - t_body;
                             }
                             if (++sB == nbs) { sB = 0; phB ^= 1u; }
                             ah_lo += (uint32_t)ntb * atom16;
@@ -459,7 +464,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             a.dbg[blockIdx.x * 12 + 1] = (unsigned long long)w_te;
             a.dbg[blockIdx.x * 12 + 2] = (unsigned long long)w_fa;
             a.dbg[blockIdx.x * 12 + 3] = (unsigned long long)w_fb;
-            a.dbg[blockIdx.x * 12 + 10] = (unsigned long long)w_try;
+            a.dbg[blockIdx.x * 12 + 10] = (unsigned long long)(a.exp & 32 ? w_body : w_try);
             a.dbg[blockIdx.x * 12 + 11] = (unsigned long long)w_issue;
         }
     } else if (warp >= 4) {
@@ -1096,16 +1101,34 @@ static double tile_cost(int bk, int ku, int kv, int stride, int chunks, int bn, 
     return 5000.0 + std::max(std::max(t_mma, t_l2), t_epi);
 }
 
+// host: output channels [n0, n1) of a packer in parallel (weights of a whole network are ~10 M values: the packers run once per
+// (model, shape) inside the first forward, i.e. inside the measured wall clock of evaluate())
+template <typename F>
+static void parallel_channels(int cout, F&& body) {
+    const int nt = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, cout / 16}));
+    if (nt <= 1) { body(0, cout); return; }
+    std::vector<std::thread> th;
+    const int per = (cout + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const int n0 = t * per, n1 = std::min(cout, n0 + per);
+        if (n0 < n1) th.emplace_back([&body, n0, n1] { body(n0, n1); });
+    }
+    for (auto& t : th) t.join();
+}
+
 void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out) {
     out.assign((size_t)2 * cout_pad * K, __float2bfloat16(0.0f));
-    for (int k = 0; k < K; ++k)
-        for (int n = 0; n < cout; ++n) {
-            const float v = w_kc[(size_t)k * cout + n];
-            const __nv_bfloat16 hi = __float2bfloat16(v);
-            const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-            out[(size_t)n * K + k] = hi;
-            out[(size_t)cout_pad * K + (size_t)n * K + k] = lo;
-        }
+    __nv_bfloat16* o = out.data();
+    parallel_channels(cout, [=](int n0, int n1) {
+        for (int nb = n0; nb < n1; nb += 16)                  // 16 columns at a time: one cache line of the source per k
+            for (int k = 0; k < K; ++k)
+                for (int n = nb; n < std::min(nb + 16, n1); ++n) {
+                    const float v = w_kc[(size_t)k * cout + n];
+                    const __nv_bfloat16 hi = __float2bfloat16(v);
+                    o[(size_t)n * K + k] = hi;
+                    o[(size_t)cout_pad * K + (size_t)n * K + k] = __float2bfloat16(v - __bfloat162float(hi));
+                }
+    });
 }
 
 // Mixed operands.  With S = S[n] (a power of two per output channel, max|w[:, n]| S in (2^17.8, 2^18.8]):
@@ -1119,21 +1142,29 @@ void pack_weights_mixed(const float* w_kc, int K, int cout, int cout_pad, std::v
     iscale.assign((size_t)cout_pad + 32, 1.0f);
     uint16_t* p0 = reinterpret_cast<uint16_t*>(out.data());
     uint8_t* p1 = reinterpret_cast<uint8_t*>(out.data() + (size_t)cout_pad * K);
-    for (int n = 0; n < cout; ++n) {
-        float wmax = 0.f;
-        for (int k = 0; k < K; ++k) wmax = std::max(wmax, std::fabs(w_kc[(size_t)k * cout + n]));
-        const float S = wmax > 0.f ? std::exp2(std::floor(std::log2(458752.0f / wmax))) : 1.0f;
-        iscale[n] = 1.0f / S;
-        for (int k = 0; k < K; ++k) {
-            const float w = w_kc[(size_t)k * cout + n];
-            const __half h = __float2half_rn(w * S * 0.0625f);
-            p0[(size_t)n * K + k] = *reinterpret_cast<const uint16_t*>(&h);
-            const float wl = w - __half2float(h) * 16.0f / S;
-            uint8_t* row = p1 + ((size_t)n * K + (size_t)(k / 64) * 64) * 2;
-            row[k % 64] = (uint8_t)__nv_cvt_float_to_fp8(wl * S, __NV_SATFINITE, __NV_E4M3);
-            row[64 + k % 64] = (uint8_t)__nv_cvt_float_to_fp8(w * S * (1.0f / 4096.0f), __NV_SATFINITE, __NV_E4M3);
+    float* isc = iscale.data();
+    parallel_channels(cout, [=](int n0, int n1) {
+        for (int nb = n0; nb < n1; nb += 16) {
+            const int ne = std::min(nb + 16, n1);
+            float wmax[16] = {0.f}, S[16];
+            for (int k = 0; k < K; ++k)
+                for (int n = nb; n < ne; ++n) wmax[n - nb] = std::max(wmax[n - nb], std::fabs(w_kc[(size_t)k * cout + n]));
+            for (int n = nb; n < ne; ++n) {
+                S[n - nb] = wmax[n - nb] > 0.f ? std::exp2(std::floor(std::log2(458752.0f / wmax[n - nb]))) : 1.0f;
+                isc[n] = 1.0f / S[n - nb];
+            }
+            for (int k = 0; k < K; ++k)
+                for (int n = nb; n < ne; ++n) {
+                    const float w = w_kc[(size_t)k * cout + n], s = S[n - nb];
+                    const __half h = __float2half_rn(w * s * 0.0625f);
+                    p0[(size_t)n * K + k] = *reinterpret_cast<const uint16_t*>(&h);
+                    const float wl = w - __half2float(h) * 16.0f / s;
+                    uint8_t* row = p1 + ((size_t)n * K + (size_t)(k / 64) * 64) * 2;
+                    row[k % 64] = (uint8_t)__nv_cvt_float_to_fp8(wl * s, __NV_SATFINITE, __NV_E4M3);
+                    row[64 + k % 64] = (uint8_t)__nv_cvt_float_to_fp8(w * s * (1.0f / 4096.0f), __NV_SATFINITE, __NV_E4M3);
+                }
         }
-    }
+    });
 }
 
 bool tc_mixed_capable(const ConvParams& p) {

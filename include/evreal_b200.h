@@ -166,6 +166,8 @@ int evk_conv2d_nhwc(const float* x, int N, int H, int W, int Cin, const float* w
  *  kind 2: stride-2 5x5 ConvLayer over pixel pairs (first encoder)                    -> [kh*3*2*Cin][Cout]
  *  kind 3: 3x3 ConvLayer over 4-pixel windows of 16-channel tensors, `group` output pixels per row (FireNet;
  *          Cin = 16 or 32 = cat(x, h))                                                -> [kh*(Cin/16)*64][group*Cout]
+ *  kind 4: mixed-operand form of a plain layer (fp16 product + two fp8 products, kh*kw*Cin % 64 == 0), DECODED back to
+ *          floats: [3][kh*kw*Cin][Cout] = the fp16 part, the e4m3 remainder, the e4m3 copy (per-channel power-of-two scales undone)
  * Row index k = position in the GEMM's K dimension, column = packed output channel; *out_len = elements written
  * (EVK_ERR_ARG if out_cap is too small).  No CUDA call is made. */
 int evk_pack_layer_weights(int kind, const float* w_oihw_host, int Cout, int Cin, int kh, int kw, int group, float* out_host,

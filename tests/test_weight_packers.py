@@ -94,3 +94,19 @@ def test_bad_arguments_fail_with_a_message():
     assert rc != 0 and n.value == 25 * 8 * 4 * 4 and b'needs' in lib.evk_last_error()
     rc = lib.evk_pack_layer_weights(9, w.ctypes.data_as(ctypes.c_void_p), 4, 8, 5, 5, 1, buf.ctypes.data_as(ctypes.c_void_p), 16, ctypes.byref(n))
     assert rc != 0 and b'unknown kind' in lib.evk_last_error()
+
+
+def test_mixed_operand_weights_decode_to_the_layer():
+    """The mixed-operand form of a plain layer (fp16 product + two fp8 products; conv.cuh, ConvParams::mixed): the fp16 part plus
+    the e4m3 remainder reproduce every weight to 2^-14 of its output channel's largest weight, the e4m3 copy to 2^-4 of the
+    value (4 significand bits) down to the format's subnormal range, with channel magnitudes spread over four decades."""
+    Cout, Cin, k = 48, 64, 3
+    w = _w(Cout, Cin, k, k, 5) * torch.logspace(-3, 1, Cout, dtype=torch.float64).view(-1, 1, 1, 1)
+    w = w.float().double()
+    K = k * k * Cin
+    d = _pack(4, w, cap=3 * K * Cout).reshape(3, k, k, Cin, Cout).permute(0, 4, 3, 1, 2)        # [part][n][c][r][q]
+    cmax = w.abs().amax(dim=(1, 2, 3), keepdim=True)
+    assert float(((d[0] + d[1] - w).abs() / cmax).max()) <= 2.0 ** -14
+    big = w.abs() >= cmax * 2.0 ** -12                                # e4m3 normal range under the channel's scale
+    assert float(((d[2] - w).abs() / w.abs())[big].max()) <= 2.0 ** -4 + 1e-9
+    assert float(((d[2] - w).abs() / cmax)[~big].max()) <= 2.0 ** -14            # below it: the subnormal step
