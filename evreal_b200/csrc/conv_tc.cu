@@ -87,6 +87,7 @@ struct TcArgs {
     const float* h_prev; const float* u_in; float* u_out; float* hr_out; __nv_bfloat16* hrs_out;   // ConvGRU epilogues
     const float* pred_w; const float* pred_skip; float* pred_out; float pred_bias; int pred_sigmoid;
     const __nv_bfloat16* pred_skip_s; long long pred_skip_plane;
+    int deal;                   // free-running issuers: K blocks dealt singly (1) or in pairs (2)
     int poll;                   // look-ahead poll of the issuer's next weight barrier: 0 before the issue (try_wait), 1 none, 2 after it (test_wait)
     int hiprio;                 // 1: producer / MMA-issuer roles on the four HIGHEST warp ids (the scheduler favours high warp ids: the
                                 //    issuers must not queue behind eight busy epilogue warps when tiles are short)
@@ -360,10 +361,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         const uint32_t nbs = (uint32_t)a.b_stages;
         const uint32_t two = a.issuers == 2 ? 1u : 0u;
         const bool own = a.own_acc != 0;
+        const uint32_t dsh = (own && a.deal == 2) ? 1u : 0u;
         const uint32_t kb_total = a.ps == 3 ? (uint32_t)(chunks * (a.ku - 1) * (a.kv - 1)) : (uint32_t)(chunks * (a.ps == 2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0)));
         uint32_t sA = 0, phA = 0, sB = 0, phB = 0, it = 0, gblk = 0;
         bool b_ready = false;
-        long long w_te = 0, w_fa = 0, w_fb = 0, w_try = 0, w_issue = 0, w_body = 0;
+        long long w_te = 0, w_fa = 0, w_fb = 0, w_try = 0, w_issue = 0, w_body = 0, w_grp = 0, w_else = 0;
         const long long t_begin = DBG ? clock64() : 0;
         for (int st = cid; st < n_super; st += ncl, ++it) {
             const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
@@ -391,7 +393,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                         ah_lo += (uint32_t)tv0 * atom16;
                         for (int j0 = tv0; j0 < tv1; j0 += a.tpb, ++blk, ++gblk) {
                             const int ntb = min(a.tpb, tv1 - j0);               // taps in this K block
-                            if (two == 0u || ((own ? gblk : blk) & 1u) == role) {
+                            const long long t_it = DBG ? clock64() : 0;
+                            // free-running issuers may take the blocks in PAIRS (a.deal == 2: blocks 4i, 4i+1 / 4i+2, 4i+3): twice the MMAs per
+                            // issue phase for the same barrier round trips (a multiple of four weight stages keeps a slot with one issuer)
+                            const uint32_t turn = own ? (gblk >> dsh) : blk;
+                            const bool mine_dbg = two == 0u || (turn & 1u) == role;
+                            if (mine_dbg) {
                                 const long long t_body = DBG ? clock64() : 0;
                                 const uint32_t bh_lo = lo_of(smem_b + sB * b_stage);
                                 const uint32_t bar_free = bar_eb + 8u * sB;
@@ -405,6 +412,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                 if (DBG) w_te += clock64() - t0;        // (DBG: the "tempty" counter also carries the per-block fence)
                                 // this issuer's NEXT block: poll its barrier now, the round trip hides behind the issue
                                 uint32_t s2 = sB + 1u + two, ph2 = phB;
+                                if (dsh) s2 = sB + ((gblk & 1u) ? 3u : 1u);
                                 if (s2 >= nbs) { s2 -= nbs; ph2 ^= 1u; }
                                 t0 = DBG ? clock64() : 0;
                                 if (a.poll == 0) b_ready = mbar_try_wait(bar_fb + 8u * s2, ph2);
@@ -451,9 +459,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             }
                             if (++sB == nbs) { sB = 0; phB ^= 1u; }
                             ah_lo += (uint32_t)ntb * atom16;
+                            if (DBG && !mine_dbg) w_else += clock64() - t_it;
                         }
+                        t0 = DBG ? clock64() : 0;
                         if (elect_one()) tc_commit(bar_ea + 8u * sA);       // `issuers` arrivals free the activation stage
                         __syncwarp();
+                        if (DBG) w_grp += clock64() - t0;
                         if (++sA == (uint32_t)a.a_stages) { sA = 0; phA ^= 1u; }
                     }
             if (elect_one()) tc_commit(bar_tfull + 8u * as);         // `issuers` arrivals: accumulator complete
@@ -464,7 +475,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             a.dbg[blockIdx.x * 12 + 1] = (unsigned long long)w_te;
             a.dbg[blockIdx.x * 12 + 2] = (unsigned long long)w_fa;
             a.dbg[blockIdx.x * 12 + 3] = (unsigned long long)w_fb;
-            a.dbg[blockIdx.x * 12 + 10] = (unsigned long long)(a.exp & 32 ? w_body : w_try);
+            a.dbg[blockIdx.x * 12 + 10] = (unsigned long long)(a.exp & 128 ? w_else : a.exp & 64 ? w_grp : a.exp & 32 ? w_body : w_try);
             a.dbg[blockIdx.x * 12 + 11] = (unsigned long long)w_issue;
         }
     } else if (warp >= 4) {
@@ -1360,6 +1371,7 @@ int tc_plan_create(ConvParams& p) {
     if (a.own_acc && (a.b_stages & 1)) {      // free-running issuers need a slot to belong to one issuer (see the kernel)
         a.b_stages -= 1; bs -= 1;
     }
+    a.deal = (p.mixed && a.own_acc && a.b_stages % 4 == 0 && env_int("EVK_TC_DEAL", 1) == 2) ? 2 : 1;      // (pairs measured 3 % slower: kept for experiments)
     uint32_t cols = 32;
     while ((int)cols < 2 * a.acc_stride) cols <<= 1;
     if (cols > 512) { delete pl; EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: accumulator does not fit tensor memory (bn=%d)", bn); }

@@ -13,7 +13,7 @@
 using namespace evk;
 namespace evk { void set_error(const char*, ...) {} }
 
-struct Args { int bn, pattern, issuers, blocks, b_stages, a_atoms; };
+struct Args { int bn, pattern, issuers, blocks, b_stages, a_atoms, waits; };     // waits: 0 none, 1 full-barrier wait + fence per block, 2 + look-ahead poll, 3 wait only (no fence), 4 fence only
 
 __global__ void __launch_bounds__(256, 1) mixed_bench(Args a, long long* out) {
     constexpr uint32_t ROW_BYTES = 128, ATOM = 1024;
@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(256, 1) mixed_bench(Args a, long long* out) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = slot;
+    if (threadIdx.x == 0) mbar_arrive(smem_u32(&bars[6]));
+    __syncthreads();
     const uint32_t a_plane = (uint32_t)a.a_atoms * ATOM, a_stage = 2 * a_plane;
     const uint32_t b_plane = (uint32_t)a.bn * ROW_BYTES, b_stage = 2 * b_plane;
     const uint32_t smem_b = base + 2 * a_stage;
@@ -50,6 +52,10 @@ __global__ void __launch_bounds__(256, 1) mixed_bench(Args a, long long* out) {
             const uint32_t al = lo_of(base + (uint32_t)(blk & 1) * a_stage + (uint32_t)(blk % 3) * ATOM);
             const uint32_t bl = lo_of(smem_b + sB * b_stage);
             if (++sB == (uint32_t)a.b_stages) sB = 0;
+            // (barrier 6 completed its phase 0 before the loop: waits on parity 0 pass immediately, like a weight stage that is ready)
+            if (a.waits == 1 || a.waits == 2 || a.waits == 3) mbar_wait(smem_u32(&bars[6]), 0);
+            if (a.waits == 1 || a.waits == 2 || a.waits == 4) tc_fence_after();
+            if (a.waits == 2) (void)mbar_try_wait(smem_u32(&bars[6]), 0);
             if (elect_one()) {
                 if (a.pattern == 0) {
 #pragma unroll
@@ -95,11 +101,13 @@ int main() {
     cudaMalloc(&d, 148 * sizeof(long long));
     cudaFuncSetAttribute(mixed_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     const char* names[5] = {"bf16x3 (N=2bn + N=bn)", "mixed f16+f8 alternating", "f16 only", "f8 only", "mixed, four f16 then four f8"};
+    for (int waits = 0; waits <= 4; ++waits)
     for (int bn : {128, 256})
         for (int issuers = 1; issuers <= 2; ++issuers)
             for (int pattern = 0; pattern < 5; ++pattern) {
                 if (bn == 256 && (pattern == 0 || issuers == 2)) continue;        // tensor memory: 512 columns
-                Args a = {bn, pattern, issuers, 2000, bn == 256 ? 2 : 4, 18};
+                if (waits > 0 && !(bn == 128 && (pattern == 0 || pattern == 1))) continue;
+                Args a = {bn, pattern, issuers, 2000, bn == 256 ? 2 : 4, 18, waits};
                 mixed_bench<<<148, 256, 210 * 1024>>>(a, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("%s: %s\n", names[pattern], cudaGetErrorString(e)); return 1; }
@@ -108,7 +116,7 @@ int main() {
                 double tot = 0;
                 for (int i = 0; i < 148; ++i) tot += h[i];
                 const double steps = (double)a.blocks * 4 * issuers;
-                printf("bn=%3d issuers=%d %-32s %.1f cyc per K step per CTA\n", bn, issuers, names[pattern], tot / 148 / steps);
+                printf("waits=%d bn=%3d issuers=%d %-32s %.1f cyc per K step per CTA\n", waits, bn, issuers, names[pattern], tot / 148 / steps);
             }
     return 0;
 }

@@ -15,6 +15,8 @@ FULL = ['Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dram__bytes_read.s
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.sum',
+        'sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.sum',
+        'sm__ops_path_tensor_op_utcqmma_src_fp4_fp6_fp8_dst_fp32_sparsity_off.sum',
         'smsp__sass_inst_executed_op_utcmma.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum', 'lts__t_sectors_op_red.sum', 'lts__t_sectors_op_atom.sum',
