@@ -87,6 +87,7 @@ struct TcArgs {
     const float* h_prev; const float* u_in; float* u_out; float* hr_out; __nv_bfloat16* hrs_out;   // ConvGRU epilogues
     const float* pred_w; const float* pred_skip; float* pred_out; float pred_bias; int pred_sigmoid;
     const __nv_bfloat16* pred_skip_s; long long pred_skip_plane;
+    int lean;                   // MIXED: the lean issuer loop (one tap per block, two free-running issuers)
     int deal;                   // free-running issuers: K blocks dealt singly (1) or in pairs (2)
     int poll;                   // look-ahead poll of the issuer's next weight barrier: 0 before the issue (try_wait), 1 none, 2 after it (test_wait)
     int hiprio;                 // 1: producer / MMA-issuer roles on the four HIGHEST warp ids (the scheduler favours high warp ids: the
@@ -234,7 +235,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
     // the issuing instruction with elect.sync: inside an `if (lane == 0)` region ptxas cannot keep descriptors in
     // uniform registers and wraps every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST waterfall loop (~100+ cycles
     // each, measured: the tensor pipe ran at ~55% of its floor because of it).
-    if (warp == 0) {
+    if (MIXED && warp == 0 && a.issuers == 3) {
+        // ===== A + B producer in ONE warp (MIXED kernels with three issuers: warp 3 issues MMAs instead).  Loads are requested in
+        // consumption order -- the activation box of a (chunk, U shift, V group), then the weight stages of its K blocks -- so a wait
+        // for a free weight slot can only be behind MMAs whose operands have already been requested.
+        const int bnp = a.bn / cs;
+        const int ctot = chunks * BK;
+        uint32_t sa_i = 0, pha = 0, sb_i = 0, phb = 0;
+        long long w_ea = 0, w_eb = 0;
+        for (int st = cid; st < n_super; st += ncl) {
+            const TileCoord t = tile_coord(a, st, crank);
+            const int row0 = t.nt * a.bn + crank * bnp;
+            int su0, su1;
+            su_range(a, t.nt, su0, su1);
+            for (int ch = 0; ch < chunks; ++ch) {
+                const bool first = ch < a.chunks1;
+                const CUtensorMap* m = first ? &tm_x1 : &tm_x2;
+                const int c0 = (first ? ch : ch - a.chunks1) * BK;
+                for (int su = su0; su < su1; ++su)
+                    for (int g = 0; g < a.n_groups; ++g) {
+                        long long t0 = DBG ? clock64() : 0;
+                        mbar_wait(bar_ea + 8u * sa_i, pha ^ 1u);
+                        if (DBG) w_ea += clock64() - t0;
+                        const int iu0 = t.ou0 * a.su - a.pad_u + su;
+                        const int iv0 = t.ov0 * a.sv - a.pad_v + a.g_tap0[g];
+                        const uint32_t sa = base + sa_i * a_stage;
+                        if (elect_one()) {
+                            if (DBG && (a.exp & 2)) {
+                                mbar_arrive(bar_fa + 8u * sa_i);
+                            } else {
+                                mbar_expect_tx(bar_fa + 8u * sa_i, a_stage);
+                                tma_load_5d(sa, m, bar_fa + 8u * sa_i, c0, iu0, iv0, t.img, 0);
+                                tma_load_5d(sa + a_plane, m, bar_fa + 8u * sa_i, c0, iu0, iv0, t.img, 1);
+                            }
+                        }
+                        __syncwarp();
+                        if (++sa_i == (uint32_t)a.a_stages) { sa_i = 0; pha ^= 1u; }
+                        int tv0, tv1;
+                        tv_range(a, t.nt, a.g_ntaps[g], tv0, tv1);
+                        for (int j0 = tv0; j0 < tv1; j0 += a.tpb) {
+                            const int ntb = min(a.tpb, tv1 - j0);
+                            t0 = DBG ? clock64() : 0;
+                            mbar_wait(bar_eb + 8u * sb_i, phb ^ 1u);
+                            if (DBG) w_eb += clock64() - t0;
+                            const uint32_t sb = smem_b + sb_i * b_stage + (uint32_t)(crank * bnp) * ROW_BYTES;
+                            if (DBG && (a.exp & 1)) {
+                                if (elect_one()) mbar_arrive(bar_fb + 8u * sb_i);
+                            } else if (elect_one()) {
+                                mbar_expect_tx(bar_fb + 8u * sb_i, (uint32_t)ntb * b_tap);
+                                for (int jj = 0; jj < ntb; ++jj) {
+                                    const int tv = a.g_tap0[g] + (j0 + jj) * a.g_step;
+                                    const int tap = a.ux ? tv * a.kw + su : su * a.kw + tv;
+                                    const int k0 = tap * ctot + ch * BK;
+                                    const uint32_t dst = sb + (uint32_t)jj * b_tap;
+                                    if (cs > 1) {
+                                        tma_load_3d_mc(dst, &tm_w, bar_fb + 8u * sb_i, k0, row0, 0, cmask);
+                                        tma_load_3d_mc(dst + b_plane, &tm_w, bar_fb + 8u * sb_i, k0, row0, 1, cmask);
+                                    } else {
+                                        tma_load_3d(dst, &tm_w, bar_fb + 8u * sb_i, k0, row0, 0);
+                                        tma_load_3d(dst + b_plane, &tm_w, bar_fb + 8u * sb_i, k0, row0, 1);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            if (++sb_i == (uint32_t)a.b_stages) { sb_i = 0; phb ^= 1u; }
+                        }
+                    }
+            }
+        }
+        if (DBG && lane == 0) { a.dbg[blockIdx.x * 12 + 4] = (unsigned long long)w_ea; a.dbg[blockIdx.x * 12 + 5] = (unsigned long long)w_eb; }
+        if (cs > 1) {
+            for (int i = 0; i < a.b_stages; ++i) {
+                mbar_wait(bar_eb + 8u * sb_i, phb ^ 1u);
+                if (++sb_i == (uint32_t)a.b_stages) { sb_i = 0; phb ^= 1u; }
+            }
+        }
+    } else if (warp == 0) {
         // ===== A producer: one halo box (both planes) per (channel chunk, U shift, V-tap group)
         uint32_t s = 0, ph = 0;
         long long w_ea = 0;
@@ -269,7 +345,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             }
         }
         if (DBG && lane == 0) a.dbg[blockIdx.x * 12 + 4] = (unsigned long long)w_ea;
-    } else if (warp == 3) {
+    } else if (warp == 3 && !(MIXED && a.issuers == 3)) {
         // ===== B producer: one K block (tpb taps x BK channels of the weight tile) per stage; with a cluster every CTA loads
         // 1/cs of the rows and multicasts them to all CTAs (same smem offset, same barrier offset everywhere)
         const int bnp = a.bn / cs;
@@ -323,7 +399,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                 if (++s == (uint32_t)a.b_stages) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 1 || (warp == 2 && a.issuers == 2)) {
+    } else if (warp == 1 || (warp == 2 && a.issuers >= 2) || (MIXED && warp == 3 && a.issuers == 3)) {
         // ===== MMA issuers (one elected thread per warp).  Per 16-deep K slice two MMAs: B_hi and B_lo are adjacent in
         // the stage, so
         //   D[:, 0:2bn]  (+)= A_hi * [B_hi; B_lo]^T      (N = 2*bn: hi*hi | hi*lo)
@@ -359,7 +435,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         auto lo_of = [](uint32_t addr) -> uint32_t { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
         const uint32_t atom16 = ATOM >> 4, a_plane16 = a_plane >> 4, btap16 = b_tap >> 4;
         const uint32_t nbs = (uint32_t)a.b_stages;
-        const uint32_t two = a.issuers == 2 ? 1u : 0u;
+        const uint32_t two = a.issuers >= 2 ? 1u : 0u;
+        const uint32_t ni = (uint32_t)a.issuers;            // (three only in MIXED kernels: strict order, round-robin handshake)
         const bool own = a.own_acc != 0;
         const uint32_t dsh = (own && a.deal == 2) ? 1u : 0u;
         const uint32_t kb_total = a.ps == 3 ? (uint32_t)(chunks * (a.ku - 1) * (a.kv - 1)) : (uint32_t)(chunks * (a.ps == 2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0)));
@@ -367,6 +444,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
         bool b_ready = false;
         long long w_te = 0, w_fa = 0, w_fb = 0, w_try = 0, w_issue = 0, w_body = 0, w_grp = 0, w_else = 0;
         const long long t_begin = DBG ? clock64() : 0;
+        if (MIXED && !DBG && a.lean) {
+            // LEAN issuer loop (MIXED, one tap per K block, two free-running issuers on their own accumulators): the same barrier
+            // protocol as the general loop below with everything that is constant per launch hoisted, no mode branches and no
+            // look-ahead poll.  ncu's instruction-level sampling of the general loop (profiles/r02b_issuer_stalls.md) showed the
+            // issuer warps blocked on the tensor pipe only a quarter of the time: ~157 mostly serial instructions per K block
+            // (kernel-parameter reloads, mode branches) cost ~1 450 cycles next to 512 cycles of MMAs.  (The same loop generalised
+            // to the bf16x3 kernels cost them registers: 88 bytes of spills and FireNet 13 % slower -- kept to MIXED.)
+            const uint32_t a_stage16 = a_stage >> 4, b_stage16 = b_stage >> 4;
+            const uint32_t a_lo_base = lo_of(base), b_lo_base = lo_of(smem_b);
+            const uint32_t nas = (uint32_t)a.a_stages;
+            const int n_groups = a.n_groups, gn0 = a.g_ntaps[0], gn1 = a.g_ntaps[1], n_tiles = a.n_tiles;
+            const uint32_t acc_stride = (uint32_t)a.acc_stride, d_role = tmem_base + role * (uint32_t)a.acc_cols;
+            for (int st = cid; st < n_super; st += ncl, ++it) {
+                const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+                mbar_wait(bar_tempty + 8u * as, aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = d_role + as * acc_stride;
+                uint32_t accf = 0u;               // 0 until this issuer's first MMA of the tile
+                const int nt_tile = st % n_tiles;
+                int su0, su1;
+                su_range(a, nt_tile, su0, su1);
+                for (int ch = 0; ch < chunks; ++ch)
+                    for (int su = su0; su < su1; ++su)
+                        for (int g = 0; g < n_groups; ++g) {
+                            int tv0, tv1;
+                            tv_range(a, nt_tile, g ? gn1 : gn0, tv0, tv1);
+                            mbar_wait(bar_fa + 8u * sA, phA);
+                            uint32_t al = a_lo_base + sA * a_stage16 + (uint32_t)tv0 * atom16;
+                            for (int j = tv0; j < tv1; ++j, ++gblk, al += atom16) {
+                                if ((gblk & 1u) == role) {
+                                    mbar_wait(bar_fb + 8u * sB, phB);
+                                    tc_fence_after();
+                                    const uint32_t bl = b_lo_base + sB * b_stage16;
+                                    if (elect_one()) {
+#pragma unroll
+                                        for (int k = 0; k < BK / 16; ++k) {
+                                            tc_mma_bf16(d_tmem, mk(al + 2 * k), mk(bl + 2 * k), idesc2, k == 0 ? accf : 1u);
+                                            tc_mma_f8(d_tmem, mk(al + a_plane16 + 2 * k), mk(bl + b2 + 2 * k), idesc1, 1u);
+                                        }
+                                        if (cs > 1) tc_commit_mc(bar_eb + 8u * sB, cmask); else tc_commit(bar_eb + 8u * sB);
+                                    }
+                                    __syncwarp();
+                                    accf = 1u;
+                                }
+                                if (++sB == nbs) { sB = 0; phB ^= 1u; }
+                            }
+                            if (elect_one()) tc_commit(bar_ea + 8u * sA);
+                            __syncwarp();
+                            if (++sA == nas) { sA = 0; phA ^= 1u; }
+                        }
+                if (elect_one()) tc_commit(bar_tfull + 8u * as);
+                __syncwarp();
+            }
+        } else
         for (int st = cid; st < n_super; st += ncl, ++it) {
             const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
             long long t0 = DBG ? clock64() : 0;
@@ -397,7 +528,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                             // free-running issuers may take the blocks in PAIRS (a.deal == 2: blocks 4i, 4i+1 / 4i+2, 4i+3): twice the MMAs per
                             // issue phase for the same barrier round trips (a multiple of four weight stages keeps a slot with one issuer)
                             const uint32_t turn = own ? (gblk >> dsh) : blk;
-                            const bool mine_dbg = two == 0u || (turn & 1u) == role;
+                            const bool mine_dbg = two == 0u || (ni == 3u ? turn % 3u : (turn & 1u)) == role;
                             if (mine_dbg) {
                                 const long long t_body = DBG ? clock64() : 0;
                                 const uint32_t bh_lo = lo_of(smem_b + sB * b_stage);
@@ -411,15 +542,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                 tc_fence_after();
                                 if (DBG) w_te += clock64() - t0;        // (DBG: the "tempty" counter also carries the per-block fence)
                                 // this issuer's NEXT block: poll its barrier now, the round trip hides behind the issue
-                                uint32_t s2 = sB + 1u + two, ph2 = phB;
+                                uint32_t s2 = sB + ni, ph2 = phB;
                                 if (dsh) s2 = sB + ((gblk & 1u) ? 3u : 1u);
                                 if (s2 >= nbs) { s2 -= nbs; ph2 ^= 1u; }
                                 t0 = DBG ? clock64() : 0;
                                 if (a.poll == 0) b_ready = mbar_try_wait(bar_fb + 8u * s2, ph2);
                                 else b_ready = false;
                                 if (DBG) w_try += clock64() - t0;
-                                if (two && !own && blk > 0) {     // my turn: the other issuer has issued block blk - 1
-                                    if (role) asm volatile("bar.sync 2, 64;" ::: "memory"); else asm volatile("bar.sync 1, 64;" ::: "memory");
+                                if (two && !own && blk > 0) {     // my turn: the previous issuer has issued block blk - 1
+                                    if (role == 0u) asm volatile("bar.sync 1, 64;" ::: "memory");
+                                    else if (role == 1u) asm volatile("bar.sync 2, 64;" ::: "memory");
+                                    else asm volatile("bar.sync 3, 64;" ::: "memory");
                                 }
                                 t0 = DBG ? clock64() : 0;
                                 if (elect_one()) {
@@ -452,8 +585,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
                                 if (a.poll == 2) b_ready = mbar_test_wait(bar_fb + 8u * s2, ph2);      // (after the issue: never delays it)
                                 if (DBG) w_issue += clock64() - t0;
                                 fresh = false;
-                                if (two && !own && blk + 1 < kb_total) {  // hand the turn to the other issuer
-                                    if (role) asm volatile("bar.arrive 1, 64;" ::: "memory"); else asm volatile("bar.arrive 2, 64;" ::: "memory");
+                                if (two && !own && blk + 1 < kb_total) {  // hand the turn to the next issuer (role + 1 mod ni waits on barrier 1 + that role)
+                                    const uint32_t nxt = role + 1u == ni ? 0u : role + 1u;
+                                    if (nxt == 0u) asm volatile("bar.arrive 1, 64;" ::: "memory");
+                                    else if (nxt == 1u) asm volatile("bar.arrive 2, 64;" ::: "memory");
+                                    else asm volatile("bar.arrive 3, 64;" ::: "memory");
                                 }
                                 if (DBG) w_body += clock64() - t_body;
                             }
@@ -1365,13 +1501,17 @@ int tc_plan_create(ConvParams& p) {
     // per accumulator stage: [hi*hi + lo*hi | hi*lo] = 2*bn columns, read in 32-column windows (bn%32 tail -> pad)
     a.acc_cols = p.mixed ? (bn + 31) / 32 * 32 : (bn + (bn + 31) / 32 * 32 + 31) / 32 * 32;      // (MIXED: one accumulator of bn columns)
     const int kb = ps3 ? (a.chunks1 + a.chunks2) * (a.ku - 1) * (a.kv - 1) : (a.chunks1 + a.chunks2) * (ps2 ? a.ku - 1 : a.ku) * ((a.g_ntaps[0] + a.tpb - 1) / a.tpb + (a.n_groups > 1 ? (a.g_ntaps[1] + a.tpb - 1) / a.tpb : 0));
-    a.issuers = (kb >= 2 && env_int("EVK_TC_ISSUERS", 2) == 2) ? 2 : 1;
+    a.issuers = (kb >= 2 && env_int("EVK_TC_ISSUERS", 2) >= 2) ? 2 : 1;
+    // MIXED: three issuers in strict order (one warp requests both operands) -- an issuer's per-block preparation (barrier round
+    // trips, ~230 instructions of descriptor set-up) then has two other issuers' blocks to hide behind instead of one
+    if (p.mixed && kb >= 3 && bs >= 4 && env_int("EVK_TC_ISSUERS", 2) == 3) a.issuers = 3;      // (measured: +3 % at most; off)
     a.own_acc = (a.issuers == 2 && 4 * a.acc_cols <= 512 && env_int("EVK_TC_OWN_ACC", 1)) ? 1 : 0;
     a.acc_stride = a.own_acc ? 2 * a.acc_cols : a.acc_cols;
     if (a.own_acc && (a.b_stages & 1)) {      // free-running issuers need a slot to belong to one issuer (see the kernel)
         a.b_stages -= 1; bs -= 1;
     }
     a.deal = (p.mixed && a.own_acc && a.b_stages % 4 == 0 && env_int("EVK_TC_DEAL", 1) == 2) ? 2 : 1;      // (pairs measured 3 % slower: kept for experiments)
+    a.lean = (p.mixed && a.tpb == 1 && a.issuers == 2 && a.own_acc && a.deal == 1 && env_int("EVK_TC_LEAN", 1)) ? 1 : 0;
     uint32_t cols = 32;
     while ((int)cols < 2 * a.acc_stride) cols <<= 1;
     if (cols > 512) { delete pl; EVK_REQUIRE(false, EVK_ERR_ARG, "conv_tc: accumulator does not fit tensor memory (bn=%d)", bn); }

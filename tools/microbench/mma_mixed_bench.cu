@@ -13,7 +13,7 @@
 using namespace evk;
 namespace evk { void set_error(const char*, ...) {} }
 
-struct Args { int bn, pattern, issuers, blocks, b_stages, a_atoms, waits; };     // waits: 0 none, 1 full-barrier wait + fence per block, 2 + look-ahead poll, 3 wait only (no fence), 4 fence only
+struct Args { int bn, pattern, issuers, blocks, b_stages, a_atoms, waits, readers, data; };   // data: 0 zeros, 1 random finite operands     // waits: 0 none, 1 full-barrier wait + fence per block, 2 + look-ahead poll, 3 wait only (no fence), 4 fence only
 
 __global__ void __launch_bounds__(256, 1) mixed_bench(Args a, long long* out) {
     constexpr uint32_t ROW_BYTES = 128, ATOM = 1024;
@@ -22,7 +22,12 @@ __global__ void __launch_bounds__(256, 1) mixed_bench(Args a, long long* out) {
     __shared__ uint64_t bars[8];
     __shared__ uint32_t slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0;
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) {
+        // random operands: every 16-bit half is a finite fp16 / bf16 (exponent field masked to stay small) and every byte a finite fp8
+        uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        reinterpret_cast<uint32_t*>(smem_raw)[i] = a.data ? (h & 0xB7B7B7B7u) : 0u;
+    }
     if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1); mbar_fence_init(); }
     if (warp == 2) tc_alloc(smem_u32(&slot), 512);
     tc_fence_before();
@@ -91,6 +96,20 @@ __global__ void __launch_bounds__(256, 1) mixed_bench(Args a, long long* out) {
         const long long t2 = clock64();
         if (lane == 0 && role == 0) out[blockIdx.x] = t2 - t0;
     }
+    if (a.readers && warp >= 4) {
+        // "epilogue" load: warps 4-7 read 32-column windows of tensor memory (columns 256.., not the accumulators) and do some math,
+        // for roughly as long as the issuers run (readers = windows per block of MMAs)
+        uint32_t v[32];
+        float acc = 0.f;
+        const uint32_t t_row = tmem_base + 256u + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int i = 0; i < a.blocks * a.readers; ++i) {
+            tc_ld_32x32(t_row + (uint32_t)((i & 3) * 32), v);
+            tc_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc += __expf(__uint_as_float(v[k]));
+        }
+        if (acc == 123.456f) out[147] = 0;
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tc_dealloc(tmem_base, 512);
@@ -101,13 +120,17 @@ int main() {
     cudaMalloc(&d, 148 * sizeof(long long));
     cudaFuncSetAttribute(mixed_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     const char* names[5] = {"bf16x3 (N=2bn + N=bn)", "mixed f16+f8 alternating", "f16 only", "f8 only", "mixed, four f16 then four f8"};
+    for (int data : {0, 1})
+    for (int readers : {0, 1, 4})
     for (int waits = 0; waits <= 4; ++waits)
     for (int bn : {128, 256})
         for (int issuers = 1; issuers <= 2; ++issuers)
             for (int pattern = 0; pattern < 5; ++pattern) {
                 if (bn == 256 && (pattern == 0 || issuers == 2)) continue;        // tensor memory: 512 columns
                 if (waits > 0 && !(bn == 128 && (pattern == 0 || pattern == 1))) continue;
-                Args a = {bn, pattern, issuers, 2000, bn == 256 ? 2 : 4, 18, waits};
+                if (data > 0 && (readers > 0 || waits > 0 || issuers != 2)) continue;
+                if (readers > 0 && !(bn == 128 && issuers == 2 && (pattern == 0 || pattern == 1) && waits <= 1)) continue;
+                Args a = {bn, pattern, issuers, 2000, bn == 256 ? 2 : 4, 18, waits, readers, data};
                 mixed_bench<<<148, 256, 210 * 1024>>>(a, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("%s: %s\n", names[pattern], cudaGetErrorString(e)); return 1; }
@@ -116,7 +139,7 @@ int main() {
                 double tot = 0;
                 for (int i = 0; i < 148; ++i) tot += h[i];
                 const double steps = (double)a.blocks * 4 * issuers;
-                printf("waits=%d bn=%3d issuers=%d %-32s %.1f cyc per K step per CTA\n", waits, bn, issuers, names[pattern], tot / 148 / steps);
+                printf("data=%d readers=%d waits=%d bn=%3d issuers=%d %-32s %.1f cyc per K step per CTA\n", data, readers, waits, bn, issuers, names[pattern], tot / 148 / steps);
             }
     return 0;
 }
