@@ -450,7 +450,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant_
             // look-ahead poll.  ncu's instruction-level sampling of the general loop (profiles/r02b_issuer_stalls.md) showed the
             // issuer warps blocked on the tensor pipe only a quarter of the time: ~157 mostly serial instructions per K block
             // (kernel-parameter reloads, mode branches) cost ~1 450 cycles next to 512 cycles of MMAs.  (The same loop generalised
-            // to the bf16x3 kernels cost them registers: 88 bytes of spills and FireNet 13 % slower -- kept to MIXED.)
+            // to the bf16x3 kernels -- in the same kernel, or as a separate instantiation with only this loop -- cost them registers:
+            // 56-88 bytes of spills, FireNet 8-13 % slower, whose layers are bound by their epilogues: kept to MIXED.  The K block
+            // as ONE asm statement with four 64-bit descriptors advanced in place changed nothing.)
             const uint32_t a_stage16 = a_stage >> 4, b_stage16 = b_stage >> 4;
             const uint32_t a_lo_base = lo_of(base), b_lo_base = lo_of(smem_b);
             const uint32_t nas = (uint32_t)a.a_stages;
