@@ -61,6 +61,7 @@ SIGNATURES = {
     "evk_u8_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "evk_quantize_u8": (_i, [_vp, _vp, _i64, _vp]),
     "evk_equalize_hist": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "evk_equalize_local": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "evk_lpips_create": (_i, [_i, _i, _i, _i, _i, _c.POINTER(_vp)]),
     "evk_lpips_load_tensor": (_i, [_vp, _c.c_char_p, _vp, _c.POINTER(_i64), _i]),
     "evk_lpips_finalize": (_i, [_vp]),

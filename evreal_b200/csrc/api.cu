@@ -28,6 +28,7 @@ int crop(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int u8_to_f32(const uint8_t*, float*, int64_t, cudaStream_t);
 int quantize_u8(const float*, uint8_t*, int64_t, cudaStream_t);
 int equalize_hist(const float*, float*, int, int, int, cudaStream_t);
+int equalize_local(const float*, float*, int, int, int, int, int, cudaStream_t);
 int voxelize_raw_batch(const evk_event_window*, int, int, int, int, float*, int*, cudaStream_t);
 int u8_to_f32_batch(const uint8_t* const*, int, int64_t, float*, cudaStream_t);
 int mse_ssim(const float*, const float*, int, int, int, int, double*, cudaStream_t);
@@ -105,6 +106,11 @@ int evk_crop(const float* in, float* out, int n, int C, int Hp, int Wp, int H, i
 int evk_u8_to_f32(const uint8_t* in, float* out, int64_t numel, void* stream) {
     EVK_REQUIRE(in && out, EVK_ERR_ARG, "evk_u8_to_f32: null pointer");
     return evk::u8_to_f32(in, out, numel, (cudaStream_t)stream);
+}
+
+int evk_equalize_local(const float* img, float* out, int n_images, int H, int W, int radius, int clip, void* stream) {
+    EVK_REQUIRE(img && out, EVK_ERR_ARG, "evk_equalize_local: null pointer");
+    return evk::equalize_local(img, out, n_images, H, W, radius, clip, (cudaStream_t)stream);
 }
 
 int evk_equalize_hist(const float* img, float* out, int n_images, int numel, int clip, void* stream) {

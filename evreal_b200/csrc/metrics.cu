@@ -394,4 +394,76 @@ int equalize_hist(const float* img, float* out, int n, int numel, int clip, cuda
     return EVK_OK;
 }
 
+// EvalMetricsTracker.histogram_equalization, hist_eq == 'local' (utils/eval_metrics.py:332-339):
+//     img_as_float32(skimage.filters.rank.equalize(img_as_ubyte(img), footprint=disk(55)))
+// scikit-image is a third-party dependency absent from the reference tree (parity unpinned); its published algorithm
+// (filters/rank/generic_cy.pyx, _kernel_equalize): for every pixel, over the footprint pixels that lie INSIDE the image
+// (pop of them), out = uint8(255 * #{v <= g} / pop) with g the pixel's own grey level (double division, truncation);
+// disk(r) = {dx^2 + dy^2 <= r^2}; img_as_ubyte = rint(v * 255) in float32, img_as_float32 = u8 * float32(1 / 255).
+// CTA = 16 x 16 output pixels; the (16 + 2r)^2 neighbourhood sits in shared memory as uint16 (0xffff = outside the image).
+constexpr int kEqTile = 16;
+
+__global__ void __launch_bounds__(kEqTile * kEqTile)
+equalize_local_kernel(const float* __restrict__ img, float* __restrict__ out, int H, int W, int r, int clip) {
+    extern __shared__ unsigned short s_px[];
+    const int span = kEqTile + 2 * r;
+    int* s_hw = reinterpret_cast<int*>(s_px + ((size_t)span * span + 1) / 2 * 2);      // half width of the disk per row offset
+    const float* v = img + (size_t)blockIdx.z * H * W;
+    float* o = out + (size_t)blockIdx.z * H * W;
+    const int x0 = blockIdx.x * kEqTile, y0 = blockIdx.y * kEqTile;
+    const int tid = threadIdx.y * kEqTile + threadIdx.x;
+    for (int i = tid; i < span * span; i += kEqTile * kEqTile) {
+        const int yy = y0 - r + i / span, xx = x0 - r + i % span;
+        unsigned short q = 0xffffu;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            float a = v[(size_t)yy * W + xx];
+            if (clip) a = fminf(fmaxf(a, 0.0f), 1.0f);
+            q = (unsigned short)fminf(fmaxf(rintf(a * 255.0f), 0.0f), 255.0f);
+        }
+        s_px[i] = q;
+    }
+    for (int d = tid; d <= 2 * r; d += kEqTile * kEqTile) {
+        const int dy = d - r;
+        int w = 0;
+        while ((w + 1) * (w + 1) + dy * dy <= r * r) ++w;
+        s_hw[d] = w;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int cx = threadIdx.x + r, cy = threadIdx.y + r;
+    const unsigned int g = s_px[cy * span + cx];
+    unsigned int pop = 0, le = 0;
+    for (int d = 0; d <= 2 * r; ++d) {
+        const int w = s_hw[d];
+        const unsigned short* row = s_px + (cy + d - r) * span + cx;
+        for (int dx = -w; dx <= w; ++dx) {
+            const unsigned int q = row[dx];
+            pop += q != 0xffffu;
+            le += q <= g;                 // (0xffff never is)
+        }
+    }
+    const double e = pop ? (double)(255ull * le) / (double)pop : 0.0;
+    o[(size_t)y * W + x] = (float)(unsigned int)e * (1.0f / 255.0f);
+}
+
+int equalize_local(const float* img, float* out, int n, int H, int W, int radius, int clip, cudaStream_t st) {
+    EVK_REQUIRE(n > 0 && H > 0 && W > 0 && radius >= 1 && radius <= 100, EVK_ERR_ARG, "evk_equalize_local: bad argument (radius 1..100)");
+    EVK_REQUIRE(img != out, EVK_ERR_ARG, "evk_equalize_local: in-place operation is not supported (every output reads a neighbourhood)");
+    const int span = kEqTile + 2 * radius;
+    const size_t smem = ((size_t)span * span + 1) / 2 * 2 * sizeof(unsigned short) + (size_t)(2 * radius + 1) * sizeof(int);
+    static bool attr_dev[64] = {false};
+    int dev = 0;
+    EVK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_dev[dev]) {
+        EVK_CHECK_CUDA(cudaFuncSetAttribute(equalize_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_dev[dev] = true;
+    }
+    EVK_REQUIRE(smem <= 200 * 1024, EVK_ERR_ARG, "evk_equalize_local: radius too large for shared memory");
+    dim3 grid((unsigned)ceil_div(W, kEqTile), (unsigned)ceil_div(H, kEqTile), (unsigned)n);
+    equalize_local_kernel<<<grid, dim3(kEqTile, kEqTile), smem, st>>>(img, out, H, W, radius, clip);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
 }  // namespace evk

@@ -155,7 +155,8 @@ class EvalMetricsTracker:
     sequence instead of one per frame); files and score lists are identical afterwards.
     Histogram equalisation (utils/eval_metrics.py:326-350): 'global' runs on the GPU (evk_equalize_hist, skimage's
     published algorithm -- parity unpinned, scikit-image is not installable offline), 'clahe' is the reference's own
-    cv2.createCLAHE call on the host, 'local' (skimage rank filter over a disk of radius 55) is not built.
+    cv2.createCLAHE call on the host, 'local' (skimage rank filter over a disk of radius 55) runs on the GPU
+    (evk_equalize_local; parity unpinned like 'global').
     """
 
     def __init__(self, save_images=False, save_processed_images=False, output_dir=None, hist_eq='none',
@@ -166,8 +167,6 @@ class EvalMetricsTracker:
             quan_eval_metric_names = ['mse', 'ssim', 'lpips']
         if hist_eq not in ('none', 'global', 'clahe', 'local'):
             raise ValueError(f"Unrecognized histogram equalization argument: {hist_eq}")
-        if hist_eq == 'local':
-            raise NotImplementedError("hist_eq 'local' (skimage.filters.rank.equalize over disk(55)) is not built")
         self.save_images = save_images
         self.save_processed_images = save_processed_images
         if hist_eq == 'none' and self.save_processed_images:
@@ -334,6 +333,14 @@ class EvalMetricsTracker:
             out = torch.empty_like(x)
             with torch.cuda.device(x.device):
                 _lib.check(_lib.load().evk_equalize_hist(_lib.ptr(x), _lib.ptr(out), 1, x.numel(), 0, _lib.stream_ptr(x.device)))
+            return out.cpu().numpy() if was_numpy else out
+        if self.hist_eq == 'local':
+            was_numpy = isinstance(img, np.ndarray)
+            x = _cuda_img(img)
+            out = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().evk_equalize_local(_lib.ptr(x), _lib.ptr(out), 1, int(x.shape[-2]), int(x.shape[-1]), 55, 0,
+                                                          _lib.stream_ptr(x.device)))
             return out.cpu().numpy() if was_numpy else out
         if self.hist_eq == 'clahe':
             import cv2

@@ -219,6 +219,12 @@ int evk_u8_to_f32_batch(const uint8_t* const* frames, int n_frames, int64_t nume
  * img/out: [n_images, numel] float32 (may alias); clip != 0 first clamps to [0,1]. */
 int evk_equalize_hist(const float* img, float* out, int n_images, int numel, int clip, void* stream);
 
+/* EvalMetricsTracker.histogram_equalization with hist_eq == 'local' (utils/eval_metrics.py:332-339):
+ * img_as_float32(skimage.filters.rank.equalize(img_as_ubyte(img), footprint=disk(radius))), radius = 55 in the reference:
+ * per pixel, over the disk's pixels inside the image, uint8(255 * #{v <= own grey level} / population) / 255.
+ * img/out: [n_images, H, W] float32, NOT aliased; clip != 0 first clamps to [0,1]. */
+int evk_equalize_local(const float* img, float* out, int n_images, int H, int W, int radius, int clip, void* stream);
+
 /* float32 frame -> uint8 for the PNG writer: uint8(round_half_even(clip(v, 0, 1) * 255))
  * (save_inferred_image, utils/eval_utils.py:80-84, after the clip of EvalMetricsTracker.update, utils/eval_metrics.py:253-255) */
 int evk_quantize_u8(const float* in, uint8_t* out, int64_t numel, void* stream);

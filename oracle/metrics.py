@@ -118,6 +118,30 @@ def equalize_hist_oracle(img, nbins=256):
     return np.interp(img.ravel(), centres, cdf).reshape(img.shape).astype(np.float32)
 
 
+def equalize_local_oracle(img, radius=55):
+    """EvalMetricsTracker.histogram_equalization, hist_eq == 'local' (utils/eval_metrics.py:332-339):
+    img_as_float32(skimage.filters.rank.equalize(img_as_ubyte(img), footprint=disk(radius))).  PARITY UNPINNED (scikit-image is
+    not installable offline); its published algorithm (filters/rank/generic_cy.pyx::_kernel_equalize): for every pixel, over the
+    footprint pixels inside the image (pop of them), uint8(255 * #{v <= g} / pop), g = the pixel's own grey level; disk(r) =
+    {dx^2 + dy^2 <= r^2}; img_as_ubyte rounds v * 255 half-to-even in float32, img_as_float32 multiplies by float32(1 / 255)."""
+    img = np.asarray(img, dtype=np.float32)
+    u8 = np.clip(np.rint(img * np.float32(255)), 0, 255).astype(np.int32)
+    H, W = u8.shape
+    pad = np.full((H + 2 * radius, W + 2 * radius), -1, dtype=np.int32)
+    pad[radius:radius + H, radius:radius + W] = u8
+    pop = np.zeros((H, W), dtype=np.int64)
+    le = np.zeros((H, W), dtype=np.int64)
+    for dy in range(-radius, radius + 1):
+        w = int(np.floor(np.sqrt(radius * radius - dy * dy)))
+        for dx in range(-w, w + 1):
+            q = pad[radius + dy:radius + dy + H, radius + dx:radius + dx + W]
+            valid = q >= 0
+            pop += valid
+            le += valid & (q <= u8)
+    out = np.where(pop > 0, (255 * le) / np.maximum(pop, 1).astype(np.float64), 0.0).astype(np.uint8)      # C cast: truncation
+    return out.astype(np.float32) * np.float32(1.0 / 255.0)
+
+
 def quantize_u8_oracle(img):
     """save_inferred_image (utils/eval_utils.py:80-84) after the tracker's clip: uint8(np.round(clip(img, 0, 1) * 255))."""
     return np.round(np.clip(np.asarray(img, dtype=np.float32), 0.0, 1.0) * 255).astype(np.uint8)

@@ -105,6 +105,39 @@ def test_global_histogram_equalisation_vs_oracle():
     assert np.allclose(out.cpu().numpy(), om.equalize_hist_oracle(const.cpu().numpy()))
 
 
+def test_local_histogram_equalisation_vs_oracle():
+    """hist_eq 'local' (utils/eval_metrics.py:332-339: rank.equalize over disk(55)) on the GPU against the numpy restatement of
+    skimage's algorithm: bit-exact (integer counts, one double division); a small radius on a non-tile size, and the reference's
+    radius 55 on an image smaller than the footprint (the population varies at every pixel)."""
+    from evreal_b200 import _lib
+    from oracle import metrics as om
+    g = np.random.default_rng(9)
+    for H, W, r in ((37, 53, 5), (48, 64, 55), (33, 20, 16)):
+        img = np.clip(g.normal(0.45, 0.25, (H, W)), 0, 1).astype(np.float32)
+        img[:3, :5] = 0.0
+        img[-2:, :] = 1.0
+        x = torch.from_numpy(img).cuda()
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().evk_equalize_local(_lib.ptr(x), _lib.ptr(out), 1, H, W, r, 0, _lib.stream_ptr()))
+        assert np.array_equal(out.cpu().numpy(), om.equalize_local_oracle(img, r)), (H, W, r)
+    with pytest.raises(ValueError):
+        _lib.check(_lib.load().evk_equalize_local(_lib.ptr(x), _lib.ptr(x), 1, H, W, r, 0, _lib.stream_ptr()))      # in place
+
+
+def test_tracker_with_local_histeq_matches_oracle_scores():
+    from evreal_b200.eval_metrics import EvalMetricsTracker
+    from oracle import metrics as om
+    g = golden('metrics')
+    img, ref = g['a7.img'][:64, :80], g['a7.ref'][:64, :80]
+    tr = EvalMetricsTracker(hist_eq='local', quan_eval_metric_names=['mse', 'ssim'], has_reference_frames=True, write_files=False)
+    tr.update(0, torch.from_numpy(np.ascontiguousarray(img)).cuda(), torch.from_numpy(np.ascontiguousarray(ref)).cuda(), 0.5, 0.5)
+    tr.finalize(0)
+    a, b = om.equalize_local_oracle(np.clip(img, 0, 1)), om.equalize_local_oracle(np.clip(ref, 0, 1))
+    means = tr.get_mean_scores()
+    assert abs(means['mse'] - om.mse_oracle(a, b)) <= 1e-4 * om.mse_oracle(a, b)
+    assert abs(means['ssim'] - om.ssim_oracle(a, b)) <= 1e-4
+
+
 def test_tracker_with_global_histeq_matches_oracle_scores():
     from evreal_b200.eval_metrics import EvalMetricsTracker
     from oracle import metrics as om

@@ -53,3 +53,16 @@ def test_lpips_restatement_properties():
         assert float(om.lpips_oracle(a, a, w, net).abs().max()) == 0.0
         d = om.lpips_oracle(a, b, w, net)
         assert d.shape == (2,) and bool((d > 0).all())
+
+
+def test_local_equalisation_oracle_known_answers():
+    """rank.equalize restatement: a constant image maps to 255/255 everywhere (every neighbour <= g), a strictly increasing ramp
+    with a footprint covering the whole image maps pixel k of n to floor(255 (k + 1) / n) / 255."""
+    from oracle import metrics as om
+    const = np.full((9, 11), 0.3, dtype=np.float32)
+    assert np.array_equal(om.equalize_local_oracle(const, 3), np.ones((9, 11), dtype=np.float32))
+    n = 12
+    ramp = (np.arange(n, dtype=np.float32) * 20 / 255).reshape(1, n)
+    got = om.equalize_local_oracle(ramp, 55)
+    want = (np.floor(255 * (np.arange(n) + 1) / n).astype(np.uint8)).astype(np.float32) * np.float32(1 / 255.0)
+    assert np.array_equal(got[0], want)
