@@ -163,7 +163,7 @@ int evk_pack_layer_weights(int kind, const float* w_oihw_host, int Cout, int Cin
             pack_weights_window(w_kc.data(), kh, kw, Cin, 16, Cout, group, out);
             break;
         case 4: {
-            // mixed operands (conv.cuh, ConvParams::mixed), DECODED: [3][K][Cout] = 16 w16 / S, wl8 / S, 4096 w8 / S
+            // mixed operands (conv.cuh, ConvParams::mixed), DECODED: [3][K][Cout] = w16 / S, wl8 / S, 256 w8 / S
             const int K = kh * kw * Cin, cp = (Cout + 31) / 32 * 32;
             EVK_REQUIRE(K % 64 == 0, EVK_ERR_ARG, "evk_pack_layer_weights: mixed operands need kh*kw*Cin %% 64 == 0");
             std::vector<__nv_bfloat16> packed;
@@ -177,9 +177,9 @@ int evk_pack_layer_weights(int kind, const float* w_oihw_host, int Cout, int Cin
                     __half_raw hr; hr.x = p0[(size_t)n * K + k];
                     const uint8_t* row = p1 + ((size_t)n * K + (size_t)(k / 64) * 64) * 2;
                     const __half_raw l = __nv_cvt_fp8_to_halfraw(row[k % 64], __NV_E4M3), w8 = __nv_cvt_fp8_to_halfraw(row[64 + k % 64], __NV_E4M3);
-                    out[((size_t)0 * K + k) * Cout + n] = __half2float(__half(hr)) * 16.0f * isc[n];
+                    out[((size_t)0 * K + k) * Cout + n] = __half2float(__half(hr)) * isc[n];
                     out[((size_t)1 * K + k) * Cout + n] = __half2float(__half(l)) * isc[n];
-                    out[((size_t)2 * K + k) * Cout + n] = __half2float(__half(w8)) * 4096.0f * isc[n];
+                    out[((size_t)2 * K + k) * Cout + n] = __half2float(__half(w8)) * 256.0f * isc[n];
                 }
             break;
         }

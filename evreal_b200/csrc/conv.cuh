@@ -98,10 +98,10 @@ struct ConvParams {
     // "mixed" operand decomposition (conv_tc.cu, MIXED kernels): x.w ~ x16.w16 + x8.wl8 + xl8.w8 -- one fp16 product and two fp8
     // products at twice the rate (2 tensor-pipe units instead of the 3 of bf16x3; measured 1.5-2.5e-5 end to end on the shipped
     // E2VID weights against 5e-6, tools/mixed_numerics_probe.py).  mixed = 1: x1s / x2s are mixed-format companions (plane 0 =
-    // fp16(16 v), plane 1 = per 64-channel chunk [e5m2(v) | e5m2(4096 (v - x16))]) and the kernel reads w_mx / w_iscale.
+    // fp16(v), plane 1 = per 64-channel chunk [e5m2(v) | e5m2(256 (v - x16))]) and the kernel reads w_mx / w_iscale.
     // Plain layers only (c1, c2 multiples of 64; no row-window / pixel-pair / row-pair forms).
     int mixed = 0;
-    const __nv_bfloat16* w_mx = nullptr;  // [2][cout_pad][K] 2-byte slots: plane 0 fp16(w S[n] / 16), plane 1 per 64-k chunk [e4m3(wl S[n]) | e4m3(w S[n] / 4096)]
+    const __nv_bfloat16* w_mx = nullptr;  // [2][cout_pad][K] 2-byte slots: plane 0 fp16(w S[n]), plane 1 per 64-k chunk [e4m3(wl S[n]) | e4m3(w S[n] / 256)]
     const float* w_iscale = nullptr;      // [cout_pad] 1 / S[n] (S[n] a power of two)
     int ys_mixed = 0, hs_mixed = 0;       // the split copy this layer writes (ys / hs_new) is in the mixed format
     struct TcPlan* tc = nullptr;          // tensor maps + tiling, built once per layer (tc_plan_create)

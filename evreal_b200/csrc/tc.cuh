@@ -213,15 +213,16 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 // ---- "mixed" split records (consumers: MIXED kernels).  A pixel of C channels (C % 64 == 0) is 2*C bytes in either plane:
-// plane 0 = fp16(16 v) [C]; plane 1 = per 64-channel chunk 64 bytes e5m2(v) then 64 bytes e5m2(4096 (v - x16)), x16 = fp16(16 v) / 16.
+// plane 0 = fp16(v) [C] (saturating at +-65504); plane 1 = per 64-channel chunk 64 bytes e5m2(v) then 64 bytes
+// e5m2(256 (v - x16)), x16 = fp16(v).
 // o = element offset of the record's first channel (2-byte units, = pixel * C + c0), c0 = that channel's index in its pixel.
 __device__ __forceinline__ void mixed_cvt2(float v0, float v1, uint32_t& h2, uint32_t& x2, uint32_t& l2) {
-    const float s0 = fminf(fmaxf(v0 * 16.0f, -65504.0f), 65504.0f), s1 = fminf(fmaxf(v1 * 16.0f, -65504.0f), 65504.0f);
+    const float s0 = fminf(fmaxf(v0, -65504.0f), 65504.0f), s1 = fminf(fmaxf(v1, -65504.0f), 65504.0f);
     const __half2 h = __floats2half2_rn(s0, s1);
     h2 = *reinterpret_cast<const uint32_t*>(&h);
     const float2 hf = __half22float2(h);
     x2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(v0, v1), __NV_SATFINITE, __NV_E5M2);
-    l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x * 0.0625f) * 4096.0f, (v1 - hf.y * 0.0625f) * 4096.0f), __NV_SATFINITE, __NV_E5M2);
+    l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * 256.0f, (v1 - hf.y) * 256.0f), __NV_SATFINITE, __NV_E5M2);
 }
 __device__ __forceinline__ void store_mixed8(__nv_bfloat16* base, long long plane, size_t o, int c0, const float* f) {
     uint32_t h[4], x[4], l[4];
@@ -252,8 +253,8 @@ __device__ __forceinline__ void load_mixed8(const __nv_bfloat16* base, long long
     for (int i = 0; i < 4; ++i) {
         const float2 hf = __half22float2(hp[i]);
         const __half_raw r0 = {(unsigned short)(lb[2 * i] << 8)}, r1 = {(unsigned short)(lb[2 * i + 1] << 8)};      // e5m2 = the high byte of an fp16
-        f[2 * i] = hf.x * 0.0625f + __half2float(__half(r0)) * (1.0f / 4096.0f);
-        f[2 * i + 1] = hf.y * 0.0625f + __half2float(__half(r1)) * (1.0f / 4096.0f);
+        f[2 * i] = hf.x + __half2float(__half(r0)) * (1.0f / 256.0f);
+        f[2 * i + 1] = hf.y + __half2float(__half(r1)) * (1.0f / 256.0f);
     }
 }
 }  // namespace evk

@@ -57,6 +57,18 @@ def emu_conv2d(x, w, b=None, stride=1, padding=0, *a, **k):
         w16 = (w * S / 16).half().float() * 16 / S
         wl8 = f8w((w - w16) * S) / S; w8 = f8w(w * S / 4096.0) * 4096.0 / S
         y = c(x16, w16) + c(x8, wl8) + c(xl8, w8)
+    elif sch == 'mixed1':
+        # the shipped form (round 2 final): x16 = fp16(x) (saturating at 65504), x8 = e5m2(x), xl8 = e5m2(256 (x - x16));
+        # w16 = fp16(w S), wl8 = e4m3((w - w16 / S) S), w8 = e4m3(w S / 256), S[n] = 2^floor(log2(28672 / max|w[n]|))
+        f8a = lambda t: t.clamp(-57344.0, 57344.0).to(torch.float8_e5m2).float()
+        f8w = lambda t: t.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+        wmax = w.abs().flatten(1).max(1).values.clamp_min(1e-30)
+        S = torch.exp2(torch.floor(torch.log2(28672.0 / wmax))).view(-1, 1, 1, 1)
+        x16 = x.clamp(-65504, 65504).half().float()
+        x8 = f8a(x); xl8 = f8a((x - x16) * 256.0) / 256.0
+        w16 = (w * S).half().float() / S
+        wl8 = f8w((w - w16) * S) / S; w8 = f8w(w * S / 256.0) * 256.0 / S
+        y = c(x16, w16) + c(x8, wl8) + c(xl8, w8)
     elif sch == 'f16':
         y = c(r16(x), r16(w))
     else:
