@@ -472,6 +472,8 @@ def run_plugin_config(tag, torch, dist, rank, world, args, seconds=None):
                   lockstep=spec['n_seq'], lpips_weights=lpw)
         # warm-up pass: page cache, kernel plans, cuDNN-free -- and the numbers a second run of the same job sees
         ev.evaluate([spec['method']], ['std'], [spec['dataset']], spec['metrics'], **kw)
+        import gc
+        gc.collect()                     # the warm-up pass's model / LPIPS handles are freed here, not inside the timed call
         barrier()
         t0 = time.perf_counter()
         res = ev.evaluate([spec['method']], ['std'], [spec['dataset']], spec['metrics'], **kw)      # (ends with the all-reduce)

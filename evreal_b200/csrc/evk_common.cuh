@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "../../include/evreal_b200.h"
 
@@ -33,6 +35,34 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr int kNumSMs = 148;   // B200
+
+// Bump allocator over a few large device chunks (zero-initialised, 1 kB aligned): a network's device program is ~300 buffers, and
+// one cudaMalloc / cudaFree each made building and -- above all -- destroying a handle cost 0.3-0.7 s of driver calls (cudaFree
+// synchronises the device), inside the wall clock of evaluate().  Chunks grow from 32 MB to 512 MB.
+struct DeviceArena {
+    std::vector<void*> chunks;
+    char* cur = nullptr;
+    size_t left = 0, next = (size_t)32 << 20;
+    void* alloc(size_t bytes) {
+        bytes = std::max<size_t>((bytes + 1023) & ~(size_t)1023, 1024);
+        if (bytes > left) {
+            const size_t csz = std::max(bytes, next);
+            void* p = nullptr;
+            if (cudaMalloc(&p, csz) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            cudaMemset(p, 0, csz);
+            chunks.push_back(p);
+            cur = static_cast<char*>(p); left = csz;
+            next = std::min(next * 2, (size_t)512 << 20);
+        }
+        void* r = cur;
+        cur += bytes; left -= bytes;
+        return r;
+    }
+    void release() {
+        for (void* p : chunks) cudaFree(p);
+        chunks.clear(); cur = nullptr; left = 0;
+    }
+};
 
 // ---- activations used by conv epilogues
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_TANH = 3 };

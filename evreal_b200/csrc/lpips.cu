@@ -280,10 +280,9 @@ struct evk_lpips {
     double* part = nullptr;
     double flops = 0.0;
 
+    DeviceArena arena;                    // (evk_common.cuh)
     void* dalloc(size_t bytes) {
-        void* p = nullptr;
-        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
-        cudaMemset(p, 0, bytes);
+        void* p = arena.alloc(bytes);
         allocs.push_back(p);
         return p;
     }
@@ -578,8 +577,7 @@ int evk_lpips_num_tc_layers(evk_lpips* l) { return l ? (int)l->plans.size() : EV
 int evk_lpips_destroy(evk_lpips* l) {
     if (!l) return EVK_OK;
     for (TcPlan* pl : l->plans) tc_plan_destroy(pl);
-    for (void* p : l->allocs)
-        if (p) cudaFree(p);
+    l->arena.release();
     delete l;
     return EVK_OK;
 }

@@ -108,18 +108,15 @@ struct evk_model {
     std::map<const float*, int> mixed_bufs;            // fp32 buffer -> channels per pixel
     int mixed_convs = 0;
 
+    DeviceArena arena;               // every device buffer of the program (evk_common.cuh)
     float* dalloc(size_t nfloat) {
-        void* p = nullptr;
-        if (cudaMalloc(&p, nfloat * sizeof(float)) != cudaSuccess) return nullptr;
-        cudaMemset(p, 0, nfloat * sizeof(float));
-        allocs.push_back(p);
-        buf_elems[(const float*)p] = nfloat;
+        void* p = arena.alloc(nfloat * sizeof(float));
+        allocs.push_back(p);             // (nullptr = out of memory: checked at the end of finalize)
+        if (p) buf_elems[(const float*)p] = nfloat;
         return (float*)p;
     }
     void* dalloc_bytes(size_t bytes) {
-        void* p = nullptr;
-        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
-        cudaMemset(p, 0, bytes);
+        void* p = arena.alloc(bytes);
         allocs.push_back(p);
         return p;
     }
@@ -1630,8 +1627,7 @@ int evk_model_destroy(evk_model* m) {
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     for (TcPlan* pl : m->plans) tc_plan_destroy(pl);
-    for (void* p : m->allocs)
-        if (p) cudaFree(p);
+    m->arena.release();
     delete m;
     return EVK_OK;
 }
