@@ -23,6 +23,8 @@ class Uploader:
         if workers is None:
             world = max(int(os.environ.get("WORLD_SIZE", "1")), 1)
             workers = max(2, min(8, (os.cpu_count() or 4) // world))
+            if os.environ.get("EVK_UPLOAD_WORKERS"):
+                workers = max(1, int(os.environ["EVK_UPLOAD_WORKERS"]))
         self.dev = torch.device(device)
         self.workers, self.chunk = workers, chunk_bytes
         self.pool = ThreadPoolExecutor(max_workers=workers)

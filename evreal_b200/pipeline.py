@@ -149,6 +149,10 @@ class SequenceBatch:
                 self._base[b] = (xy.data_ptr(), t.data_ptr(), p.data_ptr(), im.data_ptr() if im is not None else 0)
         self._windows = (_lib.EventWindow * B)()
         self._frames = (ctypes.c_void_p * B)()
+        # numpy views of the two tables the batched kernels read (filled per step with four vector assignments instead of a Python
+        # loop over the sequences: the lock-step loop of a small network is bound by this host code)
+        self._windows_np = np.frombuffer(self._windows, dtype=np.int64).reshape(B, 4)      # columns: xy, t, pol, n
+        self._frames_np = np.frombuffer(self._frames, dtype=np.int64)
         self.lpips_net = None
         if lpips is not None and compute_metrics:
             from .lpips import LpipsNet
@@ -190,6 +194,9 @@ class SequenceBatch:
             self._last_slot = 1
             self._host_windows = (_lib.EventWindow * B)()
             self._host_frames = (ctypes.c_void_p * B)()
+            self._host_windows_np = np.frombuffer(self._host_windows, dtype=np.int64).reshape(B, 4)
+            self._host_frames_np = np.frombuffer(self._host_frames, dtype=np.int64)
+            self._b_index = np.arange(B, dtype=np.int64)
         if self._stream_up is None:
             torch.cuda.synchronize(dev)
 
@@ -214,21 +221,17 @@ class SequenceBatch:
         if self._consumed[slot] is not None:
             self.copy_stream.wait_event(self._consumed[slot])      # the kernels that read this slot have finished
         win = self._win[:, idx]
-        hw = self._host_windows
-        for b in range(B):
-            i0, i1 = int(win[b, 0]), int(win[b, 1])
-            w = hw[b]
-            w.xy = int(self._base[b, 0]) + i0 * 4
-            w.t = int(self._base[b, 1]) + i0 * 8
-            w.pol = int(self._base[b, 2]) + i0
-            w.n = i1 - i0
+        hw, hn = self._host_windows, self._host_windows_np
+        hn[:, 0] = self._base[:, 0] + win[:, 0] * 4
+        hn[:, 1] = self._base[:, 1] + win[:, 0] * 8
+        hn[:, 2] = self._base[:, 2] + win[:, 0]
+        hn[:, 3] = win[:, 1] - win[:, 0]
         cs = ctypes.c_void_p(self.copy_stream.cuda_stream)
         _lib.check(lib.evk_stage_windows_h2d(hw, B, _lib.ptr(self.st_xy[slot]), _lib.ptr(self.st_t[slot]),
                                              _lib.ptr(self.st_p[slot]), self.max_win, cs))
         if self.compute_metrics:
             hf = self._host_frames
-            for b in range(B):
-                hf[b] = int(self._base[b, 3]) + int(win[b, 2]) * self.H * self.W
+            self._host_frames_np[:] = self._base[:, 3] + win[:, 2] * (self.H * self.W)
             _lib.check(lib.evk_stage_frames_h2d(hf, B, self.H * self.W, _lib.ptr(self.st_im[slot]), cs))
         self._h2d_done[slot].record(self.copy_stream)
         self._staged[slot] = idx
@@ -253,14 +256,12 @@ class SequenceBatch:
         if self.resident:
             if self._stream_up is not None:
                 self._stream_up.wait(self._slice_of[min(idx, len(self._slice_of) - 1)], pre)
-            for b in range(B):
-                i0, i1 = int(win[b, 0]), int(win[b, 1])
-                w = ws[b]
-                w.xy = int(self._base[b, 0]) + i0 * 4
-                w.t = int(self._base[b, 1]) + i0 * 8
-                w.pol = int(self._base[b, 2]) + i0
-                w.n = i1 - i0
-                fr[b] = int(self._base[b, 3]) + int(win[b, 2]) * self.H * self.W
+            wn = self._windows_np
+            wn[:, 0] = self._base[:, 0] + win[:, 0] * 4
+            wn[:, 1] = self._base[:, 1] + win[:, 0] * 8
+            wn[:, 2] = self._base[:, 2] + win[:, 0]
+            wn[:, 3] = win[:, 1] - win[:, 0]
+            self._frames_np[:] = self._base[:, 3] + win[:, 2] * (self.H * self.W)
         else:
             slot = 0 if self._staged[0] == idx else (1 if self._staged[1] == idx else None)
             if slot is None:                      # first step / non-sequential access: stage now
@@ -270,13 +271,12 @@ class SequenceBatch:
             pre.wait_event(self._h2d_done[slot])
             xy0, t0, p0, im0 = (self.st_xy[slot].data_ptr(), self.st_t[slot].data_ptr(), self.st_p[slot].data_ptr(),
                                 self.st_im[slot].data_ptr())
-            for b in range(B):
-                w = ws[b]
-                w.xy = xy0 + b * self.max_win * 4
-                w.t = t0 + b * self.max_win * 8
-                w.pol = p0 + b * self.max_win
-                w.n = int(win[b, 1] - win[b, 0])
-                fr[b] = im0 + b * self.H * self.W
+            wn, bi = self._windows_np, self._b_index
+            wn[:, 0] = xy0 + bi * (self.max_win * 4)
+            wn[:, 1] = t0 + bi * (self.max_win * 8)
+            wn[:, 2] = p0 + bi * self.max_win
+            wn[:, 3] = win[:, 1] - win[:, 0]
+            self._frames_np[:] = im0 + bi * (self.H * self.W)
             self._h2d_step = n_events * 13 + (B * self.H * self.W if self.compute_metrics else 0)
         in_ptr, _ = self.model.io_buffers()
         # empty windows -> zeros grid (dataset.py:59-71) is part of the batched call
