@@ -35,7 +35,6 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
-#include <thread>
 #include <vector>
 
 #include "conv.cuh"
@@ -1250,21 +1249,6 @@ static double tile_cost(int bk, int ku, int kv, int stride, int chunks, int bn, 
     return 5000.0 + std::max(std::max(t_mma, t_l2), t_epi);
 }
 
-// host: output channels [n0, n1) of a packer in parallel (weights of a whole network are ~10 M values: the packers run once per
-// (model, shape) inside the first forward, i.e. inside the measured wall clock of evaluate())
-template <typename F>
-static void parallel_channels(int cout, F&& body) {
-    const int nt = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, cout / 16}));
-    if (nt <= 1) { body(0, cout); return; }
-    std::vector<std::thread> th;
-    const int per = (cout + nt - 1) / nt;
-    for (int t = 0; t < nt; ++t) {
-        const int n0 = t * per, n1 = std::min(cout, n0 + per);
-        if (n0 < n1) th.emplace_back([&body, n0, n1] { body(n0, n1); });
-    }
-    for (auto& t : th) t.join();
-}
-
 void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>& out) {
     out.assign((size_t)2 * cout_pad * K, __float2bfloat16(0.0f));
     __nv_bfloat16* o = out.data();
@@ -1277,7 +1261,7 @@ void pack_weights_tc(const float* w_kc, int K, int cout, int cout_pad, std::vect
                     o[(size_t)n * K + k] = hi;
                     o[(size_t)cout_pad * K + (size_t)n * K + k] = __float2bfloat16(v - __bfloat162float(hi));
                 }
-    });
+    }, (size_t)K * cout);
 }
 
 // Mixed operands.  With S = S[n] (a power of two per output channel, max|w[:, n]| S in (14336, 28672]):
@@ -1313,7 +1297,7 @@ void pack_weights_mixed(const float* w_kc, int K, int cout, int cout_pad, std::v
                     row[64 + k % 64] = (uint8_t)__nv_cvt_float_to_fp8(w * s * (1.0f / 256.0f), __NV_SATFINITE, __NV_E4M3);
                 }
         }
-    });
+    }, (size_t)K * cout);
 }
 
 bool tc_mixed_capable(const ConvParams& p) {

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/evreal_b200.h"
@@ -35,6 +36,22 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr int kNumSMs = 148;   // B200
+
+// host: output channels [n0, n1) of a packer in parallel (weights of a whole network are ~10 M values: the packers run once per
+// (model, shape) inside the first forward, i.e. inside the measured wall clock of evaluate())
+template <typename F>
+static inline void parallel_channels(int cout, F&& body, size_t work = (size_t)1 << 30) {
+    // (threads are created per call: one per ~32 k weights, so that small layers stay on the calling thread)
+    const int nt = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, cout / 16, (int)(work >> 15)}));
+    if (nt <= 1) { body(0, cout); return; }
+    std::vector<std::thread> th;
+    const int per = ((cout + nt - 1) / nt + 15) / 16 * 16;
+    for (int n0 = 0; n0 < cout; n0 += per) {
+        const int n1 = std::min(cout, n0 + per);
+        th.emplace_back([&body, n0, n1] { body(n0, n1); });
+    }
+    for (auto& t : th) t.join();
+}
 
 // Bump allocator over a few large device chunks (zero-initialised, 1 kB aligned): a network's device program is ~300 buffers, and
 // one cudaMalloc / cudaFree each made building and -- above all -- destroying a handle cost 0.3-0.7 s of driver calls (cudaFree

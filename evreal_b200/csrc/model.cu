@@ -11,6 +11,7 @@
 // ConvGRU state are updated in place (pointwise).  Weights are repacked once at
 // finalize(): eval-mode BatchNorm folded, K-major [kh*kw*Cin][Cout], LSTM/GRU
 // gate channels interleaved so one thread owns all gates of a hidden channel.
+#include <chrono>
 #include <map>
 #include <memory>
 #include <vector>
@@ -161,24 +162,41 @@ static int pack_conv(const evk_model* m, const std::string& wname, const std::st
     out.cout = cop; out.cin = ci; out.kh = kh; out.kw = kw;
     out.w.assign((size_t)kh * kw * ci * cop, 0.f);
     out.b.assign(cop, 0.f);
-    for (int n = 0; n < cop; ++n) {
-        const int r = perm ? (*perm)[n] : n;
-        if (r < 0) continue;   // padding channel
-        double scale = 1.0, shift = bias ? (double)bias->data[r] : 0.0;
-        if (g) {
-            scale = (double)g->data[r] / std::sqrt((double)var->data[r] + 1e-5);
-            shift = (shift - (double)mean->data[r]) * scale + (double)beta->data[r];
-        }
-        out.b[n] = (float)shift;
-        for (int c = 0; c < ci; ++c)
-            for (int y = 0; y < kh; ++y)
-                for (int x = 0; x < kw; ++x) {
-                    const double wv = transposed ? (double)w->data[(((size_t)c * co + r) * kh + (kh - 1 - y)) * kw + (kw - 1 - x)]
-                                                 : (double)w->data[(((size_t)r * ci + c) * kh + y) * kw + x];
-                    const double v = wv * scale;
-                    out.w[((size_t)(y * kw + x) * ci + c) * cop + n] = (float)v;
+    // (output channels in parallel, 16 at a time so that the K-major destination rows are written a cache line at once: the
+    //  serial form of this loop was most of the 160 ms a HyperE2VID / E2VID handle took to build)
+    float* ow = out.w.data();
+    float* ob = out.b.data();
+    parallel_channels(cop, [=](int n0, int n1) {
+        for (int nb = n0; nb < n1; nb += 16) {
+            const int ne = std::min(nb + 16, n1);
+            double scale[16];
+            int src[16];
+            for (int n = nb; n < ne; ++n) {
+                const int r = perm ? (*perm)[n] : n;
+                src[n - nb] = r;
+                scale[n - nb] = 1.0;
+                if (r < 0) continue;   // padding channel
+                double shift = bias ? (double)bias->data[r] : 0.0;
+                if (g) {
+                    scale[n - nb] = (double)g->data[r] / std::sqrt((double)var->data[r] + 1e-5);
+                    shift = (shift - (double)mean->data[r]) * scale[n - nb] + (double)beta->data[r];
                 }
-    }
+                ob[n] = (float)shift;
+            }
+            for (int y = 0; y < kh; ++y)
+                for (int x = 0; x < kw; ++x)
+                    for (int c = 0; c < ci; ++c) {
+                        float* dst = ow + ((size_t)(y * kw + x) * ci + c) * cop;
+                        for (int n = nb; n < ne; ++n) {
+                            const int r = src[n - nb];
+                            if (r < 0) continue;
+                            const double wv = transposed ? (double)w->data[(((size_t)c * co + r) * kh + (kh - 1 - y)) * kw + (kw - 1 - x)]
+                                                         : (double)w->data[(((size_t)r * ci + c) * kh + y) * kw + x];
+                            dst[n] = (float)(wv * scale[n - nb]);
+                        }
+                    }
+        }
+    }, (size_t)kh * kw * ci * cop);
     return EVK_OK;
 }
 
@@ -268,7 +286,7 @@ struct Builder {
         p.kh = pk.kh; p.kw = pk.kw; p.stride = stride; p.pad = pad;
         p.Hout = (Hin + 2 * pad - pk.kh) / stride + 1;
         p.Wout = (Win + 2 * pad - pk.kw) / stride + 1;
-        p.w = m->upload(pk.w); p.bias = m->upload(pk.b); p.cout = pk.cout;
+        p.bias = m->upload(pk.b); p.cout = pk.cout;
         p.epi = EPI_LINEAR; p.act = act; p.res = res; p.y = y;
         op.flops = conv_flops(p, pk.cout);
         if (window_ok(p, pk)) {
@@ -289,6 +307,7 @@ struct Builder {
             p.w_tc = (const __nv_bfloat16*)d;
         } else {
             attach_tc_weights(p, pk);
+            if (p.w_tc == nullptr) p.w = m->upload(pk.w);      // fp32 K-major weights: only the CUDA-core kernel reads them
         }
         m->ops[0].push_back(op); m->ops[1].push_back(op);
         if (cout_out) *cout_out = pk.cout;
@@ -316,11 +335,11 @@ static int add_lstm(Builder& B, const std::string& pfx, const float* x, int C, i
     int r = pack_conv(m, pfx + ".Gates.weight", pfx + ".Gates.bias", "", &perm, pk);
     if (r != EVK_OK) return r;
     EVK_REQUIRE(pk.cin == 2 * C && pk.kh == 3, EVK_ERR_KEY, "'%s.Gates': unexpected shape", pfx.c_str());
-    const float* w = m->upload(pk.w);
     const float* b = m->upload(pk.b);
     ConvParams wt;   // carries the tensor-core weights shared by both parities
     wt.c1 = C; wt.c2 = C; wt.stride = 1; wt.cout = 4 * C; wt.epi = EPI_LSTM; wt.kh = wt.kw = 3;
     B.attach_tc_weights(wt, pk);
+    const float* w = wt.w_tc != nullptr ? nullptr : m->upload(pk.w);      // fp32 K-major weights: only the CUDA-core kernel reads them
     for (int par = 0; par < 2; ++par) {
         Op op; op.kind = OP_CONV;
         ConvParams& p = op.cp;
@@ -1468,6 +1487,8 @@ int evk_model_finalize(evk_model* m, void* stream) {
         EVK_REQUIRE(m->in_bufs[k] && m->out_bufs[k], EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
     }
     m->in_buf = m->in_bufs[0]; m->out_buf = m->out_bufs[0]; m->prev_rec = m->out_bufs[1];
+    static const bool build_timing = getenv("EVK_BUILD_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
     int r = c.arch == EVK_ARCH_UNET_RECURRENT ? build_unet(m) : c.arch == EVK_ARCH_SPADE_E2VID ? build_spade(m) : c.arch == EVK_ARCH_ETNET ? build_etnet(m)
                                                                                                   : build_firenet(m, c.arch == EVK_ARCH_FIRENET_LEGACY);
     if (r != EVK_OK) return r;
@@ -1482,8 +1503,13 @@ int evk_model_finalize(evk_model* m, void* stream) {
         swap_io(op.in); swap_out(op.out);
         swap_io(op.hp.ev_nchw); swap_io(op.hp.prev);
     }
+    const auto t_built = std::chrono::steady_clock::now();
     r = wire_tc(m);
     if (r != EVK_OK) return r;
+    if (build_timing)
+        fprintf(stderr, "evk_model_finalize: weight packing + program %.1f ms, tensor-core wiring + plans %.1f ms (%d tensor-core launches)\n",
+                std::chrono::duration<double, std::milli>(t_built - t_start).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_built).count(), m->tc_convs);
     for (void* p : m->allocs) EVK_REQUIRE(p != nullptr, EVK_ERR_CUDA, "evk_model_finalize: out of device memory");
     m->flops = 0.0;
     for (const Op& op : m->ops[0]) m->flops += op.flops;
