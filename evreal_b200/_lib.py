@@ -60,6 +60,7 @@ SIGNATURES = {
     "evk_mse_ssim": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "evk_u8_to_f32": (_i, [_vp, _vp, _i64, _vp]),
     "evk_quantize_u8": (_i, [_vp, _vp, _i64, _vp]),
+    "evk_searchsorted_f64": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp]),
     "evk_equalize_hist": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "evk_equalize_local": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "evk_lpips_create": (_i, [_i, _i, _i, _i, _i, _c.POINTER(_vp)]),

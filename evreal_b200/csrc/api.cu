@@ -27,6 +27,7 @@ int normalize_pad(const float*, float*, int, int, int, int, int, int, int, cudaS
 int crop(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int u8_to_f32(const uint8_t*, float*, int64_t, cudaStream_t);
 int quantize_u8(const float*, uint8_t*, int64_t, cudaStream_t);
+int searchsorted_f64(const double*, int64_t, const double*, int64_t, int, long long*, cudaStream_t);
 int equalize_hist(const float*, float*, int, int, int, cudaStream_t);
 int equalize_local(const float*, float*, int, int, int, int, int, cudaStream_t);
 int voxelize_raw_batch(const evk_event_window*, int, int, int, int, float*, int*, cudaStream_t);
@@ -121,6 +122,11 @@ int evk_equalize_hist(const float* img, float* out, int n_images, int numel, int
 int evk_quantize_u8(const float* in, uint8_t* out, int64_t numel, void* stream) {
     EVK_REQUIRE(in && out, EVK_ERR_ARG, "evk_quantize_u8: null pointer");
     return evk::quantize_u8(in, out, numel, (cudaStream_t)stream);
+}
+
+int evk_searchsorted_f64(const double* t, int64_t n, const double* values, int64_t m, int right, int64_t* out, void* stream) {
+    EVK_REQUIRE((t || n == 0) && values && out, EVK_ERR_ARG, "evk_searchsorted_f64: null pointer");
+    return evk::searchsorted_f64(t, n, values, m, right, reinterpret_cast<long long*>(out), (cudaStream_t)stream);
 }
 
 int evk_mse_ssim(const float* img, const float* ref, int n_images, int H, int W, int clip, double* scores, void* stream) {

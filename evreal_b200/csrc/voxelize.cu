@@ -535,4 +535,32 @@ int u8_to_f32(const uint8_t* in, float* out, int64_t n, cudaStream_t st) {
     return EVK_OK;
 }
 
+// Device-side np.searchsorted over the resident float64 timestamps: the 't_seconds' window boundaries of
+// MemMapDataset.compute_timeblock_indices (dataset.py:104-117) without a host copy of the event timestamps.  The query
+// values are the reference's own float64 expression ((t - sw) * i + t0) + t, evaluated by the caller; the search compares
+// float64 values only, so the indices are the ones numpy returns (side = 'left': first index with t[idx] >= v,
+// 'right': first index with t[idx] > v; NaN sorts last as in numpy).
+__global__ void __launch_bounds__(128) searchsorted_f64_kernel(const double* __restrict__ t, int64_t n, const double* __restrict__ values,
+                                                               int64_t m, int right, long long* __restrict__ out) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
+        const double v = values[q];
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const int64_t mid = lo + ((hi - lo) >> 1);
+            const double a = __ldg(t + mid);
+            // numpy's ordering with NaN last: a < v  <=>  a < v || (v is NaN && a is not)
+            const bool below = right ? !(v < a || (a != a && v == v)) : (a < v || (v != v && a == a));
+            if (below) lo = mid + 1; else hi = mid;
+        }
+        out[q] = (long long)lo;
+    }
+}
+
+int searchsorted_f64(const double* t, int64_t n, const double* values, int64_t m, int right, long long* out, cudaStream_t st) {
+    EVK_REQUIRE(n >= 0 && m > 0, EVK_ERR_ARG, "evk_searchsorted_f64: n = %lld, m = %lld", (long long)n, (long long)m);
+    searchsorted_f64_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(m, 128), kNumSMs * 8), 128, 0, st>>>(t, n, values, m, right, out);
+    EVK_CHECK_CUDA(cudaGetLastError());
+    return EVK_OK;
+}
+
 }  // namespace evk

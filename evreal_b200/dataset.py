@@ -100,7 +100,22 @@ class MemMapDataset(torch.utils.data.Dataset):
         the reference's float64 expression order, evaluated for all i at once -- and starts where window i-1 ended."""
         t, sw = self.voxel_method['t'], self.voxel_method['sliding_window_t']
         end_times = ((t - sw) * np.arange(len(self), dtype=np.float64) + self.t0) + t
+        if self._dev_events is not None and len(end_times) > 0:
+            # the timestamps are already resident: search them where they are (evk_searchsorted_f64, float64 compares only)
+            return self._chained(self.searchsorted_device(end_times))
         return self._chained(np.searchsorted(self.filehandle["t"], end_times, side='left'))
+
+    def searchsorted_device(self, values, side='left'):
+        """np.searchsorted(self.filehandle['t'], values, side) on the device-resident float64 timestamps."""
+        self._upload()
+        dev = self._device()
+        t = self._dev_events[1]
+        vals = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
+        out = torch.empty(vals.numel(), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().evk_searchsorted_f64(_lib.ptr(t), t.numel(), _lib.ptr(vals), vals.numel(),
+                                                        1 if side == 'right' else 0, _lib.ptr(out), _lib.stream_ptr(dev)))
+        return out.cpu().numpy()
 
     def compute_k_indices(self):
         """'k_events' windows (dataset.py:119-130)."""

@@ -229,6 +229,13 @@ int evk_equalize_local(const float* img, float* out, int n_images, int H, int W,
  * (save_inferred_image, utils/eval_utils.py:80-84, after the clip of EvalMetricsTracker.update, utils/eval_metrics.py:253-255) */
 int evk_quantize_u8(const float* in, uint8_t* out, int64_t numel, void* stream);
 
+/* np.searchsorted over DEVICE-resident float64 event timestamps: the 't_seconds' window boundaries of
+ * MemMapDataset.compute_timeblock_indices (dataset.py:104-117, `np.searchsorted(self.filehandle["t"], end_time)`, side
+ * 'left') without a host copy of the timestamps.  t [n] ascending, values [m] (the reference's float64 expression
+ * ((t - sw) * i + t0) + t, evaluated by the caller), out [m] int64, all on the device; right != 0 selects side 'right'.
+ * Float64 comparisons only: the indices are numpy's, bit for bit. */
+int evk_searchsorted_f64(const double* t, int64_t n, const double* values, int64_t m, int right, int64_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -178,3 +178,42 @@ def test_normalize_all_zero_tensor_is_left_alone():
     from evreal_b200 import normalize_event_tensor
     z = torch.zeros(1, 5, 16, 16, device='cuda')
     assert float(normalize_event_tensor(z).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('side', ['left', 'right'])
+def test_device_searchsorted_matches_numpy(side):
+    """evk_searchsorted_f64 (device-side boundaries for 't_seconds') against np.searchsorted, bit-exact:
+    duplicates, queries equal to stored values, below the first / above the last timestamp, a one-element and an empty array."""
+    from evreal_b200 import _lib
+    lib = _lib.load()
+    g = np.random.default_rng(5)
+    t = np.sort(g.uniform(3.0, 4.0, 200_003))
+    t[1000:1040] = t[1000]                                              # a run of equal timestamps
+    q = np.concatenate([g.uniform(2.9, 4.1, 5000), t[::997], t[1000:1003], [t[0], t[-1], -1.0, 1e9,
+                        np.nextafter(t[500], 0.0), np.nextafter(t[500], 10.0)]])
+    for arr in (t, t[:1], t[:0]):
+        td = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+        qd = torch.from_numpy(q).cuda()
+        out = torch.empty(len(q), dtype=torch.int64, device='cuda')
+        _lib.check(lib.evk_searchsorted_f64(_lib.ptr(td) if len(arr) else None, len(arr), _lib.ptr(qd), len(q),
+                                            1 if side == 'right' else 0, _lib.ptr(out), _lib.stream_ptr()))
+        assert np.array_equal(out.cpu().numpy(), np.searchsorted(arr, q, side=side))
+
+
+@pytest.mark.parametrize('mode', ['t_seconds', 't_seconds_sliding'])
+def test_t_seconds_table_on_device_matches_real_dataset(tmp_path, mode):
+    """The 't_seconds' window table computed from the RESIDENT timestamps equals the real MemMapDataset's
+    (tests/golden/windows.npz, dataset.py:104-117) and the host table of the same object."""
+    from evreal_b200.dataset import MemMapDataset
+    from helpers import write_sequence_from_arrays
+    vm = {'t_seconds': {'method': 't_seconds', 't': 0.04, 'sliding_window_t': 0.0},
+          't_seconds_sliding': {'method': 't_seconds', 't': 0.05, 'sliding_window_t': 0.01}}[mode]
+    g = golden('windows')
+    arrays = {k: g[k] for k in ('events_ts', 'events_xy', 'events_p', 'images_ts', 'image_event_indices')}
+    arrays['images'] = np.zeros((len(arrays['images_ts']), 32, 40, 1), dtype=np.uint8)
+    path = write_sequence_from_arrays(str(tmp_path / 'seq'), arrays, (32, 40))
+    ds = MemMapDataset(path, voxel_method=dict(vm), num_bins=5, resident=True)
+    host_table = np.array(ds.event_indices, dtype=np.int64)
+    assert np.array_equal(host_table, g[mode + '.table'])
+    ds._upload()                                                        # timestamps resident: the table is rebuilt on the device
+    assert np.array_equal(np.array(ds.compute_timeblock_indices(), dtype=np.int64), g[mode + '.table'])
