@@ -226,6 +226,41 @@ def voxelizer_roofline(pk, torch, _lib):
         sweep.append({"Mev_per_s_stream": rate, "events_per_window": n_ev, "us_per_window": ms_i * 1e3,
                       "events_per_s": n_ev / (ms_i * 1e-3), "GB_per_s": gbs_i, "frac": gbs_i / pk["hbm_gbs"]})
     ms, bytes_alg, gbs = measure(n, 20)
+    # cfg 5's second distribution: "edge-clustered" -- events on a few moving edges, the best case for merging the
+    # contributions of a warp's lanes before they reach L2.  `distinct_cells_per_warp` counts what such a merge could save:
+    # the distinct (pixel, bin group) reduction targets among 32 consecutive events.
+    uniform_sets = evs
+    def distinct_per_warp(x, y, t):
+        key = ((y.long() * Wv + x.long()) * 2 + (t / t[-1] * (bins - 1)).floor().clamp_(0, bins - 1).long() // 3)[: (n // 32) * 32].view(-1, 32)
+        srt = torch.sort(key, dim=1)[0]
+        return float(((srt[:, 1:] != srt[:, :-1]).sum(1) + 1).float().mean())
+    evs = []
+    for s in range(sets):
+        k_edges = 24
+        e = torch.randint(0, k_edges, (n,), device='cuda', generator=g)
+        t = torch.sort(torch.rand(n, device='cuda', generator=g) * 0.04)[0]
+        t = t - t[0]
+        ex0 = torch.rand(k_edges, device='cuda', generator=g) * Wv
+        ey0 = torch.rand(k_edges, device='cuda', generator=g) * Hv
+        ang = torch.rand(k_edges, device='cuda', generator=g) * 3.14159
+        length = 60.0 + torch.rand(k_edges, device='cuda', generator=g) * 200.0
+        vx = (torch.rand(k_edges, device='cuda', generator=g) - 0.5) * 4000.0            # pixels per second
+        vy = (torch.rand(k_edges, device='cuda', generator=g) - 0.5) * 4000.0
+        along = (torch.rand(n, device='cuda', generator=g) - 0.5) * length[e]
+        jitter = torch.randn(n, device='cuda', generator=g) * 0.7
+        x = (ex0[e] + vx[e] * t + along * torch.cos(ang[e]) - jitter * torch.sin(ang[e])).clamp_(0, Wv - 1).floor()
+        y = (ey0[e] + vy[e] * t + along * torch.sin(ang[e]) + jitter * torch.cos(ang[e])).clamp_(0, Hv - 1).floor()
+        p = torch.randint(0, 2, (n,), device='cuda', generator=g).float() * 2 - 1
+        evs.append((x, y, t, p))
+    clustered = []
+    for rate, n_ev in ((10, 400_000), (100, 4_000_000)):
+        ms_i, _, gbs_i = measure(n_ev, 20)
+        clustered.append({"Mev_per_s_stream": rate, "events_per_window": n_ev, "us_per_window": ms_i * 1e3,
+                          "events_per_s": n_ev / (ms_i * 1e-3), "GB_per_s": gbs_i, "frac": gbs_i / pk["hbm_gbs"]})
+    aggregation = {"distinct_cells_per_warp_uniform": distinct_per_warp(*uniform_sets[0][:3]),
+                   "distinct_cells_per_warp_edge_clustered": distinct_per_warp(*evs[0][:3]),
+                   "what": "distinct (pixel, bin-group) reduction targets among 32 consecutive events of a 4 M-event window: 32 = nothing to merge"}
+    del uniform_sets, evs
     # the launches the pipeline issues: B raw windows per call
     import ctypes
     batched = []
@@ -255,7 +290,7 @@ def voxelizer_roofline(pk, torch, _lib):
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                          "traffic": None, "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["source"],
                          "note": "one RED.ADD.V4.F32 per event into an L2-resident interleaved grid: bound by the L2 reduction request rate (~83/clk), not by HBM"},
-            "sweep_cfg5": sweep, "pipeline_sizes": batched}
+            "sweep_cfg5": sweep, "sweep_cfg5_edge_clustered": clustered, "warp_aggregation": aggregation, "pipeline_sizes": batched}
 
 
 def network_roofline(model, padded, pk, frames=6):

@@ -474,3 +474,42 @@ def _eval_dataset(eval_config, method_name, model, method_config, dataset_config
         for metric_name, score in mean_scores.items():
             local.update(metric_name, score, n_eval)
         seq.pop('dataset', None)
+
+
+def main(argv=None):
+    """The reference's command line (eval.py:447-455: -c / -m / -d / -qm) over evaluate().  Under torchrun (RANK /
+    WORLD_SIZE / LOCAL_RANK in the environment) the process joins an NCCL group and takes its shard of the sequences."""
+    import argparse
+    ap = argparse.ArgumentParser(description='event2im evaluation on the B200 hot path (flags of EVREAL eval.py)')
+    ap.add_argument('-c', '--config', nargs='+', type=str, help='evaluation configs')
+    ap.add_argument('-m', '--method', nargs='+', type=str, required=True, help='methods')
+    ap.add_argument('-d', '--dataset', nargs='+', type=str, required=True, help='datasets')
+    ap.add_argument('-qm', '--metrics', nargs='+', type=str, help='quantitative evaluation metrics')
+    ap.add_argument('--config-root', default='config')
+    ap.add_argument('--output-root', default='outputs')
+    ap.add_argument('--lockstep', type=int, default=0, help='sequences run in lock-step per GPU (0: one at a time, like the reference)')
+    ap.add_argument('--lpips-weights', default=None, help='torch file with the LPIPS tensors (pyiqa downloads them; none ship here)')
+    args = ap.parse_args(argv)
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
+    weights = torch.load(args.lpips_weights, map_location='cpu') if args.lpips_weights else None
+    results = evaluate(args.method, args.config, args.dataset, args.metrics, config_root=args.config_root,
+                       output_root=args.output_root, write_files=args.lockstep <= 1, rank=rank, world_size=world,
+                       lockstep=args.lockstep, lpips_weights=weights)
+    if rank == 0:
+        for cfg_name, per_method in results.items():
+            for method, per_dataset in per_method.items():
+                for dataset, tracker in per_dataset.items():
+                    scores = {k: v['average'] for k, v in tracker.data_dict.items()}
+                    print(f"{cfg_name} / {method} / {dataset}: {scores}")
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return results
+
+
+if __name__ == '__main__':
+    main()

@@ -132,6 +132,23 @@ def test_plugin_surface_and_sharded_means(tmp_path):
         assert abs(total / count - tr.get_average(k)) <= 1e-6 * abs(tr.get_average(k))     # voxelizer atomics: order-dependent ulps
 
 
+def test_command_line_matches_evaluate(tmp_path, capsys):
+    """`python -m evreal_b200.evaluate -m .. -c .. -d .. -qm ..` (the reference's flags, eval.py:447-455) is evaluate()."""
+    from evreal_b200 import evaluate as ev
+    g = golden('eval_loop')
+    _write_plugin_tree(tmp_path, g, 2)
+    cfg_root = str(tmp_path / 'config')
+    ref = ev.evaluate(['FireNet'], ['std'], ['SYN'], ['mse', 'ssim'], config_root=cfg_root, write_files=False)
+    got = ev.main(['-m', 'FireNet', '-c', 'std', '-d', 'SYN', '-qm', 'mse', 'ssim', '--config-root', cfg_root,
+                   '--output-root', str(tmp_path / 'out')])
+    for k in ('mse', 'ssim'):
+        a, b = got['std']['FireNet']['SYN'], ref['std']['FireNet']['SYN']
+        assert a.get_count(k) == b.get_count(k) > 0
+        assert abs(a.get_average(k) - b.get_average(k)) <= 1e-6 * abs(b.get_average(k))
+    assert 'std / FireNet / SYN' in capsys.readouterr().out
+    assert os.path.exists(tmp_path / 'out' / 'std' / 'SYN' / 'seq0' / 'FireNet' / 'mse.txt')
+
+
 def test_lockstep_evaluate_matches_sequential(tmp_path):
     """evaluate(lockstep=B): this rank's sequences run B at a time through SequenceBatch (per-sequence item ranges and
     score gates of eval.py:203-246, shorter sequences padded with empty windows) -- counts identical, dataset means equal
