@@ -186,6 +186,27 @@ def test_e2vid_full_size_vs_oracle(precision):
     assert m.last_launch_count() > 0
 
 
+def test_e2vid_and_firenet_at_the_largest_sensor_size_vs_oracle():
+    """The largest size SURVEY 8a lists (640x480, cfg 5's sensor: 279.0 GFLOP per E2VID frame): two recurrent frames of E2VID
+    and of FireNet against the CPU oracle -- every tile count, halo box and border line differs from the 240x180 runs."""
+    from evreal_b200 import E2VIDRecurrent, FireNet_legacy
+    from oracle import networks as on
+    torch.set_num_threads(8)
+    w = on.random_unet_weights(seed=13, norm_bn=True)
+    m = _load(E2VIDRecurrent(dict(E2VID_KW, base_num_channels=32, norm='BN', final_activation='sigmoid')),
+              {'unetrecurrent.' + k: v for k, v in w.items()})
+    vox = _voxels(51, 2, 1, 480, 640, 300000)
+    oracle = on.UNetRecurrentOracle(w, final_sigmoid=True)
+    ref = np.stack([oracle(torch.from_numpy(v)).numpy() for v in vox])
+    _assert_close(_frames(m, vox), ref, 'e2vid_vga')
+    assert m.flops_per_forward() == pytest.approx(279.0e9, rel=0.01)          # SURVEY 8a, a12
+    wf = on.random_firenet_weights(seed=14)
+    mf = _load(FireNet_legacy({'num_bins': 5, 'base_num_channels': 16, 'kernel_size': 3}), {'net.' + k: v for k, v in wf.items()})
+    oracle_f = on.FireNetLegacyOracle(wf)
+    ref = np.stack([oracle_f(torch.from_numpy(v)).numpy() for v in vox])
+    _assert_close(_frames(mf, vox), ref, 'firenet_vga')
+
+
 def test_firenet_full_size_vs_oracle_batch3():
     """BASELINE cfg 3 shape: FireNet at 240x180 padded to 192x240 (num_encoders falls back to 4), batch of 3 streams."""
     from evreal_b200 import FireNet_legacy
