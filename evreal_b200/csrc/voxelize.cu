@@ -110,7 +110,7 @@ template <bool kVec, bool kDirect>
 __global__ void __launch_bounds__(kVoxThreads)
 voxelize_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ t,
                     const float* __restrict__ p, int64_t n, int64_t head, VoxGeom g,
-                    float* __restrict__ grid, int* __restrict__ oob_count, int chunked) {
+                    float* __restrict__ grid, int* __restrict__ oob_count) {
     TimeNorm tn;
     tn.t0 = __ldg(t);
     tn.dt = __fsub_rn(__ldg(t + n - 1), tn.t0);
@@ -127,19 +127,7 @@ voxelize_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, co
         const float4* y4 = reinterpret_cast<const float4*>(y + head);
         const float4* t4 = reinterpret_cast<const float4*>(t + head);
         const float4* p4 = reinterpret_cast<const float4*>(p + head);
-        // chunked: CTA b walks its own contiguous slice of the window, so the CTAs in flight sample the WHOLE window's time span
-        // instead of one short span of it.  Streams whose events sit on moving edges put all the events of a pixel within the
-        // short time the edge takes to cross it: in grid-stride order they reach the pixel's L2 reduction unit together and
-        // serialise there (per-address), in chunked order they arrive spread over the kernel's run time.
-        int64_t v_begin = tid, v_end = nvec, v_step = nthreads;
-        if (chunked) {
-            const int64_t per_cta = (nvec + gridDim.x - 1) / gridDim.x;
-            const int64_t chunk = (per_cta + blockDim.x - 1) / blockDim.x * blockDim.x;
-            v_begin = (int64_t)blockIdx.x * chunk + threadIdx.x;
-            v_end = min(nvec, ((int64_t)blockIdx.x + 1) * chunk);
-            v_step = blockDim.x;
-        }
-        for (int64_t v = v_begin; v < v_end; v += v_step) {
+        for (int64_t v = tid; v < nvec; v += nthreads) {
             const float4 xv = __ldcs(x4 + v), yv = __ldcs(y4 + v), tv = __ldcs(t4 + v), pv = __ldcs(p4 + v);
             const int64_t i = head + v * 4;
             scatter_event<kDirect>(xv.x, yv.x, tn(tv.x, i + 0), pv.x, g, grid, oob);
@@ -274,15 +262,13 @@ int voxelize_f32(const float* x, const float* y, const float* t, const float* p,
     auto phase = [](const void* q) { return (int)(((uintptr_t)q >> 2) & 3); };
     const bool same = phase(x) == phase(y) && phase(y) == phase(t) && phase(t) == phase(p) &&
                       (((uintptr_t)x | (uintptr_t)y | (uintptr_t)t | (uintptr_t)p) & 3) == 0;
-    const char* ce = getenv("EVK_VOX_CHUNKED");
-    const int chunked = (ce && ce[0]) ? atoi(ce) : 0;
     if (same && n >= 64) {
         int64_t head = (4 - phase(x)) & 3;
-        if (direct) voxelize_f32_kernel<true, true><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, scratch, oob_count, chunked);
-        else voxelize_f32_kernel<true, false><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, scratch, oob_count, chunked);
+        if (direct) voxelize_f32_kernel<true, true><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, scratch, oob_count);
+        else voxelize_f32_kernel<true, false><<<vox_grid_blocks(n, 4), kVoxThreads, 0, st>>>(x, y, t, p, n, head, g, scratch, oob_count);
     } else {
-        if (direct) voxelize_f32_kernel<false, true><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, scratch, oob_count, 0);
-        else voxelize_f32_kernel<false, false><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, scratch, oob_count, 0);
+        if (direct) voxelize_f32_kernel<false, true><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, scratch, oob_count);
+        else voxelize_f32_kernel<false, false><<<vox_grid_blocks(n, 1), kVoxThreads, 0, st>>>(x, y, t, p, n, 0, g, scratch, oob_count);
     }
     EVK_CHECK_CUDA(cudaGetLastError());
     return direct ? EVK_OK : vox_scratch_end(scratch, grid, g, 1, st);
