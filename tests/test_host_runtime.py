@@ -103,3 +103,29 @@ def test_failing_rank_still_joins_every_reduce():
     n, mean = out['OK']['B']                               # rank 1 contributed the sequence it finished before failing
     assert n == 35 and abs(mean - (0.1 * 20 + 0.3 * 5 + 0.5 * 10) / 35) < 1e-12
     assert got[0][1] == 1 and got[1][1] == 2               # rank 0: model failure; rank 1: model + dataset failure
+
+
+def test_command_line_flags_reach_evaluate(monkeypatch, capsys):
+    """python -m evreal_b200.evaluate keeps eval.py's flags (-c / -m / -d / -qm, eval.py:447-455) and hands them to
+    evaluate() unchanged; lock-step runs do not write per-frame files (the lock-step form has no per-sequence tracker)."""
+    from evreal_b200 import evaluate as ev
+    seen = {}
+
+    def fake(methods, configs, datasets, metrics, **kw):
+        seen.update(methods=methods, configs=configs, datasets=datasets, metrics=metrics, **kw)
+        tr = ev.MetricTracker()
+        tr.update('mse', 0.25, 4)
+        return {'std': {'E2VID': {'ECD': tr}}}
+
+    monkeypatch.setattr(ev, 'evaluate', fake)
+    monkeypatch.delenv('RANK', raising=False)
+    monkeypatch.delenv('WORLD_SIZE', raising=False)
+    ev.main(['-m', 'E2VID', 'FireNet', '-c', 'std', '-d', 'ECD', 'HQF', '-qm', 'mse', 'ssim', 'lpips', '--lockstep', '16'])
+    assert seen['methods'] == ['E2VID', 'FireNet'] and seen['configs'] == ['std'] and seen['datasets'] == ['ECD', 'HQF']
+    assert seen['metrics'] == ['mse', 'ssim', 'lpips'] and seen['lockstep'] == 16 and seen['write_files'] is False
+    assert seen['rank'] == 0 and seen['world_size'] == 1 and seen['config_root'] == 'config'
+    assert "std / E2VID / ECD: {'mse': 0.25}" in capsys.readouterr().out
+    ev.main(['-m', 'E2VID', '-d', 'ECD'])
+    assert seen['configs'] is None and seen['metrics'] is None and seen['write_files'] is True and seen['lockstep'] == 0
+    with pytest.raises(SystemExit):
+        ev.main(['-c', 'std'])                     # -m is required
